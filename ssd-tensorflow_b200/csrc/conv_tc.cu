@@ -1,0 +1,493 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (tf32 operands, fp32
+// accumulation in tensor memory).  Replaces the cuDNN/Eigen convolutions behind
+// tf.nn.conv2d / atrous_conv2d in the reference graph (ssdvgg.py:42-65,231-332)
+// and their TF gradients (MomentumOptimizer.minimize, ssdvgg.py:585-588).
+//
+// fprop and dgrad are the same contraction -- "for every filter tap, gather the
+// source pixels at a tap-dependent shift and contract over source channels" -- so
+// one kernel serves both:
+//     fprop: src = x  [B,H,W,Cin],   dst = y  [B,Ho,Wo,Cout], shift = tap*dil - pad
+//     dgrad: src = dz [B,Ho,Wo,Cout],dst = dx [B,H,W,Cin],    shift = pad - tap*dil
+//
+// Mapping to the hardware
+//   * M tile = 128 destination pixels arranged as a TW x TH x TN box (x, y, image)
+//     chosen per layer so that TW*TH*TN <= 128 wastes the fewest rows.  A 4-D TMA
+//     tensor map over the NHWC source loads the shifted box for one tap and one
+//     32-channel slab: [rows][32 x fp32] = 128-byte rows, SWIZZLE_128B, which is
+//     exactly the K-major UMMA operand layout; padding comes from TMA zero fill.
+//   * B operand = filter rows (destination channels) x 32 source channels, K-major,
+//     from a 2-D tensor map over [taps*rows][Csrc]  (fprop: per-tap transposed copy
+//     of the HWIO filter; dgrad: the HWIO filter itself).
+//   * tcgen05.mma.cta_group::1.kind::tf32, M=128, N<=256, K=8 per instruction, 4 per
+//     32-channel slab, accumulating over taps x slabs into one of two TMEM buffers.
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue
+//     (tcgen05.ld -> bias/ReLU/mask -> global).  4-stage smem ring, persistent CTAs.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace ssdb {
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;                    // fp32 elements = 128 bytes = one swizzle row
+constexpr int MAX_N = 256;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;   // 16 KB
+constexpr int B_BYTES = MAX_N * BLOCK_K * 4;     // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps (launch error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) { printf("ssdb conv_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
+// 8-row groups 1024 B apart (SBO), rows 128 B apart, 16-byte units.
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;                      // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset
+    d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
+    return d;
+}
+
+// ------------------------------------------------------------------ kernel
+struct TcArgs {
+    // destination tile box and grid
+    int TW, TH, TN;                 // rows of a tile = TW*TH*TN <= 128
+    int tiles_x, tiles_y, tiles_n;  // destination tiling
+    int n_tiles, block_n;           // channel tiling of the destination
+    int Hd, Wd, Bn, Cd;             // destination extents (Cd = stored channel stride)
+    int cd_valid;                   // channels actually written
+    int taps, kdim;                 // filter taps (k*k), k
+    int cblocks;                    // source channels / 32
+    int rows_per_tap;               // rows of the B tensor map per tap
+    int off0, offstep;              // source shift for tap index t (per axis): off0 + t*offstep
+    int mode;                       // 0 fprop, 1 dgrad
+    float* dst;
+    const float* bias;              // fprop
+    const float* mask;              // dgrad: ReLU mask source (same shape as dst) or null
+    int relu, beta;
+    int scatter, V, n_valid, anchor_base, A;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w, const TcArgs p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B needs 1024-byte alignment
+    const uint32_t bars = base + STAGES * STAGE_BYTES;
+    // barrier layout: full[4] empty[4] tfull[2] tempty[2] then tmem pointer
+    const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
+    const uint32_t tmem_slot = tempty0 + 16;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_src) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+    const int total_tiles = m_tiles * p.n_tiles;
+    const int kblocks = p.taps * p.cblocks;
+    const uint32_t a_bytes = (uint32_t)(p.TW * p.TH * p.TN) * 128u;
+    const uint32_t b_bytes = (uint32_t)p.block_n * 128u;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+                const int tx = mt % p.tiles_x; const int r1 = mt / p.tiles_x;
+                const int ty = r1 % p.tiles_y; const int tn = r1 / p.tiles_y;
+                const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    const int kh = tap / p.kdim, kw = tap - kh * p.kdim;
+                    const int sy = y0 + p.off0 + kh * p.offstep;
+                    const int sx = x0 + p.off0 + kw * p.offstep;
+                    for (int cb = 0; cb < p.cblocks; ++cb) {
+                        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                        const uint32_t fb = full0 + 8 * stage;
+                        mbar_expect_tx(fb, a_bytes + b_bytes);
+                        const uint32_t sa = base + stage * STAGE_BYTES;
+                        tma_load_4d(sa, &map_src, fb, cb * BLOCK_K, sx, sy, n0);
+                        tma_load_2d(sa + A_BYTES, &map_w, fb, cb * BLOCK_K, tap * p.rows_per_tap + nt * p.block_n);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MAX_N);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * STAGE_BYTES;
+                    const uint64_t ad = make_kmajor_desc(sa);
+                    const uint64_t bd = make_kmajor_desc(sa + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 8; ++k) {
+                        // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
+                        tc_mma_tf32(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    tc_commit(empty0 + 8 * stage);              // frees the smem slot when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull0 + 8 * acc);                    // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int rows_valid = p.TW * p.TH * p.TN;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+            const int tx = mt % p.tiles_x; const int r1 = mt / p.tiles_x;
+            const int ty = r1 % p.tiles_y; const int tn = r1 / p.tiles_y;
+            const int lx = row % p.TW; const int r2 = row / p.TW;
+            const int ly = r2 % p.TH; const int ln = r2 / p.TH;
+            const int x = tx * p.TW + lx, y = ty * p.TH + ly, n = tn * p.TN + ln;
+            const bool ok = row < rows_valid && x < p.Wd && y < p.Hd && n < p.Bn;
+            const long long pix = ((long long)n * p.Hd + y) * p.Wd + x;
+            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (uint32_t)(acc * MAX_N) + ((uint32_t)(quarter * 32) << 16);
+            for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+                uint32_t r[32];
+                __syncwarp();
+                tc_ld32(t_row + (uint32_t)c0, r);
+                tc_wait_ld();
+                const int ch0 = nt * p.block_n + c0;
+                if (!ok) {
+                    // rows outside the destination: nothing to store
+                } else if (p.mode == 0) {
+                    if (p.scatter) {
+                        const int hw = p.Hd * p.Wd;
+                        const int pimg = y * p.Wd + x;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int ch = ch0 + j;
+                            if (ch < p.n_valid) {
+                                const int bt = ch / p.V, v = ch - bt * p.V;
+                                float val = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + ch) : 0.f);
+                                p.dst[((long long)n * p.A + p.anchor_base + (long long)bt * hw + pimg) * p.V + v] = val;
+                            }
+                        }
+                    } else {
+                        float* d = p.dst + pix * p.Cd + ch0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (ch0 + j < p.cd_valid) {
+                                float v[4];
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    v[q] = __uint_as_float(r[j + q]) + (p.bias ? __ldg(p.bias + ch0 + j + q) : 0.f);
+                                    if (p.relu) v[q] = fmaxf(v[q], 0.f);
+                                }
+                                *reinterpret_cast<float4*>(d + j) = make_float4(v[0], v[1], v[2], v[3]);
+                            }
+                        }
+                    }
+                } else {
+                    float* d = p.dst + pix * p.Cd + ch0;
+                    const float* mk = p.mask ? p.mask + pix * p.Cd + ch0 : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (ch0 + j < p.cd_valid) {
+                            float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])};
+                            if (p.beta) { float4 o = *reinterpret_cast<const float4*>(d + j); v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w; }
+                            if (mk) {
+                                float4 m4 = *reinterpret_cast<const float4*>(mk + j);
+                                v[0] = m4.x > 0.f ? v[0] : 0.f; v[1] = m4.y > 0.f ? v[1] : 0.f;
+                                v[2] = m4.z > 0.f ? v[2] : 0.f; v[3] = m4.w > 0.f ? v[3] : 0.f;
+                            }
+                            *reinterpret_cast<float4*>(d + j) = make_float4(v[0], v[1], v[2], v[3]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// per-tap transpose: w_t[tap][n][c] = w[tap][c][n] (n < Cout), zero rows for n >= Cout
+__global__ void pack_filter_t_kernel(const float* __restrict__ w, int taps, int Cin, int Cout, int cout_pad, float* __restrict__ wt) {
+    __shared__ float tile[32][33];
+    const int tap = blockIdx.z;
+    const int c0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, n = n0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < Cin && n < Cout) ? w[((long long)tap * Cin + c) * Cout + n] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int n = n0 + i, c = c0 + threadIdx.x;
+        if (n < cout_pad && c < Cin) wt[((long long)tap * cout_pad + n) * Cin + c] = tile[threadIdx.x][i];
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int encode_act_map(CUtensorMap* m, const float* ptr, int B, int H, int W, int C, int TW, int TH, int TN) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return SSDB_ECUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation %dx%dx%dx%d box %d,%d,%d) failed: %d", B, H, W, C, TW, TH, TN, (int)r); return SSDB_ECUDA; }
+    return SSDB_OK;
+}
+
+int encode_w_map(CUtensorMap* m, const float* ptr, long long rows, int K, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return SSDB_ECUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(filter rows %lld K %d box %d) failed: %d", rows, K, box_rows, (int)r); return SSDB_ECUDA; }
+    return SSDB_OK;
+}
+
+struct TileGeom { int TW, TH, TN; double eff; };
+
+// pick the TW x TH x TN destination box (<= 128 pixels) that wastes the fewest MMA rows
+TileGeom pick_tile(int B, int H, int W) {
+    TileGeom best{1, 1, 1, 0.0};
+    const double total = (double)B * H * W;
+    for (int tw = 1; tw <= W && tw <= 128; ++tw) {
+        for (int th = 1; th <= H && tw * th <= 128; ++th) {
+            int tn_max = 128 / (tw * th);
+            if (tn_max > B) tn_max = B;
+            for (int tn = 1; tn <= tn_max; ++tn) {
+                long long tiles = (long long)((W + tw - 1) / tw) * ((H + th - 1) / th) * ((B + tn - 1) / tn);
+                double eff = total / (tiles * 128.0);
+                // prefer higher efficiency; tie -> wider rows (longer contiguous TMA runs)
+                if (eff > best.eff + 1e-9 || (eff > best.eff - 1e-9 && tw > best.TW)) best = TileGeom{tw, th, tn, eff};
+            }
+        }
+    }
+    return best;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+    return n;
+}
+
+int launch_tc(const CUtensorMap& ms, const CUtensorMap& mw, const TcArgs& a, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) { SSDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr = true; }
+    long long total = (long long)a.tiles_x * a.tiles_y * a.tiles_n * a.n_tiles;
+    int grid = (int)(total < num_sms() ? total : num_sms());
+    conv_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ms, mw, a);
+    SSDB_LAUNCH_CHECK();
+    return SSDB_OK;
+}
+
+int block_n_for(int channels) {
+    int n = (channels + 15) / 16 * 16;
+    return n > MAX_N ? MAX_N : n;
+}
+
+bool tc_common_ok(const ConvGeom& g) {
+    return g.stride == 1 && g.Cin % 32 == 0 && g.Cout % 16 == 0 && g.k >= 1 && g.k <= 7;
+}
+
+}  // namespace
+
+bool conv_tc_supported_fprop(const ConvGeom& g) {
+    if (!tc_common_ok(g)) return false;
+    if (g.Cout > MAX_N && g.Cout % MAX_N != 0) return false;
+    TileGeom t = pick_tile(g.B, g.Ho, g.Wo);
+    return t.eff >= 0.45;
+}
+
+bool conv_tc_supported_dgrad(const ConvGeom& g) {
+    if (!tc_common_ok(g) || g.Cout % 32 != 0) return false;
+    if (g.Cin > MAX_N && g.Cin % MAX_N != 0) return false;
+    TileGeom t = pick_tile(g.B, g.H, g.W);
+    return t.eff >= 0.45;
+}
+
+int pack_filter_t(const float* w_hwio, int taps, int Cin, int Cout, int cout_pad, float* w_t, cudaStream_t st) {
+    dim3 grid((Cin + 31) / 32, (cout_pad + 31) / 32, taps), block(32, 8);
+    pack_filter_t_kernel<<<grid, block, 0, st>>>(w_hwio, taps, Cin, Cout, cout_pad, w_t);
+    SSDB_LAUNCH_CHECK();
+    return SSDB_OK;
+}
+
+int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_pad, const ConvEpilogue& ep, float* y, cudaStream_t st) {
+    SSDB_REQUIRE(conv_tc_supported_fprop(g), "shape not supported by the tcgen05 fprop kernel");
+    TileGeom t = pick_tile(g.B, g.Ho, g.Wo);
+    TcArgs a{};
+    a.TW = t.TW; a.TH = t.TH; a.TN = t.TN;
+    a.tiles_x = (g.Wo + t.TW - 1) / t.TW; a.tiles_y = (g.Ho + t.TH - 1) / t.TH; a.tiles_n = (g.B + t.TN - 1) / t.TN;
+    a.block_n = block_n_for(g.Cout); a.n_tiles = (g.Cout + a.block_n - 1) / a.block_n;
+    SSDB_REQUIRE(cout_pad >= a.n_tiles * a.block_n, "transposed filter is not padded enough");
+    a.Hd = g.Ho; a.Wd = g.Wo; a.Bn = g.B; a.Cd = g.Cout; a.cd_valid = g.Cout;
+    a.taps = g.k * g.k; a.kdim = g.k; a.cblocks = g.Cin / BLOCK_K; a.rows_per_tap = cout_pad;
+    a.off0 = -g.pad_t; a.offstep = g.dil; a.mode = 0;
+    SSDB_REQUIRE(g.pad_t == g.pad_l, "tcgen05 path assumes equal top/left padding");
+    a.dst = y; a.bias = ep.bias; a.mask = nullptr; a.relu = ep.relu; a.beta = 0;
+    a.scatter = ep.scatter; a.V = ep.V; a.n_valid = ep.n_valid; a.anchor_base = ep.anchor_base; a.A = ep.A;
+    CUtensorMap ms, mw;
+    int rc = encode_act_map(&ms, x, g.B, g.H, g.W, g.Cin, t.TW, t.TH, t.TN); if (rc) return rc;
+    rc = encode_w_map(&mw, w_t, (long long)a.taps * cout_pad, g.Cin, a.block_n); if (rc) return rc;
+    return launch_tc(ms, mw, a, st);
+}
+
+int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, const float* mask_x, int beta, float* dx, cudaStream_t st) {
+    SSDB_REQUIRE(conv_tc_supported_dgrad(g), "shape not supported by the tcgen05 dgrad kernel");
+    TileGeom t = pick_tile(g.B, g.H, g.W);
+    TcArgs a{};
+    a.TW = t.TW; a.TH = t.TH; a.TN = t.TN;
+    a.tiles_x = (g.W + t.TW - 1) / t.TW; a.tiles_y = (g.H + t.TH - 1) / t.TH; a.tiles_n = (g.B + t.TN - 1) / t.TN;
+    a.block_n = block_n_for(g.Cin); a.n_tiles = (g.Cin + a.block_n - 1) / a.block_n;
+    a.Hd = g.H; a.Wd = g.W; a.Bn = g.B; a.Cd = g.Cin; a.cd_valid = g.Cin;
+    a.taps = g.k * g.k; a.kdim = g.k; a.cblocks = g.Cout / BLOCK_K; a.rows_per_tap = g.Cin;
+    a.off0 = g.pad_t; a.offstep = -g.dil; a.mode = 1;
+    SSDB_REQUIRE(g.pad_t == g.pad_l, "tcgen05 path assumes equal top/left padding");
+    a.dst = dx; a.bias = nullptr; a.mask = mask_x; a.relu = 0; a.beta = beta;
+    CUtensorMap ms, mw;
+    int rc = encode_act_map(&ms, dz, g.B, g.Ho, g.Wo, g.Cout, t.TW, t.TH, t.TN); if (rc) return rc;
+    rc = encode_w_map(&mw, w_hwio, (long long)a.taps * g.Cin, g.Cout, a.block_n); if (rc) return rc;
+    return launch_tc(ms, mw, a, st);
+}
+
+bool conv_tc_supported_wgrad(const ConvGeom&) { return false; }
+size_t conv_tc_wgrad_ws(const ConvGeom&) { return 0; }
+int conv_tc_wgrad(const ConvGeom&, const float*, const float*, float*, float*, cudaStream_t) {
+    set_error("tcgen05 wgrad not built yet");
+    return SSDB_EINVAL;
+}
+
+}  // namespace ssdb

@@ -1,0 +1,278 @@
+// Fused decode_boxes + class-wise greedy NMS, one CTA per image.
+//
+// Restates on the GPU, bit-exactly, what the reference does per image in Python:
+//   ssdutils.decode_boxes (ssdutils.py:192-229): arg-max over the C object classes,
+//     top-`cap` anchors by confidence, stop below the threshold,
+//   ssdutils.decode_location (:182-189) + utils.normalize_box / prop2abs / abs2prop
+//     (utils.py:85-135): offsets -> box on the 1000x1000 grid.  Under NumPy 2 the
+//     reference computes the centre in float32 and the size in float64 and the
+//     `centre - half` subtraction in float32; the same op order is spelled out with
+//     round-to-nearest intrinsics here (no FMA contraction),
+//   ssdutils.suppress_overlaps / non_maximum_suppression (:232-318): boxes are
+//     re-quantised through prop2abs in float64 (not always a round trip), greedy NMS
+//     per class with inclusive-pixel IoU > thr in float64, output grouped by class in
+//     order of first appearance.
+//
+// Pipeline inside the CTA: arg-max/confidence pass (HBM read of the image's [A, C+5]
+// block, the only large traffic) -> exact radix select of the cap-th largest
+// confidence -> compaction -> bitonic sort of <= cap 64-bit keys (confidence desc,
+// anchor index asc) -> decode -> greedy sweep -> rank -> write.
+#include "common.cuh"
+
+namespace ssdb {
+namespace {
+
+constexpr int DT = 1024;
+constexpr int SMEM_P_MAX = 1024;     // candidate lists up to this size live in shared memory
+constexpr int CAND_WORDS = 11;       // cls, box[4], nms[4], conf bits, anchor
+
+__device__ __forceinline__ unsigned int okey(float f) {
+    unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float okey_inv(unsigned int k) {
+    unsigned int u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+
+struct DetArgs {
+    const float* pred; const double* anchors; int B, A, C;
+    float conf_thr; int cap; double iou_thr;
+    int* dets; int* counts;
+    unsigned long long* g_keys; int* g_cand; int P;   // global scratch when P > SMEM_P_MAX
+    int cap_eff;
+};
+
+__global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    unsigned int* ckey = reinterpret_cast<unsigned int*>(dyn);                 // [A] ordered confidence keys (0 = not a candidate)
+    unsigned long long* keys;                                                  // [P] sort keys
+    int* cand;                                                                 // [CAND_WORDS][P]
+    const int P = p.P;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (P <= SMEM_P_MAX) {
+        size_t off = ((size_t)p.A * 4 + 15) / 16 * 16;
+        keys = reinterpret_cast<unsigned long long*>(dyn + off);
+        cand = reinterpret_cast<int*>(dyn + off + (size_t)P * 8);
+    } else {
+        keys = p.g_keys + (size_t)b * P;
+        cand = p.g_cand + (size_t)b * P * CAND_WORDS;
+    }
+    __shared__ int hist[256];
+    __shared__ int sel_bin, sel_rem, n_gt;
+    __shared__ int scan[DT];
+    __shared__ int redi[DT / 32];
+    __shared__ int first_pos[64];
+
+    const int V = p.C + 5, A = p.A, C = p.C;
+    const float* pb = p.pred + (size_t)b * A * V;
+
+    // ---- pass 1: arg-max class and confidence per anchor ----
+    int nvalid = 0;
+    for (int a = tid; a < A; a += DT) {
+        const float* r = pb + (size_t)a * V;
+        float best = r[0];
+        for (int c = 1; c < C; ++c) { float v = r[c]; if (v > best) best = v; }
+        bool ok = !(best < p.conf_thr);
+        ckey[a] = ok ? okey(best) : 0u;       // okey() of any float is never 0 except for -NaN patterns; fine
+        nvalid += ok;
+    }
+    // block sum
+#pragma unroll
+    for (int o = 16; o; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
+    if ((tid & 31) == 0) redi[tid >> 5] = nvalid;
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int i = 0; i < DT / 32; ++i) t += redi[i]; redi[0] = t; }
+    __syncthreads();
+    nvalid = redi[0];
+    const int n = min(nvalid, p.cap_eff);
+    __syncthreads();
+
+    if (n > 0) {
+        // ---- exact n-th largest confidence key (radix select, 4 x 8 bits) ----
+        unsigned int prefix = 0, mask = 0; int remaining = n;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            for (int i = tid; i < 256; i += DT) hist[i] = 0;
+            __syncthreads();
+            for (int a = tid; a < A; a += DT) {
+                unsigned int k = ckey[a];
+                if (k != 0u && (k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255], 1);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int cum = 0, bin = 255;
+                for (; bin >= 0; --bin) { if (cum + hist[bin] >= remaining) break; cum += hist[bin]; }
+                sel_bin = bin; sel_rem = remaining - cum;
+            }
+            __syncthreads();
+            prefix |= ((unsigned int)sel_bin) << shift; mask |= 255u << shift; remaining = sel_rem;
+            __syncthreads();
+        }
+        // ---- compaction: keys above the pivot anywhere, `remaining` ties by lowest anchor index ----
+        if (tid == 0) n_gt = 0;
+        for (int i = tid; i < P; i += DT) keys[i] = 0ull;
+        __syncthreads();
+        const int per = (A + DT - 1) / DT;
+        const int a_lo = tid * per, a_hi = min(A, a_lo + per);
+        int ties = 0;
+        for (int a = a_lo; a < a_hi; ++a) if (ckey[a] == prefix) ++ties;
+        scan[tid] = ties;
+        __syncthreads();
+        for (int o = 1; o < DT; o <<= 1) {
+            int v = tid >= o ? scan[tid - o] : 0;
+            __syncthreads();
+            scan[tid] += v;
+            __syncthreads();
+        }
+        int rank = scan[tid] - ties;
+        const int base_ties = n - remaining;       // number of keys strictly above the pivot
+        for (int a = a_lo; a < a_hi; ++a) {
+            unsigned int k = ckey[a];
+            if (k == 0u) continue;
+            int slot = -1;
+            if (k > prefix) slot = atomicAdd(&n_gt, 1);
+            else if (k == prefix) { if (rank < remaining) slot = base_ties + rank; ++rank; }
+            if (slot >= 0) keys[slot] = ((unsigned long long)k << 32) | (unsigned long long)(0xffffffffu - (unsigned int)a);
+        }
+        __syncthreads();
+        // ---- bitonic sort, descending ----
+        for (int k2 = 2; k2 <= P; k2 <<= 1) {
+            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < P; i += DT) {
+                    int l = i ^ j;
+                    if (l > i) {
+                        unsigned long long x = keys[i], y = keys[l];
+                        bool desc = (i & k2) == 0;
+                        if (desc ? (x < y) : (x > y)) { keys[i] = y; keys[l] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // ---- decode the n candidates ----
+        for (int i = tid; i < C && i < 64; i += DT) first_pos[i] = 0x7fffffff;
+        __syncthreads();
+        for (int i = tid; i < n; i += DT) {
+            unsigned long long kk = keys[i];
+            int a = (int)(0xffffffffu - (unsigned int)(kk & 0xffffffffull));
+            const float* r = pb + (size_t)a * V;
+            int cls = 0; float best = r[0];
+            for (int c = 1; c < C; ++c) { float v = r[c]; if (v > best) { best = v; cls = c; } }
+            float o0 = r[C + 1], o1 = r[C + 2], o2 = r[C + 3], o3 = r[C + 4];
+            o0 = o0 > 100.f ? 100.f : o0; o1 = o1 > 100.f ? 100.f : o1;
+            o2 = o2 > 100.f ? 100.f : o2; o3 = o3 > 100.f ? 100.f : o3;
+            const double ax = p.anchors[a * 4 + 0], ay = p.anchors[a * 4 + 1], aw = p.anchors[a * 4 + 2], ah = p.anchors[a * 4 + 3];
+            float x = __fadd_rn(__fmul_rn(__fdiv_rn(o0, 10.f), (float)aw), (float)ax);
+            float y = __fadd_rn(__fmul_rn(__fdiv_rn(o1, 10.f), (float)ah), (float)ay);
+            double w = __dmul_rn(exp((double)__fdiv_rn(o2, 5.f)), aw);
+            double h = __dmul_rn(exp((double)__fdiv_rn(o3, 5.f)), ah);
+            float px = __fmul_rn(x, 1000.f), py = __fmul_rn(y, 1000.f);
+            float hw = (float)__ddiv_rn(__dmul_rn(w, 1000.0), 2.0);
+            float hh = (float)__ddiv_rn(__dmul_rn(h, 1000.0), 2.0);
+            int x0 = (int)__fsub_rn(px, hw), x1 = (int)__fadd_rn(px, hw);
+            int y0 = (int)__fsub_rn(py, hh), y1 = (int)__fadd_rn(py, hh);
+            x0 = max(x0, 0); x1 = min(x1, 999); y0 = max(y0, 0); y1 = min(y1, 999);
+            x0 = min(x0, x1); y0 = min(y0, y1);
+            // abs2prop (float64) then the NMS stage's prop2abs (float64)
+            double bw = (double)(x1 - x0), bh = (double)(y1 - y0);
+            double pcx = __ddiv_rn(__dadd_rn((double)x0, __ddiv_rn(bw, 2.0)), 1000.0);
+            double pcy = __ddiv_rn(__dadd_rn((double)y0, __ddiv_rn(bh, 2.0)), 1000.0);
+            double sw = __ddiv_rn(bw, 1000.0), sh = __ddiv_rn(bh, 1000.0);
+            double hw2 = __ddiv_rn(__dmul_rn(sw, 1000.0), 2.0), hh2 = __ddiv_rn(__dmul_rn(sh, 1000.0), 2.0);
+            double cx2 = __dmul_rn(pcx, 1000.0), cy2 = __dmul_rn(pcy, 1000.0);
+            cand[0 * P + i] = cls;
+            cand[1 * P + i] = x0; cand[2 * P + i] = x1; cand[3 * P + i] = y0; cand[4 * P + i] = y1;
+            cand[5 * P + i] = (int)__dsub_rn(cx2, hw2); cand[6 * P + i] = (int)__dadd_rn(cx2, hw2);
+            cand[7 * P + i] = (int)__dsub_rn(cy2, hh2); cand[8 * P + i] = (int)__dadd_rn(cy2, hh2);
+            cand[9 * P + i] = (int)__float_as_uint(okey_inv((unsigned int)(kk >> 32)));
+            cand[10 * P + i] = a;
+            if (cls < 64) atomicMin(&first_pos[cls], i);
+        }
+        __syncthreads();
+        // ---- greedy sweep in confidence order; alive flags reuse ckey[] ----
+        unsigned int* alive = ckey;
+        for (int i = tid; i < n; i += DT) alive[i] = 1u;
+        __syncthreads();
+        for (int i = 0; i < n; ++i) {
+            if (!alive[i]) continue;                    // uniform: written only before a barrier
+            const int ci = cand[0 * P + i];
+            const int ix0 = cand[5 * P + i], ix1 = cand[6 * P + i], iy0 = cand[7 * P + i], iy1 = cand[8 * P + i];
+            const long long area_i = (long long)(ix1 - ix0 + 1) * (iy1 - iy0 + 1);
+            for (int j = i + 1 + tid; j < n; j += DT) {
+                if (!alive[j] || cand[0 * P + j] != ci) continue;
+                int jx0 = cand[5 * P + j], jx1 = cand[6 * P + j], jy0 = cand[7 * P + j], jy1 = cand[8 * P + j];
+                int iw = min(ix1, jx1) - max(ix0, jx0) + 1; iw = iw < 0 ? 0 : iw;
+                int ih = min(iy1, jy1) - max(iy0, jy0) + 1; ih = ih < 0 ? 0 : ih;
+                long long inter = (long long)iw * ih;
+                long long uni = area_i + (long long)(jx1 - jx0 + 1) * (jy1 - jy0 + 1) - inter;
+                if (__ddiv_rn((double)inter, (double)uni) > p.iou_thr) alive[j] = 0u;
+            }
+            __syncthreads();
+        }
+        // ---- output rank: classes by first appearance, confidence order inside a class ----
+        int kept = 0;
+        for (int i = tid; i < n; i += DT) kept += alive[i] ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
+        __syncthreads();
+        if ((tid & 31) == 0) redi[tid >> 5] = kept;
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int i = 0; i < DT / 32; ++i) t += redi[i]; p.counts[b * 2] = t; p.counts[b * 2 + 1] = n; }
+        for (int i = tid; i < n; i += DT) {
+            if (!alive[i]) continue;
+            const int ci = cand[0 * P + i];
+            const int fi = ci < 64 ? first_pos[ci] : 0;
+            int rnk = 0;
+            for (int j = 0; j < n; ++j) {
+                if (!alive[j]) continue;
+                const int cj = cand[0 * P + j];
+                const int fj = cj < 64 ? first_pos[cj] : 0;
+                if (fj < fi || (fj == fi && j < i)) ++rnk;
+            }
+            int* o = p.dets + ((size_t)b * p.cap_eff + rnk) * 8;
+            o[0] = cand[9 * P + i]; o[1] = ci;
+            o[2] = cand[1 * P + i]; o[3] = cand[2 * P + i]; o[4] = cand[3 * P + i]; o[5] = cand[4 * P + i];
+            o[6] = cand[10 * P + i]; o[7] = i;
+        }
+    } else {
+        if (tid == 0) { p.counts[b * 2] = 0; p.counts[b * 2 + 1] = 0; }
+    }
+}
+
+int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+}  // namespace
+
+size_t decode_nms_scratch_bytes(int B, int A, int cap) {
+    int cap_eff = (cap > 0 && cap < A) ? cap : A;
+    int P = next_pow2(cap_eff);
+    if (P <= SMEM_P_MAX) return 0;
+    return (size_t)B * P * (8 + 4 * CAND_WORDS);
+}
+
+int decode_nms_launch(const float* pred, int B, int A, int C, const double* anchors_prop, float conf_thr, int cap,
+                      double iou_thr, int* dets_out, int* counts_out, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+    SSDB_REQUIRE(B >= 1 && A >= 1 && C >= 1 && C <= 64, "bad sizes");
+    DetArgs p;
+    p.pred = pred; p.anchors = anchors_prop; p.B = B; p.A = A; p.C = C; p.conf_thr = conf_thr; p.cap = cap; p.iou_thr = iou_thr;
+    p.dets = dets_out; p.counts = counts_out;
+    p.cap_eff = (cap > 0 && cap < A) ? cap : A;
+    p.P = next_pow2(p.cap_eff);
+    size_t sh = ((size_t)A * 4 + 15) / 16 * 16;
+    p.g_keys = nullptr; p.g_cand = nullptr;
+    if (p.P <= SMEM_P_MAX) sh += (size_t)p.P * (8 + 4 * CAND_WORDS);
+    else {
+        SSDB_REQUIRE(scratch && scratch_bytes >= decode_nms_scratch_bytes(B, A, cap), "scratch too small");
+        p.g_keys = reinterpret_cast<unsigned long long*>(scratch);
+        p.g_cand = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(scratch) + (size_t)B * p.P * 8);
+    }
+    SSDB_REQUIRE(sh <= 200 * 1024, "anchor count too large for one CTA");
+    static bool attr = false;
+    if (!attr) { SSDB_CUDA(cudaFuncSetAttribute(decode_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+    decode_nms_kernel<<<B, DT, sh, st>>>(p);
+    SSDB_LAUNCH_CHECK();
+    return SSDB_OK;
+}
+
+}  // namespace ssdb

@@ -1,0 +1,317 @@
+// Bandwidth-bound layer kernels of the SSD-VGG graph: max pools (the VGG 2x2/s2
+// SAME pools and mod_pool5 3x3/s1, reference ssdvgg.py:190-207,234), the L2
+// normalisation of conv4_3 (ssdvgg.py:80-84), head-gradient re-layout, the
+// result softmax (ssdvgg.py:368-372) and the Momentum update (ssdvgg.py:585-588).
+// All NHWC float32, vectorised float4 along channels, deterministic reductions.
+#include "common.cuh"
+
+namespace ssdb {
+namespace {
+
+__global__ void maxpool_fwd_kernel(const float* __restrict__ x, int B, int H, int W, int C4, int k, int s,
+                                   int pt, int pl, int Ho, int Wo, float* __restrict__ y) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)B * Ho * Wo * C4;
+    if (i >= total) return;
+    int c = (int)(i % C4); long long r = i / C4;
+    int ox = (int)(r % Wo); r /= Wo;
+    int oy = (int)(r % Ho); int b = (int)(r / Ho);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int dy = 0; dy < k; ++dy) {
+        int iy = oy * s + dy - pt;
+        if (iy < 0 || iy >= H) continue;
+        for (int dx = 0; dx < k; ++dx) {
+            int ix = ox * s + dx - pl;
+            if (ix < 0 || ix >= W) continue;
+            float4 v = reinterpret_cast<const float4*>(x)[(((long long)b * H + iy) * W + ix) * C4 + c];
+            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        }
+    }
+    reinterpret_cast<float4*>(y)[i] = m;
+}
+
+// one thread per input element group (float4 of channels): sum dy over the windows whose
+// first maximum (row-major scan) is this element
+__global__ void maxpool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, int B, int H, int W,
+                                   int C4, int k, int s, int pt, int pl, int Ho, int Wo, int beta, int relu_mask,
+                                   float* __restrict__ dx) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)B * H * W * C4;
+    if (i >= total) return;
+    int c = (int)(i % C4); long long r = i / C4;
+    int ix = (int)(r % W); r /= W;
+    int iy = (int)(r % H); int b = (int)(r / H);
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4 me = x4[i];
+    float mev[4] = {me.x, me.y, me.z, me.w};
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    // windows (oy,ox) with oy*s - pt <= iy <= oy*s - pt + k - 1
+    int oy_lo = (iy + pt - (k - 1) + s - 1); oy_lo = oy_lo < 0 ? 0 : oy_lo / s;
+    int oy_hi = (iy + pt) / s; if (oy_hi > Ho - 1) oy_hi = Ho - 1;
+    int ox_lo = (ix + pl - (k - 1) + s - 1); ox_lo = ox_lo < 0 ? 0 : ox_lo / s;
+    int ox_hi = (ix + pl) / s; if (ox_hi > Wo - 1) ox_hi = Wo - 1;
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+        for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+            // is (iy,ix) the first max of window (oy,ox)?
+            bool first[4] = {true, true, true, true};
+            for (int wy = 0; wy < k; ++wy) {
+                int yy = oy * s + wy - pt;
+                if (yy < 0 || yy >= H) continue;
+                for (int wx = 0; wx < k; ++wx) {
+                    int xx = ox * s + wx - pl;
+                    if (xx < 0 || xx >= W) continue;
+                    if (yy == iy && xx == ix) continue;
+                    float4 o = x4[(((long long)b * H + yy) * W + xx) * C4 + c];
+                    float ov[4] = {o.x, o.y, o.z, o.w};
+                    bool before = (yy < iy) || (yy == iy && xx < ix);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (before ? (ov[q] >= mev[q]) : (ov[q] > mev[q])) first[q] = false;
+                    }
+                }
+            }
+            float4 gy = reinterpret_cast<const float4*>(dy)[(((long long)b * Ho + oy) * Wo + ox) * C4 + c];
+            float gv[4] = {gy.x, gy.y, gy.z, gy.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (first[q]) g[q] += gv[q];
+        }
+    }
+    if (beta) { float4 o = reinterpret_cast<const float4*>(dx)[i]; g[0] += o.x; g[1] += o.y; g[2] += o.z; g[3] += o.w; }
+    if (relu_mask) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) g[q] = mev[q] > 0.f ? g[q] : 0.f;
+    }
+    reinterpret_cast<float4*>(dx)[i] = make_float4(g[0], g[1], g[2], g[3]);
+}
+
+// one warp per pixel
+__global__ void l2norm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, long long pixels, int C,
+                                  float* __restrict__ y) {
+    long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (p >= pixels) return;
+    const float* xp = x + p * C;
+    float ss = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+        float4 v = *reinterpret_cast<const float4*>(xp + c);
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    float r = rsqrtf(fmaxf(ss, 1e-12f));
+    for (int c = lane * 4; c < C; c += 128) {
+        float4 v = *reinterpret_cast<const float4*>(xp + c);
+        float4 s = *reinterpret_cast<const float4*>(scale + c);
+        *reinterpret_cast<float4*>(y + p * C + c) = make_float4(v.x * r * s.x, v.y * r * s.y, v.z * r * s.z, v.w * r * s.w);
+    }
+}
+
+// dx_c = (s_c g_c r - x_c r^3 sum_k(g_k s_k x_k)) masked by x>0 ; dscale partial per block
+__global__ void l2norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ dy,
+                                  long long pixels, int C, int beta, float* __restrict__ dx, float* __restrict__ partial) {
+    extern __shared__ float sh[];   // [warps][C] dscale partials
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    float* mine = sh + (long long)warp * C;
+    for (int c = lane; c < C; c += 32) mine[c] = 0.f;
+    __syncwarp();
+    for (long long p = (long long)blockIdx.x * nwarp + warp; p < pixels; p += (long long)gridDim.x * nwarp) {
+        const float* xp = x + p * C; const float* gp = dy + p * C;
+        float ss = 0.f, dot = 0.f;
+        for (int c = lane * 4; c < C; c += 128) {
+            float4 v = *reinterpret_cast<const float4*>(xp + c);
+            float4 g = *reinterpret_cast<const float4*>(gp + c);
+            float4 s = *reinterpret_cast<const float4*>(scale + c);
+            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            dot += g.x * s.x * v.x + g.y * s.y * v.y + g.z * s.z * v.z + g.w * s.w * v.w;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { ss += __shfl_xor_sync(0xffffffffu, ss, o); dot += __shfl_xor_sync(0xffffffffu, dot, o); }
+        bool clamped = ss < 1e-12f;
+        float r = rsqrtf(fmaxf(ss, 1e-12f));
+        float r3dot = clamped ? 0.f : r * r * r * dot;
+        for (int c = lane * 4; c < C; c += 128) {
+            float4 v = *reinterpret_cast<const float4*>(xp + c);
+            float4 g = *reinterpret_cast<const float4*>(gp + c);
+            float4 s = *reinterpret_cast<const float4*>(scale + c);
+            float vv[4] = {v.x, v.y, v.z, v.w}, gg[4] = {g.x, g.y, g.z, g.w}, sv[4] = {s.x, s.y, s.z, s.w};
+            float o[4];
+            float4 old = beta ? *reinterpret_cast<const float4*>(dx + p * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float ov[4] = {old.x, old.y, old.z, old.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float d = sv[q] * gg[q] * r - vv[q] * r3dot + ov[q];
+                o[q] = vv[q] > 0.f ? d : 0.f;
+                mine[c + q] += gg[q] * vv[q] * r;
+            }
+            *reinterpret_cast<float4*>(dx + p * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int w = 0; w < nwarp; ++w) s += sh[(long long)w * C + c];
+        partial[(long long)blockIdx.x * C + c] = s;
+    }
+}
+
+__global__ void reduce_rows_kernel(const float* __restrict__ partial, int rows, int C, float* __restrict__ out) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += partial[(long long)r * C + c];
+    out[c] = s;
+}
+
+__global__ void head_grad_gather_kernel(const float* __restrict__ grad, int B, int A, int V, int anchor_base, int HW,
+                                        int nbox, int Npad, float* __restrict__ dz) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)B * HW * Npad;
+    if (i >= total) return;
+    int n = (int)(i % Npad); long long r = i / Npad;
+    int pix = (int)(r % HW); int b = (int)(r / HW);
+    float v = 0.f;
+    if (n < nbox * V) {
+        int j = n / V, q = n - j * V;
+        v = grad[((long long)b * A + anchor_base + (long long)j * HW + pix) * V + q];
+    }
+    dz[i] = v;
+}
+
+// one thread per row: softmax over the first C+1 columns, copy the 4 offsets
+__global__ void softmax_result_kernel(const float* __restrict__ out, long long rows, int C, float* __restrict__ res) {
+    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    int V = C + 5, nc = C + 1;
+    const float* z = out + r * V;
+    float m = z[0];
+    for (int c = 1; c < nc; ++c) m = fmaxf(m, z[c]);
+    float s = 0.f;
+    for (int c = 0; c < nc; ++c) s += expf(z[c] - m);
+    float inv = 1.f / s;
+    float* o = res + r * V;
+    for (int c = 0; c < nc; ++c) o[c] = expf(z[c] - m) * inv;
+    for (int c = nc; c < V; ++c) o[c] = z[c];
+}
+
+__global__ void sgd_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict__ v, long long n,
+                           const unsigned char* __restrict__ decay, float lr, float mu, float wd, float post) {
+    long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long i = i4 * 4;
+    if (i >= n) return;
+    float d = decay[i / OPT_BLOCK] ? wd : 0.f;
+    float4 wv = reinterpret_cast<float4*>(w)[i4];
+    float4 gv = reinterpret_cast<float4*>(g)[i4];
+    float4 vv = reinterpret_cast<float4*>(v)[i4];
+    float ww[4] = {wv.x, wv.y, wv.z, wv.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w}, mm[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float gr = gg[q] * post + d * ww[q];
+        mm[q] = mu * mm[q] + gr;
+        ww[q] = ww[q] - lr * mm[q];
+    }
+    reinterpret_cast<float4*>(w)[i4] = make_float4(ww[0], ww[1], ww[2], ww[3]);
+    reinterpret_cast<float4*>(v)[i4] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+}
+
+__global__ void l2_sum_stage1(const float* __restrict__ w, long long n, const unsigned char* __restrict__ decay,
+                              float* __restrict__ partial) {
+    __shared__ float sh[32];
+    float s = 0.f;
+    for (long long blk = blockIdx.x; blk * OPT_BLOCK < n; blk += gridDim.x) {
+        if (!decay[blk]) continue;
+        long long base = blk * OPT_BLOCK;
+        for (int j = threadIdx.x; j < OPT_BLOCK && base + j < n; j += blockDim.x) { float t = w[base + j]; s += t * t; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+        partial[blockIdx.x] = t;
+    }
+}
+
+__global__ void l2_sum_stage2(const float* __restrict__ partial, int nb, float* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < nb; ++i) t += partial[i];
+        out[0] = 0.5f * t;
+    }
+}
+
+}  // namespace
+
+int maxpool_fwd(const float* x, int B, int H, int W, int C, int k, int stride, int pad_t, int pad_l, int Ho, int Wo,
+                float* y, cudaStream_t st) {
+    SSDB_REQUIRE(C % 4 == 0, "channels must be a multiple of 4");
+    long long total = (long long)B * Ho * Wo * (C / 4);
+    maxpool_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, B, H, W, C / 4, k, stride, pad_t, pad_l, Ho, Wo, y);
+    SSDB_LAUNCH_CHECK();
+    return SSDB_OK;
+}
+
+int maxpool_bwd(const float* x, const float* dy, int B, int H, int W, int C, int k, int stride, int pad_t, int pad_l,
+                int Ho, int Wo, int beta, int relu_mask, float* dx, cudaStream_t st) {
+    SSDB_REQUIRE(C % 4 == 0, "channels must be a multiple of 4");
+    long long total = (long long)B * H * W * (C / 4);
+    maxpool_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, dy, B, H, W, C / 4, k, stride, pad_t, pad_l, Ho, Wo,
+                                                                          beta, relu_mask, dx);
+    SSDB_LAUNCH_CHECK();
+    return SSDB_OK;
+}
+
+int l2norm_fwd(const float* x, const float* scale, long long pixels, int C, float* y, cudaStream_t st) {
+    SSDB_REQUIRE(C % 4 == 0, "channels must be a multiple of 4");
+    long long threads = pixels * 32;
+    l2norm_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, scale, pixels, C, y);
+    SSDB_LAUNCH_CHECK();
+    return SSDB_OK;
+}
+
+int l2norm_bwd(const float* x, const float* scale, const float* dy, long long pixels, int C, int beta, float* dx,
+               float* dscale, float* partial, cudaStream_t st) {
+    SSDB_REQUIRE(C % 4 == 0 && C <= 1024, "unsupported channel count");
+    int nb = 296;   // 2 blocks per SM
+    size_t sh = (size_t)8 * C * sizeof(float);
+    l2norm_bwd_kernel<<<nb, 256, sh, st>>>(x, scale, dy, pixels, C, beta, dx, partial);
+    SSDB_LAUNCH_CHECK();
+    reduce_rows_kernel<<<(C + 255) / 256, 256, 0, st>>>(partial, nb, C, dscale);
+    SSDB_LAUNCH_CHECK();
+    return SSDB_OK;
+}
+
+int head_grad_gather(const float* grad, int B, int A, int V, int anchor_base, int HW, int nbox, int Npad, float* dz,
+                     cudaStream_t st) {
+    long long total = (long long)B * HW * Npad;
+    head_grad_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(grad, B, A, V, anchor_base, HW, nbox, Npad, dz);
+    SSDB_LAUNCH_CHECK();
+    return SSDB_OK;
+}
+
+int softmax_result(const float* output, long long rows, int C, float* result, cudaStream_t st) {
+    softmax_result_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(output, rows, C, result);
+    SSDB_LAUNCH_CHECK();
+    return SSDB_OK;
+}
+
+int sgd_momentum(float* w, float* g, float* v, long long n, const unsigned char* decay, float lr, float mu, float wd,
+                 float post_scale, cudaStream_t st) {
+    SSDB_REQUIRE(n % 4 == 0, "flat buffer length must be a multiple of 4");
+    long long n4 = n / 4;
+    sgd_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(w, g, v, n, decay, lr, mu, wd, post_scale);
+    SSDB_LAUNCH_CHECK();
+    return SSDB_OK;
+}
+
+int l2_sum(const float* w, long long n, const unsigned char* decay, float* partial, float* out, cudaStream_t st) {
+    int nb = 592;
+    l2_sum_stage1<<<nb, 256, 0, st>>>(w, n, decay, partial);
+    SSDB_LAUNCH_CHECK();
+    l2_sum_stage2<<<1, 32, 0, st>>>(partial, nb, out);
+    SSDB_LAUNCH_CHECK();
+    return SSDB_OK;
+}
+
+}  // namespace ssdb

@@ -1,0 +1,752 @@
+// The SSD-VGG engine: layer plan, flat parameter / gradient / momentum buffers,
+// forward, multibox loss, backward and Momentum update, behind the C ABI of
+// include/ssd_b200.h.  Replaces SSDVGG.build_from_vgg / build_optimizer and the
+// tf.Session that runs them (reference ssdvgg.py:87-649, train.py:262-266,
+// infer.py:225-227).
+#include <cmath>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace ssdb {
+
+thread_local char g_err[1024] = "";
+long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+struct MapSpec { int size; double scale; std::vector<double> ratios; };
+struct Preset { std::string name; int image; std::vector<MapSpec> maps; double extra_scale; int num_anchors; };
+
+// ssdutils.SSD_PRESETS (ssdutils.py:36-62)
+const Preset* find_preset(const std::string& n) {
+    static const Preset p300{"vgg300", 300,
+        {{38, 0.1, {2, 0.5}}, {19, 0.2, {2, 3, 0.5, 1. / 3.}}, {10, 0.375, {2, 3, 0.5, 1. / 3.}},
+         {5, 0.55, {2, 3, 0.5, 1. / 3.}}, {3, 0.725, {2, 0.5}}, {1, 0.9, {2, 0.5}}}, 1.075, 8732};
+    static const Preset p512{"vgg512", 512,
+        {{64, 0.07, {2, 0.5}}, {32, 0.15, {2, 3, 0.5, 1. / 3.}}, {16, 0.3, {2, 3, 0.5, 1. / 3.}},
+         {8, 0.45, {2, 3, 0.5, 1. / 3.}}, {4, 0.6, {2, 3, 0.5, 1. / 3.}}, {2, 0.75, {2, 0.5}}, {1, 0.9, {2, 0.5}}}, 1.05, 24564};
+    if (n == "vgg300") return &p300;
+    if (n == "vgg512") return &p512;
+    return nullptr;
+}
+
+struct Buf { int H, W, C; size_t off; bool relu_out; };
+
+struct Master {            // one tensor of the flat buffer
+    std::string name; int rank; int shape[4]; size_t off; size_t count; bool decay;
+};
+struct RefTensor {         // a tensor under the reference's variable name
+    std::string name; int rank; int shape[4];
+    int master;            // index into masters
+    int col0, cols;        // column window inside the master's last dimension (classifier views)
+};
+
+enum OpType { OP_CONV = 0, OP_POOL = 1, OP_L2NORM = 2 };
+struct Op {
+    OpType type; std::string name;
+    int in, out;                       // buffer ids; in == -1: the image batch; out == -1: head output tensor
+    int k = 1, stride = 1, dil = 1, pad = 0;
+    int cin = 0, cout = 0;             // cout = stored channel count (heads: padded)
+    bool relu = false, head = false;
+    int anchor_base = 0, nbox = 0;
+    int w = -1, b = -1;                // master indices
+    size_t wt_off = 0; int cout_pad = 0; bool has_wt = false;
+};
+
+int same_pad_before(int n, int keff, int stride) {
+    int out = (n + stride - 1) / stride;
+    int total = (out - 1) * stride + keff - n;
+    if (total < 0) total = 0;
+    return total / 2;
+}
+
+}  // namespace
+}  // namespace ssdb
+
+using namespace ssdb;
+
+struct ssdb_net {
+    const Preset* preset = nullptr;
+    int C = 20, V = 25, A = 0, S = 300, max_batch = 0;
+    std::vector<Buf> bufs;
+    std::vector<Op> ops;
+    std::vector<Master> masters;
+    std::vector<RefTensor> refs;
+    std::map<std::string, int> ref_index;
+    size_t n_flat = 0, act_floats_per_image = 0, wt_floats = 0;
+    // device memory
+    float *params = nullptr, *grads = nullptr, *moms = nullptr, *wt = nullptr;
+    float *acts = nullptr, *gacts = nullptr;
+    float *out = nullptr, *out_grad = nullptr, *result = nullptr, *dz_head = nullptr;
+    float *images_stage = nullptr, *labels_stage = nullptr;
+    float *partial = nullptr; size_t partial_floats = 0;
+    float *small_ws = nullptr;         // [0..3] losses, [4..5] conf/loc, [6] l2 sum, then per-image + partials
+    unsigned int* counter = nullptr;
+    unsigned char* decay_mask = nullptr;
+    double* anchors = nullptr;
+    float* host_small = nullptr;       // pinned
+    bool wt_dirty = true, have_forward = false;
+    int conv_mode = SSDB_CONV_AUTO;
+    int swap_rb = 1; float mean[3] = {103.939f, 116.779f, 123.68f};
+    cudaStream_t own_stream = nullptr;
+    int last_B = 0;
+
+    float* act(int id, int /*B*/) { return acts + bufs[id].off * (size_t)max_batch; }
+    float* gact(int id, int /*B*/) { return gacts + bufs[id].off * (size_t)max_batch; }
+};
+
+namespace ssdb {
+namespace {
+
+__global__ void finalize_losses_kernel(const float* conf_loc, const float* l2sum, float wd, float* out4) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float l2 = wd * l2sum[0];
+        out4[0] = conf_loc[0] + conf_loc[1] + l2;   // total
+        out4[1] = conf_loc[1];                       // localization
+        out4[2] = conf_loc[0];                       // confidence
+        out4[3] = l2;
+    }
+}
+
+int add_buf(ssdb_net* n, int H, int W, int C, bool relu_out) {
+    Buf b{H, W, C, n->act_floats_per_image, relu_out};
+    n->act_floats_per_image += (size_t)H * W * C;
+    n->act_floats_per_image = (n->act_floats_per_image + 63) / 64 * 64;
+    n->bufs.push_back(b);
+    return (int)n->bufs.size() - 1;
+}
+
+int add_master(ssdb_net* n, const std::string& name, int rank, const int* shape, bool decay) {
+    Master m; m.name = name; m.rank = rank; m.count = 1;
+    for (int i = 0; i < 4; ++i) { m.shape[i] = i < rank ? shape[i] : 1; m.count *= m.shape[i]; }
+    m.off = n->n_flat; m.decay = decay;
+    n->n_flat += (m.count + OPT_BLOCK - 1) / OPT_BLOCK * OPT_BLOCK;
+    n->masters.push_back(m);
+    return (int)n->masters.size() - 1;
+}
+
+void add_ref(ssdb_net* n, const std::string& name, int rank, const int* shape, int master, int col0, int cols) {
+    RefTensor r; r.name = name; r.rank = rank;
+    for (int i = 0; i < 4; ++i) r.shape[i] = i < rank ? shape[i] : 1;
+    r.master = master; r.col0 = col0; r.cols = cols;
+    n->ref_index[name] = (int)n->refs.size();
+    n->refs.push_back(r);
+}
+
+// conv_map (ssdvgg.py:42-52) / VGG conv: returns the output buffer id
+int add_conv(ssdb_net* n, const std::string& name, int in, int k, int cout, int stride, int dil, bool same, int out_override = 0) {
+    Op op; op.type = OP_CONV; op.name = name; op.in = in; op.k = k; op.stride = stride; op.dil = dil; op.relu = true;
+    int H = in < 0 ? n->S : n->bufs[in].H, W = in < 0 ? n->S : n->bufs[in].W;
+    op.cin = in < 0 ? 3 : n->bufs[in].C; op.cout = cout;
+    int keff = (k - 1) * dil + 1, Ho, Wo;
+    if (same) { op.pad = same_pad_before(H, keff, stride); Ho = (H + stride - 1) / stride; Wo = (W + stride - 1) / stride; }
+    else { op.pad = 0; Ho = (H - keff) / stride + 1; Wo = (W - keff) / stride + 1; }
+    if (out_override) { Ho = Wo = out_override; }
+    op.out = add_buf(n, Ho, Wo, cout, true);
+    int fs[4] = {k, k, op.cin, cout};
+    op.w = add_master(n, name + "/filter", 4, fs, true);
+    int bs[1] = {cout};
+    op.b = add_master(n, name + "/biases", 1, bs, false);
+    add_ref(n, name + "/filter", 4, fs, op.w, 0, cout);
+    add_ref(n, name + "/biases", 1, bs, op.b, 0, cout);
+    n->ops.push_back(op);
+    return op.out;
+}
+
+int add_pool(ssdb_net* n, const std::string& name, int in, int k, int stride) {
+    Op op; op.type = OP_POOL; op.name = name; op.in = in; op.k = k; op.stride = stride;
+    const Buf& b = n->bufs[in];
+    op.pad = same_pad_before(b.H, k, stride);
+    op.cin = op.cout = b.C;
+    op.out = add_buf(n, (b.H + stride - 1) / stride, (b.W + stride - 1) / stride, b.C, false);
+    n->ops.push_back(op);
+    return op.out;
+}
+
+void build_plan(ssdb_net* n) {
+    const Preset& P = *n->preset;
+    int x = -1;
+    x = add_conv(n, "conv1_1", x, 3, 64, 1, 1, true);  x = add_conv(n, "conv1_2", x, 3, 64, 1, 1, true);
+    x = add_pool(n, "pool1", x, 2, 2);
+    x = add_conv(n, "conv2_1", x, 3, 128, 1, 1, true); x = add_conv(n, "conv2_2", x, 3, 128, 1, 1, true);
+    x = add_pool(n, "pool2", x, 2, 2);
+    x = add_conv(n, "conv3_1", x, 3, 256, 1, 1, true); x = add_conv(n, "conv3_2", x, 3, 256, 1, 1, true);
+    x = add_conv(n, "conv3_3", x, 3, 256, 1, 1, true);
+    x = add_pool(n, "pool3", x, 2, 2);
+    x = add_conv(n, "conv4_1", x, 3, 512, 1, 1, true); x = add_conv(n, "conv4_2", x, 3, 512, 1, 1, true);
+    int c43 = add_conv(n, "conv4_3", x, 3, 512, 1, 1, true);
+    x = add_pool(n, "pool4", c43, 2, 2);
+    x = add_conv(n, "conv5_1", x, 3, 512, 1, 1, true); x = add_conv(n, "conv5_2", x, 3, 512, 1, 1, true);
+    x = add_conv(n, "conv5_3", x, 3, 512, 1, 1, true);
+    x = add_pool(n, "mod_pool5", x, 3, 1);                                   // ssdvgg.py:234
+    x = add_conv(n, "mod_conv6", x, 3, 1024, 1, 6, true);                    // a-trous, rate 6 (ssdvgg.py:260)
+    int c7 = add_conv(n, "mod_conv7", x, 1, 1024, 1, 1, true);
+    const bool seven = P.maps.size() >= 7;
+    x = add_conv(n, "conv8_1", c7, 1, 256, 1, 1, true);   int c82 = add_conv(n, "conv8_2", x, 3, 512, 2, 1, true);
+    x = add_conv(n, "conv9_1", c82, 1, 128, 1, 1, true);  int c92 = add_conv(n, "conv9_2", x, 3, 256, 2, 1, true);
+    x = add_conv(n, "conv10_1", c92, 1, 128, 1, 1, true);
+    int c102 = add_conv(n, "conv10_2", x, 3, 256, seven ? 2 : 1, 1, seven);
+    x = add_conv(n, "conv11_1", c102, 1, 128, 1, 1, true);
+    int c112 = add_conv(n, "conv11_2", x, 3, 256, 1, 1, false);
+    std::vector<int> fmaps;
+    // l2_normalization of conv4_3 (ssdvgg.py:80-84,335-337)
+    {
+        Op op; op.type = OP_L2NORM; op.name = "l2_norm_conv4_3"; op.in = c43;
+        const Buf& b = n->bufs[c43];
+        op.cin = op.cout = b.C;
+        op.out = add_buf(n, b.H, b.W, b.C, false);
+        int ss[1] = {b.C};
+        op.w = add_master(n, "l2_norm_conv4_3/scale", 1, ss, false);
+        add_ref(n, "l2_norm_conv4_3/scale", 1, ss, op.w, 0, b.C);
+        n->ops.push_back(op);
+        fmaps.push_back(op.out);
+    }
+    fmaps.push_back(c7); fmaps.push_back(c82); fmaps.push_back(c92); fmaps.push_back(c102); fmaps.push_back(c112);
+    if (seven) {
+        x = add_conv(n, "conv12_1", c112, 1, 128, 1, 1, true);
+        // zero-pad bottom/right by one, then 3x3 VALID (ssdvgg.py:326-331) == pad-after-only conv with a 1x1 output
+        int c122 = add_conv(n, "conv12_2", x, 3, 256, 1, 1, false, 1);
+        fmaps.push_back(c122);
+    }
+    // classifiers (ssdvgg.py:55-65,353-366): the box types of one map share a merged filter
+    int base = 0;
+    for (size_t i = 0; i < P.maps.size(); ++i) {
+        int nbox = 2 + (int)P.maps[i].ratios.size();
+        const Buf& fb = n->bufs[fmaps[i]];
+        Op op; op.type = OP_CONV; op.name = "classifiers/map" + std::to_string(i); op.in = fmaps[i]; op.out = -1;
+        op.k = 3; op.stride = 1; op.dil = 1; op.pad = 1; op.cin = fb.C; op.relu = false; op.head = true;
+        op.nbox = nbox; op.anchor_base = base;
+        op.cout = (nbox * n->V + 31) / 32 * 32;
+        int fs[4] = {3, 3, fb.C, op.cout};
+        op.w = add_master(n, op.name + "/filter", 4, fs, true);
+        int bs[1] = {op.cout};
+        op.b = add_master(n, op.name + "/biases", 1, bs, false);
+        for (int j = 0; j < nbox; ++j) {
+            std::string rn = "classifiers/classifier" + std::to_string(i) + "_" + std::to_string(j);
+            int rfs[4] = {3, 3, fb.C, n->V};
+            add_ref(n, rn + "/filter", 4, rfs, op.w, j * n->V, n->V);
+            int rbs[1] = {n->V};
+            add_ref(n, rn + "/biases", 1, rbs, op.b, j * n->V, n->V);
+        }
+        n->ops.push_back(op);
+        base += nbox * fb.H * fb.W;
+    }
+    n->A = base;
+    // transposed filter copies for the tcgen05 fprop kernel
+    for (Op& op : n->ops) {
+        if (op.type != OP_CONV || op.stride != 1 || op.cin % 32 != 0) continue;
+        int bn = op.cout > 256 ? 256 : (op.cout + 15) / 16 * 16;
+        op.cout_pad = (op.cout + bn - 1) / bn * bn;
+        op.wt_off = n->wt_floats; op.has_wt = true;
+        n->wt_floats += (size_t)op.k * op.k * op.cout_pad * op.cin;
+    }
+}
+
+ConvGeom geom_of(const ssdb_net* n, const Op& op, int B) {
+    ConvGeom g;
+    g.B = B;
+    g.H = op.in < 0 ? n->S : n->bufs[op.in].H; g.W = op.in < 0 ? n->S : n->bufs[op.in].W; g.Cin = op.cin;
+    if (op.out >= 0) { g.Ho = n->bufs[op.out].H; g.Wo = n->bufs[op.out].W; } else { g.Ho = g.H; g.Wo = g.W; }
+    g.Cout = op.cout; g.k = op.k; g.stride = op.stride; g.dil = op.dil; g.pad_t = op.pad; g.pad_l = op.pad;
+    return g;
+}
+
+bool use_tc(const ssdb_net* n, bool supported) {
+    if (n->conv_mode == SSDB_CONV_SIMT) return false;
+    return supported;
+}
+
+int repack_filters(ssdb_net* n, cudaStream_t st) {
+    for (const Op& op : n->ops) {
+        if (!op.has_wt) continue;
+        int rc = pack_filter_t(n->params + n->masters[op.w].off, op.k * op.k, op.cin, op.cout, op.cout_pad, n->wt + op.wt_off, st);
+        if (rc) return rc;
+    }
+    n->wt_dirty = false;
+    return SSDB_OK;
+}
+
+int run_forward(ssdb_net* n, const float* images, int B, cudaStream_t st) {
+    SSDB_REQUIRE(B >= 1 && B <= n->max_batch, "batch size out of range");
+    if (n->wt_dirty) { int rc = repack_filters(n, st); if (rc) return rc; }
+    for (const Op& op : n->ops) {
+        int rc = SSDB_OK;
+        if (op.type == OP_CONV) {
+            ConvGeom g = geom_of(n, op, B);
+            ConvEpilogue ep;
+            ep.bias = n->params + n->masters[op.b].off; ep.relu = op.relu ? 1 : 0;
+            const float* x = op.in < 0 ? images : n->act(op.in, B);
+            float* y = op.out >= 0 ? n->act(op.out, B) : n->out;
+            if (op.head) { ep.scatter = 1; ep.V = n->V; ep.n_valid = op.nbox * n->V; ep.anchor_base = op.anchor_base; ep.A = n->A; }
+            if (op.in < 0) { ep.preprocess = 1; ep.swap_rb = n->swap_rb; ep.mean[0] = n->mean[0]; ep.mean[1] = n->mean[1]; ep.mean[2] = n->mean[2]; }
+            if (op.has_wt && use_tc(n, conv_tc_supported_fprop(g)))
+                rc = conv_tc_fprop(g, x, n->wt + op.wt_off, op.cout_pad, ep, y, st);
+            else
+                rc = conv_simt_fprop(g, x, n->params + n->masters[op.w].off, ep, y, st);
+        } else if (op.type == OP_POOL) {
+            const Buf& bi = n->bufs[op.in]; const Buf& bo = n->bufs[op.out];
+            rc = maxpool_fwd(n->act(op.in, B), B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W, n->act(op.out, B), st);
+        } else {
+            const Buf& bi = n->bufs[op.in];
+            rc = l2norm_fwd(n->act(op.in, B), n->params + n->masters[op.w].off, (long long)B * bi.H * bi.W, bi.C, n->act(op.out, B), st);
+        }
+        if (rc) return rc;
+    }
+    n->have_forward = true; n->last_B = B;
+    return SSDB_OK;
+}
+
+int run_backward(ssdb_net* n, int B, cudaStream_t st) {
+    SSDB_REQUIRE(n->have_forward && n->last_B == B, "backward without a matching forward");
+    std::vector<char> written(n->bufs.size(), 0);
+    for (int oi = (int)n->ops.size() - 1; oi >= 0; --oi) {
+        const Op& op = n->ops[oi];
+        int rc = SSDB_OK;
+        if (op.type == OP_CONV) {
+            ConvGeom g = geom_of(n, op, B);
+            const float* dz;
+            if (op.head) {
+                const Buf& fb = n->bufs[op.in];
+                rc = head_grad_gather(n->out_grad, B, n->A, n->V, op.anchor_base, fb.H * fb.W, op.nbox, op.cout, n->dz_head, st);
+                if (rc) return rc;
+                dz = n->dz_head;
+            } else {
+                SSDB_REQUIRE(written[op.out], "internal: gradient of a conv output was never produced");
+                dz = n->gact(op.out, B);
+            }
+            const float* x = op.in < 0 ? nullptr : n->act(op.in, B);
+            float* dw = n->grads + n->masters[op.w].off;
+            float* db = n->grads + n->masters[op.b].off;
+            long long pixels = (long long)B * g.Ho * g.Wo;
+            rc = bias_grad(dz, pixels, op.cout, db, n->partial, st);
+            if (rc) return rc;
+            ConvEpilogue ep;
+            if (op.in < 0) { ep.preprocess = 1; ep.swap_rb = n->swap_rb; ep.mean[0] = n->mean[0]; ep.mean[1] = n->mean[1]; ep.mean[2] = n->mean[2]; }
+            if (op.in >= 0 && use_tc(n, conv_tc_supported_wgrad(g)))
+                rc = conv_tc_wgrad(g, x, dz, dw, n->partial, st);
+            else
+                rc = conv_simt_wgrad(g, op.in < 0 ? n->images_stage : x, dz, ep, dw, n->partial, st);
+            if (rc) return rc;
+            if (op.in >= 0) {
+                const float* mask = n->bufs[op.in].relu_out ? x : nullptr;
+                int beta = written[op.in] ? 1 : 0;
+                if (use_tc(n, conv_tc_supported_dgrad(g)))
+                    rc = conv_tc_dgrad(g, dz, n->params + n->masters[op.w].off, mask, beta, n->gact(op.in, B), st);
+                else
+                    rc = conv_simt_dgrad(g, dz, n->params + n->masters[op.w].off, mask, beta, n->gact(op.in, B), st);
+                written[op.in] = 1;
+            }
+        } else if (op.type == OP_POOL) {
+            SSDB_REQUIRE(written[op.out], "internal: gradient of a pool output was never produced");
+            const Buf& bi = n->bufs[op.in]; const Buf& bo = n->bufs[op.out];
+            rc = maxpool_bwd(n->act(op.in, B), n->gact(op.out, B), B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W,
+                             written[op.in] ? 1 : 0, bi.relu_out ? 1 : 0, n->gact(op.in, B), st);
+            written[op.in] = 1;
+        } else {
+            SSDB_REQUIRE(written[op.out], "internal: gradient of the L2-norm output was never produced");
+            const Buf& bi = n->bufs[op.in];
+            rc = l2norm_bwd(n->act(op.in, B), n->params + n->masters[op.w].off, n->gact(op.out, B), (long long)B * bi.H * bi.W, bi.C,
+                            written[op.in] ? 1 : 0, n->gact(op.in, B), n->grads + n->masters[op.w].off, n->partial, st);
+            written[op.in] = 1;
+        }
+        if (rc) return rc;
+    }
+    return SSDB_OK;
+}
+
+// images for the conv1_1 weight gradient: the backward needs the raw batch again
+int remember_images(ssdb_net* n, const float* images, int B, cudaStream_t st) {
+    if (images == n->images_stage) return SSDB_OK;
+    SSDB_CUDA(cudaMemcpyAsync(n->images_stage, images, (size_t)B * n->S * n->S * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return SSDB_OK;
+}
+
+void anchors_host(const Preset& P, std::vector<double>& out) {
+    // get_anchors_for_preset (ssdutils.py:76-117)
+    for (size_t k = 0; k < P.maps.size(); ++k) {
+        const MapSpec& m = P.maps[k];
+        std::vector<std::pair<double, double>> sizes;
+        std::vector<double> rs; rs.push_back(1.0); for (double r : m.ratios) rs.push_back(r);
+        for (double r : rs) { double q = std::sqrt(r); sizes.push_back({m.scale * q, m.scale / q}); }
+        double nxt = k + 1 < P.maps.size() ? P.maps[k + 1].scale : P.extra_scale;
+        double sp = std::sqrt(m.scale * nxt);
+        sizes.push_back({sp, sp});
+        for (auto& s : sizes)
+            for (int j = 0; j < m.size; ++j)
+                for (int i = 0; i < m.size; ++i) {
+                    out.push_back((i + 0.5) / (double)m.size); out.push_back((j + 0.5) / (double)m.size);
+                    out.push_back(s.first); out.push_back(s.second);
+                }
+    }
+}
+
+}  // namespace
+}  // namespace ssdb
+
+// ============================================================================ C ABI
+extern "C" {
+
+int ssdb_version(void) { return 100; }
+const char* ssdb_last_error(void) { return ssdb::g_err; }
+long long ssdb_launch_count(void) { return ssdb::g_launches; }
+
+int ssdb_device_ok(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_error("no CUDA device: this library has no CPU fallback"); return SSDB_ENOGPU; }
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess || major != 10) {
+        set_error("device compute capability %d.x is not sm_100: this library is built for B200 only", major);
+        return SSDB_ENOGPU;
+    }
+    return SSDB_OK;
+}
+
+int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned flags, ssdb_net** out) {
+    (void)flags;
+    SSDB_REQUIRE(preset && out && max_batch >= 1 && num_classes >= 1 && num_classes + 5 <= 32, "bad arguments");
+    int rc = ssdb_device_ok(); if (rc) return rc;
+    const Preset* P = find_preset(preset);
+    if (!P) { set_error("No such preset: %s", preset); return SSDB_ENOTFOUND; }
+    ssdb_net* n = new ssdb_net();
+    n->preset = P; n->C = num_classes; n->V = num_classes + 5; n->S = P->image; n->max_batch = max_batch;
+    const char* mode = getenv("SSDB_CONV");
+    if (mode && !strcmp(mode, "simt")) n->conv_mode = SSDB_CONV_SIMT;
+    build_plan(n);
+    if (n->A != P->num_anchors) { set_error("internal: anchor count %d != %d", n->A, P->num_anchors); delete n; return SSDB_EINVAL; }
+    // workspace sizes
+    size_t partial = 296 * 1024 + 1024 * 256;
+    size_t dzh = 0;
+    for (const Op& op : n->ops) {
+        if (op.type != OP_CONV) continue;
+        ConvGeom g = geom_of(n, op, max_batch);
+        size_t w = conv_simt_wgrad_ws(g); if (w > partial) partial = w;
+        w = conv_tc_wgrad_ws(g); if (w > partial) partial = w;
+        if (op.head) { size_t d = (size_t)max_batch * g.H * g.W * op.cout; if (d > dzh) dzh = d; }
+    }
+    n->partial_floats = partial;
+    size_t bav = (size_t)max_batch * n->A * n->V;
+    size_t img = (size_t)max_batch * n->S * n->S * 3;
+#define ALLOC(ptr, count, type) SSDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&(ptr)), (size_t)(count) * sizeof(type)))
+    ALLOC(n->params, n->n_flat, float); ALLOC(n->grads, n->n_flat, float); ALLOC(n->moms, n->n_flat, float);
+    ALLOC(n->wt, n->wt_floats ? n->wt_floats : 1, float);
+    ALLOC(n->acts, n->act_floats_per_image * max_batch, float); ALLOC(n->gacts, n->act_floats_per_image * max_batch, float);
+    ALLOC(n->out, bav, float); ALLOC(n->out_grad, bav, float); ALLOC(n->result, bav, float); ALLOC(n->labels_stage, bav, float);
+    ALLOC(n->dz_head, dzh ? dzh : 1, float); ALLOC(n->images_stage, img, float);
+    ALLOC(n->partial, partial, float); ALLOC(n->small_ws, 4096 + 2 * (size_t)max_batch, float);
+    ALLOC(n->counter, 1, unsigned int); ALLOC(n->decay_mask, n->n_flat / OPT_BLOCK, unsigned char);
+    ALLOC(n->anchors, (size_t)n->A * 4, double);
+#undef ALLOC
+    SSDB_CUDA(cudaMemset(n->params, 0, n->n_flat * sizeof(float)));
+    SSDB_CUDA(cudaMemset(n->grads, 0, n->n_flat * sizeof(float)));
+    SSDB_CUDA(cudaMemset(n->moms, 0, n->n_flat * sizeof(float)));
+    SSDB_CUDA(cudaMemset(n->wt, 0, (n->wt_floats ? n->wt_floats : 1) * sizeof(float)));
+    SSDB_CUDA(cudaMemset(n->counter, 0, sizeof(unsigned int)));
+    SSDB_CUDA(cudaMemset(n->gacts, 0, n->act_floats_per_image * max_batch * sizeof(float)));
+    std::vector<unsigned char> mask(n->n_flat / OPT_BLOCK, 0);
+    for (const Master& m : n->masters)
+        if (m.decay) for (size_t b = m.off / OPT_BLOCK; b < (m.off + m.count + OPT_BLOCK - 1) / OPT_BLOCK; ++b) mask[b] = 1;
+    SSDB_CUDA(cudaMemcpy(n->decay_mask, mask.data(), mask.size(), cudaMemcpyHostToDevice));
+    std::vector<double> anc; anchors_host(*P, anc);
+    SSDB_CUDA(cudaMemcpy(n->anchors, anc.data(), anc.size() * sizeof(double), cudaMemcpyHostToDevice));
+    SSDB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&n->host_small), 64 * sizeof(float)));
+    SSDB_CUDA(cudaStreamCreateWithFlags(&n->own_stream, cudaStreamNonBlocking));
+    *out = n;
+    return SSDB_OK;
+}
+
+int ssdb_destroy(ssdb_net* n) {
+    if (!n) return SSDB_OK;
+    cudaDeviceSynchronize();
+    void* ptrs[] = {n->params, n->grads, n->moms, n->wt, n->acts, n->gacts, n->out, n->out_grad, n->result, n->labels_stage,
+                    n->dz_head, n->images_stage, n->partial, n->small_ws, n->counter, n->decay_mask, n->anchors};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (n->host_small) cudaFreeHost(n->host_small);
+    if (n->own_stream) cudaStreamDestroy(n->own_stream);
+    delete n;
+    return SSDB_OK;
+}
+
+int ssdb_num_anchors(const ssdb_net* n) { return n ? n->A : SSDB_EINVAL; }
+int ssdb_image_size(const ssdb_net* n) { return n ? n->S : SSDB_EINVAL; }
+int ssdb_num_tensors(const ssdb_net* n) { return n ? (int)n->refs.size() : SSDB_EINVAL; }
+
+int ssdb_tensor_info(const ssdb_net* n, int index, char* name_out, int name_cap, int* rank_out, int shape_out[4]) {
+    SSDB_REQUIRE(n && index >= 0 && index < (int)n->refs.size(), "bad tensor index");
+    const RefTensor& r = n->refs[index];
+    if (name_out && name_cap > 0) { strncpy(name_out, r.name.c_str(), name_cap - 1); name_out[name_cap - 1] = 0; }
+    if (rank_out) *rank_out = r.rank;
+    if (shape_out) for (int i = 0; i < 4; ++i) shape_out[i] = r.shape[i];
+    return SSDB_OK;
+}
+
+static int tensor_io(ssdb_net* n, const char* name, int which, float* host, long long count, bool write) {
+    SSDB_REQUIRE(n && name && host && which >= 0 && which <= 2, "bad arguments");
+    auto it = n->ref_index.find(name);
+    if (it == n->ref_index.end()) { set_error("no such tensor: %s", name); return SSDB_ENOTFOUND; }
+    const RefTensor& r = n->refs[it->second];
+    const Master& m = n->masters[r.master];
+    long long want = 1; for (int i = 0; i < r.rank; ++i) want *= r.shape[i];
+    SSDB_REQUIRE(count == want, "element count does not match the tensor shape");
+    float* base = (which == 0 ? n->params : which == 1 ? n->grads : n->moms) + m.off;
+    SSDB_CUDA(cudaDeviceSynchronize());
+    int last = m.shape[m.rank - 1];
+    if (r.cols == last && r.col0 == 0) {
+        if (write) SSDB_CUDA(cudaMemcpy(base, host, count * sizeof(float), cudaMemcpyHostToDevice));
+        else SSDB_CUDA(cudaMemcpy(host, base, count * sizeof(float), cudaMemcpyDeviceToHost));
+    } else {
+        long long rows = (long long)m.count / last;
+        if (write) SSDB_CUDA(cudaMemcpy2D(base + r.col0, (size_t)last * sizeof(float), host, (size_t)r.cols * sizeof(float),
+                                          (size_t)r.cols * sizeof(float), (size_t)rows, cudaMemcpyHostToDevice));
+        else SSDB_CUDA(cudaMemcpy2D(host, (size_t)r.cols * sizeof(float), base + r.col0, (size_t)last * sizeof(float),
+                                    (size_t)r.cols * sizeof(float), (size_t)rows, cudaMemcpyDeviceToHost));
+    }
+    if (write && which == 0) n->wt_dirty = true;
+    return SSDB_OK;
+}
+
+int ssdb_get_tensor(ssdb_net* n, const char* name, int which, float* host_out, long long count) { return tensor_io(n, name, which, host_out, count, false); }
+int ssdb_set_tensor(ssdb_net* n, const char* name, int which, const float* host_in, long long count) { return tensor_io(n, name, which, const_cast<float*>(host_in), count, true); }
+
+int ssdb_flat_buffer(ssdb_net* n, int which, void** dev_ptr_out, long long* count_out) {
+    SSDB_REQUIRE(n && which >= 0 && which <= 2 && dev_ptr_out && count_out, "bad arguments");
+    *dev_ptr_out = which == 0 ? n->params : which == 1 ? n->grads : n->moms;
+    *count_out = (long long)n->n_flat;
+    return SSDB_OK;
+}
+
+int ssdb_set_preprocess(ssdb_net* n, int swap_rb, const float mean[3]) {
+    SSDB_REQUIRE(n && mean, "bad arguments");
+    n->swap_rb = swap_rb ? 1 : 0; n->mean[0] = mean[0]; n->mean[1] = mean[1]; n->mean[2] = mean[2];
+    return SSDB_OK;
+}
+
+int ssdb_forward(ssdb_net* n, const float* images_dev, int B, float* result_dev, void* stream) {
+    SSDB_REQUIRE(n && images_dev, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = run_forward(n, images_dev, B, st); if (rc) return rc;
+    rc = softmax_result(n->out, (long long)B * n->A, n->C, result_dev ? result_dev : n->result, st);
+    return rc;
+}
+
+int ssdb_forward_host(ssdb_net* n, const float* images_host, int B, float* result_host) {
+    SSDB_REQUIRE(n && images_host && result_host && B >= 1 && B <= n->max_batch, "bad arguments");
+    cudaStream_t st = n->own_stream;
+    SSDB_CUDA(cudaMemcpyAsync(n->images_stage, images_host, (size_t)B * n->S * n->S * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = ssdb_forward(n, n->images_stage, B, n->result, st); if (rc) return rc;
+    SSDB_CUDA(cudaMemcpyAsync(result_host, n->result, (size_t)B * n->A * n->V * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SSDB_CUDA(cudaStreamSynchronize(st));
+    return SSDB_OK;
+}
+
+static int loss_and_finalize(ssdb_net* n, const float* labels_dev, const double* gt_dev, const int* gt_count_dev, int G, int B,
+                             float weight_decay, float grad_scale, bool want_grad, float* losses_out_dev, float* result_dev, cudaStream_t st) {
+    float* conf_loc = n->small_ws + 4;
+    float* l2s = n->small_ws + 6;
+    float* per_image = n->small_ws + 4096;
+    int rc = multibox_loss_launch(n->out, labels_dev, gt_dev, gt_count_dev, G, n->anchors, B, n->A, n->C, grad_scale, conf_loc,
+                                  want_grad ? n->out_grad : nullptr, result_dev ? result_dev : n->result, nullptr, per_image, n->counter, st);
+    if (rc) return rc;
+    rc = l2_sum(n->params, (long long)n->n_flat, n->decay_mask, n->small_ws + 8, l2s, st); if (rc) return rc;
+    finalize_losses_kernel<<<1, 32, 0, st>>>(conf_loc, l2s, weight_decay, losses_out_dev ? losses_out_dev : n->small_ws);
+    SSDB_LAUNCH_CHECK();
+    return SSDB_OK;
+}
+
+int ssdb_apply_update(ssdb_net* n, float lr, float momentum, float weight_decay, float grad_post_scale, void* stream) {
+    SSDB_REQUIRE(n, "bad arguments");
+    int rc = sgd_momentum(n->params, n->grads, n->moms, (long long)n->n_flat, n->decay_mask, lr, momentum, weight_decay, grad_post_scale,
+                          (cudaStream_t)stream);
+    n->wt_dirty = true; n->have_forward = false;
+    return rc;
+}
+
+int ssdb_train_step(ssdb_net* n, const float* images_dev, const float* labels_dev, const double* gt_dev, const int* gt_count_dev, int G,
+                    int B, float lr, float momentum, float weight_decay, float grad_scale, int apply_update, float* losses_out_dev,
+                    float* result_dev, void* stream) {
+    SSDB_REQUIRE(n && images_dev && (labels_dev || (gt_dev && gt_count_dev)), "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = remember_images(n, images_dev, B, st); if (rc) return rc;
+    rc = run_forward(n, images_dev, B, st); if (rc) return rc;
+    rc = loss_and_finalize(n, labels_dev, gt_dev, gt_count_dev, G, B, weight_decay, grad_scale, true, losses_out_dev, result_dev, st); if (rc) return rc;
+    rc = run_backward(n, B, st); if (rc) return rc;
+    if (apply_update) rc = ssdb_apply_update(n, lr, momentum, weight_decay, 1.0f, stream);
+    return rc;
+}
+
+int ssdb_train_step_host(ssdb_net* n, const float* images_host, const float* labels_host, int B, float lr, float momentum,
+                         float weight_decay, float* losses_out_host, float* result_host) {
+    SSDB_REQUIRE(n && images_host && labels_host && B >= 1 && B <= n->max_batch, "bad arguments");
+    cudaStream_t st = n->own_stream;
+    SSDB_CUDA(cudaMemcpyAsync(n->images_stage, images_host, (size_t)B * n->S * n->S * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    SSDB_CUDA(cudaMemcpyAsync(n->labels_stage, labels_host, (size_t)B * n->A * n->V * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = ssdb_train_step(n, n->images_stage, n->labels_stage, nullptr, nullptr, 0, B, lr, momentum, weight_decay, 1.0f, 1, n->small_ws,
+                             n->result, st);
+    if (rc) return rc;
+    if (result_host) SSDB_CUDA(cudaMemcpyAsync(result_host, n->result, (size_t)B * n->A * n->V * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SSDB_CUDA(cudaMemcpyAsync(n->host_small, n->small_ws, 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SSDB_CUDA(cudaStreamSynchronize(st));
+    if (losses_out_host) memcpy(losses_out_host, n->host_small, 4 * sizeof(float));
+    return SSDB_OK;
+}
+
+int ssdb_eval_step(ssdb_net* n, const float* images_dev, const float* labels_dev, int B, float weight_decay, float* losses_out_dev,
+                   float* result_dev, void* stream) {
+    SSDB_REQUIRE(n && images_dev && labels_dev, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = run_forward(n, images_dev, B, st); if (rc) return rc;
+    return loss_and_finalize(n, labels_dev, nullptr, nullptr, 0, B, weight_decay, 1.0f, false, losses_out_dev, result_dev, st);
+}
+
+// ---------------------------------------------------------------- stateless ops
+int ssdb_match_anchors(const double* gt_dev, const int* gt_count_dev, int B, int G, const double* anchors_prop_dev, int A, int C,
+                       int* match_out_dev, float* labels_out_dev, void* stream) {
+    SSDB_REQUIRE(gt_dev && gt_count_dev && anchors_prop_dev, "bad arguments");
+    return match_anchors_launch(gt_dev, gt_count_dev, B, G, anchors_prop_dev, A, C, match_out_dev, labels_out_dev, (cudaStream_t)stream);
+}
+
+int ssdb_match_anchors_host(const double* gt, const int* gt_count, int B, int G, const double* anchors, int A, int C, int* match_out,
+                            float* labels_out) {
+    SSDB_REQUIRE(gt && gt_count && anchors && B >= 1 && G >= 1, "bad arguments");
+    int rc = ssdb_device_ok(); if (rc) return rc;
+    double *d_gt = nullptr, *d_anc = nullptr; int *d_cnt = nullptr, *d_match = nullptr; float* d_lab = nullptr;
+    SSDB_CUDA(cudaMalloc(&d_gt, (size_t)B * G * 5 * 8)); SSDB_CUDA(cudaMalloc(&d_anc, (size_t)A * 4 * 8));
+    SSDB_CUDA(cudaMalloc(&d_cnt, (size_t)B * 4));
+    if (match_out) SSDB_CUDA(cudaMalloc(&d_match, (size_t)B * A * 4));
+    if (labels_out) SSDB_CUDA(cudaMalloc(&d_lab, (size_t)B * A * (C + 5) * 4));
+    SSDB_CUDA(cudaMemcpy(d_gt, gt, (size_t)B * G * 5 * 8, cudaMemcpyHostToDevice));
+    SSDB_CUDA(cudaMemcpy(d_anc, anchors, (size_t)A * 4 * 8, cudaMemcpyHostToDevice));
+    SSDB_CUDA(cudaMemcpy(d_cnt, gt_count, (size_t)B * 4, cudaMemcpyHostToDevice));
+    rc = match_anchors_launch(d_gt, d_cnt, B, G, d_anc, A, C, d_match, d_lab, nullptr);
+    if (!rc && match_out) SSDB_CUDA(cudaMemcpy(match_out, d_match, (size_t)B * A * 4, cudaMemcpyDeviceToHost));
+    if (!rc && labels_out) SSDB_CUDA(cudaMemcpy(labels_out, d_lab, (size_t)B * A * (C + 5) * 4, cudaMemcpyDeviceToHost));
+    SSDB_CUDA(cudaDeviceSynchronize());
+    cudaFree(d_gt); cudaFree(d_anc); cudaFree(d_cnt); if (d_match) cudaFree(d_match); if (d_lab) cudaFree(d_lab);
+    return rc;
+}
+
+int ssdb_decode_nms(const float* pred_dev, int B, int A, int C, const double* anchors_prop_dev, float conf_thr, int cap, double iou_thr,
+                    int* dets_out_dev, int* counts_out_dev, void* stream) {
+    SSDB_REQUIRE(pred_dev && anchors_prop_dev && dets_out_dev && counts_out_dev, "bad arguments");
+    size_t sb = decode_nms_scratch_bytes(B, A, cap);
+    void* scratch = nullptr;
+    if (sb) SSDB_CUDA(cudaMallocAsync(&scratch, sb, (cudaStream_t)stream));
+    int rc = decode_nms_launch(pred_dev, B, A, C, anchors_prop_dev, conf_thr, cap, iou_thr, dets_out_dev, counts_out_dev, scratch, sb, (cudaStream_t)stream);
+    if (scratch) cudaFreeAsync(scratch, (cudaStream_t)stream);
+    return rc;
+}
+
+int ssdb_decode_nms_host(const float* pred, int B, int A, int C, const double* anchors, float conf_thr, int cap, double iou_thr,
+                         int* dets_out, int* counts_out) {
+    SSDB_REQUIRE(pred && anchors && dets_out && counts_out && B >= 1, "bad arguments");
+    int rc = ssdb_device_ok(); if (rc) return rc;
+    int cap_eff = (cap > 0 && cap < A) ? cap : A;
+    float* d_pred = nullptr; double* d_anc = nullptr; int *d_dets = nullptr, *d_cnt = nullptr;
+    size_t pb = (size_t)B * A * (C + 5) * 4, db = (size_t)B * cap_eff * 8 * 4;
+    SSDB_CUDA(cudaMalloc(&d_pred, pb)); SSDB_CUDA(cudaMalloc(&d_anc, (size_t)A * 4 * 8));
+    SSDB_CUDA(cudaMalloc(&d_dets, db)); SSDB_CUDA(cudaMalloc(&d_cnt, (size_t)B * 2 * 4));
+    SSDB_CUDA(cudaMemcpy(d_pred, pred, pb, cudaMemcpyHostToDevice));
+    SSDB_CUDA(cudaMemcpy(d_anc, anchors, (size_t)A * 4 * 8, cudaMemcpyHostToDevice));
+    SSDB_CUDA(cudaMemset(d_dets, 0, db));
+    rc = ssdb_decode_nms(d_pred, B, A, C, d_anc, conf_thr, cap, iou_thr, d_dets, d_cnt, nullptr);
+    if (!rc) { SSDB_CUDA(cudaMemcpy(dets_out, d_dets, db, cudaMemcpyDeviceToHost)); SSDB_CUDA(cudaMemcpy(counts_out, d_cnt, (size_t)B * 2 * 4, cudaMemcpyDeviceToHost)); }
+    cudaFree(d_pred); cudaFree(d_anc); cudaFree(d_dets); cudaFree(d_cnt);
+    return rc;
+}
+
+static int loss_ws(int B, float** per_image, unsigned int** counter) {
+    static float* ws = nullptr; static unsigned int* cnt = nullptr; static int cap = 0;
+    if (B > cap) {
+        if (ws) cudaFree(ws);
+        SSDB_CUDA(cudaMalloc(&ws, (size_t)B * 2 * sizeof(float))); cap = B;
+    }
+    if (!cnt) { SSDB_CUDA(cudaMalloc(&cnt, sizeof(unsigned int))); SSDB_CUDA(cudaMemset(cnt, 0, sizeof(unsigned int))); }
+    *per_image = ws; *counter = cnt;
+    return SSDB_OK;
+}
+
+int ssdb_multibox_loss(const float* output_dev, const float* labels_dev, int B, int A, int C, float grad_scale, float* losses_out_dev,
+                       float* grad_out_dev, float* result_out_dev, void* stream) {
+    SSDB_REQUIRE(output_dev && labels_dev && losses_out_dev, "bad arguments");
+    float* pi; unsigned int* cnt; int rc = loss_ws(B, &pi, &cnt); if (rc) return rc;
+    return multibox_loss_launch(output_dev, labels_dev, nullptr, nullptr, 0, nullptr, B, A, C, grad_scale, losses_out_dev, grad_out_dev,
+                                result_out_dev, nullptr, pi, cnt, (cudaStream_t)stream);
+}
+
+int ssdb_multibox_loss_gt(const float* output_dev, const double* gt_dev, const int* gt_count_dev, int B, int G, const double* anchors_prop_dev,
+                          int A, int C, float grad_scale, float* losses_out_dev, float* grad_out_dev, float* result_out_dev,
+                          int* match_out_dev, void* stream) {
+    SSDB_REQUIRE(output_dev && gt_dev && gt_count_dev && anchors_prop_dev && losses_out_dev, "bad arguments");
+    float* pi; unsigned int* cnt; int rc = loss_ws(B, &pi, &cnt); if (rc) return rc;
+    return multibox_loss_launch(output_dev, nullptr, gt_dev, gt_count_dev, G, anchors_prop_dev, B, A, C, grad_scale, losses_out_dev,
+                                grad_out_dev, result_out_dev, match_out_dev, pi, cnt, (cudaStream_t)stream);
+}
+
+static ConvGeom make_geom(int B, int H, int W, int Cin, int Cout, int k, int stride, int dil, int pad_t, int pad_l, int Ho, int Wo) {
+    ConvGeom g; g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Ho = Ho; g.Wo = Wo; g.Cout = Cout; g.k = k; g.stride = stride; g.dil = dil;
+    g.pad_t = pad_t; g.pad_l = pad_l;
+    return g;
+}
+
+int ssdb_op_conv_fprop(int impl, const float* x, const float* w_hwio, const float* bias, int B, int H, int W, int Cin, int Cout, int k,
+                       int stride, int dil, int pad_t, int pad_l, int Ho, int Wo, int relu, float* y, void* stream) {
+    SSDB_REQUIRE(x && w_hwio && y, "bad arguments");
+    ConvGeom g = make_geom(B, H, W, Cin, Cout, k, stride, dil, pad_t, pad_l, Ho, Wo);
+    ConvEpilogue ep; ep.bias = bias; ep.relu = relu;
+    cudaStream_t st = (cudaStream_t)stream;
+    bool tc = impl == SSDB_CONV_TC || (impl == SSDB_CONV_AUTO && conv_tc_supported_fprop(g));
+    if (!tc) return conv_simt_fprop(g, x, w_hwio, ep, y, st);
+    SSDB_REQUIRE(conv_tc_supported_fprop(g), "shape not supported by the tcgen05 kernel");
+    int bn = Cout > 256 ? 256 : (Cout + 15) / 16 * 16;
+    int cout_pad = (Cout + bn - 1) / bn * bn;
+    float* wt = nullptr;
+    SSDB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&wt), (size_t)k * k * cout_pad * Cin * sizeof(float), st));
+    int rc = pack_filter_t(w_hwio, k * k, Cin, Cout, cout_pad, wt, st);
+    if (!rc) rc = conv_tc_fprop(g, x, wt, cout_pad, ep, y, st);
+    cudaFreeAsync(wt, st);
+    return rc;
+}
+
+int ssdb_op_conv_dgrad(int impl, const float* dz, const float* w_hwio, const float* mask_x, int B, int H, int W, int Cin, int Cout, int k,
+                       int stride, int dil, int pad_t, int pad_l, int Ho, int Wo, int beta, float* dx, void* stream) {
+    SSDB_REQUIRE(dz && w_hwio && dx, "bad arguments");
+    ConvGeom g = make_geom(B, H, W, Cin, Cout, k, stride, dil, pad_t, pad_l, Ho, Wo);
+    bool tc = impl == SSDB_CONV_TC || (impl == SSDB_CONV_AUTO && conv_tc_supported_dgrad(g));
+    if (!tc) return conv_simt_dgrad(g, dz, w_hwio, mask_x, beta, dx, (cudaStream_t)stream);
+    return conv_tc_dgrad(g, dz, w_hwio, mask_x, beta, dx, (cudaStream_t)stream);
+}
+
+int ssdb_op_conv_wgrad(int impl, const float* x, const float* dz, int B, int H, int W, int Cin, int Cout, int k, int stride, int dil,
+                       int pad_t, int pad_l, int Ho, int Wo, float* dw, float* db, void* stream) {
+    SSDB_REQUIRE(x && dz && dw, "bad arguments");
+    ConvGeom g = make_geom(B, H, W, Cin, Cout, k, stride, dil, pad_t, pad_l, Ho, Wo);
+    cudaStream_t st = (cudaStream_t)stream;
+    bool tc = impl == SSDB_CONV_TC || (impl == SSDB_CONV_AUTO && conv_tc_supported_wgrad(g));
+    size_t ws = tc ? conv_tc_wgrad_ws(g) : conv_simt_wgrad_ws(g);
+    if (ws < (size_t)256 * Cout) ws = (size_t)256 * Cout;
+    float* partial = nullptr;
+    SSDB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&partial), ws * sizeof(float), st));
+    ConvEpilogue ep;
+    int rc = tc ? conv_tc_wgrad(g, x, dz, dw, partial, st) : conv_simt_wgrad(g, x, dz, ep, dw, partial, st);
+    if (!rc && db) rc = bias_grad(dz, (long long)B * Ho * Wo, Cout, db, partial, st);
+    cudaFreeAsync(partial, st);
+    return rc;
+}
+
+int ssdb_profile_step(ssdb_net*, const float*, const float*, int, char (*)[32], float*, int*, int) {
+    set_error("ssdb_profile_step: not built in this revision");
+    return SSDB_EINVAL;
+}
+
+}  // extern "C"

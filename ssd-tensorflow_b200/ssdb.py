@@ -1,0 +1,220 @@
+"""ctypes binding of libssd_b200.so (include/ssd_b200.h).
+
+There is NO CPU fallback: importing this module only loads the library; every
+compute entry point fails loudly (``SSDBError``) when no B200 is present or the
+library is missing.  Device pointers are plain integers (e.g. ``tensor.data_ptr()``).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libssd_b200.so')
+
+CONV_AUTO, CONV_SIMT, CONV_TC = 0, 1, 2
+PARAM, GRAD, MOMENTUM = 0, 1, 2
+
+
+class SSDBError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """The loaded library.  Raises if it was not built (python ssd-tensorflow_b200/build.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SSDBError('libssd_b200.so is not built: run `python ssd-tensorflow_b200/build.py` '
+                            '(or __graft_entry__.build()); there is no CPU fallback')
+        _lib = C.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+_p = C.c_void_p
+_i = C.c_int
+_f = C.c_float
+_d = C.c_double
+_ll = C.c_longlong
+
+# name -> (restype, argtypes); mirrors include/ssd_b200.h one to one
+SIGNATURES = {
+    'ssdb_version': (_i, []),
+    'ssdb_last_error': (C.c_char_p, []),
+    'ssdb_device_ok': (_i, []),
+    'ssdb_match_anchors': (_i, [_p, _p, _i, _i, _p, _i, _i, _p, _p, _p]),
+    'ssdb_match_anchors_host': (_i, [_p, _p, _i, _i, _p, _i, _i, _p, _p]),
+    'ssdb_decode_nms': (_i, [_p, _i, _i, _i, _p, _f, _i, _d, _p, _p, _p]),
+    'ssdb_decode_nms_host': (_i, [_p, _i, _i, _i, _p, _f, _i, _d, _p, _p]),
+    'ssdb_multibox_loss': (_i, [_p, _p, _i, _i, _i, _f, _p, _p, _p, _p]),
+    'ssdb_multibox_loss_gt': (_i, [_p, _p, _p, _i, _i, _p, _i, _i, _f, _p, _p, _p, _p, _p]),
+    'ssdb_op_conv_fprop': (_i, [_i, _p, _p, _p] + [_i] * 13 + [_p, _p]),
+    'ssdb_op_conv_dgrad': (_i, [_i, _p, _p, _p] + [_i] * 13 + [_p, _p]),
+    'ssdb_op_conv_wgrad': (_i, [_i, _p, _p] + [_i] * 12 + [_p, _p, _p]),
+    'ssdb_create': (_i, [C.c_char_p, _i, _i, C.c_uint, C.POINTER(_p)]),
+    'ssdb_destroy': (_i, [_p]),
+    'ssdb_num_anchors': (_i, [_p]),
+    'ssdb_image_size': (_i, [_p]),
+    'ssdb_num_tensors': (_i, [_p]),
+    'ssdb_tensor_info': (_i, [_p, _i, C.c_char_p, _i, C.POINTER(_i), C.POINTER(_i)]),
+    'ssdb_get_tensor': (_i, [_p, C.c_char_p, _i, _p, _ll]),
+    'ssdb_set_tensor': (_i, [_p, C.c_char_p, _i, _p, _ll]),
+    'ssdb_flat_buffer': (_i, [_p, _i, C.POINTER(_p), C.POINTER(_ll)]),
+    'ssdb_set_preprocess': (_i, [_p, _i, C.POINTER(_f)]),
+    'ssdb_forward': (_i, [_p, _p, _i, _p, _p]),
+    'ssdb_forward_host': (_i, [_p, _p, _i, _p]),
+    'ssdb_train_step': (_i, [_p, _p, _p, _p, _p, _i, _i, _f, _f, _f, _f, _i, _p, _p, _p]),
+    'ssdb_train_step_host': (_i, [_p, _p, _p, _i, _f, _f, _f, _p, _p]),
+    'ssdb_eval_step': (_i, [_p, _p, _p, _i, _f, _p, _p, _p]),
+    'ssdb_apply_update': (_i, [_p, _f, _f, _f, _f, _p]),
+    'ssdb_launch_count': (_ll, []),
+    'ssdb_profile_step': (_i, [_p, _p, _p, _i, _p, _p, _p, _i]),
+}
+
+
+def _declare(l):
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(l, name)          # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+
+
+def check(rc):
+    if rc != 0:
+        raise SSDBError('libssd_b200 error %d: %s' % (rc, lib().ssdb_last_error().decode('utf-8', 'replace')))
+
+
+def require_device():
+    check(lib().ssdb_device_ok())
+
+
+def _np(a, dtype):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a, a.ctypes.data_as(_p)
+
+
+# ---------------------------------------------------------------- host-buffer box path
+def match_anchors_host(gt, gt_count, anchors_prop, num_classes, want_labels=True, want_match=True):
+    """gt [B,G,5] float64, gt_count [B] -> (match [B,A] int32, labels [B,A,C+5] float32)."""
+    gt, pgt = _np(gt, np.float64)
+    cnt, pcnt = _np(gt_count, np.int32)
+    anc, panc = _np(anchors_prop, np.float64)
+    B, G = gt.shape[0], gt.shape[1]
+    A = anc.shape[0]
+    match = np.empty((B, A), np.int32) if want_match else None
+    labels = np.empty((B, A, num_classes + 5), np.float32) if want_labels else None
+    check(lib().ssdb_match_anchors_host(pgt, pcnt, B, G, panc, A, num_classes,
+                                        match.ctypes.data_as(_p) if want_match else None,
+                                        labels.ctypes.data_as(_p) if want_labels else None))
+    return match, labels
+
+
+def decode_nms_host(pred, anchors_prop, conf_thr=0.01, cap=200, iou_thr=0.45):
+    """pred [B,A,C+5] float32 -> (dets [B,cap_eff,8] int32, counts [B,2] int32)."""
+    pred, pp = _np(pred, np.float32)
+    anc, panc = _np(anchors_prop, np.float64)
+    B, A, V = pred.shape
+    cap_i = int(cap) if cap is not None else 0
+    cap_eff = cap_i if 0 < cap_i < A else A
+    dets = np.zeros((B, cap_eff, 8), np.int32)
+    counts = np.zeros((B, 2), np.int32)
+    check(lib().ssdb_decode_nms_host(pp, B, A, V - 5, panc, float(np.float32(conf_thr)), cap_i, float(iou_thr),
+                                     dets.ctypes.data_as(_p), counts.ctypes.data_as(_p)))
+    return dets, counts
+
+
+# ---------------------------------------------------------------- engine handle
+class Net:
+    """Owner of one ssdb_net handle (one per GPU, not thread-safe)."""
+
+    def __init__(self, preset, num_classes=20, max_batch=8):
+        require_device()
+        self._h = _p()
+        check(lib().ssdb_create(preset.encode(), int(num_classes), int(max_batch), 0, C.byref(self._h)))
+        self.preset = preset
+        self.num_classes = int(num_classes)
+        self.max_batch = int(max_batch)
+        self.num_anchors = lib().ssdb_num_anchors(self._h)
+        self.image_size = lib().ssdb_image_size(self._h)
+        self.row = self.num_classes + 5
+
+    def close(self):
+        if self._h:
+            lib().ssdb_destroy(self._h)
+            self._h = _p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def tensors(self):
+        out = []
+        name = C.create_string_buffer(128)
+        rank = _i()
+        shape = (_i * 4)()
+        for k in range(lib().ssdb_num_tensors(self._h)):
+            check(lib().ssdb_tensor_info(self._h, k, name, 128, C.byref(rank), shape))
+            out.append((name.value.decode(), tuple(shape[:rank.value])))
+        return out
+
+    def set_tensor(self, name, array, which=PARAM):
+        a, pa = _np(array, np.float32)
+        check(lib().ssdb_set_tensor(self._h, name.encode(), which, pa, a.size))
+
+    def get_tensor(self, name, shape, which=PARAM):
+        a = np.empty(shape, np.float32)
+        check(lib().ssdb_get_tensor(self._h, name.encode(), which, a.ctypes.data_as(_p), a.size))
+        return a
+
+    def flat_buffer(self, which):
+        ptr = _p()
+        cnt = _ll()
+        check(lib().ssdb_flat_buffer(self._h, which, C.byref(ptr), C.byref(cnt)))
+        return ptr.value, cnt.value
+
+    def set_preprocess(self, swap_rb, mean):
+        m = (_f * 3)(*[float(v) for v in mean])
+        check(lib().ssdb_set_preprocess(self._h, int(bool(swap_rb)), m))
+
+    # host-buffer calls (what the SSDVGG facade uses: copies are inside)
+    def forward_host(self, images):
+        x, px = _np(images, np.float32)
+        B = x.shape[0]
+        res = np.empty((B, self.num_anchors, self.row), np.float32)
+        check(lib().ssdb_forward_host(self._h, px, B, res.ctypes.data_as(_p)))
+        return res
+
+    def train_step_host(self, images, labels, lr, momentum, weight_decay, want_result=True, result_out=None):
+        x, px = _np(images, np.float32)
+        y, py = _np(labels, np.float32)
+        B = x.shape[0]
+        res = result_out if result_out is not None else (np.empty((B, self.num_anchors, self.row), np.float32) if want_result else None)
+        losses = np.empty(4, np.float32)
+        check(lib().ssdb_train_step_host(self._h, px, py, B, lr, momentum, weight_decay, losses.ctypes.data_as(_p),
+                                         res.ctypes.data_as(_p) if res is not None else None))
+        return res, losses
+
+    # device-pointer calls
+    def forward(self, images_ptr, B, result_ptr=None, stream=None):
+        check(lib().ssdb_forward(self._h, images_ptr, B, result_ptr, stream))
+
+    def train_step(self, images_ptr, B, labels_ptr=None, gt_ptr=None, gt_count_ptr=None, G=0, lr=0.00075, momentum=0.9,
+                   weight_decay=0.0005, grad_scale=1.0, apply_update=True, losses_ptr=None, result_ptr=None, stream=None):
+        check(lib().ssdb_train_step(self._h, images_ptr, labels_ptr, gt_ptr, gt_count_ptr, G, B, lr, momentum, weight_decay,
+                                    grad_scale, 1 if apply_update else 0, losses_ptr, result_ptr, stream))
+
+    def eval_step(self, images_ptr, labels_ptr, B, weight_decay=0.0005, losses_ptr=None, result_ptr=None, stream=None):
+        check(lib().ssdb_eval_step(self._h, images_ptr, labels_ptr, B, weight_decay, losses_ptr, result_ptr, stream))
+
+    def apply_update(self, lr, momentum, weight_decay, grad_post_scale=1.0, stream=None):
+        check(lib().ssdb_apply_update(self._h, lr, momentum, weight_decay, grad_post_scale, stream))
+
+
+def launch_count():
+    return int(lib().ssdb_launch_count())

@@ -1,0 +1,69 @@
+"""GPU parity of the convolution kernels (SIMT and tcgen05) against a float64 torch-CPU
+restatement of tf.nn.conv2d / atrous_conv2d + bias + relu and its gradients."""
+import numpy as np
+import pytest
+import torch
+
+import ssdb
+from gpu_util import conv_case, rel_err, run_dgrad, run_fprop, run_wgrad, torch_conv_ref
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 2e-5     # fp32 accumulate, different summation order
+TF32_TOL = 2e-3     # tf32 operands (10-bit mantissa), fp32 accumulate; relative to max |ref|
+
+# (B, H, Cin, Cout, k, stride, dil, padding)
+SIMT_CASES = [
+    (2, 20, 3, 64, 3, 1, 1, 'SAME'),       # conv1_1-like (Cin = 3)
+    (2, 19, 64, 64, 3, 1, 1, 'SAME'),
+    (2, 19, 32, 64, 3, 2, 1, 'SAME'),      # stride 2, pad 1/1
+    (2, 10, 32, 64, 3, 2, 1, 'SAME'),      # stride 2, pad 0/1
+    (2, 9, 32, 32, 3, 1, 6, 'SAME'),       # dilation 6
+    (3, 5, 64, 32, 3, 1, 1, 'VALID'),
+    (2, 7, 64, 128, 1, 1, 1, 'SAME'),
+]
+TC_CASES = [
+    (2, 20, 64, 64, 3, 1, 1, 'SAME'),
+    (2, 38, 64, 128, 3, 1, 1, 'SAME'),
+    (3, 19, 128, 512, 3, 1, 1, 'SAME'),    # two N tiles of 256
+    (2, 19, 64, 96, 3, 1, 6, 'SAME'),      # dilation 6, N = 96
+    (4, 10, 256, 128, 1, 1, 1, 'SAME'),    # 1x1
+    (8, 5, 64, 160, 3, 1, 1, 'SAME'),      # head-like N = 160, tile spans images
+    (2, 33, 32, 64, 3, 1, 1, 'VALID'),
+]
+
+
+def _check_all(impl, case, tol):
+    B, H, Cin, Cout, k, stride, dil, padding = case
+    x, w, b, pad, Ho = conv_case(B, H, Cin, Cout, k, stride, dil, padding, seed=H + Cin)
+    xt, wt, bt, y = torch_conv_ref(x, w, b, stride, dil, pad, Ho, relu=True)
+    got = run_fprop(impl, x, w, b, k, stride, dil, pad, Ho, relu=True)
+    ref = y.detach().permute(0, 2, 3, 1).numpy()
+    assert rel_err(got, ref) < tol, ('fprop', case, rel_err(got, ref))
+    # backward through the pre-activation: dz arbitrary, no relu
+    xt, wt, bt, z = torch_conv_ref(x, w, b, stride, dil, pad, Ho, relu=False)
+    rng = np.random.default_rng(1)
+    dz = rng.standard_normal((B, Ho, Ho, Cout), dtype=np.float32)
+    z.backward(torch.tensor(dz).permute(0, 3, 1, 2).to(z.dtype))
+    dw, db = run_wgrad(impl if impl == ssdb.CONV_SIMT else ssdb.CONV_AUTO, x, dz, k, stride, dil, pad)
+    assert rel_err(dw, wt.grad.numpy()) < tol, ('wgrad', case, rel_err(dw, wt.grad.numpy()))
+    assert rel_err(db, bt.grad.numpy()) < FP32_TOL * 10, ('bgrad', case)
+    if Cin % 4 == 0:
+        dx_ref = xt.grad.permute(0, 2, 3, 1).numpy()
+        mask = x
+        got = run_dgrad(impl, dz, w, mask, x.shape, k, stride, dil, pad, beta=0)
+        want = dx_ref * (x > 0)
+        assert rel_err(got, want) < tol, ('dgrad', case, rel_err(got, want))
+        old = rng.standard_normal(x.shape, dtype=np.float32)
+        got = run_dgrad(impl, dz, w, None, x.shape, k, stride, dil, pad, beta=1, dx0=old)
+        assert rel_err(got, dx_ref + old) < tol, ('dgrad beta', case)
+
+
+@pytest.mark.parametrize('case', SIMT_CASES)
+def test_simt_conv_matches_oracle(case):
+    _check_all(ssdb.CONV_SIMT, case, FP32_TOL)
+
+
+@pytest.mark.parametrize('case', TC_CASES)
+def test_tcgen05_conv_matches_oracle(case):
+    _check_all(ssdb.CONV_TC, case, TF32_TOL)
