@@ -90,6 +90,16 @@ int ssdb_decode_nms_host(const float* pred_host, int B, int A, int C, const doub
                          float conf_thr, int cap, double iou_thr,
                          int* dets_out_host, int* counts_out_host);
 
+/* Class-wise greedy NMS over already-decoded boxes: ssdutils.suppress_overlaps /
+ * non_maximum_suppression (:232-318) when a caller runs them separately from decode_boxes.
+ *   boxes_abs [n,4] int32 (xmin,xmax,ymin,ymax) exactly as utils.prop2abs(box, 1000x1000) yields
+ *   labelid   [n] int32 in [0, nclass)    conf [n] float32
+ *   keep_out  [n] int32: indices of the kept boxes in the reference's output order (classes by
+ *             first appearance in the input list, confidence-descending inside a class)
+ *   count_out [1] int32 */
+int ssdb_nms_host(const int* boxes_abs_host, const int* labelid_host, const float* conf_host, int n, int nclass,
+                  double iou_thr, int* keep_out_host, int* count_out_host);
+
 /* ------------------------------------------------------------------------
  * Multibox loss (stateless).  Replaces SSDVGG.build_optimizer's loss graph
  * (ssdvgg.py:380-580): softmax-CE + smooth-L1 (:68-71), per-image 3:1 hard

@@ -129,5 +129,6 @@ int decode_nms_launch(const float* pred, int B, int A, int C, const double* anch
                       int cap, double iou_thr, int* dets_out, int* counts_out, void* scratch,
                       size_t scratch_bytes, cudaStream_t st);
 size_t decode_nms_scratch_bytes(int B, int A, int cap);
+int nms_only_host(const int* boxes, const int* cls, const float* conf, int n, int nclass, double iou_thr, int* keep_out, int* count_out);
 
 }  // namespace ssdb

@@ -240,6 +240,78 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
     }
 }
 
+
+// Stand-alone class-wise greedy NMS over already-decoded boxes (the reference calls
+// suppress_overlaps / non_maximum_suppression on decode_boxes' output, ssdutils.py:232-318).
+// boxes: [n,4] int (xmin,xmax,ymin,ymax) as prop2abs yields them; one CTA; global scratch.
+__global__ void __launch_bounds__(DT) nms_only_kernel(const int* __restrict__ boxes, const int* __restrict__ cls,
+                                                       const float* __restrict__ conf, int n, int P, double iou_thr,
+                                                       unsigned long long* __restrict__ keys, unsigned int* __restrict__ alive,
+                                                       int* __restrict__ first_pos, int nclass, int* __restrict__ keep_out,
+                                                       int* __restrict__ count_out) {
+    const int tid = threadIdx.x;
+    __shared__ int redi[DT / 32];
+    for (int i = tid; i < P; i += DT)
+        keys[i] = i < n ? (((unsigned long long)okey(conf[i]) << 32) | (unsigned long long)(0xffffffffu - (unsigned int)i)) : 0ull;
+    for (int i = tid; i < nclass; i += DT) first_pos[i] = 0x7fffffff;
+    __syncthreads();
+    for (int i = tid; i < n; i += DT) atomicMin(&first_pos[cls[i]], i);      // class order = first appearance in the INPUT list
+    for (int k2 = 2; k2 <= P; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < P; i += DT) {
+                int l = i ^ j;
+                if (l > i) {
+                    unsigned long long x = keys[i], y = keys[l];
+                    bool desc = (i & k2) == 0;
+                    if (desc ? (x < y) : (x > y)) { keys[i] = y; keys[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < n; i += DT) alive[i] = 1u;
+    __syncthreads();
+    for (int i = 0; i < n; ++i) {
+        if (!alive[i]) continue;
+        const int a = (int)(0xffffffffu - (unsigned int)(keys[i] & 0xffffffffull));
+        const int ci = cls[a];
+        const int ix0 = boxes[a * 4], ix1 = boxes[a * 4 + 1], iy0 = boxes[a * 4 + 2], iy1 = boxes[a * 4 + 3];
+        const long long area_i = (long long)(ix1 - ix0 + 1) * (iy1 - iy0 + 1);
+        for (int j = i + 1 + tid; j < n; j += DT) {
+            if (!alive[j]) continue;
+            const int bj = (int)(0xffffffffu - (unsigned int)(keys[j] & 0xffffffffull));
+            if (cls[bj] != ci) continue;
+            int jx0 = boxes[bj * 4], jx1 = boxes[bj * 4 + 1], jy0 = boxes[bj * 4 + 2], jy1 = boxes[bj * 4 + 3];
+            int iw = min(ix1, jx1) - max(ix0, jx0) + 1; iw = iw < 0 ? 0 : iw;
+            int ih = min(iy1, jy1) - max(iy0, jy0) + 1; ih = ih < 0 ? 0 : ih;
+            long long inter = (long long)iw * ih;
+            long long uni = area_i + (long long)(jx1 - jx0 + 1) * (jy1 - jy0 + 1) - inter;
+            if (__ddiv_rn((double)inter, (double)uni) > iou_thr) alive[j] = 0u;
+        }
+        __syncthreads();
+    }
+    int kept = 0;
+    for (int i = tid; i < n; i += DT) kept += alive[i] ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
+    if ((tid & 31) == 0) redi[tid >> 5] = kept;
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int i = 0; i < DT / 32; ++i) t += redi[i]; count_out[0] = t; }
+    for (int i = tid; i < n; i += DT) {
+        if (!alive[i]) continue;
+        const int a = (int)(0xffffffffu - (unsigned int)(keys[i] & 0xffffffffull));
+        const int fi = first_pos[cls[a]];
+        int rnk = 0;
+        for (int j = 0; j < n; ++j) {
+            if (!alive[j]) continue;
+            const int bj = (int)(0xffffffffu - (unsigned int)(keys[j] & 0xffffffffull));
+            const int fj = first_pos[cls[bj]];
+            if (fj < fi || (fj == fi && j < i)) ++rnk;
+        }
+        keep_out[rnk] = a;
+    }
+}
+
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 }  // namespace
@@ -272,6 +344,29 @@ int decode_nms_launch(const float* pred, int B, int A, int C, const double* anch
     if (!attr) { SSDB_CUDA(cudaFuncSetAttribute(decode_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
     decode_nms_kernel<<<B, DT, sh, st>>>(p);
     SSDB_LAUNCH_CHECK();
+    return SSDB_OK;
+}
+
+
+int nms_only_host(const int* boxes, const int* cls, const float* conf, int n, int nclass, double iou_thr, int* keep_out, int* count_out) {
+    SSDB_REQUIRE(n >= 1 && nclass >= 1 && boxes && cls && conf && keep_out && count_out, "bad arguments");
+    int P = next_pow2(n);
+    unsigned char* d = nullptr;
+    size_t off_cls = (size_t)n * 16, off_conf = off_cls + (size_t)n * 4, off_keys = (off_conf + (size_t)n * 4 + 7) / 8 * 8;
+    size_t off_alive = off_keys + (size_t)P * 8, off_first = off_alive + (size_t)n * 4, off_keep = off_first + (size_t)nclass * 4;
+    size_t total = off_keep + (size_t)n * 4 + 4;
+    SSDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&d), total));
+    SSDB_CUDA(cudaMemcpy(d, boxes, (size_t)n * 16, cudaMemcpyHostToDevice));
+    SSDB_CUDA(cudaMemcpy(d + off_cls, cls, (size_t)n * 4, cudaMemcpyHostToDevice));
+    SSDB_CUDA(cudaMemcpy(d + off_conf, conf, (size_t)n * 4, cudaMemcpyHostToDevice));
+    nms_only_kernel<<<1, DT>>>(reinterpret_cast<int*>(d), reinterpret_cast<int*>(d + off_cls), reinterpret_cast<float*>(d + off_conf), n, P,
+                               iou_thr, reinterpret_cast<unsigned long long*>(d + off_keys), reinterpret_cast<unsigned int*>(d + off_alive),
+                               reinterpret_cast<int*>(d + off_first), nclass, reinterpret_cast<int*>(d + off_keep),
+                               reinterpret_cast<int*>(d + off_keep + (size_t)n * 4));
+    SSDB_LAUNCH_CHECK();
+    SSDB_CUDA(cudaMemcpy(count_out, d + off_keep + (size_t)n * 4, 4, cudaMemcpyDeviceToHost));
+    SSDB_CUDA(cudaMemcpy(keep_out, d + off_keep, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d);
     return SSDB_OK;
 }
 

@@ -665,6 +665,11 @@ int ssdb_decode_nms_host(const float* pred, int B, int A, int C, const double* a
     return rc;
 }
 
+int ssdb_nms_host(const int* boxes, const int* labelid, const float* conf, int n, int nclass, double iou_thr, int* keep_out, int* count_out) {
+    int rc = ssdb_device_ok(); if (rc) return rc;
+    return nms_only_host(boxes, labelid, conf, n, nclass, iou_thr, keep_out, count_out);
+}
+
 static int loss_ws(int B, float** per_image, unsigned int** counter) {
     static float* ws = nullptr; static unsigned int* cnt = nullptr; static int cap = 0;
     if (B > cap) {

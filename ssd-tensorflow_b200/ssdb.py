@@ -50,6 +50,7 @@ SIGNATURES = {
     'ssdb_match_anchors_host': (_i, [_p, _p, _i, _i, _p, _i, _i, _p, _p]),
     'ssdb_decode_nms': (_i, [_p, _i, _i, _i, _p, _f, _i, _d, _p, _p, _p]),
     'ssdb_decode_nms_host': (_i, [_p, _i, _i, _i, _p, _f, _i, _d, _p, _p]),
+    'ssdb_nms_host': (_i, [_p, _p, _p, _i, _i, _d, _p, _p]),
     'ssdb_multibox_loss': (_i, [_p, _p, _i, _i, _i, _f, _p, _p, _p, _p]),
     'ssdb_multibox_loss_gt': (_i, [_p, _p, _p, _i, _i, _p, _i, _i, _f, _p, _p, _p, _p, _p]),
     'ssdb_op_conv_fprop': (_i, [_i, _p, _p, _p] + [_i] * 13 + [_p, _p]),
@@ -125,6 +126,18 @@ def decode_nms_host(pred, anchors_prop, conf_thr=0.01, cap=200, iou_thr=0.45):
     check(lib().ssdb_decode_nms_host(pp, B, A, V - 5, panc, float(np.float32(conf_thr)), cap_i, float(iou_thr),
                                      dets.ctypes.data_as(_p), counts.ctypes.data_as(_p)))
     return dets, counts
+
+
+def nms_host(boxes_abs, labelid, conf, iou_thr):
+    """boxes_abs [n,4] int32, labelid [n] int32, conf [n] float32 -> kept indices in reference order."""
+    b, pb = _np(boxes_abs, np.int32)
+    l, pl = _np(labelid, np.int32)
+    c, pc = _np(conf, np.float32)
+    n = b.shape[0]
+    keep = np.zeros(n, np.int32)
+    cnt = np.zeros(1, np.int32)
+    check(lib().ssdb_nms_host(pb, pl, pc, n, int(l.max()) + 1, float(iou_thr), keep.ctypes.data_as(_p), cnt.ctypes.data_as(_p)))
+    return keep[:cnt[0]]
 
 
 # ---------------------------------------------------------------- engine handle

@@ -1,0 +1,305 @@
+"""SSDVGG -- the reference's model class (ssdvgg.py:87-649) on the B200 engine.
+
+Keeps the Python surface the reference's train.py / infer.py consume:
+
+    net = SSDVGG(session, preset)
+    net.build_from_vgg(vgg_dir, num_classes)            # ssdvgg.py:96
+    net.build_optimizer(learning_rate=..., weight_decay=..., momentum=..., global_step=...)   # :375
+    result, losses, _ = session.run([net.result, net.losses, net.optimizer],
+                                    feed_dict={net.image_input: x, net.labels: y})     # train.py:262-266
+    result = session.run(net.result, feed_dict={net.image_input: x, net.keep_prob: 1})   # infer.py:225-227
+
+but there is no TensorFlow graph behind it: ``Session.run`` resolves the fetches to
+ONE call into libssd_b200 (forward / forward+loss / forward+loss+backward+update,
+hand-written sm_100a kernels), with the host<->device copies of the feeds and
+fetches inside that call.  ``Session`` is the small stand-in for ``tf.Session``
+that the re-authored entry scripts construct (the reference constructs
+``tf.Session()`` itself, train.py:166 / infer.py:211).
+"""
+import math
+import os
+
+import numpy as np
+
+import ssdb
+from ssdutils import get_preset_by_name
+
+
+class Fetch:
+    """A named handle usable as a fetch or as a feed_dict key (stands in for a tf.Tensor)."""
+    def __init__(self, name):
+        self.name = name
+
+    def __repr__(self):
+        return '<ssd_b200 tensor %s>' % self.name
+
+
+class Session:
+    """Minimal tf.Session stand-in: ``run(fetches, feed_dict)`` over one SSDVGG."""
+    def __init__(self):
+        self.model = None
+
+    def run(self, fetches, feed_dict=None):
+        if self.model is None:
+            raise RuntimeError('no model has been built in this session')
+        return self.model._run(fetches, feed_dict or {})
+
+    def close(self):
+        if self.model is not None:
+            self.model.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class GlobalStep:
+    """tf.Variable(0, trainable=False) stand-in (train.py:169)."""
+    def __init__(self, value=0):
+        self.value = int(value)
+
+
+def piecewise_constant(global_step, boundaries, values):
+    """tf.train.piecewise_constant (train.py:43-47,187): x <= b0 -> v0; b0 < x <= b1 -> v1; ..."""
+    def lr():
+        x = global_step.value
+        for b, v in zip(boundaries, values):
+            if x <= b:
+                return v
+        return values[-1]
+    return lr
+
+
+def _trunk_scope(name):
+    return name.startswith(('conv1_', 'conv2_', 'conv3_', 'conv4_', 'conv5_', 'mod_conv'))
+
+
+class SSDVGG:
+    def __init__(self, session, preset):
+        self.preset = preset if not isinstance(preset, str) else get_preset_by_name(preset)
+        self.session = session
+        session.model = self
+        self._built = False
+        self._engine = None
+        self._host_params = None     # name -> ndarray, until an engine exists (and to survive re-creation)
+        self._opt = None
+        self._build_names()
+        # fetch / feed handles (same attribute names as the reference)
+        self.image_input = Fetch('image_input:0')
+        self.keep_prob = Fetch('keep_prob:0')
+        self.labels = Fetch('labels:0')
+        self.result = Fetch('result/result:0')
+        self.logits = Fetch('output/logits')
+        self.classifier = Fetch('result/classifier')
+        self.locator = Fetch('result/locator')
+        self.loss = Fetch('total_loss/loss:0')
+        self.confidence_loss = Fetch('confidence_loss/confidence_loss:0')
+        self.localization_loss = Fetch('localization_loss/localization_loss:0')
+        self.l2_loss = Fetch('total_loss/l2_loss:0')
+        self.optimizer = Fetch('optimizer/optimizer')
+        self.losses = {'total': self.loss, 'localization': self.localization_loss,
+                       'confidence': self.confidence_loss, 'l2': self.l2_loss}
+
+    # ------------------------------------------------------------------ building
+    def build_from_vgg(self, vgg_dir, num_classes, a_trous=True, progress_hook='tqdm'):
+        """ssdvgg.py:96-118.  The reference downloads a pretrained VGG-16 saved-model
+        (ssdvgg.py:153-187, network access) and decimates fc6/fc7 into conv6/conv7.
+        Here: if ``<vgg_dir>/vgg16_ssd_init.npz`` exists its tensors (reference variable
+        names) are loaded; otherwise the trunk gets a He-normal stand-in (no network in
+        this environment) and the new layers the reference's Xavier-uniform / zero-bias /
+        scale-20 initialisers (ssdvgg.py:46-47,59-60,336)."""
+        if not a_trous:
+            raise NotImplementedError('only the a-trous variant (the reference default, used by both CLIs) is built')
+        self.num_classes = num_classes + 1
+        self.num_vars = num_classes + 5
+        self._host_params = self._initial_params(num_classes, seed=7)
+        path = os.path.join(vgg_dir or '', 'vgg16_ssd_init.npz')
+        if vgg_dir and os.path.exists(path):
+            with np.load(path) as z:
+                for k in z.files:
+                    if k in self._host_params:
+                        self._host_params[k] = z[k].astype(np.float32)
+        self._built = True
+
+    def build_from_metagraph(self, metagraph_file, checkpoint_file):
+        """ssdvgg.py:120-130: restore a trained model.  `checkpoint_file` is an .npz written
+        by ``save`` (tensors under the reference's variable names); the metagraph argument is
+        accepted for signature compatibility and ignored (there is no TF graph to import)."""
+        with np.load(checkpoint_file if checkpoint_file.endswith('.npz') else checkpoint_file + '.npz') as z:
+            self._host_params = {k: z[k].astype(np.float32) for k in z.files if not k.startswith('__')}
+            row = int(z['__num_vars']) if '__num_vars' in z.files else 25
+        self.num_vars = row
+        self.num_classes = row - 4
+        self._built = True
+
+    def build_optimizer(self, learning_rate=0.001, weight_decay=0.0005, momentum=0.9, global_step=None):
+        """ssdvgg.py:375-599.  `learning_rate` is a float or a zero-argument callable
+        (see piecewise_constant)."""
+        self._opt = dict(lr=learning_rate, wd=float(weight_decay), mu=float(momentum), step=global_step)
+
+    def build_optimizer_from_metagraph(self):
+        """ssdvgg.py:133-150: re-attach the optimizer of a restored model (defaults of train.py)."""
+        if self._opt is None:
+            self._opt = dict(lr=0.00075, wd=0.0005, mu=0.9, step=None)
+
+    def build_summaries(self, restore):
+        """ssdvgg.py:625-649: TensorBoard histograms are observability, out of scope; a handle is
+        returned so callers that fetch it keep working (it evaluates to None)."""
+        return Fetch('net_summaries/net_summaries:0')
+
+    def save(self, path):
+        """Write every trainable tensor under the reference's variable names (.npz)."""
+        arrays = self.get_params()
+        arrays['__num_vars'] = np.array(self.num_vars)
+        np.savez(path if path.endswith('.npz') else path + '.npz', **arrays)
+
+    def close(self):
+        if self._engine is not None:
+            self._host_params = self.get_params()
+            self._engine.close()
+            self._engine = None
+
+    # ------------------------------------------------------------------ parameters
+    def _conv_table(self, num_classes):
+        maps = self.preset.maps
+        seven = len(maps) >= 7
+        t = []
+        cin = 3
+        for blk, n, cout in (('conv1', 2, 64), ('conv2', 2, 128), ('conv3', 3, 256), ('conv4', 3, 512), ('conv5', 3, 512)):
+            for i in range(n):
+                t.append(('%s_%d' % (blk, i + 1), 3, cin, cout)); cin = cout
+        t += [('mod_conv6', 3, 512, 1024), ('mod_conv7', 1, 1024, 1024), ('conv8_1', 1, 1024, 256), ('conv8_2', 3, 256, 512),
+              ('conv9_1', 1, 512, 128), ('conv9_2', 3, 128, 256), ('conv10_1', 1, 256, 128), ('conv10_2', 3, 128, 256),
+              ('conv11_1', 1, 256, 128), ('conv11_2', 3, 128, 256)]
+        if seven:
+            t += [('conv12_1', 1, 256, 128), ('conv12_2', 3, 128, 256)]
+        src = [512, 1024, 512, 256, 256, 256, 256]
+        for i, m in enumerate(maps):
+            for j in range(2 + len(m.aspect_ratios)):
+                t.append(('classifiers/classifier%d_%d' % (i, j), 3, src[i], num_classes + 5))
+        return t
+
+    def _initial_params(self, num_classes, seed):
+        rng = np.random.default_rng(seed)
+        P = {}
+        for name, k, cin, cout in self._conv_table(num_classes):
+            if _trunk_scope(name):
+                w = rng.normal(0, math.sqrt(2.0 / (k * k * cin)), (k, k, cin, cout))
+            else:
+                lim = math.sqrt(6.0 / (k * k * cin + k * k * cout))      # xavier_initializer(), uniform
+                w = rng.uniform(-lim, lim, (k, k, cin, cout))
+            P[name + '/filter'] = w.astype(np.float32)
+            P[name + '/biases'] = np.zeros(cout, np.float32)
+        P['l2_norm_conv4_3/scale'] = np.full(512, 20.0, np.float32)
+        return P
+
+    def set_params(self, params):
+        """name -> array under the reference's variable names (e.g. 'conv4_3/filter' [3,3,512,512])."""
+        if self._engine is not None:
+            for k, v in params.items():
+                self._engine.set_tensor(k, v)
+        else:
+            self._host_params.update({k: np.asarray(v, np.float32) for k, v in params.items()})
+
+    def get_params(self, which=ssdb.PARAM):
+        if self._engine is None:
+            return dict(self._host_params)
+        return {k: self._engine.get_tensor(k, shape, which) for k, shape in self._engine.tensors()}
+
+    def _ensure_engine(self, batch):
+        if not self._built:
+            raise RuntimeError('call build_from_vgg or build_from_metagraph first')
+        if self._engine is not None and batch <= self._engine.max_batch:
+            return self._engine
+        state = None
+        if self._engine is not None:
+            state = [self.get_params(w) for w in (ssdb.PARAM, ssdb.MOMENTUM)]
+            self._engine.close()
+        eng = ssdb.Net(self.preset.name, self.num_vars - 5, max_batch=batch)
+        src = state[0] if state else self._host_params
+        for k, shape in eng.tensors():
+            if tuple(src[k].shape) != tuple(shape):
+                raise ValueError('tensor %s has shape %s, expected %s' % (k, src[k].shape, shape))
+            eng.set_tensor(k, src[k])
+            if state:
+                eng.set_tensor(k, state[1][k], ssdb.MOMENTUM)
+        self._engine = eng
+        return eng
+
+    # ------------------------------------------------------------------ execution
+    def _run(self, fetches, feed):
+        flat = []
+
+        def walk(f):
+            if isinstance(f, (list, tuple)):
+                for v in f: walk(v)
+            elif isinstance(f, dict):
+                for v in f.values(): walk(v)
+            else:
+                flat.append(f)
+        walk(fetches)
+        if self.image_input not in feed:
+            raise ValueError('feed_dict must provide net.image_input')
+        x = np.ascontiguousarray(feed[self.image_input], np.float32)
+        if x.ndim != 4 or x.shape[1] != self.preset.image_size.h or x.shape[2] != self.preset.image_size.w or x.shape[3] != 3:
+            raise ValueError('image_input must be [B, %d, %d, 3]' % (self.preset.image_size.h, self.preset.image_size.w))
+        loss_handles = set(self.losses.values())
+        want_train = any(f is self.optimizer for f in flat)
+        want_loss = any(f in loss_handles for f in flat)
+        eng = self._ensure_engine(x.shape[0])
+        values = {}
+        if want_train or want_loss:
+            if self.labels not in feed:
+                raise ValueError('feed_dict must provide net.labels for loss / optimizer fetches')
+            if self._opt is None:
+                raise RuntimeError('call build_optimizer first')
+            y = np.ascontiguousarray(feed[self.labels], np.float32)
+            lr = self._opt['lr']() if callable(self._opt['lr']) else float(self._opt['lr'])
+            if want_train:
+                res, ls = eng.train_step_host(x, y, lr, self._opt['mu'], self._opt['wd'])
+                if self._opt['step'] is not None:
+                    self._opt['step'].value += 1
+            else:
+                res, ls = self._eval_host(eng, x, y)
+            values[self.loss], values[self.localization_loss] = ls[0], ls[1]
+            values[self.confidence_loss], values[self.l2_loss] = ls[2], ls[3]
+        else:
+            res = eng.forward_host(x)
+        nc = self.num_vars - 4
+        values[self.result] = res
+        values[self.classifier] = res[..., :nc]
+        values[self.locator] = res[..., nc:]
+        values[self.optimizer] = None
+
+        def build(f):
+            if isinstance(f, (list, tuple)):
+                return [build(v) for v in f]
+            if isinstance(f, dict):
+                return {k: build(v) for k, v in f.items()}
+            if f is self.logits:
+                raise NotImplementedError('raw logits are not exported; fetch net.result / net.classifier')
+            return values.get(f)
+        return build(fetches)
+
+    def _eval_host(self, eng, x, y):
+        import torch                      # device-memory plumbing only
+        xd = torch.from_numpy(x).cuda(); yd = torch.from_numpy(y).cuda()
+        res = torch.empty((x.shape[0], eng.num_anchors, eng.row), dtype=torch.float32, device='cuda')
+        ls = torch.empty(4, dtype=torch.float32, device='cuda')
+        st = torch.cuda.current_stream().cuda_stream
+        eng.eval_step(xd.data_ptr(), yd.data_ptr(), x.shape[0], self._opt['wd'], ls.data_ptr(), res.data_ptr(), st)
+        return res.cpu().numpy(), ls.cpu().numpy()
+
+    # ------------------------------------------------------------------ names
+    def _build_names(self):
+        """ssdvgg.py:602-622."""
+        self.original_scopes = ['conv1_1', 'conv1_2', 'conv2_1', 'conv2_2', 'conv3_1', 'conv3_2', 'conv3_3', 'conv4_1',
+                                'conv4_2', 'conv4_3', 'conv5_1', 'conv5_2', 'conv5_3', 'mod_conv6', 'mod_conv7']
+        self.new_scopes = ['conv8_1', 'conv8_2', 'conv9_1', 'conv9_2', 'conv10_1', 'conv10_2', 'conv11_1', 'conv11_2']
+        if len(self.preset.maps) == 7:
+            self.new_scopes += ['conv12_1', 'conv12_2']
+        for i, m in enumerate(self.preset.maps):
+            for j in range(2 + len(m.aspect_ratios)):
+                self.new_scopes.append('classifiers/classifier{}_{}'.format(i, j))
