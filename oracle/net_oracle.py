@@ -182,7 +182,8 @@ def multibox_loss(out, labels, num_classes=20):
     zeros = torch.zeros_like(ce)
     pos_sum = torch.where(pos_mask, ce, zeros).sum(dim=-1)
     negatives = torch.where(~pos_mask, ce, zeros)
-    top = torch.topk(negatives, A, dim=1, sorted=True)[0]
+    # tf.nn.top_k(k=A): sorted descending, ties -> lower index first == stable descending sort
+    top = torch.sort(negatives, dim=1, descending=True, stable=True)[0]
     kmax = torch.minimum(neg_num, 3 * pos_num).unsqueeze(1)
     keep = torch.arange(A).unsqueeze(0) < kmax
     neg_sum = torch.where(keep, top, torch.zeros_like(top)).sum(dim=-1)

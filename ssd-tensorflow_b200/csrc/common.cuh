@@ -64,13 +64,24 @@ struct ConvEpilogue {
     int preprocess = 0;
     int swap_rb = 0;
     float mean[3] = {0, 0, 0};
+    // round the stored activation to tf32 (round-to-nearest) so that the tensor-core kernels that
+    // read it later see exactly representable operands (the MMA itself truncates)
+    int round_tf32 = 0;
 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+#endif
 
 // ---- SIMT (CUDA-core) implicit GEMM: every shape, used for tails / stride 2 / Cin=3 ----
 int conv_simt_fprop(const ConvGeom& g, const float* x, const float* w, const ConvEpilogue& ep,
                     float* y, cudaStream_t st);
 int conv_simt_dgrad(const ConvGeom& g, const float* dz, const float* w, const float* mask_x,
-                    int beta, float* dx, cudaStream_t st);
+                    int beta, int round_out, float* dx, cudaStream_t st);
 // partial: workspace of at least conv_simt_wgrad_ws(g) floats
 size_t conv_simt_wgrad_ws(const ConvGeom& g);
 int conv_simt_wgrad(const ConvGeom& g, const float* x, const float* dz, const ConvEpilogue& ep,
@@ -86,7 +97,7 @@ bool conv_tc_supported_wgrad(const ConvGeom& g);
 int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_pad,
                   const ConvEpilogue& ep, float* y, cudaStream_t st);
 int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, const float* mask_x,
-                  int beta, float* dx, cudaStream_t st);
+                  int beta, int round_out, float* dx, cudaStream_t st);
 size_t conv_tc_wgrad_ws(const ConvGeom& g);
 int conv_tc_wgrad(const ConvGeom& g, const float* x, const float* dz, float* dw, float* partial,
                   cudaStream_t st);
@@ -98,15 +109,17 @@ int maxpool_fwd(const float* x, int B, int H, int W, int C, int k, int stride, i
                 int Ho, int Wo, float* y, cudaStream_t st);
 // dx = (beta*dx + routed dy) * (x > 0)
 int maxpool_bwd(const float* x, const float* dy, int B, int H, int W, int C, int k, int stride,
-                int pad_t, int pad_l, int Ho, int Wo, int beta, int relu_mask, float* dx, cudaStream_t st);
-int l2norm_fwd(const float* x, const float* scale, long long pixels, int C, float* y, cudaStream_t st);
+                int pad_t, int pad_l, int Ho, int Wo, int beta, int relu_mask, int round_out, float* dx, cudaStream_t st);
+int l2norm_fwd(const float* x, const float* scale, long long pixels, int C, int round_out, float* y, cudaStream_t st);
 int l2norm_bwd(const float* x, const float* scale, const float* dy, long long pixels, int C, int beta,
-               float* dx, float* dscale, float* partial, cudaStream_t st);
+               int round_out, float* dx, float* dscale, float* partial, cudaStream_t st);
 
 // ---- head layout helpers ----
 // dz[B,H,W,Npad] (NHWC, zero padded channels) <- grad[B,A,V]
 int head_grad_gather(const float* grad, int B, int A, int V, int anchor_base, int HW, int nbox,
-                     int Npad, float* dz, cudaStream_t st);
+                     int Npad, int round_out, float* dz, cudaStream_t st);
+// dst[i] = tf32_rn(src[i])
+int round_tf32_copy(const float* src, float* dst, long long n, cudaStream_t st);
 int softmax_result(const float* output, long long rows, int C, float* result, cudaStream_t st);
 
 // ---- optimizer ----

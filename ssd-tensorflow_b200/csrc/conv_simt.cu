@@ -21,7 +21,7 @@ struct SimtArgs {
     const float* b;        // fprop: w, dgrad: w,  wgrad: dz
     float* out;            // fprop: y, dgrad: dx, wgrad: partial
     const float* aux;      // fprop: bias, dgrad: mask_x
-    int relu, beta;
+    int relu, beta, round_out;
     int scatter, V, n_valid, anchor_base, A;
     int preprocess, swap_rb;
     float mean0, mean1, mean2;
@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(SimtArgs p) {
                     for (int j = 0; j < 4; ++j) {
                         r[j] = acc[i][j] + (p.aux ? p.aux[n + j] : 0.f);
                         if (p.relu) r[j] = fmaxf(r[j], 0.f);
+                        if (p.round_out) r[j] = tf32_rn(r[j]);
                     }
                     *reinterpret_cast<float4*>(p.out + m * g.Cout + n) = make_float4(r[0], r[1], r[2], r[3]);
                 }
@@ -221,6 +222,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(SimtArgs p) {
                     r[0] = mk.x > 0.f ? r[0] : 0.f; r[1] = mk.y > 0.f ? r[1] : 0.f;
                     r[2] = mk.z > 0.f ? r[2] : 0.f; r[3] = mk.w > 0.f ? r[3] : 0.f;
                 }
+                if (p.round_out) { r[0] = tf32_rn(r[0]); r[1] = tf32_rn(r[1]); r[2] = tf32_rn(r[2]); r[3] = tf32_rn(r[3]); }
                 *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
             }
         } else {
@@ -264,7 +266,7 @@ int wgrad_splits(const ConvGeom& g) {
 }
 
 void fill_common(SimtArgs& p, const ConvGeom& g) {
-    p.g = g; p.relu = 0; p.beta = 0; p.scatter = 0; p.V = 0; p.n_valid = 0; p.anchor_base = 0; p.A = 0;
+    p.g = g; p.relu = 0; p.beta = 0; p.round_out = 0; p.scatter = 0; p.V = 0; p.n_valid = 0; p.anchor_base = 0; p.A = 0;
     p.preprocess = 0; p.swap_rb = 0; p.mean0 = p.mean1 = p.mean2 = 0.f; p.aux = nullptr; p.red_per_split = 0;
 }
 
@@ -273,7 +275,7 @@ void fill_common(SimtArgs& p, const ConvGeom& g) {
 int conv_simt_fprop(const ConvGeom& g, const float* x, const float* w, const ConvEpilogue& ep, float* y, cudaStream_t st) {
     SSDB_REQUIRE(g.Cout % 4 == 0, "Cout must be a multiple of 4");
     SimtArgs p; fill_common(p, g);
-    p.a = x; p.b = w; p.out = y; p.aux = ep.bias; p.relu = ep.relu;
+    p.a = x; p.b = w; p.out = y; p.aux = ep.bias; p.relu = ep.relu; p.round_out = ep.round_tf32;
     p.scatter = ep.scatter; p.V = ep.V; p.n_valid = ep.n_valid; p.anchor_base = ep.anchor_base; p.A = ep.A;
     p.preprocess = ep.preprocess; p.swap_rb = ep.swap_rb; p.mean0 = ep.mean[0]; p.mean1 = ep.mean[1]; p.mean2 = ep.mean[2];
     p.M = (long long)g.B * g.Ho * g.Wo; p.K = (long long)g.k * g.k * g.Cin; p.N = g.Cout;
@@ -284,10 +286,10 @@ int conv_simt_fprop(const ConvGeom& g, const float* x, const float* w, const Con
     return SSDB_OK;
 }
 
-int conv_simt_dgrad(const ConvGeom& g, const float* dz, const float* w, const float* mask_x, int beta, float* dx, cudaStream_t st) {
+int conv_simt_dgrad(const ConvGeom& g, const float* dz, const float* w, const float* mask_x, int beta, int round_out, float* dx, cudaStream_t st) {
     SSDB_REQUIRE(g.Cout % 4 == 0 && g.Cin % 4 == 0, "channels must be multiples of 4");
     SimtArgs p; fill_common(p, g);
-    p.a = dz; p.b = w; p.out = dx; p.aux = mask_x; p.beta = beta;
+    p.a = dz; p.b = w; p.out = dx; p.aux = mask_x; p.beta = beta; p.round_out = round_out;
     p.M = (long long)g.B * g.H * g.W; p.K = (long long)g.k * g.k * g.Cout; p.N = g.Cin;
     dim3 grid((unsigned)((p.M + BM - 1) / BM), (unsigned)((p.N + BN - 1) / BN));
     conv_simt_kernel<DGRAD, 4><<<grid, NT, 0, st>>>(p);

@@ -136,7 +136,7 @@ struct TcArgs {
     float* dst;
     const float* bias;              // fprop
     const float* mask;              // dgrad: ReLU mask source (same shape as dst) or null
-    int relu, beta;
+    int relu, beta, round_out;
     int scatter, V, n_valid, anchor_base, A;
 };
 
@@ -277,6 +277,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
                                 for (int q = 0; q < 4; ++q) {
                                     v[q] = __uint_as_float(r[j + q]) + (p.bias ? __ldg(p.bias + ch0 + j + q) : 0.f);
                                     if (p.relu) v[q] = fmaxf(v[q], 0.f);
+                                    if (p.round_out) v[q] = tf32_rn(v[q]);
                                 }
                                 *reinterpret_cast<float4*>(d + j) = make_float4(v[0], v[1], v[2], v[3]);
                             }
@@ -295,6 +296,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
                                 v[0] = m4.x > 0.f ? v[0] : 0.f; v[1] = m4.y > 0.f ? v[1] : 0.f;
                                 v[2] = m4.z > 0.f ? v[2] : 0.f; v[3] = m4.w > 0.f ? v[3] : 0.f;
                             }
+                            if (p.round_out) { v[0] = tf32_rn(v[0]); v[1] = tf32_rn(v[1]); v[2] = tf32_rn(v[2]); v[3] = tf32_rn(v[3]); }
                             *reinterpret_cast<float4*>(d + j) = make_float4(v[0], v[1], v[2], v[3]);
                         }
                     }
@@ -315,6 +317,185 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
     }
 }
 
+// MN-major, SWIZZLE_128B descriptor: the matrix dimension that is NOT contracted (channels) is the
+// contiguous one.  A 32-channel x P-pixel block is [P rows][128 B]; blocks of 32 channels are
+// `lbo_bytes` apart (leading byte offset), groups of 8 pixel rows 1024 B apart (stride byte offset).
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// ------------------------------------------------------------------ wgrad kernel
+//   dW[tap][c][n] = sum over pixels of  x[pixel + shift(tap)][c] * dz[pixel][n]
+// GEMM view: M = 128 "filter rows" = 4 slots of 32 input channels, each slot = (tap, 32-channel
+// block) so that layers with Cin = 64 still fill the MMA; N = up to 256 output channels; the
+// contraction runs over pixels, P (a multiple of 8, <= 64) per pipeline stage.  Both operands are
+// MN-major: the same [pixels][32 ch] TMA boxes as in fprop, only the descriptor says "transposed".
+// The pixel range is split over CTAs; partial filters go to a workspace and are summed in a fixed
+// order afterwards (deterministic).
+struct WgArgs {
+    int PW, PH, PN, P;              // pixel box, P = PW*PH*PN
+    int ptx, pty, ptn;              // pixel tiling of the dz map
+    int cblocks, taps, kdim;        // Cin/32, k*k, k
+    int slots, m_tiles;             // taps*cblocks, ceil(slots/4)
+    int n_tiles, block_n;           // Cout tiling
+    int Cin, Cout;                  // Cout = stored channel stride of dz and of the HWIO filter
+    int off0, offstep;              // source shift per axis for tap index t: off0 + t*offstep
+    int splits, tiles_per_split;    // pixel-tile ranges
+    float* partial;                 // [splits][taps*Cin*Cout]
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz, const WgArgs p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t bars = base + STAGES * STAGE_BYTES;
+    const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
+    const uint32_t tmem_slot = tempty0 + 16;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dz) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int units = p.m_tiles * p.n_tiles * p.splits;
+    const int pix_tiles = p.ptx * p.pty * p.ptn;
+    const uint32_t blk_bytes = (uint32_t)p.P * 128u;          // one 32-channel column block
+    const int nblk_b = p.block_n / 32;
+    const uint32_t b_off = 4u * blk_bytes;                     // B blocks follow the 4 A blocks
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int sp = u % p.splits; const int r1 = u / p.splits;
+                const int nt = r1 % p.n_tiles; const int mt = r1 / p.n_tiles;
+                const int q0 = sp * p.tiles_per_split;
+                const int q1 = min(pix_tiles, q0 + p.tiles_per_split);
+                int na = p.slots - mt * 4; na = na > 4 ? 4 : na;
+                for (int q = q0; q < q1; ++q) {
+                    const int qx = q % p.ptx; const int r2 = q / p.ptx;
+                    const int qy = r2 % p.pty; const int qn = r2 / p.pty;
+                    const int x0 = qx * p.PW, y0 = qy * p.PH, n0 = qn * p.PN;
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t fb = full0 + 8 * stage;
+                    mbar_expect_tx(fb, (uint32_t)(na + nblk_b) * blk_bytes);
+                    const uint32_t sa = base + stage * STAGE_BYTES;
+                    for (int j = 0; j < na; ++j) {
+                        const int slot = mt * 4 + j;
+                        const int tap = slot / p.cblocks, cb = slot - tap * p.cblocks;
+                        const int kh = tap / p.kdim, kw = tap - kh * p.kdim;
+                        tma_load_4d(sa + (uint32_t)j * blk_bytes, &map_x, fb, cb * 32, x0 + p.off0 + kw * p.offstep,
+                                    y0 + p.off0 + kh * p.offstep, n0);
+                    }
+                    for (int j = 0; j < nblk_b; ++j)
+                        tma_load_4d(sa + b_off + (uint32_t)j * blk_bytes, &map_dz, fb, nt * p.block_n + j * 32, x0, y0, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int sp = u % p.splits;
+                const int q0 = sp * p.tiles_per_split;
+                const int q1 = min(pix_tiles, q0 + p.tiles_per_split);
+                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MAX_N);
+                for (int q = q0; q < q1; ++q) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * STAGE_BYTES;
+                    const uint64_t ad = make_mnmajor_desc(sa, blk_bytes);
+                    const uint64_t bd = make_mnmajor_desc(sa + b_off, blk_bytes);
+                    const int ksteps = p.P / 8;
+                    for (int k = 0; k < ksteps; ++k)      // 8 pixel rows = 1024 bytes = +64 in 16-byte units
+                        tc_mma_tf32(d_tmem, ad + (uint64_t)(k * 64), bd + (uint64_t)(k * 64), idesc, (q > q0 || k > 0) ? 1u : 0u);
+                    tc_commit(empty0 + 8 * stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull0 + 8 * acc);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        const long long wsize = (long long)p.taps * p.Cin * p.Cout;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int sp = u % p.splits; const int r1 = u / p.splits;
+            const int nt = r1 % p.n_tiles; const int mt = r1 / p.n_tiles;
+            const int slot = mt * 4 + quarter;
+            const bool ok = slot < p.slots;
+            const int tap = ok ? slot / p.cblocks : 0, cb = ok ? slot - tap * p.cblocks : 0;
+            float* drow = p.partial + (long long)sp * wsize + ((long long)tap * p.Cin + cb * 32 + lane) * p.Cout;
+            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (uint32_t)(acc * MAX_N) + ((uint32_t)(quarter * 32) << 16);
+            for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+                uint32_t r[32];
+                __syncwarp();
+                tc_ld32(t_row + (uint32_t)c0, r);
+                tc_wait_ld();
+                const int ch0 = nt * p.block_n + c0;
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        if (ch0 + j < p.Cout)
+                            *reinterpret_cast<float4*>(drow + ch0 + j) =
+                                make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, long long n, int splits, float* __restrict__ out) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < splits; ++z) {
+        float4 v = *reinterpret_cast<const float4*>(partial + (long long)z * n + i);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + i) = s;
+}
+
 // per-tap transpose: w_t[tap][n][c] = w[tap][c][n] (n < Cout), zero rows for n >= Cout
 __global__ void pack_filter_t_kernel(const float* __restrict__ w, int taps, int Cin, int Cout, int cout_pad, float* __restrict__ wt) {
     __shared__ float tile[32][33];
@@ -322,7 +503,7 @@ __global__ void pack_filter_t_kernel(const float* __restrict__ w, int taps, int 
     const int c0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int c = c0 + i, n = n0 + threadIdx.x;
-        tile[i][threadIdx.x] = (c < Cin && n < Cout) ? w[((long long)tap * Cin + c) * Cout + n] : 0.f;
+        tile[i][threadIdx.x] = (c < Cin && n < Cout) ? tf32_rn(w[((long long)tap * Cin + c) * Cout + n]) : 0.f;
     }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -457,7 +638,7 @@ int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_
     a.taps = g.k * g.k; a.kdim = g.k; a.cblocks = g.Cin / BLOCK_K; a.rows_per_tap = cout_pad;
     a.off0 = -g.pad_t; a.offstep = g.dil; a.mode = 0;
     SSDB_REQUIRE(g.pad_t == g.pad_l, "tcgen05 path assumes equal top/left padding");
-    a.dst = y; a.bias = ep.bias; a.mask = nullptr; a.relu = ep.relu; a.beta = 0;
+    a.dst = y; a.bias = ep.bias; a.mask = nullptr; a.relu = ep.relu; a.beta = 0; a.round_out = ep.round_tf32;
     a.scatter = ep.scatter; a.V = ep.V; a.n_valid = ep.n_valid; a.anchor_base = ep.anchor_base; a.A = ep.A;
     CUtensorMap ms, mw;
     int rc = encode_act_map(&ms, x, g.B, g.H, g.W, g.Cin, t.TW, t.TH, t.TN); if (rc) return rc;
@@ -465,7 +646,7 @@ int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_
     return launch_tc(ms, mw, a, st);
 }
 
-int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, const float* mask_x, int beta, float* dx, cudaStream_t st) {
+int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, const float* mask_x, int beta, int round_out, float* dx, cudaStream_t st) {
     SSDB_REQUIRE(conv_tc_supported_dgrad(g), "shape not supported by the tcgen05 dgrad kernel");
     TileGeom t = pick_tile(g.B, g.H, g.W);
     TcArgs a{};
@@ -476,18 +657,97 @@ int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, const
     a.taps = g.k * g.k; a.kdim = g.k; a.cblocks = g.Cout / BLOCK_K; a.rows_per_tap = g.Cin;
     a.off0 = g.pad_t; a.offstep = -g.dil; a.mode = 1;
     SSDB_REQUIRE(g.pad_t == g.pad_l, "tcgen05 path assumes equal top/left padding");
-    a.dst = dx; a.bias = nullptr; a.mask = mask_x; a.relu = 0; a.beta = beta;
+    a.dst = dx; a.bias = nullptr; a.mask = mask_x; a.relu = 0; a.beta = beta; a.round_out = round_out;
     CUtensorMap ms, mw;
     int rc = encode_act_map(&ms, dz, g.B, g.Ho, g.Wo, g.Cout, t.TW, t.TH, t.TN); if (rc) return rc;
     rc = encode_w_map(&mw, w_hwio, (long long)a.taps * g.Cin, g.Cout, a.block_n); if (rc) return rc;
     return launch_tc(ms, mw, a, st);
 }
 
-bool conv_tc_supported_wgrad(const ConvGeom&) { return false; }
-size_t conv_tc_wgrad_ws(const ConvGeom&) { return 0; }
-int conv_tc_wgrad(const ConvGeom&, const float*, const float*, float*, float*, cudaStream_t) {
-    set_error("tcgen05 wgrad not built yet");
-    return SSDB_EINVAL;
+namespace {
+
+struct PixGeom { int PW, PH, PN, P; double eff; };
+
+// pixel box for the wgrad contraction: P = PW*PH*PN a multiple of 8, at most p_max, least waste
+PixGeom pick_pix(int B, int H, int W, int p_max) {
+    PixGeom best{0, 0, 0, 0, 0.0};
+    const double total = (double)B * H * W;
+    for (int pw = 1; pw <= W && pw <= p_max; ++pw)
+        for (int ph = 1; ph <= H && pw * ph <= p_max; ++ph)
+            for (int pn = 1; pn <= B && pw * ph * pn <= p_max; ++pn) {
+                int P = pw * ph * pn;
+                if (P % 8) continue;
+                long long tiles = (long long)((W + pw - 1) / pw) * ((H + ph - 1) / ph) * ((B + pn - 1) / pn);
+                double eff = total / ((double)tiles * P);
+                double score = eff + 1e-4 * P;                 // prefer larger boxes among near-equals
+                double bscore = best.eff + 1e-4 * best.P;
+                if (score > bscore) best = PixGeom{pw, ph, pn, P, eff};
+            }
+    return best;
+}
+
+struct WgPlan { WgArgs a; bool ok; };
+
+WgPlan plan_wgrad(const ConvGeom& g) {
+    WgPlan pl{}; pl.ok = false;
+    if (g.stride != 1 || g.Cin % 32 != 0 || g.Cout % 32 != 0 || g.pad_t != g.pad_l || g.k < 1 || g.k > 7) return pl;
+    if (g.Cout > MAX_N && g.Cout % MAX_N != 0) return pl;
+    WgArgs& a = pl.a;
+    a.block_n = g.Cout > MAX_N ? MAX_N : g.Cout;
+    a.n_tiles = g.Cout / a.block_n;
+    int blocks = 4 + a.block_n / 32;
+    int p_max = STAGE_BYTES / (blocks * 128);
+    p_max = p_max / 8 * 8; if (p_max > 64) p_max = 64;
+    PixGeom pg = pick_pix(g.B, g.Ho, g.Wo, p_max);
+    if (pg.P == 0 || pg.eff < 0.4) return pl;
+    a.PW = pg.PW; a.PH = pg.PH; a.PN = pg.PN; a.P = pg.P;
+    a.ptx = (g.Wo + pg.PW - 1) / pg.PW; a.pty = (g.Ho + pg.PH - 1) / pg.PH; a.ptn = (g.B + pg.PN - 1) / pg.PN;
+    a.cblocks = g.Cin / 32; a.taps = g.k * g.k; a.kdim = g.k;
+    a.slots = a.taps * a.cblocks; a.m_tiles = (a.slots + 3) / 4;
+    a.Cin = g.Cin; a.Cout = g.Cout;
+    a.off0 = -g.pad_t; a.offstep = g.dil;
+    long long pix_tiles = (long long)a.ptx * a.pty * a.ptn;
+    long long base_units = (long long)a.m_tiles * a.n_tiles;
+    long long want = (2LL * num_sms() + base_units - 1) / base_units;     // ~2 units per SM
+    long long max_splits = (pix_tiles + 7) / 8;                            // at least 8 stages per unit
+    if (want > max_splits) want = max_splits;
+    if (want < 1) want = 1;
+    if (want > 256) want = 256;
+    a.tiles_per_split = (int)((pix_tiles + want - 1) / want);
+    a.splits = (int)((pix_tiles + a.tiles_per_split - 1) / a.tiles_per_split);
+    a.partial = nullptr;
+    pl.ok = true;
+    return pl;
+}
+
+}  // namespace
+
+bool conv_tc_supported_wgrad(const ConvGeom& g) { return plan_wgrad(g).ok; }
+
+size_t conv_tc_wgrad_ws(const ConvGeom& g) {
+    WgPlan pl = plan_wgrad(g);
+    if (!pl.ok) return 0;
+    return (size_t)pl.a.splits * pl.a.taps * g.Cin * g.Cout;
+}
+
+int conv_tc_wgrad(const ConvGeom& g, const float* x, const float* dz, float* dw, float* partial, cudaStream_t st) {
+    WgPlan pl = plan_wgrad(g);
+    SSDB_REQUIRE(pl.ok, "shape not supported by the tcgen05 wgrad kernel");
+    WgArgs a = pl.a;
+    a.partial = partial;
+    CUtensorMap mx, mz;
+    int rc = encode_act_map(&mx, x, g.B, g.H, g.W, g.Cin, a.PW, a.PH, a.PN); if (rc) return rc;
+    rc = encode_act_map(&mz, dz, g.B, g.Ho, g.Wo, g.Cout, a.PW, a.PH, a.PN); if (rc) return rc;
+    static bool attr = false;
+    if (!attr) { SSDB_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr = true; }
+    long long units = (long long)a.m_tiles * a.n_tiles * a.splits;
+    int grid = (int)(units < num_sms() ? units : num_sms());
+    conv_tc_wgrad_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mx, mz, a);
+    SSDB_LAUNCH_CHECK();
+    long long n = (long long)a.taps * g.Cin * g.Cout;
+    reduce_partials_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(partial, n, a.splits, dw);
+    SSDB_LAUNCH_CHECK();
+    return SSDB_OK;
 }
 
 }  // namespace ssdb

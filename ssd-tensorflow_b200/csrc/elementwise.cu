@@ -33,7 +33,7 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ x, int B, int H, in
 // one thread per input element group (float4 of channels): sum dy over the windows whose
 // first maximum (row-major scan) is this element
 __global__ void maxpool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, int B, int H, int W,
-                                   int C4, int k, int s, int pt, int pl, int Ho, int Wo, int beta, int relu_mask,
+                                   int C4, int k, int s, int pt, int pl, int Ho, int Wo, int beta, int relu_mask, int round_out,
                                    float* __restrict__ dx) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)B * H * W * C4;
@@ -81,12 +81,13 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ x, const float* __r
 #pragma unroll
         for (int q = 0; q < 4; ++q) g[q] = mev[q] > 0.f ? g[q] : 0.f;
     }
+    if (round_out) { g[0] = tf32_rn(g[0]); g[1] = tf32_rn(g[1]); g[2] = tf32_rn(g[2]); g[3] = tf32_rn(g[3]); }
     reinterpret_cast<float4*>(dx)[i] = make_float4(g[0], g[1], g[2], g[3]);
 }
 
 // one warp per pixel
 __global__ void l2norm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, long long pixels, int C,
-                                  float* __restrict__ y) {
+                                  int round_out, float* __restrict__ y) {
     long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (p >= pixels) return;
@@ -102,13 +103,15 @@ __global__ void l2norm_fwd_kernel(const float* __restrict__ x, const float* __re
     for (int c = lane * 4; c < C; c += 128) {
         float4 v = *reinterpret_cast<const float4*>(xp + c);
         float4 s = *reinterpret_cast<const float4*>(scale + c);
-        *reinterpret_cast<float4*>(y + p * C + c) = make_float4(v.x * r * s.x, v.y * r * s.y, v.z * r * s.z, v.w * r * s.w);
+        float4 o = make_float4(v.x * r * s.x, v.y * r * s.y, v.z * r * s.z, v.w * r * s.w);
+        if (round_out) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
+        *reinterpret_cast<float4*>(y + p * C + c) = o;
     }
 }
 
 // dx_c = (s_c g_c r - x_c r^3 sum_k(g_k s_k x_k)) masked by x>0 ; dscale partial per block
 __global__ void l2norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ dy,
-                                  long long pixels, int C, int beta, float* __restrict__ dx, float* __restrict__ partial) {
+                                  long long pixels, int C, int beta, int round_out, float* __restrict__ dx, float* __restrict__ partial) {
     extern __shared__ float sh[];   // [warps][C] dscale partials
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     float* mine = sh + (long long)warp * C;
@@ -141,6 +144,7 @@ __global__ void l2norm_bwd_kernel(const float* __restrict__ x, const float* __re
             for (int q = 0; q < 4; ++q) {
                 float d = sv[q] * gg[q] * r - vv[q] * r3dot + ov[q];
                 o[q] = vv[q] > 0.f ? d : 0.f;
+                if (round_out) o[q] = tf32_rn(o[q]);
                 mine[c + q] += gg[q] * vv[q] * r;
             }
             *reinterpret_cast<float4*>(dx + p * C + c) = make_float4(o[0], o[1], o[2], o[3]);
@@ -163,7 +167,7 @@ __global__ void reduce_rows_kernel(const float* __restrict__ partial, int rows, 
 }
 
 __global__ void head_grad_gather_kernel(const float* __restrict__ grad, int B, int A, int V, int anchor_base, int HW,
-                                        int nbox, int Npad, float* __restrict__ dz) {
+                                        int nbox, int Npad, int round_out, float* __restrict__ dz) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)B * HW * Npad;
     if (i >= total) return;
@@ -174,7 +178,12 @@ __global__ void head_grad_gather_kernel(const float* __restrict__ grad, int B, i
         int j = n / V, q = n - j * V;
         v = grad[((long long)b * A + anchor_base + (long long)j * HW + pix) * V + q];
     }
-    dz[i] = v;
+    dz[i] = round_out ? tf32_rn(v) : v;
+}
+
+__global__ void round_tf32_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = tf32_rn(src[i]);
 }
 
 // one thread per row: softmax over the first C+1 columns, copy the 4 offsets
@@ -253,39 +262,45 @@ int maxpool_fwd(const float* x, int B, int H, int W, int C, int k, int stride, i
 }
 
 int maxpool_bwd(const float* x, const float* dy, int B, int H, int W, int C, int k, int stride, int pad_t, int pad_l,
-                int Ho, int Wo, int beta, int relu_mask, float* dx, cudaStream_t st) {
+                int Ho, int Wo, int beta, int relu_mask, int round_out, float* dx, cudaStream_t st) {
     SSDB_REQUIRE(C % 4 == 0, "channels must be a multiple of 4");
     long long total = (long long)B * H * W * (C / 4);
     maxpool_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, dy, B, H, W, C / 4, k, stride, pad_t, pad_l, Ho, Wo,
-                                                                          beta, relu_mask, dx);
+                                                                          beta, relu_mask, round_out, dx);
     SSDB_LAUNCH_CHECK();
     return SSDB_OK;
 }
 
-int l2norm_fwd(const float* x, const float* scale, long long pixels, int C, float* y, cudaStream_t st) {
+int l2norm_fwd(const float* x, const float* scale, long long pixels, int C, int round_out, float* y, cudaStream_t st) {
     SSDB_REQUIRE(C % 4 == 0, "channels must be a multiple of 4");
     long long threads = pixels * 32;
-    l2norm_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, scale, pixels, C, y);
+    l2norm_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, scale, pixels, C, round_out, y);
     SSDB_LAUNCH_CHECK();
     return SSDB_OK;
 }
 
-int l2norm_bwd(const float* x, const float* scale, const float* dy, long long pixels, int C, int beta, float* dx,
+int l2norm_bwd(const float* x, const float* scale, const float* dy, long long pixels, int C, int beta, int round_out, float* dx,
                float* dscale, float* partial, cudaStream_t st) {
     SSDB_REQUIRE(C % 4 == 0 && C <= 1024, "unsupported channel count");
     int nb = 296;   // 2 blocks per SM
     size_t sh = (size_t)8 * C * sizeof(float);
-    l2norm_bwd_kernel<<<nb, 256, sh, st>>>(x, scale, dy, pixels, C, beta, dx, partial);
+    l2norm_bwd_kernel<<<nb, 256, sh, st>>>(x, scale, dy, pixels, C, beta, round_out, dx, partial);
     SSDB_LAUNCH_CHECK();
     reduce_rows_kernel<<<(C + 255) / 256, 256, 0, st>>>(partial, nb, C, dscale);
     SSDB_LAUNCH_CHECK();
     return SSDB_OK;
 }
 
-int head_grad_gather(const float* grad, int B, int A, int V, int anchor_base, int HW, int nbox, int Npad, float* dz,
+int head_grad_gather(const float* grad, int B, int A, int V, int anchor_base, int HW, int nbox, int Npad, int round_out, float* dz,
                      cudaStream_t st) {
     long long total = (long long)B * HW * Npad;
-    head_grad_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(grad, B, A, V, anchor_base, HW, nbox, Npad, dz);
+    head_grad_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(grad, B, A, V, anchor_base, HW, nbox, Npad, round_out, dz);
+    SSDB_LAUNCH_CHECK();
+    return SSDB_OK;
+}
+
+int round_tf32_copy(const float* src, float* dst, long long n, cudaStream_t st) {
+    round_tf32_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, n);
     SSDB_LAUNCH_CHECK();
     return SSDB_OK;
 }

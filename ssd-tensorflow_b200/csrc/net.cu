@@ -89,6 +89,8 @@ struct ssdb_net {
     size_t n_flat = 0, act_floats_per_image = 0, wt_floats = 0;
     // device memory
     float *params = nullptr, *grads = nullptr, *moms = nullptr, *wt = nullptr;
+    float *wr = nullptr;               // tf32-rounded copy of the parameters (dgrad B operand)
+    bool round = true;                 // activations / gradients are stored tf32-rounded (off in pure-SIMT mode)
     float *acts = nullptr, *gacts = nullptr;
     float *out = nullptr, *out_grad = nullptr, *result = nullptr, *dz_head = nullptr;
     float *images_stage = nullptr, *labels_stage = nullptr;
@@ -275,6 +277,7 @@ int repack_filters(ssdb_net* n, cudaStream_t st) {
         int rc = pack_filter_t(n->params + n->masters[op.w].off, op.k * op.k, op.cin, op.cout, op.cout_pad, n->wt + op.wt_off, st);
         if (rc) return rc;
     }
+    if (n->round) { int rc = round_tf32_copy(n->params, n->wr, (long long)n->n_flat, st); if (rc) return rc; }
     n->wt_dirty = false;
     return SSDB_OK;
 }
@@ -288,6 +291,7 @@ int run_forward(ssdb_net* n, const float* images, int B, cudaStream_t st) {
             ConvGeom g = geom_of(n, op, B);
             ConvEpilogue ep;
             ep.bias = n->params + n->masters[op.b].off; ep.relu = op.relu ? 1 : 0;
+            ep.round_tf32 = (n->round && !op.head) ? 1 : 0;
             const float* x = op.in < 0 ? images : n->act(op.in, B);
             float* y = op.out >= 0 ? n->act(op.out, B) : n->out;
             if (op.head) { ep.scatter = 1; ep.V = n->V; ep.n_valid = op.nbox * n->V; ep.anchor_base = op.anchor_base; ep.A = n->A; }
@@ -301,7 +305,7 @@ int run_forward(ssdb_net* n, const float* images, int B, cudaStream_t st) {
             rc = maxpool_fwd(n->act(op.in, B), B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W, n->act(op.out, B), st);
         } else {
             const Buf& bi = n->bufs[op.in];
-            rc = l2norm_fwd(n->act(op.in, B), n->params + n->masters[op.w].off, (long long)B * bi.H * bi.W, bi.C, n->act(op.out, B), st);
+            rc = l2norm_fwd(n->act(op.in, B), n->params + n->masters[op.w].off, (long long)B * bi.H * bi.W, bi.C, n->round ? 1 : 0, n->act(op.out, B), st);
         }
         if (rc) return rc;
     }
@@ -320,7 +324,7 @@ int run_backward(ssdb_net* n, int B, cudaStream_t st) {
             const float* dz;
             if (op.head) {
                 const Buf& fb = n->bufs[op.in];
-                rc = head_grad_gather(n->out_grad, B, n->A, n->V, op.anchor_base, fb.H * fb.W, op.nbox, op.cout, n->dz_head, st);
+                rc = head_grad_gather(n->out_grad, B, n->A, n->V, op.anchor_base, fb.H * fb.W, op.nbox, op.cout, n->round ? 1 : 0, n->dz_head, st);
                 if (rc) return rc;
                 dz = n->dz_head;
             } else {
@@ -344,22 +348,22 @@ int run_backward(ssdb_net* n, int B, cudaStream_t st) {
                 const float* mask = n->bufs[op.in].relu_out ? x : nullptr;
                 int beta = written[op.in] ? 1 : 0;
                 if (use_tc(n, conv_tc_supported_dgrad(g)))
-                    rc = conv_tc_dgrad(g, dz, n->params + n->masters[op.w].off, mask, beta, n->gact(op.in, B), st);
+                    rc = conv_tc_dgrad(g, dz, n->wr + n->masters[op.w].off, mask, beta, 1, n->gact(op.in, B), st);
                 else
-                    rc = conv_simt_dgrad(g, dz, n->params + n->masters[op.w].off, mask, beta, n->gact(op.in, B), st);
+                    rc = conv_simt_dgrad(g, dz, n->params + n->masters[op.w].off, mask, beta, n->round ? 1 : 0, n->gact(op.in, B), st);
                 written[op.in] = 1;
             }
         } else if (op.type == OP_POOL) {
             SSDB_REQUIRE(written[op.out], "internal: gradient of a pool output was never produced");
             const Buf& bi = n->bufs[op.in]; const Buf& bo = n->bufs[op.out];
             rc = maxpool_bwd(n->act(op.in, B), n->gact(op.out, B), B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W,
-                             written[op.in] ? 1 : 0, bi.relu_out ? 1 : 0, n->gact(op.in, B), st);
+                             written[op.in] ? 1 : 0, bi.relu_out ? 1 : 0, n->round ? 1 : 0, n->gact(op.in, B), st);
             written[op.in] = 1;
         } else {
             SSDB_REQUIRE(written[op.out], "internal: gradient of the L2-norm output was never produced");
             const Buf& bi = n->bufs[op.in];
             rc = l2norm_bwd(n->act(op.in, B), n->params + n->masters[op.w].off, n->gact(op.out, B), (long long)B * bi.H * bi.W, bi.C,
-                            written[op.in] ? 1 : 0, n->gact(op.in, B), n->grads + n->masters[op.w].off, n->partial, st);
+                            written[op.in] ? 1 : 0, n->round ? 1 : 0, n->gact(op.in, B), n->grads + n->masters[op.w].off, n->partial, st);
             written[op.in] = 1;
         }
         if (rc) return rc;
@@ -422,7 +426,7 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
     ssdb_net* n = new ssdb_net();
     n->preset = P; n->C = num_classes; n->V = num_classes + 5; n->S = P->image; n->max_batch = max_batch;
     const char* mode = getenv("SSDB_CONV");
-    if (mode && !strcmp(mode, "simt")) n->conv_mode = SSDB_CONV_SIMT;
+    if (mode && !strcmp(mode, "simt")) { n->conv_mode = SSDB_CONV_SIMT; n->round = false; }
     build_plan(n);
     if (n->A != P->num_anchors) { set_error("internal: anchor count %d != %d", n->A, P->num_anchors); delete n; return SSDB_EINVAL; }
     // workspace sizes
@@ -440,7 +444,7 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
     size_t img = (size_t)max_batch * n->S * n->S * 3;
 #define ALLOC(ptr, count, type) SSDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&(ptr)), (size_t)(count) * sizeof(type)))
     ALLOC(n->params, n->n_flat, float); ALLOC(n->grads, n->n_flat, float); ALLOC(n->moms, n->n_flat, float);
-    ALLOC(n->wt, n->wt_floats ? n->wt_floats : 1, float);
+    ALLOC(n->wt, n->wt_floats ? n->wt_floats : 1, float); ALLOC(n->wr, n->n_flat, float);
     ALLOC(n->acts, n->act_floats_per_image * max_batch, float); ALLOC(n->gacts, n->act_floats_per_image * max_batch, float);
     ALLOC(n->out, bav, float); ALLOC(n->out_grad, bav, float); ALLOC(n->result, bav, float); ALLOC(n->labels_stage, bav, float);
     ALLOC(n->dz_head, dzh ? dzh : 1, float); ALLOC(n->images_stage, img, float);
@@ -469,7 +473,7 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
 int ssdb_destroy(ssdb_net* n) {
     if (!n) return SSDB_OK;
     cudaDeviceSynchronize();
-    void* ptrs[] = {n->params, n->grads, n->moms, n->wt, n->acts, n->gacts, n->out, n->out_grad, n->result, n->labels_stage,
+    void* ptrs[] = {n->wr, n->params, n->grads, n->moms, n->wt, n->acts, n->gacts, n->out, n->out_grad, n->result, n->labels_stage,
                     n->dz_head, n->images_stage, n->partial, n->small_ws, n->counter, n->decay_mask, n->anchors};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (n->host_small) cudaFreeHost(n->host_small);
@@ -715,11 +719,14 @@ int ssdb_op_conv_fprop(int impl, const float* x, const float* w_hwio, const floa
     SSDB_REQUIRE(conv_tc_supported_fprop(g), "shape not supported by the tcgen05 kernel");
     int bn = Cout > 256 ? 256 : (Cout + 15) / 16 * 16;
     int cout_pad = (Cout + bn - 1) / bn * bn;
-    float* wt = nullptr;
+    float *wt = nullptr, *xr = nullptr;
+    long long nx = (long long)B * H * W * Cin;
     SSDB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&wt), (size_t)k * k * cout_pad * Cin * sizeof(float), st));
+    SSDB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&xr), (size_t)nx * sizeof(float), st));
     int rc = pack_filter_t(w_hwio, k * k, Cin, Cout, cout_pad, wt, st);
-    if (!rc) rc = conv_tc_fprop(g, x, wt, cout_pad, ep, y, st);
-    cudaFreeAsync(wt, st);
+    if (!rc) rc = round_tf32_copy(x, xr, nx, st);          // the engine stores activations tf32-rounded
+    if (!rc) rc = conv_tc_fprop(g, xr, wt, cout_pad, ep, y, st);
+    cudaFreeAsync(wt, st); cudaFreeAsync(xr, st);
     return rc;
 }
 
@@ -728,8 +735,17 @@ int ssdb_op_conv_dgrad(int impl, const float* dz, const float* w_hwio, const flo
     SSDB_REQUIRE(dz && w_hwio && dx, "bad arguments");
     ConvGeom g = make_geom(B, H, W, Cin, Cout, k, stride, dil, pad_t, pad_l, Ho, Wo);
     bool tc = impl == SSDB_CONV_TC || (impl == SSDB_CONV_AUTO && conv_tc_supported_dgrad(g));
-    if (!tc) return conv_simt_dgrad(g, dz, w_hwio, mask_x, beta, dx, (cudaStream_t)stream);
-    return conv_tc_dgrad(g, dz, w_hwio, mask_x, beta, dx, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!tc) return conv_simt_dgrad(g, dz, w_hwio, mask_x, beta, 0, dx, st);
+    float *zr = nullptr, *wr = nullptr;
+    long long nz = (long long)B * Ho * Wo * Cout, nw = (long long)k * k * Cin * Cout;
+    SSDB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&zr), (size_t)nz * sizeof(float), st));
+    SSDB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&wr), (size_t)nw * sizeof(float), st));
+    int rc = round_tf32_copy(dz, zr, nz, st);
+    if (!rc) rc = round_tf32_copy(w_hwio, wr, nw, st);
+    if (!rc) rc = conv_tc_dgrad(g, zr, wr, mask_x, beta, 0, dx, st);
+    cudaFreeAsync(zr, st); cudaFreeAsync(wr, st);
+    return rc;
 }
 
 int ssdb_op_conv_wgrad(int impl, const float* x, const float* dz, int B, int H, int W, int Cin, int Cout, int k, int stride, int dil,
@@ -743,7 +759,20 @@ int ssdb_op_conv_wgrad(int impl, const float* x, const float* dz, int B, int H, 
     float* partial = nullptr;
     SSDB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&partial), ws * sizeof(float), st));
     ConvEpilogue ep;
-    int rc = tc ? conv_tc_wgrad(g, x, dz, dw, partial, st) : conv_simt_wgrad(g, x, dz, ep, dw, partial, st);
+    int rc = SSDB_OK;
+    if (tc) {
+        SSDB_REQUIRE(conv_tc_supported_wgrad(g), "shape not supported by the tcgen05 wgrad kernel");
+        float *xr = nullptr, *zr = nullptr;
+        long long nx = (long long)B * H * W * Cin, nz = (long long)B * Ho * Wo * Cout;
+        SSDB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&xr), (size_t)nx * sizeof(float), st));
+        SSDB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&zr), (size_t)nz * sizeof(float), st));
+        rc = round_tf32_copy(x, xr, nx, st);
+        if (!rc) rc = round_tf32_copy(dz, zr, nz, st);
+        if (!rc) rc = conv_tc_wgrad(g, xr, zr, dw, partial, st);
+        cudaFreeAsync(xr, st); cudaFreeAsync(zr, st);
+    } else {
+        rc = conv_simt_wgrad(g, x, dz, ep, dw, partial, st);
+    }
     if (!rc && db) rc = bias_grad(dz, (long long)B * Ho * Wo, Cout, db, partial, st);
     cudaFreeAsync(partial, st);
     return rc;

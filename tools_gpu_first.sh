@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 LOG=gpurun_out/pytest_gpu.log
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 : > $LOG
-run() { echo "=== $*" >> $LOG; timeout 900 python -m pytest "$@" -q --timeout 600 -p no:cacheprovider >> $LOG 2>&1; echo "exit $?" >> $LOG; }
+run() { echo "=== $*" >> $LOG; timeout 900 python -m pytest "$@" -q -s --timeout 600 -p no:cacheprovider >> $LOG 2>&1; echo "exit $?" >> $LOG; }
 run tests/test_gpu_box.py -m gpu
 run tests/test_gpu_loss.py -m gpu
 run tests/test_gpu_conv.py -m gpu -k simt
