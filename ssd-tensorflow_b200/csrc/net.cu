@@ -105,6 +105,10 @@ struct ssdb_net {
     int swap_rb = 1; float mean[3] = {103.939f, 116.779f, 123.68f};
     cudaStream_t own_stream = nullptr;
     int last_B = 0;
+    // per-op device timing (ssdb_profile_step)
+    bool prof = false;
+    struct ProfEntry { std::string label; cudaEvent_t a, b; long long launches; double flops; };
+    std::vector<ProfEntry> prof_entries;
 
     float* act(int id, int /*B*/) { return acts + bufs[id].off * (size_t)max_batch; }
     float* gact(int id, int /*B*/) { return gacts + bufs[id].off * (size_t)max_batch; }
@@ -282,11 +286,30 @@ int repack_filters(ssdb_net* n, cudaStream_t st) {
     return SSDB_OK;
 }
 
+struct ProfScope {
+    ssdb_net* n; cudaStream_t st; int idx = -1; long long l0 = 0;
+    ProfScope(ssdb_net* n_, cudaStream_t st_, const std::string& label, double flops = 0.0) : n(n_), st(st_) {
+        if (!n->prof) return;
+        ssdb_net::ProfEntry e; e.label = label; e.launches = 0; e.flops = flops;
+        cudaEventCreate(&e.a); cudaEventCreate(&e.b);
+        cudaEventRecord(e.a, st);
+        n->prof_entries.push_back(e); idx = (int)n->prof_entries.size() - 1; l0 = g_launches;
+    }
+    ~ProfScope() {
+        if (idx < 0) return;
+        cudaEventRecord(n->prof_entries[idx].b, st);
+        n->prof_entries[idx].launches = g_launches - l0;
+    }
+};
+
+double conv_flops(const ConvGeom& g) { return 2.0 * g.B * g.Ho * g.Wo * (double)g.k * g.k * g.Cin * g.Cout; }
+
 int run_forward(ssdb_net* n, const float* images, int B, cudaStream_t st) {
     SSDB_REQUIRE(B >= 1 && B <= n->max_batch, "batch size out of range");
-    if (n->wt_dirty) { int rc = repack_filters(n, st); if (rc) return rc; }
+    if (n->wt_dirty) { ProfScope ps(n, st, "repack"); int rc = repack_filters(n, st); if (rc) return rc; }
     for (const Op& op : n->ops) {
         int rc = SSDB_OK;
+        ProfScope ps(n, st, std::string("fwd:") + op.name, op.type == OP_CONV ? conv_flops(geom_of(n, op, B)) : 0.0);
         if (op.type == OP_CONV) {
             ConvGeom g = geom_of(n, op, B);
             ConvEpilogue ep;
@@ -335,16 +358,19 @@ int run_backward(ssdb_net* n, int B, cudaStream_t st) {
             float* dw = n->grads + n->masters[op.w].off;
             float* db = n->grads + n->masters[op.b].off;
             long long pixels = (long long)B * g.Ho * g.Wo;
-            rc = bias_grad(dz, pixels, op.cout, db, n->partial, st);
+            { ProfScope ps(n, st, std::string("bwd_b:") + op.name); rc = bias_grad(dz, pixels, op.cout, db, n->partial, st); }
             if (rc) return rc;
+            ProfScope* psw = new ProfScope(n, st, std::string("bwd_w:") + op.name, conv_flops(g));
             ConvEpilogue ep;
             if (op.in < 0) { ep.preprocess = 1; ep.swap_rb = n->swap_rb; ep.mean[0] = n->mean[0]; ep.mean[1] = n->mean[1]; ep.mean[2] = n->mean[2]; }
             if (op.in >= 0 && use_tc(n, conv_tc_supported_wgrad(g)))
                 rc = conv_tc_wgrad(g, x, dz, dw, n->partial, st);
             else
                 rc = conv_simt_wgrad(g, op.in < 0 ? n->images_stage : x, dz, ep, dw, n->partial, st);
+            delete psw;
             if (rc) return rc;
             if (op.in >= 0) {
+                ProfScope psd(n, st, std::string("bwd_d:") + op.name, conv_flops(g));
                 const float* mask = n->bufs[op.in].relu_out ? x : nullptr;
                 int beta = written[op.in] ? 1 : 0;
                 if (use_tc(n, conv_tc_supported_dgrad(g)))
@@ -354,12 +380,14 @@ int run_backward(ssdb_net* n, int B, cudaStream_t st) {
                 written[op.in] = 1;
             }
         } else if (op.type == OP_POOL) {
+            ProfScope ps(n, st, std::string("bwd:") + op.name);
             SSDB_REQUIRE(written[op.out], "internal: gradient of a pool output was never produced");
             const Buf& bi = n->bufs[op.in]; const Buf& bo = n->bufs[op.out];
             rc = maxpool_bwd(n->act(op.in, B), n->gact(op.out, B), B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W,
                              written[op.in] ? 1 : 0, bi.relu_out ? 1 : 0, n->round ? 1 : 0, n->gact(op.in, B), st);
             written[op.in] = 1;
         } else {
+            ProfScope ps(n, st, std::string("bwd:") + op.name);
             SSDB_REQUIRE(written[op.out], "internal: gradient of the L2-norm output was never produced");
             const Buf& bi = n->bufs[op.in];
             rc = l2norm_bwd(n->act(op.in, B), n->params + n->masters[op.w].off, n->gact(op.out, B), (long long)B * bi.H * bi.W, bi.C,
@@ -559,6 +587,7 @@ static int loss_and_finalize(ssdb_net* n, const float* labels_dev, const double*
     float* conf_loc = n->small_ws + 4;
     float* l2s = n->small_ws + 6;
     float* per_image = n->small_ws + 4096;
+    ProfScope ps(n, st, "loss");
     int rc = multibox_loss_launch(n->out, labels_dev, gt_dev, gt_count_dev, G, n->anchors, B, n->A, n->C, grad_scale, conf_loc,
                                   want_grad ? n->out_grad : nullptr, result_dev ? result_dev : n->result, nullptr, per_image, n->counter, st);
     if (rc) return rc;
@@ -570,6 +599,7 @@ static int loss_and_finalize(ssdb_net* n, const float* labels_dev, const double*
 
 int ssdb_apply_update(ssdb_net* n, float lr, float momentum, float weight_decay, float grad_post_scale, void* stream) {
     SSDB_REQUIRE(n, "bad arguments");
+    ProfScope ps(n, (cudaStream_t)stream, "update");
     int rc = sgd_momentum(n->params, n->grads, n->moms, (long long)n->n_flat, n->decay_mask, lr, momentum, weight_decay, grad_post_scale,
                           (cudaStream_t)stream);
     n->wt_dirty = true; n->have_forward = false;
@@ -778,9 +808,29 @@ int ssdb_op_conv_wgrad(int impl, const float* x, const float* dz, int B, int H, 
     return rc;
 }
 
-int ssdb_profile_step(ssdb_net*, const float*, const float*, int, char (*)[32], float*, int*, int) {
-    set_error("ssdb_profile_step: not built in this revision");
-    return SSDB_EINVAL;
+int ssdb_profile_step(ssdb_net* n, const float* images_dev, const float* labels_dev, int B, char (*names_out)[32], float* ms_out,
+                      int* launches_out, int cap) {
+    SSDB_REQUIRE(n && images_dev && labels_dev && names_out && ms_out && launches_out && cap > 0, "bad arguments");
+    cudaStream_t st = n->own_stream;
+    SSDB_CUDA(cudaStreamSynchronize(st));
+    n->prof = true; n->prof_entries.clear();
+    int rc = ssdb_train_step(n, images_dev, labels_dev, nullptr, nullptr, 0, B, 0.00075f, 0.9f, 0.0005f, 1.0f, 1, nullptr, nullptr, st);
+    n->prof = false;
+    cudaError_t e = cudaStreamSynchronize(st);
+    int count = 0;
+    for (auto& pe : n->prof_entries) {
+        float ms = 0.f;
+        if (!rc && e == cudaSuccess) cudaEventElapsedTime(&ms, pe.a, pe.b);
+        if (count < cap) {
+            strncpy(names_out[count], pe.label.c_str(), 31); names_out[count][31] = 0;
+            ms_out[count] = ms; launches_out[count] = (int)pe.launches; ++count;
+        }
+        cudaEventDestroy(pe.a); cudaEventDestroy(pe.b);
+    }
+    n->prof_entries.clear();
+    if (rc) return rc;
+    if (e != cudaSuccess) { set_error("profile step failed: %s", cudaGetErrorString(e)); return SSDB_ECUDA; }
+    return count;
 }
 
 }  // extern "C"
