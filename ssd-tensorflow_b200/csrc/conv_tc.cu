@@ -317,16 +317,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
     }
 }
 
-// MN-major, SWIZZLE_128B descriptor: the matrix dimension that is NOT contracted (channels) is the
-// contiguous one.  A 32-channel x P-pixel block is [P rows][128 B]; blocks of 32 channels are
-// `lbo_bytes` apart (leading byte offset), groups of 8 pixel rows 1024 B apart (stride byte offset).
+// MN-major descriptor: the matrix dimension that is NOT contracted (channels) is the contiguous one.
+// For 32-bit (tf32) operands the only MN-major shared-memory layout the tensor core accepts is
+// SWIZZLE_128B_BASE32B (layout type 1): 128-byte rows, 32-byte chunks XOR-swizzled with (row & 3),
+// written by TMA with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  A 32-channel x P-pixel block is
+// [P rows][128 B]; blocks of 32 channels are `lbo_bytes` apart (leading byte offset) and groups of
+// 4 pixel rows 512 B apart (stride byte offset); one K=8 instruction spans two such groups.
 __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)(512 >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)1 << 61;
     return d;
 }
 
@@ -335,7 +338,8 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32
 // GEMM view: M = 128 "filter rows" = 4 slots of 32 input channels, each slot = (tap, 32-channel
 // block) so that layers with Cin = 64 still fill the MMA; N = up to 256 output channels; the
 // contraction runs over pixels, P (a multiple of 8, <= 64) per pipeline stage.  Both operands are
-// MN-major: the same [pixels][32 ch] TMA boxes as in fprop, only the descriptor says "transposed".
+// MN-major: the same [pixels][32 ch] TMA boxes as in fprop, in the 32-byte-atom swizzle that tf32
+// MN-major operands require, with a descriptor that says "transposed".
 // The pixel range is split over CTAs; partial filters go to a workspace and are summed in a fixed
 // order afterwards (deterministic).
 struct WgArgs {
@@ -529,7 +533,8 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-int encode_act_map(CUtensorMap* m, const float* ptr, int B, int H, int W, int C, int TW, int TH, int TN) {
+int encode_act_map(CUtensorMap* m, const float* ptr, int B, int H, int W, int C, int TW, int TH, int TN,
+                   CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return SSDB_ECUDA; }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -537,7 +542,7 @@ int encode_act_map(CUtensorMap* m, const float* ptr, int B, int H, int W, int C,
     cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation %dx%dx%dx%d box %d,%d,%d) failed: %d", B, H, W, C, TW, TH, TN, (int)r); return SSDB_ECUDA; }
     return SSDB_OK;
@@ -736,8 +741,8 @@ int conv_tc_wgrad(const ConvGeom& g, const float* x, const float* dz, float* dw,
     WgArgs a = pl.a;
     a.partial = partial;
     CUtensorMap mx, mz;
-    int rc = encode_act_map(&mx, x, g.B, g.H, g.W, g.Cin, a.PW, a.PH, a.PN); if (rc) return rc;
-    rc = encode_act_map(&mz, dz, g.B, g.Ho, g.Wo, g.Cout, a.PW, a.PH, a.PN); if (rc) return rc;
+    int rc = encode_act_map(&mx, x, g.B, g.H, g.W, g.Cin, a.PW, a.PH, a.PN, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); if (rc) return rc;
+    rc = encode_act_map(&mz, dz, g.B, g.Ho, g.Wo, g.Cout, a.PW, a.PH, a.PN, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); if (rc) return rc;
     static bool attr = false;
     if (!attr) { SSDB_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr = true; }
     long long units = (long long)a.m_tiles * a.n_tiles * a.splits;

@@ -225,6 +225,16 @@ class Net:
     def eval_step(self, images_ptr, labels_ptr, B, weight_decay=0.0005, losses_ptr=None, result_ptr=None, stream=None):
         check(lib().ssdb_eval_step(self._h, images_ptr, labels_ptr, B, weight_decay, losses_ptr, result_ptr, stream))
 
+    def profile_step(self, images_ptr, labels_ptr, B, cap=512):
+        """One training step with CUDA events around every op: list of (label, ms, launches)."""
+        names = ((C.c_char * 32) * cap)()
+        ms = (_f * cap)()
+        launches = (_i * cap)()
+        n = lib().ssdb_profile_step(self._h, images_ptr, labels_ptr, B, names, ms, launches, cap)
+        if n < 0:
+            check(n)
+        return [(names[k].value.decode(), float(ms[k]), int(launches[k])) for k in range(n)]
+
     def apply_update(self, lr, momentum, weight_decay, grad_post_scale=1.0, stream=None):
         check(lib().ssdb_apply_update(self._h, lr, momentum, weight_decay, grad_post_scale, stream))
 

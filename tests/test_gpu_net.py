@@ -34,7 +34,7 @@ def test_forward_and_train_step(preset, B, mode):
         net = ssdb.Net(preset, 20, max_batch=B)
     finally:
         os.environ.pop('SSDB_CONV', None)
-    tol = 2e-4 if mode == 'simt' else 4e-3
+    tol = 1e-3 if mode == 'simt' else 4e-3     # gradients: tol*10 (ReLU / max-pool / mining decisions can flip)
     side = bo.PRESETS[preset]['image']
     P = no.init_params(preset, dtype=torch.float64)
     _load(net, P)
@@ -48,6 +48,7 @@ def test_forward_and_train_step(preset, B, mode):
     report = {'preset': preset, 'mode': mode, 'B': B}
     report['softmax_abs'] = float(np.abs(res[..., :21] - ref[..., :21]).max())
     report['locator_rel'] = _relmax(res[..., 21:], ref[..., 21:])
+    report['locator_rel_rms'] = float(np.sqrt(((res[..., 21:] - ref[..., 21:]) ** 2).mean() / (ref[..., 21:] ** 2).mean()))
     if mode == 'simt':
         # fp32 accumulate in another order than the float64 oracle; |logit| ~ 1e3 on this input, so 1e-6
         # relative on a logit is ~1e-3 absolute before the softmax
