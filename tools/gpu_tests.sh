@@ -11,4 +11,8 @@ run tests/test_gpu_conv.py -m gpu -k simt
 run tests/test_gpu_conv.py -m gpu -k tcgen05
 run tests/test_gpu_net.py -m gpu -k simt
 run tests/test_gpu_net.py -m gpu -k auto
-grep -E "^===|^exit|passed|failed|Error|error" $LOG | head -80
+grep -E "^===|^exit|passed|failed|Error|error|PARITY" $LOG | cut -c1-300 | head -80
+echo "=== quick bench" >> $LOG
+timeout 600 python tools/quick_bench.py vgg300 32 >> $LOG 2>&1
+timeout 600 python tools/quick_bench.py vgg300 64 >> $LOG 2>&1
+tail -70 $LOG | cut -c1-200
