@@ -197,6 +197,10 @@ int ssdb_eval_step(ssdb_net* net, const float* images_dev, const float* labels_d
 int ssdb_apply_update(ssdb_net* net, float lr, float momentum, float weight_decay,
                       float grad_post_scale, void* stream);
 
+/* page-locked host memory for feeds / fetches (cudaHostAlloc): makes the host entry points' copies asynchronous DMA */
+int ssdb_pinned_alloc(long long bytes, void** host_ptr_out);
+int ssdb_pinned_free(void* host_ptr);
+
 /* number of kernels this library launched since load (bench.py's gpu_launches) */
 long long ssdb_launch_count(void);
 /* per-kernel-family device time of the LAST ssdb_profile_step (ms): fills up to cap

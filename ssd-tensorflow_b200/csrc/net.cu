@@ -808,6 +808,18 @@ int ssdb_op_conv_wgrad(int impl, const float* x, const float* dz, int B, int H, 
     return rc;
 }
 
+int ssdb_pinned_alloc(long long bytes, void** host_ptr_out) {
+    SSDB_REQUIRE(bytes > 0 && host_ptr_out, "bad arguments");
+    int rc = ssdb_device_ok(); if (rc) return rc;
+    SSDB_CUDA(cudaHostAlloc(host_ptr_out, (size_t)bytes, cudaHostAllocDefault));
+    return SSDB_OK;
+}
+
+int ssdb_pinned_free(void* host_ptr) {
+    if (host_ptr) SSDB_CUDA(cudaFreeHost(host_ptr));
+    return SSDB_OK;
+}
+
 int ssdb_profile_step(ssdb_net* n, const float* images_dev, const float* labels_dev, int B, char (*names_out)[32], float* ms_out,
                       int* launches_out, int cap) {
     SSDB_REQUIRE(n && images_dev && labels_dev && names_out && ms_out && launches_out && cap > 0, "bad arguments");

@@ -72,6 +72,8 @@ SIGNATURES = {
     'ssdb_train_step_host': (_i, [_p, _p, _p, _i, _f, _f, _f, _p, _p]),
     'ssdb_eval_step': (_i, [_p, _p, _p, _i, _f, _p, _p, _p]),
     'ssdb_apply_update': (_i, [_p, _f, _f, _f, _f, _p]),
+    'ssdb_pinned_alloc': (_i, [_ll, C.POINTER(_p)]),
+    'ssdb_pinned_free': (_i, [_p]),
     'ssdb_launch_count': (_ll, []),
     'ssdb_profile_step': (_i, [_p, _p, _p, _i, _p, _p, _p, _i]),
 }
@@ -140,6 +142,22 @@ def nms_host(boxes_abs, labelid, conf, iou_thr):
     return keep[:cnt[0]]
 
 
+class PinnedArray:
+    """float32 NumPy view of page-locked host memory owned by the library."""
+    def __init__(self, shape):
+        self.ptr = _p()
+        n = int(np.prod(shape))
+        check(lib().ssdb_pinned_alloc(n * 4, C.byref(self.ptr)))
+        buf = (C.c_float * n).from_address(self.ptr.value)
+        self.array = np.frombuffer(buf, dtype=np.float32).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().ssdb_pinned_free(self.ptr)
+            self.ptr = _p()
+
+
 # ---------------------------------------------------------------- engine handle
 class Net:
     """Owner of one ssdb_net handle (one per GPU, not thread-safe)."""
@@ -154,8 +172,18 @@ class Net:
         self.num_anchors = lib().ssdb_num_anchors(self._h)
         self.image_size = lib().ssdb_image_size(self._h)
         self.row = self.num_classes + 5
+        self._pinned_result = None
+
+    def result_buffer(self, B):
+        """Pinned [B, A, C+5] view reused by the host entry points (valid until the next call)."""
+        if self._pinned_result is None:
+            self._pinned_result = PinnedArray((self.max_batch, self.num_anchors, self.row))
+        return self._pinned_result.array[:B]
 
     def close(self):
+        if self._pinned_result is not None:
+            self._pinned_result.free()
+            self._pinned_result = None
         if self._h:
             lib().ssdb_destroy(self._h)
             self._h = _p()
@@ -199,7 +227,7 @@ class Net:
     def forward_host(self, images):
         x, px = _np(images, np.float32)
         B = x.shape[0]
-        res = np.empty((B, self.num_anchors, self.row), np.float32)
+        res = self.result_buffer(B)
         check(lib().ssdb_forward_host(self._h, px, B, res.ctypes.data_as(_p)))
         return res
 
@@ -207,7 +235,7 @@ class Net:
         x, px = _np(images, np.float32)
         y, py = _np(labels, np.float32)
         B = x.shape[0]
-        res = result_out if result_out is not None else (np.empty((B, self.num_anchors, self.row), np.float32) if want_result else None)
+        res = result_out if result_out is not None else (self.result_buffer(B) if want_result else None)
         losses = np.empty(4, np.float32)
         check(lib().ssdb_train_step_host(self._h, px, py, B, lr, momentum, weight_decay, losses.ctypes.data_as(_p),
                                          res.ctypes.data_as(_p) if res is not None else None))

@@ -75,7 +75,7 @@ NET_SHAPES = [
     (300, 64, 64, 3, 1, 'SAME'), (150, 64, 128, 3, 1, 'SAME'), (150, 128, 128, 3, 1, 'SAME'), (75, 128, 256, 3, 1, 'SAME'),
     (75, 256, 256, 3, 1, 'SAME'), (38, 256, 512, 3, 1, 'SAME'), (38, 512, 512, 3, 1, 'SAME'), (19, 512, 512, 3, 1, 'SAME'),
     (19, 512, 1024, 3, 6, 'SAME'), (19, 1024, 1024, 1, 1, 'SAME'), (19, 1024, 256, 1, 1, 'SAME'), (10, 512, 128, 1, 1, 'SAME'),
-    (5, 256, 128, 1, 1, 'SAME'), (5, 128, 256, 3, 1, 'VALID'), (3, 128, 256, 3, 1, 'VALID'),
+    (5, 256, 128, 1, 1, 'SAME'), (5, 128, 256, 3, 1, 'VALID'),
     (38, 512, 128, 3, 1, 'SAME'), (19, 1024, 160, 3, 1, 'SAME'), (10, 512, 160, 3, 1, 'SAME'), (5, 256, 160, 3, 1, 'SAME'),
     (64, 512, 512, 3, 1, 'SAME'), (32, 512, 1024, 3, 6, 'SAME'), (16, 512, 160, 3, 1, 'SAME'), (8, 256, 160, 3, 1, 'SAME'),
 ]
