@@ -77,6 +77,8 @@ def init_params(preset_name, num_classes=20, seed=7, dtype=torch.float64):
         trunk = s['name'].startswith(('conv1_', 'conv2_', 'conv3_', 'conv4_', 'conv5_', 'mod_conv'))
         if trunk:
             w = g.normal(0, math.sqrt(2.0 / (k * k * cin)), (k, k, cin, cout))
+            if s['name'] == 'conv1_1':
+                w = w / (255.0 / math.sqrt(12.0))     # raw 0..255 pixels in, O(1) activations out
         else:
             lim = math.sqrt(6.0 / (k * k * cin + k * k * cout))
             w = g.uniform(-lim, lim, (k, k, cin, cout))

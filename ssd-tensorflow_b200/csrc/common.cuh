@@ -86,7 +86,7 @@ int conv_simt_dgrad(const ConvGeom& g, const float* dz, const float* w, const fl
 size_t conv_simt_wgrad_ws(const ConvGeom& g);
 int conv_simt_wgrad(const ConvGeom& g, const float* x, const float* dz, const ConvEpilogue& ep,
                     float* dw, float* partial, cudaStream_t st);
-// db[n] = sum over pixels of dz[p][n]  (deterministic two-stage), partial >= 256*Cout floats
+// db[n] = sum over pixels of dz[p][n]  (deterministic two-stage), partial >= 1184*Cout floats
 int bias_grad(const float* dz, long long pixels, int Cout, float* db, float* partial, cudaStream_t st);
 
 // ---- tcgen05 / TMEM / TMA implicit GEMM (tf32 operands, fp32 accumulate) ----
@@ -99,7 +99,8 @@ int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_
 int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, const float* mask_x,
                   int beta, int round_out, float* dx, cudaStream_t st);
 size_t conv_tc_wgrad_ws(const ConvGeom& g);
-int conv_tc_wgrad(const ConvGeom& g, const float* x, const float* dz, float* dw, float* partial,
+// db != null: the bias gradient is produced by the same kernel (all-ones slot)
+int conv_tc_wgrad(const ConvGeom& g, const float* x, const float* dz, float* dw, float* db, float* partial,
                   cudaStream_t st);
 int pack_filter_t(const float* w_hwio, int taps, int Cin, int Cout, int cout_pad, float* w_t,
                   cudaStream_t st);

@@ -244,12 +244,42 @@ __global__ void reduce_splits_kernel(const float* __restrict__ partial, long lon
     out[i] = s;
 }
 
-// stage 1 of the bias gradient: block j sums rows j, j+nb, ... for all channels
-__global__ void bias_grad_stage1(const float* __restrict__ dz, long long pixels, int C, float* __restrict__ partial) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float s = 0.f;
-        for (long long p = blockIdx.x; p < pixels; p += gridDim.x) s += dz[p * C + c];
-        partial[(long long)blockIdx.x * C + c] = s;
+// stage 1 of the bias gradient (column sums of dz[pixels][C]): a block owns a contiguous slab of
+// pixel rows; threads are (C/4 float4 columns) x (256/(C/4) row lanes), 4 independent 16-byte loads
+// in flight per thread, shared-memory reduction over the row lanes, one partial row per block.
+__global__ void __launch_bounds__(256) bias_grad_stage1(const float* __restrict__ dz, long long pixels, int C,
+                                                         long long rows_per_block, float* __restrict__ partial) {
+    __shared__ float4 red[256];
+    const int c4n = C >> 2;                       // float4 columns (<= 256)
+    const int lanes = 256 / c4n;                  // row lanes per block
+    const int col = threadIdx.x % c4n, lane = threadIdx.x / c4n;
+    float4 acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < lanes) {
+        const long long r0 = (long long)blockIdx.x * rows_per_block;
+        const long long r1 = min(pixels, r0 + rows_per_block);
+        const float4* base = reinterpret_cast<const float4*>(dz);
+        long long r = r0 + lane;
+        for (; r + 3LL * lanes < r1; r += 4LL * lanes) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float4 v = __ldg(base + (r + (long long)u * lanes) * c4n + col);
+                acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
+            }
+        }
+        for (; r < r1; r += lanes) {
+            float4 v = __ldg(base + r * c4n + col);
+            acc[0].x += v.x; acc[0].y += v.y; acc[0].z += v.z; acc[0].w += v.w;
+        }
+    }
+    float4 s = make_float4(acc[0].x + acc[1].x + acc[2].x + acc[3].x, acc[0].y + acc[1].y + acc[2].y + acc[3].y,
+                           acc[0].z + acc[1].z + acc[2].z + acc[3].z, acc[0].w + acc[1].w + acc[2].w + acc[3].w);
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (lane == 0 && threadIdx.x < c4n) {
+        for (int l = 1; l < lanes; ++l) { float4 o = red[l * c4n + col]; s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w; }
+        reinterpret_cast<float4*>(partial + (long long)blockIdx.x * C)[col] = s;
     }
 }
 
@@ -323,9 +353,13 @@ int conv_simt_wgrad(const ConvGeom& g, const float* x, const float* dz, const Co
 }
 
 int bias_grad(const float* dz, long long pixels, int Cout, float* db, float* partial, cudaStream_t st) {
-    int nb = (int)(pixels < 256 ? pixels : 256);
+    SSDB_REQUIRE(Cout % 4 == 0 && Cout <= 1024, "bias gradient needs Cout % 4 == 0 and Cout <= 1024");
+    long long want = 148 * 8;
+    long long rows_per_block = (pixels + want - 1) / want;
+    if (rows_per_block < 32) rows_per_block = 32;
+    int nb = (int)((pixels + rows_per_block - 1) / rows_per_block);
     if (nb < 1) nb = 1;
-    bias_grad_stage1<<<nb, 256, 0, st>>>(dz, pixels, Cout, partial);
+    bias_grad_stage1<<<nb, 256, 0, st>>>(dz, pixels, Cout, rows_per_block, partial);
     SSDB_LAUNCH_CHECK();
     reduce_splits_kernel<<<(Cout + 255) / 256, 256, 0, st>>>(partial, Cout, nb, db);
     SSDB_LAUNCH_CHECK();

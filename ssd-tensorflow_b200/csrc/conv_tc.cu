@@ -334,25 +334,42 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32
 }
 
 // ------------------------------------------------------------------ wgrad kernel
-//   dW[tap][c][n] = sum over pixels of  x[pixel + shift(tap)][c] * dz[pixel][n]
+//   dW[tap][c][n] = sum over pixels of  x[pixel + shift(tap)][c] * dz[pixel][n]      db[n] = sum over pixels of dz[pixel][n]
 // GEMM view: M = 128 "filter rows" = 4 slots of 32 input channels, each slot = (tap, 32-channel
 // block) so that layers with Cin = 64 still fill the MMA; N = up to 256 output channels; the
 // contraction runs over pixels, P (a multiple of 8, <= 64) per pipeline stage.  Both operands are
-// MN-major: the same [pixels][32 ch] TMA boxes as in fprop, in the 32-byte-atom swizzle that tf32
-// MN-major operands require, with a descriptor that says "transposed".
+// MN-major: the same [pixels][32 ch] boxes as in fprop, in the 32-byte-atom swizzle that tf32
+// MN-major operands require, with a descriptor that says "transposed".  The tensor maps are 5-D
+// (c32, x, y, image, channel block) so ONE TMA instruction brings all channel blocks of an operand.
+// The bias gradient rides along as one extra slot whose A block is all ones.
 // The pixel range is split over CTAs; partial filters go to a workspace and are summed in a fixed
 // order afterwards (deterministic).
 struct WgArgs {
     int PW, PH, PN, P;              // pixel box, P = PW*PH*PN
     int ptx, pty, ptn;              // pixel tiling of the dz map
     int cblocks, taps, kdim;        // Cin/32, k*k, k
-    int slots, m_tiles;             // taps*cblocks, ceil(slots/4)
+    int slots, m_tiles;             // taps*cblocks (+1 with the bias slot), ceil(slots/4)
+    int bias_slot;                  // slot index of the all-ones block, or -1
+    int load_blocks;                // channel blocks per x TMA load = min(4, cblocks)
     int n_tiles, block_n;           // Cout tiling
     int Cin, Cout;                  // Cout = stored channel stride of dz and of the HWIO filter
     int off0, offstep;              // source shift per axis for tap index t: off0 + t*offstep
+    int sstride;                    // conv stride (x coordinates = pixel*sstride + shift)
     int splits, tiles_per_split;    // pixel-tile ranges
-    float* partial;                 // [splits][taps*Cin*Cout]
+    long long psize;                // floats per split in the workspace = taps*Cin*Cout + Cout
+    float* partial;                 // [splits][psize]
+    const float* ones;              // >= 64*32 floats of 1.0f
 };
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz, const WgArgs p) {
@@ -395,7 +412,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 const int nt = r1 % p.n_tiles; const int mt = r1 / p.n_tiles;
                 const int q0 = sp * p.tiles_per_split;
                 const int q1 = min(pix_tiles, q0 + p.tiles_per_split);
-                int na = p.slots - mt * 4; na = na > 4 ? 4 : na;
+                int na = p.slots - mt * 4; na = na > 4 ? 4 : na;           // valid A blocks of this tile
                 for (int q = q0; q < q1; ++q) {
                     const int qx = q % p.ptx; const int r2 = q / p.ptx;
                     const int qy = r2 % p.pty; const int qn = r2 / p.pty;
@@ -404,15 +421,15 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     const uint32_t fb = full0 + 8 * stage;
                     mbar_expect_tx(fb, (uint32_t)(na + nblk_b) * blk_bytes);
                     const uint32_t sa = base + stage * STAGE_BYTES;
-                    for (int j = 0; j < na; ++j) {
+                    for (int j = 0; j < na; j += p.load_blocks) {
                         const int slot = mt * 4 + j;
+                        if (slot == p.bias_slot) { bulk_load_1d(sa + (uint32_t)j * blk_bytes, p.ones, blk_bytes, fb); break; }
                         const int tap = slot / p.cblocks, cb = slot - tap * p.cblocks;
                         const int kh = tap / p.kdim, kw = tap - kh * p.kdim;
-                        tma_load_4d(sa + (uint32_t)j * blk_bytes, &map_x, fb, cb * 32, x0 + p.off0 + kw * p.offstep,
-                                    y0 + p.off0 + kh * p.offstep, n0);
+                        tma_load_5d(sa + (uint32_t)j * blk_bytes, &map_x, fb, 0, x0 * p.sstride + p.off0 + kw * p.offstep,
+                                    y0 * p.sstride + p.off0 + kh * p.offstep, n0, cb);
                     }
-                    for (int j = 0; j < nblk_b; ++j)
-                        tma_load_4d(sa + b_off + (uint32_t)j * blk_bytes, &map_dz, fb, nt * p.block_n + j * 32, x0, y0, n0);
+                    tma_load_5d(sa + b_off, &map_dz, fb, 0, x0, y0, n0, nt * nblk_b);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -454,9 +471,11 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             const int sp = u % p.splits; const int r1 = u / p.splits;
             const int nt = r1 % p.n_tiles; const int mt = r1 / p.n_tiles;
             const int slot = mt * 4 + quarter;
-            const bool ok = slot < p.slots;
-            const int tap = ok ? slot / p.cblocks : 0, cb = ok ? slot - tap * p.cblocks : 0;
-            float* drow = p.partial + (long long)sp * wsize + ((long long)tap * p.Cin + cb * 32 + lane) * p.Cout;
+            const bool is_bias = slot == p.bias_slot;
+            const bool ok = slot < p.slots && (!is_bias || lane == 0);
+            const int tap = (ok && !is_bias) ? slot / p.cblocks : 0, cb = (ok && !is_bias) ? slot - tap * p.cblocks : 0;
+            float* drow = p.partial + (long long)sp * p.psize +
+                          (is_bias ? wsize : ((long long)tap * p.Cin + cb * 32 + lane) * p.Cout);
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t)(acc * MAX_N) + ((uint32_t)(quarter * 32) << 16);
@@ -489,15 +508,19 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     }
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, long long n, int splits, float* __restrict__ out) {
+// out[i] = sum_z partial[z][i]; the first nw floats go to dw, the remaining (bias) ones to db
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, long long psize, long long nw, int splits,
+                                       float* __restrict__ dw, float* __restrict__ db) {
     long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i >= n) return;
+    if (i >= psize) return;
+    if (i >= nw && db == nullptr) return;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int z = 0; z < splits; ++z) {
-        float4 v = *reinterpret_cast<const float4*>(partial + (long long)z * n + i);
+        float4 v = *reinterpret_cast<const float4*>(partial + (long long)z * psize + i);
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
-    *reinterpret_cast<float4*>(out + i) = s;
+    if (i < nw) *reinterpret_cast<float4*>(dw + i) = s;
+    else *reinterpret_cast<float4*>(db + (i - nw)) = s;
 }
 
 // per-tap transpose: w_t[tap][n][c] = w[tap][c][n] (n < Cout), zero rows for n >= Cout
@@ -691,11 +714,36 @@ PixGeom pick_pix(int B, int H, int W, int p_max) {
     return best;
 }
 
+// 5-D view of an NHWC tensor: (c within a 32-channel block, x, y, image, channel block)
+int encode_act_map5(CUtensorMap* m, const float* ptr, int B, int H, int W, int C, int PW, int PH, int PN, int nblk, int estride) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return SSDB_ECUDA; }
+    cuuint64_t dims[5] = {32, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)(C / 32)};
+    cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4, 128};
+    cuuint32_t box[5] = {32, (cuuint32_t)(PW * estride), (cuuint32_t)(PH * estride), (cuuint32_t)PN, (cuuint32_t)nblk};
+    cuuint32_t es[5] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(5-D activation %dx%dx%dx%d box %d,%d,%d,%d) failed: %d", B, H, W, C, PW, PH, PN, nblk, (int)r); return SSDB_ECUDA; }
+    return SSDB_OK;
+}
+
+const float* ones_buffer() {
+    static float* d = nullptr;
+    if (!d) {
+        std::vector<float> h(64 * 32, 1.0f);
+        if (cudaMalloc(reinterpret_cast<void**>(&d), h.size() * sizeof(float)) != cudaSuccess) return nullptr;
+        cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice);
+    }
+    return d;
+}
+
 struct WgPlan { WgArgs a; bool ok; };
 
 WgPlan plan_wgrad(const ConvGeom& g) {
     WgPlan pl{}; pl.ok = false;
-    if (g.stride != 1 || g.Cin % 32 != 0 || g.Cout % 32 != 0 || g.pad_t != g.pad_l || g.k < 1 || g.k > 7) return pl;
+    if ((g.stride != 1 && g.stride != 2) || g.Cin % 32 != 0 || g.Cout % 32 != 0 || g.pad_t != g.pad_l || g.k < 1 || g.k > 7) return pl;
     if (g.Cout > MAX_N && g.Cout % MAX_N != 0) return pl;
     WgArgs& a = pl.a;
     a.block_n = g.Cout > MAX_N ? MAX_N : g.Cout;
@@ -703,14 +751,20 @@ WgPlan plan_wgrad(const ConvGeom& g) {
     int blocks = 4 + a.block_n / 32;
     int p_max = STAGE_BYTES / (blocks * 128);
     p_max = p_max / 8 * 8; if (p_max > 64) p_max = 64;
+    if (g.stride == 2 && p_max > 32) p_max = 32;            // strided boxes: keep every box dimension <= 256 / stride
     PixGeom pg = pick_pix(g.B, g.Ho, g.Wo, p_max);
     if (pg.P == 0 || pg.eff < 0.4) return pl;
+    if (pg.PW * g.stride > 256 || pg.PH * g.stride > 256) return pl;
     a.PW = pg.PW; a.PH = pg.PH; a.PN = pg.PN; a.P = pg.P;
     a.ptx = (g.Wo + pg.PW - 1) / pg.PW; a.pty = (g.Ho + pg.PH - 1) / pg.PH; a.ptn = (g.B + pg.PN - 1) / pg.PN;
     a.cblocks = g.Cin / 32; a.taps = g.k * g.k; a.kdim = g.k;
-    a.slots = a.taps * a.cblocks; a.m_tiles = (a.slots + 3) / 4;
+    a.load_blocks = a.cblocks < 4 ? a.cblocks : 4;
+    if (a.cblocks % a.load_blocks) return pl;
+    a.bias_slot = a.taps * a.cblocks;                        // the all-ones slot comes after the real ones
+    a.slots = a.bias_slot + 1; a.m_tiles = (a.slots + 3) / 4;
     a.Cin = g.Cin; a.Cout = g.Cout;
-    a.off0 = -g.pad_t; a.offstep = g.dil;
+    a.off0 = -g.pad_t; a.offstep = g.dil; a.sstride = g.stride;
+    a.psize = (long long)a.taps * g.Cin * g.Cout + g.Cout;
     long long pix_tiles = (long long)a.ptx * a.pty * a.ptn;
     long long base_units = (long long)a.m_tiles * a.n_tiles;
     long long want = (2LL * num_sms() + base_units - 1) / base_units;     // ~2 units per SM
@@ -720,7 +774,7 @@ WgPlan plan_wgrad(const ConvGeom& g) {
     if (want > 256) want = 256;
     a.tiles_per_split = (int)((pix_tiles + want - 1) / want);
     a.splits = (int)((pix_tiles + a.tiles_per_split - 1) / a.tiles_per_split);
-    a.partial = nullptr;
+    a.partial = nullptr; a.ones = nullptr;
     pl.ok = true;
     return pl;
 }
@@ -732,25 +786,28 @@ bool conv_tc_supported_wgrad(const ConvGeom& g) { return plan_wgrad(g).ok; }
 size_t conv_tc_wgrad_ws(const ConvGeom& g) {
     WgPlan pl = plan_wgrad(g);
     if (!pl.ok) return 0;
-    return (size_t)pl.a.splits * pl.a.taps * g.Cin * g.Cout;
+    return (size_t)pl.a.splits * (size_t)pl.a.psize;
 }
 
-int conv_tc_wgrad(const ConvGeom& g, const float* x, const float* dz, float* dw, float* partial, cudaStream_t st) {
+int conv_tc_wgrad(const ConvGeom& g, const float* x, const float* dz, float* dw, float* db, float* partial, cudaStream_t st) {
     WgPlan pl = plan_wgrad(g);
     SSDB_REQUIRE(pl.ok, "shape not supported by the tcgen05 wgrad kernel");
     WgArgs a = pl.a;
     a.partial = partial;
+    a.ones = ones_buffer();
+    SSDB_REQUIRE(a.ones != nullptr, "could not allocate the ones buffer");
+    if (!db) { a.bias_slot = -1; a.slots = a.taps * a.cblocks; a.m_tiles = (a.slots + 3) / 4; }
     CUtensorMap mx, mz;
-    int rc = encode_act_map(&mx, x, g.B, g.H, g.W, g.Cin, a.PW, a.PH, a.PN, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); if (rc) return rc;
-    rc = encode_act_map(&mz, dz, g.B, g.Ho, g.Wo, g.Cout, a.PW, a.PH, a.PN, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); if (rc) return rc;
+    int rc = encode_act_map5(&mx, x, g.B, g.H, g.W, g.Cin, a.PW, a.PH, a.PN, a.load_blocks, g.stride); if (rc) return rc;
+    rc = encode_act_map5(&mz, dz, g.B, g.Ho, g.Wo, g.Cout, a.PW, a.PH, a.PN, a.block_n / 32, 1); if (rc) return rc;
     static bool attr = false;
     if (!attr) { SSDB_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr = true; }
     long long units = (long long)a.m_tiles * a.n_tiles * a.splits;
     int grid = (int)(units < num_sms() ? units : num_sms());
     conv_tc_wgrad_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mx, mz, a);
     SSDB_LAUNCH_CHECK();
-    long long n = (long long)a.taps * g.Cin * g.Cout;
-    reduce_partials_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(partial, n, a.splits, dw);
+    long long nw = (long long)a.taps * g.Cin * g.Cout;
+    reduce_partials_kernel<<<(unsigned)((a.psize / 4 + 255) / 256), 256, 0, st>>>(partial, a.psize, nw, a.splits, dw, db);
     SSDB_LAUNCH_CHECK();
     return SSDB_OK;
 }

@@ -85,6 +85,54 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ x, const float* __r
     reinterpret_cast<float4*>(dx)[i] = make_float4(g[0], g[1], g[2], g[3]);
 }
 
+// 2x2 stride-2 windows do not overlap: one thread per (window, 4 channels) reads its (up to) 4 inputs once,
+// routes dy to the first maximum and writes all 4 gradients.  pad_before is 0 for these pools
+// (TF SAME on even sizes; 75 -> 38 pads after), so windows only clip at the bottom / right edge.
+__global__ void maxpool2x2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, int B, int H, int W, int C4,
+                                      int Ho, int Wo, int beta, int relu_mask, int round_out, float* __restrict__ dx) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)B * Ho * Wo * C4;
+    if (i >= total) return;
+    int c = (int)(i % C4); long long r = i / C4;
+    int ox = (int)(r % Wo); r /= Wo;
+    int oy = (int)(r % Ho); int b = (int)(r / Ho);
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* dx4 = reinterpret_cast<float4*>(dx);
+    float4 gy = reinterpret_cast<const float4*>(dy)[i];
+    float gv[4] = {gy.x, gy.y, gy.z, gy.w};
+    float v[4][4]; long long idx[4]; bool ok[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        int iy = oy * 2 + (t >> 1), ix = ox * 2 + (t & 1);
+        ok[t] = iy < H && ix < W;
+        idx[t] = (((long long)b * H + iy) * W + ix) * C4 + c;
+        float4 q = ok[t] ? x4[idx[t]] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        v[t][0] = q.x; v[t][1] = q.y; v[t][2] = q.z; v[t][3] = q.w;
+    }
+    int arg[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        int a = 0; float m = v[0][q];
+#pragma unroll
+        for (int t = 1; t < 4; ++t) if (v[t][q] > m) { m = v[t][q]; a = t; }
+        arg[q] = a;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        if (!ok[t]) continue;
+        float g[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) g[q] = arg[q] == t ? gv[q] : 0.f;
+        if (beta) { float4 o = dx4[idx[t]]; g[0] += o.x; g[1] += o.y; g[2] += o.z; g[3] += o.w; }
+        if (relu_mask) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) g[q] = v[t][q] > 0.f ? g[q] : 0.f;
+        }
+        if (round_out) { g[0] = tf32_rn(g[0]); g[1] = tf32_rn(g[1]); g[2] = tf32_rn(g[2]); g[3] = tf32_rn(g[3]); }
+        dx4[idx[t]] = make_float4(g[0], g[1], g[2], g[3]);
+    }
+}
+
 // one warp per pixel
 __global__ void l2norm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, long long pixels, int C,
                                   int round_out, float* __restrict__ y) {
@@ -264,6 +312,12 @@ int maxpool_fwd(const float* x, int B, int H, int W, int C, int k, int stride, i
 int maxpool_bwd(const float* x, const float* dy, int B, int H, int W, int C, int k, int stride, int pad_t, int pad_l,
                 int Ho, int Wo, int beta, int relu_mask, int round_out, float* dx, cudaStream_t st) {
     SSDB_REQUIRE(C % 4 == 0, "channels must be a multiple of 4");
+    if (k == 2 && stride == 2 && pad_t == 0 && pad_l == 0) {
+        long long tw = (long long)B * Ho * Wo * (C / 4);
+        maxpool2x2_bwd_kernel<<<(unsigned)((tw + 255) / 256), 256, 0, st>>>(x, dy, B, H, W, C / 4, Ho, Wo, beta, relu_mask, round_out, dx);
+        SSDB_LAUNCH_CHECK();
+        return SSDB_OK;
+    }
     long long total = (long long)B * H * W * (C / 4);
     maxpool_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, dy, B, H, W, C / 4, k, stride, pad_t, pad_l, Ho, Wo,
                                                                           beta, relu_mask, round_out, dx);

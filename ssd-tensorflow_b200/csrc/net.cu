@@ -358,13 +358,14 @@ int run_backward(ssdb_net* n, int B, cudaStream_t st) {
             float* dw = n->grads + n->masters[op.w].off;
             float* db = n->grads + n->masters[op.b].off;
             long long pixels = (long long)B * g.Ho * g.Wo;
-            { ProfScope ps(n, st, std::string("bwd_b:") + op.name); rc = bias_grad(dz, pixels, op.cout, db, n->partial, st); }
+            const bool tcw = op.in >= 0 && use_tc(n, conv_tc_supported_wgrad(g));
+            if (!tcw) { ProfScope ps(n, st, std::string("bwd_b:") + op.name); rc = bias_grad(dz, pixels, op.cout, db, n->partial, st); }
             if (rc) return rc;
             ProfScope* psw = new ProfScope(n, st, std::string("bwd_w:") + op.name, conv_flops(g));
             ConvEpilogue ep;
             if (op.in < 0) { ep.preprocess = 1; ep.swap_rb = n->swap_rb; ep.mean[0] = n->mean[0]; ep.mean[1] = n->mean[1]; ep.mean[2] = n->mean[2]; }
-            if (op.in >= 0 && use_tc(n, conv_tc_supported_wgrad(g)))
-                rc = conv_tc_wgrad(g, x, dz, dw, n->partial, st);
+            if (tcw)
+                rc = conv_tc_wgrad(g, x, dz, dw, db, n->partial, st);
             else
                 rc = conv_simt_wgrad(g, op.in < 0 ? n->images_stage : x, dz, ep, dw, n->partial, st);
             delete psw;
@@ -458,7 +459,7 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
     build_plan(n);
     if (n->A != P->num_anchors) { set_error("internal: anchor count %d != %d", n->A, P->num_anchors); delete n; return SSDB_EINVAL; }
     // workspace sizes
-    size_t partial = 296 * 1024 + 1024 * 256;
+    size_t partial = (size_t)1184 * 1024 + 296 * 1024;
     size_t dzh = 0;
     for (const Op& op : n->ops) {
         if (op.type != OP_CONV) continue;
@@ -785,7 +786,7 @@ int ssdb_op_conv_wgrad(int impl, const float* x, const float* dz, int B, int H, 
     cudaStream_t st = (cudaStream_t)stream;
     bool tc = impl == SSDB_CONV_TC || (impl == SSDB_CONV_AUTO && conv_tc_supported_wgrad(g));
     size_t ws = tc ? conv_tc_wgrad_ws(g) : conv_simt_wgrad_ws(g);
-    if (ws < (size_t)256 * Cout) ws = (size_t)256 * Cout;
+    if (ws < (size_t)1184 * Cout) ws = (size_t)1184 * Cout;
     float* partial = nullptr;
     SSDB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&partial), ws * sizeof(float), st));
     ConvEpilogue ep;
@@ -798,12 +799,12 @@ int ssdb_op_conv_wgrad(int impl, const float* x, const float* dz, int B, int H, 
         SSDB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&zr), (size_t)nz * sizeof(float), st));
         rc = round_tf32_copy(x, xr, nx, st);
         if (!rc) rc = round_tf32_copy(dz, zr, nz, st);
-        if (!rc) rc = conv_tc_wgrad(g, xr, zr, dw, partial, st);
+        if (!rc) rc = conv_tc_wgrad(g, xr, zr, dw, db, partial, st);      // db from the all-ones slot (of the ROUNDED dz)
         cudaFreeAsync(xr, st); cudaFreeAsync(zr, st);
     } else {
         rc = conv_simt_wgrad(g, x, dz, ep, dw, partial, st);
+        if (!rc && db) rc = bias_grad(dz, (long long)B * Ho * Wo, Cout, db, partial, st);
     }
-    if (!rc && db) rc = bias_grad(dz, (long long)B * Ho * Wo, Cout, db, partial, st);
     cudaFreeAsync(partial, st);
     return rc;
 }

@@ -72,6 +72,9 @@ def piecewise_constant(global_step, boundaries, values):
     return lr
 
 
+INPUT_STD = 255.0 / math.sqrt(12.0)     # standard deviation of a U[0,255) pixel
+
+
 def _trunk_scope(name):
     return name.startswith(('conv1_', 'conv2_', 'conv3_', 'conv4_', 'conv5_', 'mod_conv'))
 
@@ -187,6 +190,8 @@ class SSDVGG:
         for name, k, cin, cout in self._conv_table(num_classes):
             if _trunk_scope(name):
                 w = rng.normal(0, math.sqrt(2.0 / (k * k * cin)), (k, k, cin, cout))
+                if name == 'conv1_1':
+                    w /= INPUT_STD           # raw 0..255 pixels: keep the activations O(1) like the pretrained net
             else:
                 lim = math.sqrt(6.0 / (k * k * cin + k * k * cout))      # xavier_initializer(), uniform
                 w = rng.uniform(-lim, lim, (k, k, cin, cout))
