@@ -24,6 +24,7 @@
 //     (tcgen05.ld -> bias/ReLU/mask -> global).  4-stage smem ring, persistent CTAs.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -359,6 +360,7 @@ struct WgArgs {
     long long psize;                // floats per split in the workspace = taps*Cin*Cout + Cout
     float* partial;                 // [splits][psize]
     const float* ones;              // >= 64*32 floats of 1.0f
+    int debug;                      // bring-up switches (SSDB_WG_DEBUG): 1 skip x loads, 2 skip dz loads, 4 skip MMAs
 };
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
@@ -419,9 +421,10 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     const int x0 = qx * p.PW, y0 = qy * p.PH, n0 = qn * p.PN;
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t fb = full0 + 8 * stage;
-                    mbar_expect_tx(fb, (uint32_t)(na + nblk_b) * blk_bytes);
+                    const uint32_t ea = (p.debug & 1) ? 0u : (uint32_t)na * blk_bytes, eb = (p.debug & 2) ? 0u : (uint32_t)nblk_b * blk_bytes;
+                    if (ea + eb) mbar_expect_tx(fb, ea + eb); else mbar_arrive(fb);
                     const uint32_t sa = base + stage * STAGE_BYTES;
-                    for (int j = 0; j < na; j += p.load_blocks) {
+                    for (int j = 0; j < na && !(p.debug & 1); j += p.load_blocks) {
                         const int slot = mt * 4 + j;
                         if (slot == p.bias_slot) { bulk_load_1d(sa + (uint32_t)j * blk_bytes, p.ones, blk_bytes, fb); break; }
                         const int tap = slot / p.cblocks, cb = slot - tap * p.cblocks;
@@ -429,7 +432,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                         tma_load_5d(sa + (uint32_t)j * blk_bytes, &map_x, fb, 0, x0 * p.sstride + p.off0 + kw * p.offstep,
                                     y0 * p.sstride + p.off0 + kh * p.offstep, n0, cb);
                     }
-                    tma_load_5d(sa + b_off, &map_dz, fb, 0, x0, y0, n0, nt * nblk_b);
+                    if (!(p.debug & 2)) tma_load_5d(sa + b_off, &map_dz, fb, 0, x0, y0, n0, nt * nblk_b);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -454,7 +457,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     const uint64_t ad = make_mnmajor_desc(sa, blk_bytes);
                     const uint64_t bd = make_mnmajor_desc(sa + b_off, blk_bytes);
                     const int ksteps = p.P / 8;
-                    for (int k = 0; k < ksteps; ++k)      // 8 pixel rows = 1024 bytes = +64 in 16-byte units
+                    for (int k = 0; k < ksteps && !(p.debug & 4); ++k)      // 8 pixel rows = 1024 bytes = +64 in 16-byte units
                         tc_mma_tf32(d_tmem, ad + (uint64_t)(k * 64), bd + (uint64_t)(k * 64), idesc, (q > q0 || k > 0) ? 1u : 0u);
                     tc_commit(empty0 + 8 * stage);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -795,6 +798,7 @@ int conv_tc_wgrad(const ConvGeom& g, const float* x, const float* dz, float* dw,
     WgArgs a = pl.a;
     a.partial = partial;
     a.ones = ones_buffer();
+    { const char* dbg = getenv("SSDB_WG_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
     SSDB_REQUIRE(a.ones != nullptr, "could not allocate the ones buffer");
     if (!db) { a.bias_slot = -1; a.slots = a.taps * a.cblocks; a.m_tiles = (a.slots + 3) / 4; }
     CUtensorMap mx, mz;
