@@ -756,6 +756,12 @@ WgPlan plan_wgrad(const ConvGeom& g) {
     p_max = p_max / 8 * 8; if (p_max > 64) p_max = 64;
     if (g.stride == 2 && p_max > 32) p_max = 32;            // strided boxes: keep every box dimension <= 256 / stride
     PixGeom pg = pick_pix(g.B, g.Ho, g.Wo, p_max);
+    if (const char* ov = getenv("SSDB_WG_BOX")) {          // bring-up override: "PW,PH,PN"
+        int a1 = 0, a2 = 0, a3 = 0;
+        if (sscanf(ov, "%d,%d,%d", &a1, &a2, &a3) == 3 && a1 * a2 * a3 % 8 == 0 && a1 * a2 * a3 <= p_max) {
+            pg.PW = a1; pg.PH = a2; pg.PN = a3; pg.P = a1 * a2 * a3; pg.eff = 1.0;
+        }
+    }
     if (pg.P == 0 || pg.eff < 0.4) return pl;
     if (pg.PW * g.stride > 256 || pg.PH * g.stride > 256) return pl;
     a.PW = pg.PW; a.PH = pg.PH; a.PN = pg.PN; a.P = pg.P;
