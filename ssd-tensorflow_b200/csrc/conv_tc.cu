@@ -710,8 +710,10 @@ PixGeom pick_pix(int B, int H, int W, int p_max) {
                 if (P % 8) continue;
                 long long tiles = (long long)((W + pw - 1) / pw) * ((H + ph - 1) / ph) * ((B + pn - 1) / pn);
                 double eff = total / ((double)tiles * P);
-                double score = eff + 1e-4 * P;                 // prefer larger boxes among near-equals
-                double bscore = best.eff + 1e-4 * best.P;
+                // a pipeline stage is one box: small boxes starve the tensor core (one MMA per 8 pixels and a
+                // barrier round trip per stage), so the box size weighs more than a few percent of padding
+                double score = eff * (P >= 32 ? 1.0 + 0.05 * (P - 32) / 32.0 : 0.25 + 0.5 * P / 32.0);
+                double bscore = best.P ? best.eff * (best.P >= 32 ? 1.0 + 0.05 * (best.P - 32) / 32.0 : 0.25 + 0.5 * best.P / 32.0) : -1.0;
                 if (score > bscore) best = PixGeom{pw, ph, pn, P, eff};
             }
     return best;
