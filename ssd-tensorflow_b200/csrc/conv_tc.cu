@@ -712,8 +712,14 @@ PixGeom pick_pix(int B, int H, int W, int p_max) {
                 double eff = total / ((double)tiles * P);
                 // a pipeline stage is one box: small boxes starve the tensor core (one MMA per 8 pixels and a
                 // barrier round trip per stage), so the box size weighs more than a few percent of padding
-                double score = eff * (P >= 32 ? 1.0 + 0.05 * (P - 32) / 32.0 : 0.25 + 0.5 * P / 32.0);
-                double bscore = best.P ? best.eff * (best.P >= 32 ? 1.0 + 0.05 * (best.P - 32) / 32.0 : 0.25 + 0.5 * best.P / 32.0) : -1.0;
+                // measured on B200: boxes that span more than 4 images run ~2.4x slower (each image is megabytes
+                // away: the TMA unit walks far-apart pages), so those only win when nothing else fits
+                auto weight = [](int P_, int pn_) {
+                    double w = P_ >= 32 ? 1.0 + 0.05 * (P_ - 32) / 32.0 : 0.25 + 0.5 * P_ / 32.0;
+                    return pn_ > 4 ? 0.45 * w : w;
+                };
+                double score = eff * weight(P, pn);
+                double bscore = best.P ? best.eff * weight(best.P, best.PN) : -1.0;
                 if (score > bscore) best = PixGeom{pw, ph, pn, P, eff};
             }
     return best;

@@ -13,9 +13,9 @@ def timeit(fn, n=5):
     for _ in range(n): fn()
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / n
-cases = [((64, 38, 512, 512, 3), ['2,4,4', '8,4,1', '4,8,1', '16,2,1', '32,1,1', '8,1,4', '8,2,2', '1,8,4', '4,2,4']),
-         ((64, 300, 64, 64, 3), ['4,4,4', '60,1,1', '20,2,1', '10,4,1', '30,2,1', '12,4,1', '4,16,1', '64,1,1', '32,2,1', '16,4,1']),
-         ((64, 75, 256, 256, 3), ['5,8,1', '8,4,1', '16,2,1', '32,1,1', '25,1,1', '4,8,1'])]
+cases = [((64, 38, 512, 512, 3), ['2,4,4', '2,2,8', '4,1,8', '1,1,32', '2,8,2', '8,4,1']),
+         ((64, 300, 64, 64, 3), ['4,4,4', '4,2,8', '2,2,16', '8,8,1', '4,4,2', '4,2,2', '10,4,1', '20,2,1']),
+         ((64, 75, 256, 256, 3), ['8,4,1', '1,4,8', '5,1,8', '1,1,32', '4,4,2'])]
 for (B, H, Cin, Cout, k), boxes in cases:
     x = torch.randn((B, H, H, Cin), device='cuda'); dz = torch.randn((B, H, H, Cout), device='cuda')
     dw = torch.empty((k, k, Cin, Cout), device='cuda'); db = torch.empty(Cout, device='cuda')
