@@ -115,6 +115,13 @@ int l2norm_fwd(const float* x, const float* scale, long long pixels, int C, int 
 int l2norm_bwd(const float* x, const float* scale, const float* dy, long long pixels, int C, int beta,
                int round_out, float* dx, float* dscale, float* partial, cudaStream_t st);
 
+// ---- conv1_1 (Cin = 3): explicit 3x3 patch matrix so that the layer runs as a 1x1 tensor-core conv ----
+// patches[B*S*S][32]: 27 pre-processed (mean-subtracted, optionally R/B-swapped) taps in (kh, kw, c) order + 5 zeros,
+// tf32-rounded; SAME padding (zeros outside the image, after pre-processing, as in the graph)
+int conv1_im2col(const float* images, int B, int S, int swap_rb, const float mean[3], float* patches, cudaStream_t st);
+// w32[32][Cout] <- w[27][Cout] (rows 27..31 zero)
+int conv1_pad_filter(const float* w27, int Cout, float* w32, cudaStream_t st);
+
 // ---- head layout helpers ----
 // dz[B,H,W,Npad] (NHWC, zero padded channels) <- grad[B,A,V]
 int head_grad_gather(const float* grad, int B, int A, int V, int anchor_base, int HW, int nbox,

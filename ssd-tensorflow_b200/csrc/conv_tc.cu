@@ -129,10 +129,13 @@ struct TcArgs {
     int n_tiles, block_n;           // channel tiling of the destination
     int Hd, Wd, Bn, Cd;             // destination extents (Cd = stored channel stride)
     int cd_valid;                   // channels actually written
-    int taps, kdim;                 // filter taps (k*k), k
+    int taps;                       // number of filter taps this launch contracts over (<= 49)
+    signed char tap_dy[49], tap_dx[49];   // source shift of each tap (added to dst*sstride)
+    unsigned char tap_w[49];        // filter tap index (row block of the B tensor map)
+    int sstride;                    // fprop with stride s: source pixel = dst pixel * s + shift
+    int dscale, dpy, dpx;           // dgrad of a strided conv: this launch writes dst pixels (i*dscale+dpy, j*dscale+dpx)
     int cblocks;                    // source channels / 32
     int rows_per_tap;               // rows of the B tensor map per tap
-    int off0, offstep;              // source shift for tap index t (per axis): off0 + t*offstep
     int mode;                       // 0 fprop, 1 dgrad
     float* dst;
     const float* bias;              // fprop
@@ -186,16 +189,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
                 const int ty = r1 % p.tiles_y; const int tn = r1 / p.tiles_y;
                 const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
                 for (int tap = 0; tap < p.taps; ++tap) {
-                    const int kh = tap / p.kdim, kw = tap - kh * p.kdim;
-                    const int sy = y0 + p.off0 + kh * p.offstep;
-                    const int sx = x0 + p.off0 + kw * p.offstep;
+                    const int sy = y0 * p.sstride + p.tap_dy[tap];
+                    const int sx = x0 * p.sstride + p.tap_dx[tap];
+                    const int wrow = (int)p.tap_w[tap] * p.rows_per_tap;
                     for (int cb = 0; cb < p.cblocks; ++cb) {
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
                         const uint32_t fb = full0 + 8 * stage;
                         mbar_expect_tx(fb, a_bytes + b_bytes);
                         const uint32_t sa = base + stage * STAGE_BYTES;
                         tma_load_4d(sa, &map_src, fb, cb * BLOCK_K, sx, sy, n0);
-                        tma_load_2d(sa + A_BYTES, &map_w, fb, cb * BLOCK_K, tap * p.rows_per_tap + nt * p.block_n);
+                        tma_load_2d(sa + A_BYTES, &map_w, fb, cb * BLOCK_K, wrow + nt * p.block_n);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -241,7 +244,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
             const int ty = r1 % p.tiles_y; const int tn = r1 / p.tiles_y;
             const int lx = row % p.TW; const int r2 = row / p.TW;
             const int ly = r2 % p.TH; const int ln = r2 / p.TH;
-            const int x = tx * p.TW + lx, y = ty * p.TH + ly, n = tn * p.TN + ln;
+            const int xi = tx * p.TW + lx, yi = ty * p.TH + ly, n = tn * p.TN + ln;       // tile-grid coordinates
+            const int x = xi * p.dscale + p.dpx, y = yi * p.dscale + p.dpy;              // destination pixel
             const bool ok = row < rows_valid && x < p.Wd && y < p.Hd && n < p.Bn;
             const long long pix = ((long long)n * p.Hd + y) * p.Wd + x;
             mbar_wait(tfull0 + 8 * acc, acc_phase);
@@ -560,13 +564,13 @@ EncodeTiledFn get_encode() {
 }
 
 int encode_act_map(CUtensorMap* m, const float* ptr, int B, int H, int W, int C, int TW, int TH, int TN,
-                   CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                   CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, int estride = 1) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return SSDB_ECUDA; }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(TW * estride), (cuuint32_t)(TH * estride), (cuuint32_t)TN};
+    cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -631,7 +635,7 @@ int block_n_for(int channels) {
 }
 
 bool tc_common_ok(const ConvGeom& g) {
-    return g.stride == 1 && g.Cin % 32 == 0 && g.Cout % 16 == 0 && g.k >= 1 && g.k <= 7;
+    return (g.stride == 1 || g.stride == 2) && g.pad_t == g.pad_l && g.Cin % 32 == 0 && g.Cout % 16 == 0 && g.k >= 1 && g.k <= 7;
 }
 
 }  // namespace
@@ -646,7 +650,16 @@ bool conv_tc_supported_fprop(const ConvGeom& g) {
 bool conv_tc_supported_dgrad(const ConvGeom& g) {
     if (!tc_common_ok(g) || g.Cout % 32 != 0) return false;
     if (g.Cin > MAX_N && g.Cin % MAX_N != 0) return false;
-    TileGeom t = pick_tile(g.B, g.H, g.W);
+    const int s = g.stride;
+    if (s == 2) {
+        // every parity class of the destination needs at least one tap (true for k = 3, false for 1x1 stride 2)
+        for (int py = 0; py < s; ++py) {
+            bool any = false;
+            for (int kh = 0; kh < g.k; ++kh) if ((((py + g.pad_t - kh * g.dil) % s) + s) % s == 0) any = true;
+            if (!any) return false;
+        }
+    }
+    TileGeom t = pick_tile(g.B, (g.H + s - 1) / s, (g.W + s - 1) / s);
     return t.eff >= 0.45;
 }
 
@@ -666,33 +679,58 @@ int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_
     a.block_n = block_n_for(g.Cout); a.n_tiles = (g.Cout + a.block_n - 1) / a.block_n;
     SSDB_REQUIRE(cout_pad >= a.n_tiles * a.block_n, "transposed filter is not padded enough");
     a.Hd = g.Ho; a.Wd = g.Wo; a.Bn = g.B; a.Cd = g.Cout; a.cd_valid = g.Cout;
-    a.taps = g.k * g.k; a.kdim = g.k; a.cblocks = g.Cin / BLOCK_K; a.rows_per_tap = cout_pad;
-    a.off0 = -g.pad_t; a.offstep = g.dil; a.mode = 0;
+    a.taps = g.k * g.k; a.cblocks = g.Cin / BLOCK_K; a.rows_per_tap = cout_pad;
+    for (int t = 0; t < a.taps; ++t) {
+        a.tap_dy[t] = (signed char)((t / g.k) * g.dil - g.pad_t); a.tap_dx[t] = (signed char)((t % g.k) * g.dil - g.pad_l); a.tap_w[t] = (unsigned char)t;
+    }
+    a.sstride = g.stride; a.dscale = 1; a.dpy = a.dpx = 0; a.mode = 0;
     SSDB_REQUIRE(g.pad_t == g.pad_l, "tcgen05 path assumes equal top/left padding");
     a.dst = y; a.bias = ep.bias; a.mask = nullptr; a.relu = ep.relu; a.beta = 0; a.round_out = ep.round_tf32;
     a.scatter = ep.scatter; a.V = ep.V; a.n_valid = ep.n_valid; a.anchor_base = ep.anchor_base; a.A = ep.A;
     CUtensorMap ms, mw;
-    int rc = encode_act_map(&ms, x, g.B, g.H, g.W, g.Cin, t.TW, t.TH, t.TN); if (rc) return rc;
+    int rc = encode_act_map(&ms, x, g.B, g.H, g.W, g.Cin, t.TW, t.TH, t.TN, CU_TENSOR_MAP_SWIZZLE_128B, g.stride); if (rc) return rc;
     rc = encode_w_map(&mw, w_t, (long long)a.taps * cout_pad, g.Cin, a.block_n); if (rc) return rc;
     return launch_tc(ms, mw, a, st);
 }
 
 int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, const float* mask_x, int beta, int round_out, float* dx, cudaStream_t st) {
     SSDB_REQUIRE(conv_tc_supported_dgrad(g), "shape not supported by the tcgen05 dgrad kernel");
-    TileGeom t = pick_tile(g.B, g.H, g.W);
-    TcArgs a{};
-    a.TW = t.TW; a.TH = t.TH; a.TN = t.TN;
-    a.tiles_x = (g.W + t.TW - 1) / t.TW; a.tiles_y = (g.H + t.TH - 1) / t.TH; a.tiles_n = (g.B + t.TN - 1) / t.TN;
-    a.block_n = block_n_for(g.Cin); a.n_tiles = (g.Cin + a.block_n - 1) / a.block_n;
-    a.Hd = g.H; a.Wd = g.W; a.Bn = g.B; a.Cd = g.Cin; a.cd_valid = g.Cin;
-    a.taps = g.k * g.k; a.kdim = g.k; a.cblocks = g.Cout / BLOCK_K; a.rows_per_tap = g.Cin;
-    a.off0 = g.pad_t; a.offstep = -g.dil; a.mode = 1;
-    SSDB_REQUIRE(g.pad_t == g.pad_l, "tcgen05 path assumes equal top/left padding");
-    a.dst = dx; a.bias = nullptr; a.mask = mask_x; a.relu = 0; a.beta = beta; a.round_out = round_out;
-    CUtensorMap ms, mw;
-    int rc = encode_act_map(&ms, dz, g.B, g.Ho, g.Wo, g.Cout, t.TW, t.TH, t.TN); if (rc) return rc;
-    rc = encode_w_map(&mw, w_hwio, (long long)a.taps * g.Cin, g.Cout, a.block_n); if (rc) return rc;
-    return launch_tc(ms, mw, a, st);
+    // A conv with stride s scatters: destination pixel (y, x) only sees taps with (y + pad - kh*dil) % s == 0.  Launch one
+    // unit-stride contraction per parity class (py, px) of the destination, each with its own tap subset.
+    const int s = g.stride;
+    for (int py = 0; py < s; ++py) {
+        for (int px = 0; px < s; ++px) {
+            const int Hc = (g.H - py + s - 1) / s, Wc = (g.W - px + s - 1) / s;       // pixels of this class
+            if (Hc <= 0 || Wc <= 0) continue;
+            TileGeom t = pick_tile(g.B, Hc, Wc);
+            TcArgs a{};
+            a.TW = t.TW; a.TH = t.TH; a.TN = t.TN;
+            a.tiles_x = (Wc + t.TW - 1) / t.TW; a.tiles_y = (Hc + t.TH - 1) / t.TH; a.tiles_n = (g.B + t.TN - 1) / t.TN;
+            a.block_n = block_n_for(g.Cin); a.n_tiles = (g.Cin + a.block_n - 1) / a.block_n;
+            a.Hd = g.H; a.Wd = g.W; a.Bn = g.B; a.Cd = g.Cin; a.cd_valid = g.Cin;
+            a.cblocks = g.Cout / BLOCK_K; a.rows_per_tap = g.Cin;
+            a.taps = 0;
+            for (int kh = 0; kh < g.k; ++kh) {
+                int ny = py + g.pad_t - kh * g.dil;
+                if (((ny % s) + s) % s) continue;
+                for (int kw = 0; kw < g.k; ++kw) {
+                    int nx = px + g.pad_l - kw * g.dil;
+                    if (((nx % s) + s) % s) continue;
+                    // floor division: ny, nx are multiples of s here
+                    a.tap_dy[a.taps] = (signed char)(ny / s); a.tap_dx[a.taps] = (signed char)(nx / s);
+                    a.tap_w[a.taps] = (unsigned char)(kh * g.k + kw); ++a.taps;
+                }
+            }
+            SSDB_REQUIRE(a.taps > 0, "tcgen05 dgrad: a destination parity class without any filter tap");
+            a.sstride = 1; a.dscale = s; a.dpy = py; a.dpx = px; a.mode = 1;
+            a.dst = dx; a.bias = nullptr; a.mask = mask_x; a.relu = 0; a.beta = beta; a.round_out = round_out;
+            CUtensorMap ms, mw;
+            int rc = encode_act_map(&ms, dz, g.B, g.Ho, g.Wo, g.Cout, t.TW, t.TH, t.TN); if (rc) return rc;
+            rc = encode_w_map(&mw, w_hwio, (long long)g.k * g.k * g.Cin, g.Cout, a.block_n); if (rc) return rc;
+            rc = launch_tc(ms, mw, a, st); if (rc) return rc;
+        }
+    }
+    return SSDB_OK;
 }
 
 namespace {

@@ -234,6 +234,37 @@ __global__ void round_tf32_copy_kernel(const float* __restrict__ src, float* __r
     if (i < n) dst[i] = tf32_rn(src[i]);
 }
 
+// one thread per pixel: 27 taps (kh, kw, c) + 5 zeros = one 128-byte row
+__global__ void conv1_im2col_kernel(const float* __restrict__ img, int B, int S, int swap_rb, float m0, float m1, float m2,
+                                    float* __restrict__ patches) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)B * S * S;
+    if (i >= total) return;
+    int x = (int)(i % S); long long r = i / S;
+    int y = (int)(r % S); int b = (int)(r / S);
+    float v[32];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        int iy = y + t / 3 - 1, ix = x + t % 3 - 1;
+        bool ok = iy >= 0 && iy < S && ix >= 0 && ix < S;
+        const float* px = img + (((long long)b * S + (ok ? iy : 0)) * S + (ok ? ix : 0)) * 3;
+        float p0 = px[0], p1 = px[1], p2 = px[2];
+        float c0 = (swap_rb ? p2 : p0) - m0, c1 = p1 - m1, c2 = (swap_rb ? p0 : p2) - m2;
+        v[t * 3 + 0] = ok ? tf32_rn(c0) : 0.f; v[t * 3 + 1] = ok ? tf32_rn(c1) : 0.f; v[t * 3 + 2] = ok ? tf32_rn(c2) : 0.f;
+    }
+#pragma unroll
+    for (int t = 27; t < 32; ++t) v[t] = 0.f;
+    float4* o = reinterpret_cast<float4*>(patches + i * 32);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+}
+
+__global__ void conv1_pad_filter_kernel(const float* __restrict__ w27, int Cout, float* __restrict__ w32) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 32 * Cout) return;
+    w32[i] = i < 27 * Cout ? w27[i] : 0.f;
+}
+
 // one thread per row: softmax over the first C+1 columns, copy the 4 offsets
 __global__ void softmax_result_kernel(const float* __restrict__ out, long long rows, int C, float* __restrict__ res) {
     long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -355,6 +386,19 @@ int head_grad_gather(const float* grad, int B, int A, int V, int anchor_base, in
 
 int round_tf32_copy(const float* src, float* dst, long long n, cudaStream_t st) {
     round_tf32_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, n);
+    SSDB_LAUNCH_CHECK();
+    return SSDB_OK;
+}
+
+int conv1_im2col(const float* images, int B, int S, int swap_rb, const float mean[3], float* patches, cudaStream_t st) {
+    long long total = (long long)B * S * S;
+    conv1_im2col_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(images, B, S, swap_rb, mean[0], mean[1], mean[2], patches);
+    SSDB_LAUNCH_CHECK();
+    return SSDB_OK;
+}
+
+int conv1_pad_filter(const float* w27, int Cout, float* w32, cudaStream_t st) {
+    conv1_pad_filter_kernel<<<(32 * Cout + 255) / 256, 256, 0, st>>>(w27, Cout, w32);
     SSDB_LAUNCH_CHECK();
     return SSDB_OK;
 }

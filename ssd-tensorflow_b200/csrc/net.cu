@@ -90,6 +90,8 @@ struct ssdb_net {
     // device memory
     float *params = nullptr, *grads = nullptr, *moms = nullptr, *wt = nullptr;
     float *wr = nullptr;               // tf32-rounded copy of the parameters (dgrad B operand)
+    // conv1_1 as a 1x1 tensor-core conv over an explicit 3x3x3 patch matrix (Cin = 3 cannot feed the MMA directly)
+    float *patches = nullptr, *c1_w32 = nullptr, *c1_wt = nullptr, *c1_dw32 = nullptr;
     bool round = true;                 // activations / gradients are stored tf32-rounded (off in pure-SIMT mode)
     float *acts = nullptr, *gacts = nullptr;
     float *out = nullptr, *out_grad = nullptr, *result = nullptr, *dz_head = nullptr;
@@ -253,7 +255,7 @@ void build_plan(ssdb_net* n) {
     n->A = base;
     // transposed filter copies for the tcgen05 fprop kernel
     for (Op& op : n->ops) {
-        if (op.type != OP_CONV || op.stride != 1 || op.cin % 32 != 0) continue;
+        if (op.type != OP_CONV || op.cin % 32 != 0) continue;
         int bn = op.cout > 256 ? 256 : (op.cout + 15) / 16 * 16;
         op.cout_pad = (op.cout + bn - 1) / bn * bn;
         op.wt_off = n->wt_floats; op.has_wt = true;
@@ -282,6 +284,11 @@ int repack_filters(ssdb_net* n, cudaStream_t st) {
         if (rc) return rc;
     }
     if (n->round) { int rc = round_tf32_copy(n->params, n->wr, (long long)n->n_flat, st); if (rc) return rc; }
+    if (n->patches) {
+        const Op& c1 = n->ops[0];
+        int rc = conv1_pad_filter(n->params + n->masters[c1.w].off, c1.cout, n->c1_w32, st); if (rc) return rc;
+        rc = pack_filter_t(n->c1_w32, 1, 32, c1.cout, c1.cout, n->c1_wt, st); if (rc) return rc;
+    }
     n->wt_dirty = false;
     return SSDB_OK;
 }
@@ -319,7 +326,12 @@ int run_forward(ssdb_net* n, const float* images, int B, cudaStream_t st) {
             float* y = op.out >= 0 ? n->act(op.out, B) : n->out;
             if (op.head) { ep.scatter = 1; ep.V = n->V; ep.n_valid = op.nbox * n->V; ep.anchor_base = op.anchor_base; ep.A = n->A; }
             if (op.in < 0) { ep.preprocess = 1; ep.swap_rb = n->swap_rb; ep.mean[0] = n->mean[0]; ep.mean[1] = n->mean[1]; ep.mean[2] = n->mean[2]; }
-            if (op.has_wt && use_tc(n, conv_tc_supported_fprop(g)))
+            if (op.in < 0 && n->patches) {
+                rc = conv1_im2col(images, B, n->S, n->swap_rb, n->mean, n->patches, st); if (rc) return rc;
+                ConvGeom g1 = g; g1.Cin = 32; g1.k = 1; g1.pad_t = g1.pad_l = 0; g1.dil = 1;
+                ConvEpilogue e1 = ep; e1.preprocess = 0;
+                rc = conv_tc_fprop(g1, n->patches, n->c1_wt, op.cout, e1, y, st);
+            } else if (op.has_wt && use_tc(n, conv_tc_supported_fprop(g)))
                 rc = conv_tc_fprop(g, x, n->wt + op.wt_off, op.cout_pad, ep, y, st);
             else
                 rc = conv_simt_fprop(g, x, n->params + n->masters[op.w].off, ep, y, st);
@@ -358,6 +370,13 @@ int run_backward(ssdb_net* n, int B, cudaStream_t st) {
             float* dw = n->grads + n->masters[op.w].off;
             float* db = n->grads + n->masters[op.b].off;
             long long pixels = (long long)B * g.Ho * g.Wo;
+            if (op.in < 0 && n->patches) {
+                ProfScope ps(n, st, std::string("bwd_w:") + op.name, conv_flops(g));
+                ConvGeom g1 = g; g1.Cin = 32; g1.k = 1; g1.pad_t = g1.pad_l = 0; g1.dil = 1;
+                rc = conv_tc_wgrad(g1, n->patches, dz, n->c1_dw32, db, n->partial, st); if (rc) return rc;
+                SSDB_CUDA(cudaMemcpyAsync(dw, n->c1_dw32, (size_t)27 * op.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                continue;
+            }
             const bool tcw = op.in >= 0 && use_tc(n, conv_tc_supported_wgrad(g));
             if (!tcw) { ProfScope ps(n, st, std::string("bwd_b:") + op.name); rc = bias_grad(dz, pixels, op.cout, db, n->partial, st); }
             if (rc) return rc;
@@ -480,6 +499,16 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
     ALLOC(n->partial, partial, float); ALLOC(n->small_ws, 4096 + 2 * (size_t)max_batch, float);
     ALLOC(n->counter, 1, unsigned int); ALLOC(n->decay_mask, n->n_flat / OPT_BLOCK, unsigned char);
     ALLOC(n->anchors, (size_t)n->A * 4, double);
+    if (n->round) {
+        const Op& c1 = n->ops[0];
+        ConvGeom g1 = geom_of(n, c1, max_batch); g1.Cin = 32; g1.k = 1; g1.pad_t = g1.pad_l = 0;
+        if (conv_tc_supported_fprop(g1) && conv_tc_supported_wgrad(g1)) {
+            ALLOC(n->patches, (size_t)max_batch * n->S * n->S * 32, float);
+            ALLOC(n->c1_w32, 32 * c1.cout, float); ALLOC(n->c1_wt, 32 * c1.cout, float); ALLOC(n->c1_dw32, 32 * c1.cout, float);
+            size_t w = conv_tc_wgrad_ws(g1);
+            if (w > n->partial_floats) { cudaFree(n->partial); n->partial_floats = w; ALLOC(n->partial, w, float); }
+        }
+    }
 #undef ALLOC
     SSDB_CUDA(cudaMemset(n->params, 0, n->n_flat * sizeof(float)));
     SSDB_CUDA(cudaMemset(n->grads, 0, n->n_flat * sizeof(float)));
@@ -502,7 +531,7 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
 int ssdb_destroy(ssdb_net* n) {
     if (!n) return SSDB_OK;
     cudaDeviceSynchronize();
-    void* ptrs[] = {n->wr, n->params, n->grads, n->moms, n->wt, n->acts, n->gacts, n->out, n->out_grad, n->result, n->labels_stage,
+    void* ptrs[] = {n->patches, n->c1_w32, n->c1_wt, n->c1_dw32, n->wr, n->params, n->grads, n->moms, n->wt, n->acts, n->gacts, n->out, n->out_grad, n->result, n->labels_stage,
                     n->dz_head, n->images_stage, n->partial, n->small_ws, n->counter, n->decay_mask, n->anchors};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (n->host_small) cudaFreeHost(n->host_small);

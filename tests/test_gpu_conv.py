@@ -100,7 +100,7 @@ def test_tcgen05_matches_simt_on_network_shapes(shape):
 
 
 @pytest.mark.parametrize('case', [(4, 19, 256, 512, 3, 2, 1, 'SAME'), (4, 10, 128, 256, 3, 2, 1, 'SAME'), (2, 32, 64, 64, 3, 2, 1, 'SAME')])
-def test_tcgen05_wgrad_stride2_matches_simt(case):
+def test_tcgen05_stride2_matches_simt(case):
     B, H, Cin, Cout, k, stride, dil, padding = case
     x, w, b, pad, Ho = conv_case(B, H, Cin, Cout, k, stride, dil, padding, seed=11)
     rng = np.random.default_rng(5)
@@ -109,3 +109,13 @@ def test_tcgen05_wgrad_stride2_matches_simt(case):
     w_t, b_t = run_wgrad(ssdb.CONV_TC, x, dz, k, stride, dil, pad)
     assert rel_err(w_t, w_s) < TF32_TOL, ('wgrad s2', case, rel_err(w_t, w_s))
     assert rel_err(b_t, b_s) < TF32_TOL, ('bias s2', case, rel_err(b_t, b_s))
+    y_s = run_fprop(ssdb.CONV_SIMT, x, w, b, k, stride, dil, pad, Ho)
+    y_t = run_fprop(ssdb.CONV_TC, x, w, b, k, stride, dil, pad, Ho)
+    assert rel_err(y_t, y_s) < TF32_TOL, ('fprop s2', case, rel_err(y_t, y_s))
+    d_s = run_dgrad(ssdb.CONV_SIMT, dz, w, x, x.shape, k, stride, dil, pad)
+    d_t = run_dgrad(ssdb.CONV_TC, dz, w, x, x.shape, k, stride, dil, pad)
+    assert rel_err(d_t, d_s) < TF32_TOL, ('dgrad s2', case, rel_err(d_t, d_s))
+    old = rng.standard_normal(x.shape, dtype=np.float32)
+    d_s = run_dgrad(ssdb.CONV_SIMT, dz, w, None, x.shape, k, stride, dil, pad, beta=1, dx0=old)
+    d_t = run_dgrad(ssdb.CONV_TC, dz, w, None, x.shape, k, stride, dil, pad, beta=1, dx0=old)
+    assert rel_err(d_t, d_s) < TF32_TOL, ('dgrad s2 beta', case, rel_err(d_t, d_s))
