@@ -105,7 +105,8 @@ struct ssdb_net {
     bool wt_dirty = true, have_forward = false;
     int conv_mode = SSDB_CONV_AUTO;
     int swap_rb = 1; float mean[3] = {103.939f, 116.779f, 123.68f};
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_labels = nullptr, ev_result = nullptr;
     int last_B = 0;
     // per-op device timing (ssdb_profile_step)
     bool prof = false;
@@ -524,6 +525,9 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
     SSDB_CUDA(cudaMemcpy(n->anchors, anc.data(), anc.size() * sizeof(double), cudaMemcpyHostToDevice));
     SSDB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&n->host_small), 64 * sizeof(float)));
     SSDB_CUDA(cudaStreamCreateWithFlags(&n->own_stream, cudaStreamNonBlocking));
+    SSDB_CUDA(cudaStreamCreateWithFlags(&n->copy_stream, cudaStreamNonBlocking));
+    SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_labels, cudaEventDisableTiming));
+    SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_result, cudaEventDisableTiming));
     *out = n;
     return SSDB_OK;
 }
@@ -536,6 +540,9 @@ int ssdb_destroy(ssdb_net* n) {
     for (void* p : ptrs) if (p) cudaFree(p);
     if (n->host_small) cudaFreeHost(n->host_small);
     if (n->own_stream) cudaStreamDestroy(n->own_stream);
+    if (n->copy_stream) cudaStreamDestroy(n->copy_stream);
+    if (n->ev_labels) cudaEventDestroy(n->ev_labels);
+    if (n->ev_result) cudaEventDestroy(n->ev_result);
     delete n;
     return SSDB_OK;
 }
@@ -652,15 +659,26 @@ int ssdb_train_step(ssdb_net* n, const float* images_dev, const float* labels_de
 int ssdb_train_step_host(ssdb_net* n, const float* images_host, const float* labels_host, int B, float lr, float momentum,
                          float weight_decay, float* losses_out_host, float* result_host) {
     SSDB_REQUIRE(n && images_host && labels_host && B >= 1 && B <= n->max_batch, "bad arguments");
-    cudaStream_t st = n->own_stream;
+    // copies ride a second stream: the labels arrive while the forward runs (they are first needed by the loss) and the
+    // result leaves while the backward runs; only the image upload is on the critical path
+    cudaStream_t st = n->own_stream, cs = n->copy_stream;
+    const size_t bav = (size_t)B * n->A * n->V * sizeof(float);
+    SSDB_CUDA(cudaMemcpyAsync(n->labels_stage, labels_host, bav, cudaMemcpyHostToDevice, cs));
+    SSDB_CUDA(cudaEventRecord(n->ev_labels, cs));
     SSDB_CUDA(cudaMemcpyAsync(n->images_stage, images_host, (size_t)B * n->S * n->S * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
-    SSDB_CUDA(cudaMemcpyAsync(n->labels_stage, labels_host, (size_t)B * n->A * n->V * sizeof(float), cudaMemcpyHostToDevice, st));
-    int rc = ssdb_train_step(n, n->images_stage, n->labels_stage, nullptr, nullptr, 0, B, lr, momentum, weight_decay, 1.0f, 1, n->small_ws,
-                             n->result, st);
-    if (rc) return rc;
-    if (result_host) SSDB_CUDA(cudaMemcpyAsync(result_host, n->result, (size_t)B * n->A * n->V * sizeof(float), cudaMemcpyDeviceToHost, st));
+    int rc = run_forward(n, n->images_stage, B, st); if (rc) return rc;
+    SSDB_CUDA(cudaStreamWaitEvent(st, n->ev_labels, 0));
+    rc = loss_and_finalize(n, n->labels_stage, nullptr, nullptr, 0, B, weight_decay, 1.0f, true, n->small_ws, n->result, st); if (rc) return rc;
+    if (result_host) {
+        SSDB_CUDA(cudaEventRecord(n->ev_result, st));
+        SSDB_CUDA(cudaStreamWaitEvent(cs, n->ev_result, 0));
+        SSDB_CUDA(cudaMemcpyAsync(result_host, n->result, bav, cudaMemcpyDeviceToHost, cs));
+    }
+    rc = run_backward(n, B, st); if (rc) return rc;
+    rc = ssdb_apply_update(n, lr, momentum, weight_decay, 1.0f, st); if (rc) return rc;
     SSDB_CUDA(cudaMemcpyAsync(n->host_small, n->small_ws, 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
     SSDB_CUDA(cudaStreamSynchronize(st));
+    SSDB_CUDA(cudaStreamSynchronize(cs));
     if (losses_out_host) memcpy(losses_out_host, n->host_small, 4 * sizeof(float));
     return SSDB_OK;
 }
