@@ -37,10 +37,13 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;                    // fp32 elements = 128 bytes = one swizzle row
 constexpr int MAX_N = 256;
-constexpr int STAGES = 4;
-constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;   // 16 KB
+constexpr int STAGES = 3;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;   // 16 KB per M tile
 constexpr int B_BYTES = MAX_N * BLOCK_K * 4;     // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+// A CTA works on TWO M tiles that share one B tile: 8 MMAs per 64 KB stage instead of 4 per 48 KB,
+// i.e. 1.5x less L2 -> shared-memory traffic per FLOP (the kernels are L2-bandwidth bound, not MMA bound).
+constexpr int STAGE_BYTES = 2 * A_BYTES + B_BYTES;   // 64 KB
+constexpr int ACC_STRIDE = 256;                  // TMEM columns per accumulator buffer
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
@@ -144,13 +147,83 @@ struct TcArgs {
     int scatter, V, n_valid, anchor_base, A;
 };
 
+// epilogue of one 128-row tile: TMEM -> registers -> bias / ReLU / tf32 rounding (fprop) or beta / mask (dgrad) -> global
+__device__ __forceinline__ void epilogue_tile(const TcArgs& p, int mt, int nt, uint32_t t_row, int row, int lane) {
+    const int rows_valid = p.TW * p.TH * p.TN;
+    const int tx = mt % p.tiles_x; const int r1 = mt / p.tiles_x;
+    const int ty = r1 % p.tiles_y; const int tn = r1 / p.tiles_y;
+    const int lx = row % p.TW; const int r2 = row / p.TW;
+    const int ly = r2 % p.TH; const int ln = r2 / p.TH;
+    const int xi = tx * p.TW + lx, yi = ty * p.TH + ly, n = tn * p.TN + ln;       // tile-grid coordinates
+    const int x = xi * p.dscale + p.dpx, y = yi * p.dscale + p.dpy;              // destination pixel
+    const bool ok = row < rows_valid && x < p.Wd && y < p.Hd && n < p.Bn;
+    const long long pix = ((long long)n * p.Hd + y) * p.Wd + x;
+    for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t r[32];
+        __syncwarp();
+        tc_ld32(t_row + (uint32_t)c0, r);
+        tc_wait_ld();
+        const int ch0 = nt * p.block_n + c0;
+        if (!ok) {
+            // rows outside the destination: nothing to store
+        } else if (p.mode == 0) {
+            if (p.scatter) {
+                const int hw = p.Hd * p.Wd;
+                const int pimg = y * p.Wd + x;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int ch = ch0 + j;
+                    if (ch < p.n_valid) {
+                        const int bt = ch / p.V, v = ch - bt * p.V;
+                        float val = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + ch) : 0.f);
+                        p.dst[((long long)n * p.A + p.anchor_base + (long long)bt * hw + pimg) * p.V + v] = val;
+                    }
+                }
+            } else {
+                float* d = p.dst + pix * p.Cd + ch0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (ch0 + j < p.cd_valid) {
+                        float v[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            v[q] = __uint_as_float(r[j + q]) + (p.bias ? __ldg(p.bias + ch0 + j + q) : 0.f);
+                            if (p.relu) v[q] = fmaxf(v[q], 0.f);
+                            if (p.round_out) v[q] = tf32_rn(v[q]);
+                        }
+                        *reinterpret_cast<float4*>(d + j) = make_float4(v[0], v[1], v[2], v[3]);
+                    }
+                }
+            }
+        } else {
+            float* d = p.dst + pix * p.Cd + ch0;
+            const float* mk = p.mask ? p.mask + pix * p.Cd + ch0 : nullptr;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                if (ch0 + j < p.cd_valid) {
+                    float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])};
+                    if (p.beta) { float4 o = *reinterpret_cast<const float4*>(d + j); v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w; }
+                    if (mk) {
+                        float4 m4 = *reinterpret_cast<const float4*>(mk + j);
+                        v[0] = m4.x > 0.f ? v[0] : 0.f; v[1] = m4.y > 0.f ? v[1] : 0.f;
+                        v[2] = m4.z > 0.f ? v[2] : 0.f; v[3] = m4.w > 0.f ? v[3] : 0.f;
+                    }
+                    if (p.round_out) { v[0] = tf32_rn(v[0]); v[1] = tf32_rn(v[1]); v[2] = tf32_rn(v[2]); v[3] = tf32_rn(v[3]); }
+                    *reinterpret_cast<float4*>(d + j) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+            }
+        }
+    }
+    (void)lane;
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w, const TcArgs p) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B needs 1024-byte alignment
     const uint32_t bars = base + STAGES * STAGE_BYTES;
-    // barrier layout: full[4] empty[4] tfull[2] tempty[2] then tmem pointer
+    // barrier layout: full[STAGES] empty[STAGES] tfull[2] tempty[2] then tmem pointer
     const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
     const uint32_t tmem_slot = tempty0 + 16;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
@@ -173,32 +246,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
+    // a unit = two consecutive M tiles (the second may not exist) x one N tile
     const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
-    const int total_tiles = m_tiles * p.n_tiles;
+    const int m_pairs = (m_tiles + 1) >> 1;
+    const int total_units = m_pairs * p.n_tiles;
     const int kblocks = p.taps * p.cblocks;
     const uint32_t a_bytes = (uint32_t)(p.TW * p.TH * p.TN) * 128u;
     const uint32_t b_bytes = (uint32_t)p.block_n * 128u;
+    const int noff = (p.block_n + 31) & ~31;                       // TMEM column offset of the second tile's accumulator
+    const int acc_stages = (2 * noff <= ACC_STRIDE) ? 2 : 1;       // two accumulator buffers when both tiles fit in 256 columns
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-                const int tx = mt % p.tiles_x; const int r1 = mt / p.tiles_x;
-                const int ty = r1 % p.tiles_y; const int tn = r1 / p.tiles_y;
-                const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
+            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+                const int mp = u / p.n_tiles, nt = u - mp * p.n_tiles;
+                int x0[2], y0[2], n0[2];
+                const bool two = 2 * mp + 1 < m_tiles;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int mt = 2 * mp + j;
+                    const int tx = mt % p.tiles_x; const int r1 = mt / p.tiles_x;
+                    x0[j] = tx * p.TW; y0[j] = (r1 % p.tiles_y) * p.TH; n0[j] = (r1 / p.tiles_y) * p.TN;
+                }
                 for (int tap = 0; tap < p.taps; ++tap) {
-                    const int sy = y0 * p.sstride + p.tap_dy[tap];
-                    const int sx = x0 * p.sstride + p.tap_dx[tap];
+                    const int dy = p.tap_dy[tap], dx = p.tap_dx[tap];
                     const int wrow = (int)p.tap_w[tap] * p.rows_per_tap;
                     for (int cb = 0; cb < p.cblocks; ++cb) {
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
                         const uint32_t fb = full0 + 8 * stage;
-                        mbar_expect_tx(fb, a_bytes + b_bytes);
+                        mbar_expect_tx(fb, (two ? 2u : 1u) * a_bytes + b_bytes);
                         const uint32_t sa = base + stage * STAGE_BYTES;
-                        tma_load_4d(sa, &map_src, fb, cb * BLOCK_K, sx, sy, n0);
-                        tma_load_2d(sa + A_BYTES, &map_w, fb, cb * BLOCK_K, wrow + nt * p.block_n);
+                        tma_load_4d(sa, &map_src, fb, cb * BLOCK_K, x0[0] * p.sstride + dx, y0[0] * p.sstride + dy, n0[0]);
+                        if (two) tma_load_4d(sa + A_BYTES, &map_src, fb, cb * BLOCK_K, x0[1] * p.sstride + dx, y0[1] * p.sstride + dy, n0[1]);
+                        tma_load_2d(sa + 2 * A_BYTES, &map_w, fb, cb * BLOCK_K, wrow + nt * p.block_n);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -210,107 +292,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+                const int mp = u / p.n_tiles;
+                const bool two = 2 * mp + 1 < m_tiles;
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MAX_N);
+                const uint32_t d0 = tmem_base + (uint32_t)(acc * ACC_STRIDE);
+                const uint32_t d1 = d0 + (uint32_t)noff;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(full0 + 8 * stage, phase);
                     tc_fence_after();
                     const uint32_t sa = base + stage * STAGE_BYTES;
-                    const uint64_t ad = make_kmajor_desc(sa);
-                    const uint64_t bd = make_kmajor_desc(sa + A_BYTES);
+                    const uint64_t a0 = make_kmajor_desc(sa);
+                    const uint64_t a1 = make_kmajor_desc(sa + A_BYTES);
+                    const uint64_t bd = make_kmajor_desc(sa + 2 * A_BYTES);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 8; ++k) {
                         // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
-                        tc_mma_tf32(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                        tc_mma_tf32(d0, a0 + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (two) tc_mma_tf32(d1, a1 + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     tc_commit(empty0 + 8 * stage);              // frees the smem slot when these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(tfull0 + 8 * acc);                    // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                tc_commit(tfull0 + 8 * acc);                    // accumulators complete -> epilogue
+                if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
         // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
-        const int rows_valid = p.TW * p.TH * p.TN;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-            const int tx = mt % p.tiles_x; const int r1 = mt / p.tiles_x;
-            const int ty = r1 % p.tiles_y; const int tn = r1 / p.tiles_y;
-            const int lx = row % p.TW; const int r2 = row / p.TW;
-            const int ly = r2 % p.TH; const int ln = r2 / p.TH;
-            const int xi = tx * p.TW + lx, yi = ty * p.TH + ly, n = tn * p.TN + ln;       // tile-grid coordinates
-            const int x = xi * p.dscale + p.dpx, y = yi * p.dscale + p.dpy;              // destination pixel
-            const bool ok = row < rows_valid && x < p.Wd && y < p.Hd && n < p.Bn;
-            const long long pix = ((long long)n * p.Hd + y) * p.Wd + x;
+        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+            const int mp = u / p.n_tiles, nt = u - mp * p.n_tiles;
+            const bool two = 2 * mp + 1 < m_tiles;
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + (uint32_t)(acc * MAX_N) + ((uint32_t)(quarter * 32) << 16);
-            for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-                uint32_t r[32];
-                __syncwarp();
-                tc_ld32(t_row + (uint32_t)c0, r);
-                tc_wait_ld();
-                const int ch0 = nt * p.block_n + c0;
-                if (!ok) {
-                    // rows outside the destination: nothing to store
-                } else if (p.mode == 0) {
-                    if (p.scatter) {
-                        const int hw = p.Hd * p.Wd;
-                        const int pimg = y * p.Wd + x;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int ch = ch0 + j;
-                            if (ch < p.n_valid) {
-                                const int bt = ch / p.V, v = ch - bt * p.V;
-                                float val = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + ch) : 0.f);
-                                p.dst[((long long)n * p.A + p.anchor_base + (long long)bt * hw + pimg) * p.V + v] = val;
-                            }
-                        }
-                    } else {
-                        float* d = p.dst + pix * p.Cd + ch0;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            if (ch0 + j < p.cd_valid) {
-                                float v[4];
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    v[q] = __uint_as_float(r[j + q]) + (p.bias ? __ldg(p.bias + ch0 + j + q) : 0.f);
-                                    if (p.relu) v[q] = fmaxf(v[q], 0.f);
-                                    if (p.round_out) v[q] = tf32_rn(v[q]);
-                                }
-                                *reinterpret_cast<float4*>(d + j) = make_float4(v[0], v[1], v[2], v[3]);
-                            }
-                        }
-                    }
-                } else {
-                    float* d = p.dst + pix * p.Cd + ch0;
-                    const float* mk = p.mask ? p.mask + pix * p.Cd + ch0 : nullptr;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        if (ch0 + j < p.cd_valid) {
-                            float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])};
-                            if (p.beta) { float4 o = *reinterpret_cast<const float4*>(d + j); v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w; }
-                            if (mk) {
-                                float4 m4 = *reinterpret_cast<const float4*>(mk + j);
-                                v[0] = m4.x > 0.f ? v[0] : 0.f; v[1] = m4.y > 0.f ? v[1] : 0.f;
-                                v[2] = m4.z > 0.f ? v[2] : 0.f; v[3] = m4.w > 0.f ? v[3] : 0.f;
-                            }
-                            if (p.round_out) { v[0] = tf32_rn(v[0]); v[1] = tf32_rn(v[1]); v[2] = tf32_rn(v[2]); v[3] = tf32_rn(v[3]); }
-                            *reinterpret_cast<float4*>(d + j) = make_float4(v[0], v[1], v[2], v[3]);
-                        }
-                    }
-                }
-            }
+            const uint32_t t_row = tmem_base + (uint32_t)(acc * ACC_STRIDE) + ((uint32_t)(quarter * 32) << 16);
+            epilogue_tile(p, 2 * mp, nt, t_row, row, lane);
+            if (two) epilogue_tile(p, 2 * mp + 1, nt, t_row + (uint32_t)noff, row, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
         }
     }
 
@@ -353,7 +378,7 @@ struct WgArgs {
     int PW, PH, PN, P;              // pixel box, P = PW*PH*PN
     int ptx, pty, ptn;              // pixel tiling of the dz map
     int cblocks, taps, kdim;        // Cin/32, k*k, k
-    int slots, m_tiles;             // taps*cblocks (+1 with the bias slot), ceil(slots/4)
+    int slots, m_tiles;             // taps*cblocks (+1 with the bias slot), ceil(slots/8): a unit owns 8 slots = two 128-row MMA tiles
     int bias_slot;                  // slot index of the all-ones block, or -1
     int load_blocks;                // channel blocks per x TMA load = min(4, cblocks)
     int n_tiles, block_n;           // Cout tiling
@@ -408,7 +433,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const int pix_tiles = p.ptx * p.pty * p.ptn;
     const uint32_t blk_bytes = (uint32_t)p.P * 128u;          // one 32-channel column block
     const int nblk_b = p.block_n / 32;
-    const uint32_t b_off = 4u * blk_bytes;                     // B blocks follow the 4 A blocks
+    const uint32_t b_off = 8u * blk_bytes;                     // B blocks follow the 2 x 4 A blocks
 
     if (warp == 0) {
         if (lane == 0) {
@@ -418,7 +443,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 const int nt = r1 % p.n_tiles; const int mt = r1 / p.n_tiles;
                 const int q0 = sp * p.tiles_per_split;
                 const int q1 = min(pix_tiles, q0 + p.tiles_per_split);
-                int na = p.slots - mt * 4; na = na > 4 ? 4 : na;           // valid A blocks of this tile
+                int na = p.slots - mt * 8; na = na > 8 ? 8 : na;           // valid A blocks of this pair of tiles
                 for (int q = q0; q < q1; ++q) {
                     const int qx = q % p.ptx; const int r2 = q / p.ptx;
                     const int qy = r2 % p.pty; const int qn = r2 / p.pty;
@@ -429,7 +454,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     if (ea + eb) mbar_expect_tx(fb, ea + eb); else mbar_arrive(fb);
                     const uint32_t sa = base + stage * STAGE_BYTES;
                     for (int j = 0; j < na && !(p.debug & 1); j += p.load_blocks) {
-                        const int slot = mt * 4 + j;
+                        const int slot = mt * 8 + j;
                         if (slot == p.bias_slot) { bulk_load_1d(sa + (uint32_t)j * blk_bytes, p.ones, blk_bytes, fb); break; }
                         const int tap = slot / p.cblocks, cb = slot - tap * p.cblocks;
                         const int kh = tap / p.kdim, kw = tap - kh * p.kdim;
@@ -448,26 +473,30 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const int sp = u % p.splits;
+                const int sp = u % p.splits; const int mt = (u / p.splits) / p.n_tiles;
                 const int q0 = sp * p.tiles_per_split;
                 const int q1 = min(pix_tiles, q0 + p.tiles_per_split);
+                const bool two = p.slots - mt * 8 > 4;                  // the second 128-row tile has at least one valid slot
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MAX_N);
+                const uint32_t d0 = tmem_base, d1 = tmem_base + (uint32_t)MAX_N;      // both accumulators live at once: one TMEM stage
                 for (int q = q0; q < q1; ++q) {
                     mbar_wait(full0 + 8 * stage, phase);
                     tc_fence_after();
                     const uint32_t sa = base + stage * STAGE_BYTES;
-                    const uint64_t ad = make_mnmajor_desc(sa, blk_bytes);
+                    const uint64_t a0 = make_mnmajor_desc(sa, blk_bytes);
+                    const uint64_t a1 = make_mnmajor_desc(sa + 4u * blk_bytes, blk_bytes);
                     const uint64_t bd = make_mnmajor_desc(sa + b_off, blk_bytes);
                     const int ksteps = p.P / 8;
-                    for (int k = 0; k < ksteps && !(p.debug & 4); ++k)      // 8 pixel rows = 1024 bytes = +64 in 16-byte units
-                        tc_mma_tf32(d_tmem, ad + (uint64_t)(k * 64), bd + (uint64_t)(k * 64), idesc, (q > q0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < ksteps && !(p.debug & 4); ++k) {     // 8 pixel rows = 1024 bytes = +64 in 16-byte units
+                        tc_mma_tf32(d0, a0 + (uint64_t)(k * 64), bd + (uint64_t)(k * 64), idesc, (q > q0 || k > 0) ? 1u : 0u);
+                        if (two) tc_mma_tf32(d1, a1 + (uint64_t)(k * 64), bd + (uint64_t)(k * 64), idesc, (q > q0 || k > 0) ? 1u : 0u);
+                    }
                     tc_commit(empty0 + 8 * stage);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(tfull0 + 8 * acc);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                acc_phase ^= 1;
             }
         }
     } else {
@@ -477,33 +506,36 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
             const int sp = u % p.splits; const int r1 = u / p.splits;
             const int nt = r1 % p.n_tiles; const int mt = r1 / p.n_tiles;
-            const int slot = mt * 4 + quarter;
-            const bool is_bias = slot == p.bias_slot;
-            const bool ok = slot < p.slots && (!is_bias || lane == 0);
-            const int tap = (ok && !is_bias) ? slot / p.cblocks : 0, cb = (ok && !is_bias) ? slot - tap * p.cblocks : 0;
-            float* drow = p.partial + (long long)sp * p.psize +
-                          (is_bias ? wsize : ((long long)tap * p.Cin + cb * 32 + lane) * p.Cout);
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + (uint32_t)(acc * MAX_N) + ((uint32_t)(quarter * 32) << 16);
-            for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-                uint32_t r[32];
-                __syncwarp();
-                tc_ld32(t_row + (uint32_t)c0, r);
-                tc_wait_ld();
-                const int ch0 = nt * p.block_n + c0;
-                if (ok) {
+            for (int half = 0; half < 2; ++half) {
+                const int slot = mt * 8 + half * 4 + quarter;
+                if (mt * 8 + half * 4 >= p.slots) break;              // warp-uniform: the whole second tile is absent
+                const bool is_bias = slot == p.bias_slot;
+                const bool ok = slot < p.slots && (!is_bias || lane == 0);
+                const int tap = (ok && !is_bias) ? slot / p.cblocks : 0, cb = (ok && !is_bias) ? slot - tap * p.cblocks : 0;
+                float* drow = p.partial + (long long)sp * p.psize +
+                              (is_bias ? wsize : ((long long)tap * p.Cin + cb * 32 + lane) * p.Cout);
+                const uint32_t t_row = tmem_base + (uint32_t)(half * MAX_N) + ((uint32_t)(quarter * 32) << 16);
+                for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+                    uint32_t r[32];
+                    __syncwarp();
+                    tc_ld32(t_row + (uint32_t)c0, r);
+                    tc_wait_ld();
+                    const int ch0 = nt * p.block_n + c0;
+                    if (ok) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        if (ch0 + j < p.Cout)
-                            *reinterpret_cast<float4*>(drow + ch0 + j) =
-                                make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                        for (int j = 0; j < 32; j += 4)
+                            if (ch0 + j < p.Cout)
+                                *reinterpret_cast<float4*>(drow + ch0 + j) =
+                                    make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            acc_phase ^= 1;
         }
     }
 
@@ -622,7 +654,8 @@ int num_sms() {
 int launch_tc(const CUtensorMap& ms, const CUtensorMap& mw, const TcArgs& a, cudaStream_t st) {
     static bool attr = false;
     if (!attr) { SSDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr = true; }
-    long long total = (long long)a.tiles_x * a.tiles_y * a.tiles_n * a.n_tiles;
+    long long m_tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_n;
+    long long total = ((m_tiles + 1) / 2) * a.n_tiles;
     int grid = (int)(total < num_sms() ? total : num_sms());
     conv_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ms, mw, a);
     SSDB_LAUNCH_CHECK();
@@ -797,7 +830,7 @@ WgPlan plan_wgrad(const ConvGeom& g) {
     WgArgs& a = pl.a;
     a.block_n = g.Cout > MAX_N ? MAX_N : g.Cout;
     a.n_tiles = g.Cout / a.block_n;
-    int blocks = 4 + a.block_n / 32;
+    int blocks = 8 + a.block_n / 32;
     int p_max = STAGE_BYTES / (blocks * 128);
     p_max = p_max / 8 * 8; if (p_max > 64) p_max = 64;
     if (g.stride == 2 && p_max > 32) p_max = 32;            // strided boxes: keep every box dimension <= 256 / stride
@@ -816,7 +849,7 @@ WgPlan plan_wgrad(const ConvGeom& g) {
     a.load_blocks = a.cblocks < 4 ? a.cblocks : 4;
     if (a.cblocks % a.load_blocks) return pl;
     a.bias_slot = a.taps * a.cblocks;                        // the all-ones slot comes after the real ones
-    a.slots = a.bias_slot + 1; a.m_tiles = (a.slots + 3) / 4;
+    a.slots = a.bias_slot + 1; a.m_tiles = (a.slots + 7) / 8;
     a.Cin = g.Cin; a.Cout = g.Cout;
     a.off0 = -g.pad_t; a.offstep = g.dil; a.sstride = g.stride;
     a.psize = (long long)a.taps * g.Cin * g.Cout + g.Cout;
@@ -852,7 +885,7 @@ int conv_tc_wgrad(const ConvGeom& g, const float* x, const float* dz, float* dw,
     a.ones = ones_buffer();
     { const char* dbg = getenv("SSDB_WG_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
     SSDB_REQUIRE(a.ones != nullptr, "could not allocate the ones buffer");
-    if (!db) { a.bias_slot = -1; a.slots = a.taps * a.cblocks; a.m_tiles = (a.slots + 3) / 4; }
+    if (!db) { a.bias_slot = -1; a.slots = a.taps * a.cblocks; a.m_tiles = (a.slots + 7) / 8; }
     CUtensorMap mx, mz;
     int rc = encode_act_map5(&mx, x, g.B, g.H, g.W, g.Cin, a.PW, a.PH, a.PN, a.load_blocks, g.stride); if (rc) return rc;
     rc = encode_act_map5(&mz, dz, g.B, g.Ho, g.Wo, g.Cout, a.PW, a.PH, a.PN, a.block_n / 32, 1); if (rc) return rc;
