@@ -37,14 +37,18 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;                    // fp32 elements = 128 bytes = one swizzle row
 constexpr int MAX_N = 256;
-constexpr int STAGES = 3;
+constexpr int MAX_STAGES = 4;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;   // 16 KB per M tile
 constexpr int B_BYTES = MAX_N * BLOCK_K * 4;     // 32 KB
-// A CTA works on TWO M tiles that share one B tile: 8 MMAs per 64 KB stage instead of 4 per 48 KB,
-// i.e. 1.5x less L2 -> shared-memory traffic per FLOP (the kernels are L2-bandwidth bound, not MMA bound).
-constexpr int STAGE_BYTES = 2 * A_BYTES + B_BYTES;   // 64 KB
+// A unit is `mtu` (1 or 2) M tiles sharing one B tile.  mtu = 1: 4 stages x 48 KB, two TMEM accumulator buffers (the
+// epilogue overlaps the next tile).  mtu = 2: 3 stages x 64 KB, 8 MMAs per stage, 1.5x less L2 -> smem traffic per FLOP,
+// but with N = 256 both accumulators fill TMEM and the epilogue is exposed.  Measured on B200: mtu = 2 pays off in the
+// wgrad kernel for N >= 128 (long units), not in fprop / dgrad, whose mid layers already run at ~88% of the tf32 peak.
+constexpr int RING_BYTES = 192 * 1024;           // 4 x 48 KB = 3 x 64 KB
 constexpr int ACC_STRIDE = 256;                  // TMEM columns per accumulator buffer
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+__host__ __device__ constexpr int stage_bytes_for(int mtu) { return mtu * A_BYTES + B_BYTES; }
+__host__ __device__ constexpr int stages_for(int mtu) { return mtu == 1 ? 4 : 3; }
+constexpr int SMEM_BYTES = 192 * 1024 + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
 
@@ -140,6 +144,7 @@ struct TcArgs {
     int cblocks;                    // source channels / 32
     int rows_per_tap;               // rows of the B tensor map per tap
     int mode;                       // 0 fprop, 1 dgrad
+    int mtu;                        // M tiles per unit (1 or 2)
     float* dst;
     const float* bias;              // fprop
     const float* mask;              // dgrad: ReLU mask source (same shape as dst) or null
@@ -222,16 +227,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B needs 1024-byte alignment
-    const uint32_t bars = base + STAGES * STAGE_BYTES;
-    // barrier layout: full[STAGES] empty[STAGES] tfull[2] tempty[2] then tmem pointer
-    const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
+    const uint32_t bars = base + RING_BYTES;
+    // barrier layout: full[MAX_STAGES] empty[MAX_STAGES] tfull[2] tempty[2] then tmem pointer
+    const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
     const uint32_t tmem_slot = tempty0 + 16;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+    const int STAGES = stages_for(p.mtu);
+    const int STAGE_BYTES = stage_bytes_for(p.mtu);
+    const uint32_t b_off = (uint32_t)(p.mtu * A_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_src) : "memory");
@@ -246,15 +254,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    // a unit = two consecutive M tiles (the second may not exist) x one N tile
+    // a unit = mtu consecutive M tiles (the second may not exist) x one N tile
     const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
-    const int m_pairs = (m_tiles + 1) >> 1;
+    const int m_pairs = (m_tiles + p.mtu - 1) / p.mtu;
     const int total_units = m_pairs * p.n_tiles;
     const int kblocks = p.taps * p.cblocks;
     const uint32_t a_bytes = (uint32_t)(p.TW * p.TH * p.TN) * 128u;
     const uint32_t b_bytes = (uint32_t)p.block_n * 128u;
     const int noff = (p.block_n + 31) & ~31;                       // TMEM column offset of the second tile's accumulator
-    const int acc_stages = (2 * noff <= ACC_STRIDE) ? 2 : 1;       // two accumulator buffers when both tiles fit in 256 columns
+    const int acc_stages = (p.mtu * noff <= ACC_STRIDE) ? 2 : 1;   // two accumulator buffers when a unit fits in 256 columns
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -263,10 +271,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
             for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
                 const int mp = u / p.n_tiles, nt = u - mp * p.n_tiles;
                 int x0[2], y0[2], n0[2];
-                const bool two = 2 * mp + 1 < m_tiles;
+                const bool two = p.mtu == 2 && 2 * mp + 1 < m_tiles;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const int mt = 2 * mp + j;
+                    const int mt = p.mtu * mp + j;
                     const int tx = mt % p.tiles_x; const int r1 = mt / p.tiles_x;
                     x0[j] = tx * p.TW; y0[j] = (r1 % p.tiles_y) * p.TH; n0[j] = (r1 / p.tiles_y) * p.TN;
                 }
@@ -280,7 +288,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
                         const uint32_t sa = base + stage * STAGE_BYTES;
                         tma_load_4d(sa, &map_src, fb, cb * BLOCK_K, x0[0] * p.sstride + dx, y0[0] * p.sstride + dy, n0[0]);
                         if (two) tma_load_4d(sa + A_BYTES, &map_src, fb, cb * BLOCK_K, x0[1] * p.sstride + dx, y0[1] * p.sstride + dy, n0[1]);
-                        tma_load_2d(sa + 2 * A_BYTES, &map_w, fb, cb * BLOCK_K, wrow + nt * p.block_n);
+                        tma_load_2d(sa + b_off, &map_w, fb, cb * BLOCK_K, wrow + nt * p.block_n);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -294,7 +302,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
             int acc = 0; uint32_t acc_phase = 0;
             for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
                 const int mp = u / p.n_tiles;
-                const bool two = 2 * mp + 1 < m_tiles;
+                const bool two = p.mtu == 2 && 2 * mp + 1 < m_tiles;
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(acc * ACC_STRIDE);
@@ -305,7 +313,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
                     const uint32_t sa = base + stage * STAGE_BYTES;
                     const uint64_t a0 = make_kmajor_desc(sa);
                     const uint64_t a1 = make_kmajor_desc(sa + A_BYTES);
-                    const uint64_t bd = make_kmajor_desc(sa + 2 * A_BYTES);
+                    const uint64_t bd = make_kmajor_desc(sa + b_off);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 8; ++k) {
                         // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
@@ -326,11 +334,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
         int acc = 0; uint32_t acc_phase = 0;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
             const int mp = u / p.n_tiles, nt = u - mp * p.n_tiles;
-            const bool two = 2 * mp + 1 < m_tiles;
+            const bool two = p.mtu == 2 && 2 * mp + 1 < m_tiles;
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t)(acc * ACC_STRIDE) + ((uint32_t)(quarter * 32) << 16);
-            epilogue_tile(p, 2 * mp, nt, t_row, row, lane);
+            epilogue_tile(p, p.mtu * mp, nt, t_row, row, lane);
             if (two) epilogue_tile(p, 2 * mp + 1, nt, t_row + (uint32_t)noff, row, lane);
             tc_fence_before();
             __syncwarp();
@@ -386,6 +394,7 @@ struct WgArgs {
     int off0, offstep;              // source shift per axis for tap index t: off0 + t*offstep
     int sstride;                    // conv stride (x coordinates = pixel*sstride + shift)
     int splits, tiles_per_split;    // pixel-tile ranges
+    int mtu;                        // 128-row MMA tiles per unit (1 or 2): a unit owns 4*mtu slots
     long long psize;                // floats per split in the workspace = taps*Cin*Cout + Cout
     float* partial;                 // [splits][psize]
     const float* ones;              // >= 64*32 floats of 1.0f
@@ -407,14 +416,17 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
-    const uint32_t bars = base + STAGES * STAGE_BYTES;
-    const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
+    const uint32_t bars = base + RING_BYTES;
+    const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
     const uint32_t tmem_slot = tempty0 + 16;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int STAGES = stages_for(p.mtu);
+    const int STAGE_BYTES = stage_bytes_for(p.mtu);
+    const int spu = 4 * p.mtu;                                  // slots per unit
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -433,7 +445,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const int pix_tiles = p.ptx * p.pty * p.ptn;
     const uint32_t blk_bytes = (uint32_t)p.P * 128u;          // one 32-channel column block
     const int nblk_b = p.block_n / 32;
-    const uint32_t b_off = 8u * blk_bytes;                     // B blocks follow the 2 x 4 A blocks
+    const uint32_t b_off = (uint32_t)spu * blk_bytes;          // B blocks follow the mtu x 4 A blocks
 
     if (warp == 0) {
         if (lane == 0) {
@@ -443,7 +455,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 const int nt = r1 % p.n_tiles; const int mt = r1 / p.n_tiles;
                 const int q0 = sp * p.tiles_per_split;
                 const int q1 = min(pix_tiles, q0 + p.tiles_per_split);
-                int na = p.slots - mt * 8; na = na > 8 ? 8 : na;           // valid A blocks of this pair of tiles
+                int na = p.slots - mt * spu; na = na > spu ? spu : na;      // valid A blocks of this unit
                 for (int q = q0; q < q1; ++q) {
                     const int qx = q % p.ptx; const int r2 = q / p.ptx;
                     const int qy = r2 % p.pty; const int qn = r2 / p.pty;
@@ -454,7 +466,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     if (ea + eb) mbar_expect_tx(fb, ea + eb); else mbar_arrive(fb);
                     const uint32_t sa = base + stage * STAGE_BYTES;
                     for (int j = 0; j < na && !(p.debug & 1); j += p.load_blocks) {
-                        const int slot = mt * 8 + j;
+                        const int slot = mt * spu + j;
                         if (slot == p.bias_slot) { bulk_load_1d(sa + (uint32_t)j * blk_bytes, p.ones, blk_bytes, fb); break; }
                         const int tap = slot / p.cblocks, cb = slot - tap * p.cblocks;
                         const int kh = tap / p.kdim, kw = tap - kh * p.kdim;
@@ -476,7 +488,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 const int sp = u % p.splits; const int mt = (u / p.splits) / p.n_tiles;
                 const int q0 = sp * p.tiles_per_split;
                 const int q1 = min(pix_tiles, q0 + p.tiles_per_split);
-                const bool two = p.slots - mt * 8 > 4;                  // the second 128-row tile has at least one valid slot
+                const bool two = p.mtu == 2 && p.slots - mt * 8 > 4;     // the second 128-row tile has at least one valid slot
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d0 = tmem_base, d1 = tmem_base + (uint32_t)MAX_N;      // both accumulators live at once: one TMEM stage
@@ -509,8 +521,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
             for (int half = 0; half < 2; ++half) {
-                const int slot = mt * 8 + half * 4 + quarter;
-                if (mt * 8 + half * 4 >= p.slots) break;              // warp-uniform: the whole second tile is absent
+                const int slot = mt * spu + half * 4 + quarter;
+                if (half >= p.mtu || mt * spu + half * 4 >= p.slots) break;   // warp-uniform: no (valid) second tile
                 const bool is_bias = slot == p.bias_slot;
                 const bool ok = slot < p.slots && (!is_bias || lane == 0);
                 const int tap = (ok && !is_bias) ? slot / p.cblocks : 0, cb = (ok && !is_bias) ? slot - tap * p.cblocks : 0;
@@ -655,11 +667,16 @@ int launch_tc(const CUtensorMap& ms, const CUtensorMap& mw, const TcArgs& a, cud
     static bool attr = false;
     if (!attr) { SSDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr = true; }
     long long m_tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_n;
-    long long total = ((m_tiles + 1) / 2) * a.n_tiles;
+    long long total = ((m_tiles + a.mtu - 1) / a.mtu) * a.n_tiles;
     int grid = (int)(total < num_sms() ? total : num_sms());
     conv_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ms, mw, a);
     SSDB_LAUNCH_CHECK();
     return SSDB_OK;
+}
+
+int tc_mtu() {
+    if (const char* ov = getenv("SSDB_TC_MTU")) { int v = atoi(ov); if (v == 1 || v == 2) return v; }
+    return 1;
 }
 
 int block_n_for(int channels) {
@@ -716,7 +733,7 @@ int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_
     for (int t = 0; t < a.taps; ++t) {
         a.tap_dy[t] = (signed char)((t / g.k) * g.dil - g.pad_t); a.tap_dx[t] = (signed char)((t % g.k) * g.dil - g.pad_l); a.tap_w[t] = (unsigned char)t;
     }
-    a.sstride = g.stride; a.dscale = 1; a.dpy = a.dpx = 0; a.mode = 0;
+    a.sstride = g.stride; a.dscale = 1; a.dpy = a.dpx = 0; a.mode = 0; a.mtu = tc_mtu();
     SSDB_REQUIRE(g.pad_t == g.pad_l, "tcgen05 path assumes equal top/left padding");
     a.dst = y; a.bias = ep.bias; a.mask = nullptr; a.relu = ep.relu; a.beta = 0; a.round_out = ep.round_tf32;
     a.scatter = ep.scatter; a.V = ep.V; a.n_valid = ep.n_valid; a.anchor_base = ep.anchor_base; a.A = ep.A;
@@ -755,7 +772,7 @@ int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, const
                 }
             }
             SSDB_REQUIRE(a.taps > 0, "tcgen05 dgrad: a destination parity class without any filter tap");
-            a.sstride = 1; a.dscale = s; a.dpy = py; a.dpx = px; a.mode = 1;
+            a.sstride = 1; a.dscale = s; a.dpy = py; a.dpx = px; a.mode = 1; a.mtu = tc_mtu();
             a.dst = dx; a.bias = nullptr; a.mask = mask_x; a.relu = 0; a.beta = beta; a.round_out = round_out;
             CUtensorMap ms, mw;
             int rc = encode_act_map(&ms, dz, g.B, g.Ho, g.Wo, g.Cout, t.TW, t.TH, t.TN); if (rc) return rc;
@@ -830,8 +847,10 @@ WgPlan plan_wgrad(const ConvGeom& g) {
     WgArgs& a = pl.a;
     a.block_n = g.Cout > MAX_N ? MAX_N : g.Cout;
     a.n_tiles = g.Cout / a.block_n;
-    int blocks = 8 + a.block_n / 32;
-    int p_max = STAGE_BYTES / (blocks * 128);
+    a.mtu = a.block_n >= 128 ? 2 : 1;
+    if (const char* ov = getenv("SSDB_WG_MTU")) { int v = atoi(ov); if (v == 1 || v == 2) a.mtu = v; }
+    int blocks = 4 * a.mtu + a.block_n / 32;
+    int p_max = stage_bytes_for(a.mtu) / (blocks * 128);
     p_max = p_max / 8 * 8; if (p_max > 64) p_max = 64;
     if (g.stride == 2 && p_max > 32) p_max = 32;            // strided boxes: keep every box dimension <= 256 / stride
     PixGeom pg = pick_pix(g.B, g.Ho, g.Wo, p_max);
@@ -849,7 +868,7 @@ WgPlan plan_wgrad(const ConvGeom& g) {
     a.load_blocks = a.cblocks < 4 ? a.cblocks : 4;
     if (a.cblocks % a.load_blocks) return pl;
     a.bias_slot = a.taps * a.cblocks;                        // the all-ones slot comes after the real ones
-    a.slots = a.bias_slot + 1; a.m_tiles = (a.slots + 7) / 8;
+    a.slots = a.bias_slot + 1; a.m_tiles = (a.slots + 4 * a.mtu - 1) / (4 * a.mtu);
     a.Cin = g.Cin; a.Cout = g.Cout;
     a.off0 = -g.pad_t; a.offstep = g.dil; a.sstride = g.stride;
     a.psize = (long long)a.taps * g.Cin * g.Cout + g.Cout;
@@ -885,7 +904,7 @@ int conv_tc_wgrad(const ConvGeom& g, const float* x, const float* dz, float* dw,
     a.ones = ones_buffer();
     { const char* dbg = getenv("SSDB_WG_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
     SSDB_REQUIRE(a.ones != nullptr, "could not allocate the ones buffer");
-    if (!db) { a.bias_slot = -1; a.slots = a.taps * a.cblocks; a.m_tiles = (a.slots + 7) / 8; }
+    if (!db) { a.bias_slot = -1; a.slots = a.taps * a.cblocks; a.m_tiles = (a.slots + 4 * a.mtu - 1) / (4 * a.mtu); }
     CUtensorMap mx, mz;
     int rc = encode_act_map5(&mx, x, g.B, g.H, g.W, g.Cin, a.PW, a.PH, a.PN, a.load_blocks, g.stride); if (rc) return rc;
     rc = encode_act_map5(&mz, dz, g.B, g.Ho, g.Wo, g.Cout, a.PW, a.PH, a.PN, a.block_n / 32, 1); if (rc) return rc;
