@@ -674,9 +674,11 @@ int launch_tc(const CUtensorMap& ms, const CUtensorMap& mw, const TcArgs& a, cud
     return SSDB_OK;
 }
 
-int tc_mtu() {
+// measured on B200 (tools/ab_probe.sh): two tiles per unit win for N <= 128 (short units are TMA-issue bound; the shared
+// B tile halves the barrier traffic per FLOP and TMEM still double-buffers), one tile per unit wins for N = 256
+int tc_mtu(int block_n) {
     if (const char* ov = getenv("SSDB_TC_MTU")) { int v = atoi(ov); if (v == 1 || v == 2) return v; }
-    return 1;
+    return block_n <= 128 ? 2 : 1;
 }
 
 int block_n_for(int channels) {
@@ -733,7 +735,7 @@ int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_
     for (int t = 0; t < a.taps; ++t) {
         a.tap_dy[t] = (signed char)((t / g.k) * g.dil - g.pad_t); a.tap_dx[t] = (signed char)((t % g.k) * g.dil - g.pad_l); a.tap_w[t] = (unsigned char)t;
     }
-    a.sstride = g.stride; a.dscale = 1; a.dpy = a.dpx = 0; a.mode = 0; a.mtu = tc_mtu();
+    a.sstride = g.stride; a.dscale = 1; a.dpy = a.dpx = 0; a.mode = 0; a.mtu = tc_mtu(a.block_n);
     SSDB_REQUIRE(g.pad_t == g.pad_l, "tcgen05 path assumes equal top/left padding");
     a.dst = y; a.bias = ep.bias; a.mask = nullptr; a.relu = ep.relu; a.beta = 0; a.round_out = ep.round_tf32;
     a.scatter = ep.scatter; a.V = ep.V; a.n_valid = ep.n_valid; a.anchor_base = ep.anchor_base; a.A = ep.A;
@@ -772,7 +774,7 @@ int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, const
                 }
             }
             SSDB_REQUIRE(a.taps > 0, "tcgen05 dgrad: a destination parity class without any filter tap");
-            a.sstride = 1; a.dscale = s; a.dpy = py; a.dpx = px; a.mode = 1; a.mtu = tc_mtu();
+            a.sstride = 1; a.dscale = s; a.dpy = py; a.dpx = px; a.mode = 1; a.mtu = tc_mtu(a.block_n);
             a.dst = dx; a.bias = nullptr; a.mask = mask_x; a.relu = 0; a.beta = beta; a.round_out = round_out;
             CUtensorMap ms, mw;
             int rc = encode_act_map(&ms, dz, g.B, g.Ho, g.Wo, g.Cout, t.TW, t.TH, t.TN); if (rc) return rc;
