@@ -106,7 +106,7 @@ struct ssdb_net {
     int conv_mode = SSDB_CONV_AUTO;
     int swap_rb = 1; float mean[3] = {103.939f, 116.779f, 123.68f};
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev_labels = nullptr, ev_result = nullptr;
+    cudaEvent_t ev_labels = nullptr, ev_result = nullptr, ev_images = nullptr;
     int last_B = 0;
     // per-op device timing (ssdb_profile_step)
     bool prof = false;
@@ -528,6 +528,7 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
     SSDB_CUDA(cudaStreamCreateWithFlags(&n->copy_stream, cudaStreamNonBlocking));
     SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_labels, cudaEventDisableTiming));
     SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_result, cudaEventDisableTiming));
+    SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_images, cudaEventDisableTiming));
     *out = n;
     return SSDB_OK;
 }
@@ -543,6 +544,7 @@ int ssdb_destroy(ssdb_net* n) {
     if (n->copy_stream) cudaStreamDestroy(n->copy_stream);
     if (n->ev_labels) cudaEventDestroy(n->ev_labels);
     if (n->ev_result) cudaEventDestroy(n->ev_result);
+    if (n->ev_images) cudaEventDestroy(n->ev_images);
     delete n;
     return SSDB_OK;
 }
@@ -663,9 +665,12 @@ int ssdb_train_step_host(ssdb_net* n, const float* images_host, const float* lab
     // result leaves while the backward runs; only the image upload is on the critical path
     cudaStream_t st = n->own_stream, cs = n->copy_stream;
     const size_t bav = (size_t)B * n->A * n->V * sizeof(float);
+    // both uploads share one DMA direction: images first (critical path), labels behind them
+    SSDB_CUDA(cudaMemcpyAsync(n->images_stage, images_host, (size_t)B * n->S * n->S * 3 * sizeof(float), cudaMemcpyHostToDevice, cs));
+    SSDB_CUDA(cudaEventRecord(n->ev_images, cs));
     SSDB_CUDA(cudaMemcpyAsync(n->labels_stage, labels_host, bav, cudaMemcpyHostToDevice, cs));
     SSDB_CUDA(cudaEventRecord(n->ev_labels, cs));
-    SSDB_CUDA(cudaMemcpyAsync(n->images_stage, images_host, (size_t)B * n->S * n->S * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    SSDB_CUDA(cudaStreamWaitEvent(st, n->ev_images, 0));
     int rc = run_forward(n, n->images_stage, B, st); if (rc) return rc;
     SSDB_CUDA(cudaStreamWaitEvent(st, n->ev_labels, 0));
     rc = loss_and_finalize(n, n->labels_stage, nullptr, nullptr, 0, B, weight_decay, 1.0f, true, n->small_ws, n->result, st); if (rc) return rc;
