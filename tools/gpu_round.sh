@@ -7,6 +7,7 @@ run() { echo "=== $*" >> $LOG; timeout 900 python -m pytest "$@" -q -s --timeout
 run tests/test_gpu_box.py tests/test_gpu_loss.py -m gpu
 run tests/test_gpu_conv.py -m gpu
 run tests/test_gpu_net.py -m gpu
+run tests/test_gpu_surface.py -m gpu
 grep -E "^===|^exit|passed|failed|Error|error|PARITY" $LOG | cut -c1-420 | head -60
 echo "=== quick bench"
 timeout 600 python tools/quick_bench.py vgg300 64 2>&1 | tail -32 | cut -c1-200
