@@ -44,11 +44,11 @@ constexpr int B_BYTES = MAX_N * BLOCK_K * 4;     // 32 KB
 // epilogue overlaps the next tile).  mtu = 2: 3 stages x 64 KB, 8 MMAs per stage, 1.5x less L2 -> smem traffic per FLOP,
 // but with N = 256 both accumulators fill TMEM and the epilogue is exposed.  Measured on B200: mtu = 2 pays off in the
 // wgrad kernel for N >= 128 (long units), not in fprop / dgrad, whose mid layers already run at ~88% of the tf32 peak.
-constexpr int RING_BYTES = 192 * 1024;           // 4 x 48 KB = 3 x 64 KB
+constexpr int RING_BYTES = 204 * 1024;           // 4 x 48 KB, 3 x 64 KB, or 3 x 68 KB (row-window mode, N = 128)
 constexpr int ACC_STRIDE = 256;                  // TMEM columns per accumulator buffer
+constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 __host__ __device__ constexpr int stage_bytes_for(int mtu) { return mtu * A_BYTES + B_BYTES; }
 __host__ __device__ constexpr int stages_for(int mtu) { return mtu == 1 ? 4 : 3; }
-constexpr int SMEM_BYTES = 192 * 1024 + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
 
@@ -118,12 +118,13 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
 // 8-row groups 1024 B apart (SBO), rows 128 B apart, 16-byte units.
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t sbo_bytes = 1024) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
     d |= (uint64_t)1 << 16;                      // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;   // stride byte offset between 8-row groups
     d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
+    d |= (uint64_t)((smem_addr >> 7) & 7) << 49; // base offset: swizzle phase of a start that is not 1024-byte aligned
     d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
     return d;
 }
@@ -136,9 +137,20 @@ struct TcArgs {
     int n_tiles, block_n;           // channel tiling of the destination
     int Hd, Wd, Bn, Cd;             // destination extents (Cd = stored channel stride)
     int cd_valid;                   // channels actually written
-    int taps;                       // number of filter taps this launch contracts over (<= 49)
-    signed char tap_dy[49], tap_dx[49];   // source shift of each tap (added to dst*sstride)
-    unsigned char tap_w[49];        // filter tap index (row block of the B tensor map)
+    // Filter taps come in groups that share ONE source box: plain mode = one tap per group (box = the destination box
+    // shifted by the tap); row-window mode (3x3, dilation 1, TW = 8) = the three taps of a filter row share a box that is
+    // two pixels wider, and tap t reads the rows starting `g_win` pixels into it (an MMA descriptor with a 128-byte row
+    // offset and SBO = box width * 128) -- one third of the A traffic from L2.
+    int ngroups;
+    signed char g_dy[9], g_dx[9];   // source shift of the group's box (added to dst*sstride)
+    unsigned char g_nt[9];          // taps in the group (1..3)
+    unsigned char g_win[9][3];      // row offset of each tap's window inside the box
+    unsigned char g_w[9][3];        // filter tap index of each tap (row block of the B tensor map)
+    int a_rows;                     // rows of one source box (TWbox*TH*TN)
+    int a_slot;                     // bytes reserved per source box in a stage (multiple of 1024)
+    int a_sbo;                      // bytes between 8-row groups of the A operand
+    int b_tiles;                    // B tiles per stage = max taps per group
+    int stage_bytes, stages;
     int sstride;                    // fprop with stride s: source pixel = dst pixel * s + shift
     int dscale, dpy, dpx;           // dgrad of a strided conv: this launch writes dst pixels (i*dscale+dpy, j*dscale+dpx)
     int cblocks;                    // source channels / 32
@@ -232,9 +244,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
     const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
     const uint32_t tmem_slot = tempty0 + 16;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
-    const int STAGES = stages_for(p.mtu);
-    const int STAGE_BYTES = stage_bytes_for(p.mtu);
-    const uint32_t b_off = (uint32_t)(p.mtu * A_BYTES);
+    const int STAGES = p.stages;
+    const int STAGE_BYTES = p.stage_bytes;
+    const uint32_t b_off = (uint32_t)(p.mtu * p.a_slot);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -258,8 +270,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
     const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
     const int m_pairs = (m_tiles + p.mtu - 1) / p.mtu;
     const int total_units = m_pairs * p.n_tiles;
-    const int kblocks = p.taps * p.cblocks;
-    const uint32_t a_bytes = (uint32_t)(p.TW * p.TH * p.TN) * 128u;
+    const uint32_t a_bytes = (uint32_t)p.a_rows * 128u;
     const uint32_t b_bytes = (uint32_t)p.block_n * 128u;
     const int noff = (p.block_n + 31) & ~31;                       // TMEM column offset of the second tile's accumulator
     const int acc_stages = (p.mtu * noff <= ACC_STRIDE) ? 2 : 1;   // two accumulator buffers when a unit fits in 256 columns
@@ -278,17 +289,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
                     const int tx = mt % p.tiles_x; const int r1 = mt / p.tiles_x;
                     x0[j] = tx * p.TW; y0[j] = (r1 % p.tiles_y) * p.TH; n0[j] = (r1 / p.tiles_y) * p.TN;
                 }
-                for (int tap = 0; tap < p.taps; ++tap) {
-                    const int dy = p.tap_dy[tap], dx = p.tap_dx[tap];
-                    const int wrow = (int)p.tap_w[tap] * p.rows_per_tap;
+                for (int gi = 0; gi < p.ngroups; ++gi) {
+                    const int dy = p.g_dy[gi], dx = p.g_dx[gi], ntap = p.g_nt[gi];
                     for (int cb = 0; cb < p.cblocks; ++cb) {
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
                         const uint32_t fb = full0 + 8 * stage;
-                        mbar_expect_tx(fb, (two ? 2u : 1u) * a_bytes + b_bytes);
+                        mbar_expect_tx(fb, (two ? 2u : 1u) * a_bytes + (uint32_t)ntap * b_bytes);
                         const uint32_t sa = base + stage * STAGE_BYTES;
                         tma_load_4d(sa, &map_src, fb, cb * BLOCK_K, x0[0] * p.sstride + dx, y0[0] * p.sstride + dy, n0[0]);
-                        if (two) tma_load_4d(sa + A_BYTES, &map_src, fb, cb * BLOCK_K, x0[1] * p.sstride + dx, y0[1] * p.sstride + dy, n0[1]);
-                        tma_load_2d(sa + b_off, &map_w, fb, cb * BLOCK_K, wrow + nt * p.block_n);
+                        if (two) tma_load_4d(sa + p.a_slot, &map_src, fb, cb * BLOCK_K, x0[1] * p.sstride + dx, y0[1] * p.sstride + dy, n0[1]);
+                        for (int t = 0; t < ntap; ++t)
+                            tma_load_2d(sa + b_off + (uint32_t)t * b_bytes, &map_w, fb, cb * BLOCK_K, (int)p.g_w[gi][t] * p.rows_per_tap + nt * p.block_n);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -307,21 +318,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(acc * ACC_STRIDE);
                 const uint32_t d1 = d0 + (uint32_t)noff;
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(full0 + 8 * stage, phase);
-                    tc_fence_after();
-                    const uint32_t sa = base + stage * STAGE_BYTES;
-                    const uint64_t a0 = make_kmajor_desc(sa);
-                    const uint64_t a1 = make_kmajor_desc(sa + A_BYTES);
-                    const uint64_t bd = make_kmajor_desc(sa + b_off);
+                uint32_t started = 0;
+                for (int gi = 0; gi < p.ngroups; ++gi) {
+                    const int ntap = p.g_nt[gi];
+                    for (int cb = 0; cb < p.cblocks; ++cb) {
+                        mbar_wait(full0 + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint32_t sa = base + stage * STAGE_BYTES;
+                        for (int t = 0; t < ntap; ++t) {
+                            const uint32_t woff = (uint32_t)p.g_win[gi][t] * 128u;
+                            const uint64_t a0 = make_kmajor_desc(sa + woff, (uint32_t)p.a_sbo);
+                            const uint64_t a1 = make_kmajor_desc(sa + (uint32_t)p.a_slot + woff, (uint32_t)p.a_sbo);
+                            const uint64_t bd = make_kmajor_desc(sa + b_off + (uint32_t)t * b_bytes);
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / 8; ++k) {
-                        // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
-                        tc_mma_tf32(d0, a0 + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-                        if (two) tc_mma_tf32(d1, a1 + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < BLOCK_K / 8; ++k) {
+                                // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
+                                tc_mma_tf32(d0, a0 + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, started);
+                                if (two) tc_mma_tf32(d1, a1 + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, started);
+                                started = 1;
+                            }
+                        }
+                        tc_commit(empty0 + 8 * stage);              // frees the smem slot when these MMAs retire
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
-                    tc_commit(empty0 + 8 * stage);              // frees the smem slot when these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(tfull0 + 8 * acc);                    // accumulators complete -> epilogue
                 if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
@@ -681,13 +700,58 @@ int tc_mtu(int block_n) {
     return block_n <= 128 ? 2 : 1;
 }
 
+// fill the tap-group table: plain (one tap per group) or row-window (3 taps of a filter row per group, TW must be 8)
+void fill_groups(TcArgs& a, int k, const int* dy, const int* dx, bool row_window) {
+    const int taps = k * k;
+    if (!row_window) {
+        a.ngroups = taps;
+        for (int t = 0; t < taps; ++t) {
+            a.g_dy[t] = (signed char)dy[t]; a.g_dx[t] = (signed char)dx[t]; a.g_nt[t] = 1; a.g_win[t][0] = 0; a.g_w[t][0] = (unsigned char)t;
+        }
+        a.a_rows = a.TW * a.TH * a.TN; a.a_slot = A_BYTES; a.a_sbo = 1024; a.b_tiles = 1;
+    } else {
+        a.ngroups = k;
+        for (int kh = 0; kh < k; ++kh) {
+            int dmin = dx[kh * k];
+            for (int kw = 1; kw < k; ++kw) if (dx[kh * k + kw] < dmin) dmin = dx[kh * k + kw];
+            a.g_dy[kh] = (signed char)dy[kh * k]; a.g_dx[kh] = (signed char)dmin; a.g_nt[kh] = (unsigned char)k;
+            for (int kw = 0; kw < k; ++kw) { a.g_win[kh][kw] = (unsigned char)(dx[kh * k + kw] - dmin); a.g_w[kh][kw] = (unsigned char)(kh * k + kw); }
+        }
+        a.a_rows = (a.TW + k - 1) * a.TH * a.TN; a.a_slot = (a.a_rows * 128 + 1023) / 1024 * 1024; a.a_sbo = (a.TW + k - 1) * 128; a.b_tiles = k;
+    }
+    a.stage_bytes = a.mtu * a.a_slot + a.b_tiles * a.block_n * 128;
+    a.stage_bytes = (a.stage_bytes + 1023) / 1024 * 1024;
+    a.stages = RING_BYTES / a.stage_bytes; if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
+}
+
+// row-window geometry: TW = 8 and TH*TN = 16 (128 rows); returns efficiency, 0 if impossible
+double pick_window_tile(int B, int H, int W, int* th, int* tn) {
+    double best = 0.0;
+    for (int t = 1; t <= 16; t <<= 1) {
+        int h = 16 / t;                          // TH = h, TN = t
+        if (h > H && h > 1) continue;
+        if (t > B) continue;
+        long long tiles = (long long)((W + 7) / 8) * ((H + h - 1) / h) * ((B + t - 1) / t);
+        double eff = (double)B * H * W / (tiles * 128.0);
+        if (eff > best) { best = eff; *th = h; *tn = t; }
+    }
+    return best;
+}
+
+bool want_row_window(const ConvGeom& g, int block_n, int B, int Hd, int Wd, double plain_eff, int* th, int* tn) {
+    if (const char* ov = getenv("SSDB_KW3")) { if (atoi(ov) == 0) return false; }
+    if (g.k != 3 || g.dil != 1 || g.stride != 1 || block_n > 128) return false;
+    double e = pick_window_tile(B, Hd, Wd, th, tn);
+    return e >= 0.9 * plain_eff && e >= 0.6;
+}
+
 int block_n_for(int channels) {
     int n = (channels + 15) / 16 * 16;
     return n > MAX_N ? MAX_N : n;
 }
 
 bool tc_common_ok(const ConvGeom& g) {
-    return (g.stride == 1 || g.stride == 2) && g.pad_t == g.pad_l && g.Cin % 32 == 0 && g.Cout % 16 == 0 && g.k >= 1 && g.k <= 7;
+    return (g.stride == 1 || g.stride == 2) && g.pad_t == g.pad_l && g.Cin % 32 == 0 && g.Cout % 16 == 0 && g.k >= 1 && g.k <= 3;
 }
 
 }  // namespace
@@ -731,17 +795,25 @@ int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_
     a.block_n = block_n_for(g.Cout); a.n_tiles = (g.Cout + a.block_n - 1) / a.block_n;
     SSDB_REQUIRE(cout_pad >= a.n_tiles * a.block_n, "transposed filter is not padded enough");
     a.Hd = g.Ho; a.Wd = g.Wo; a.Bn = g.B; a.Cd = g.Cout; a.cd_valid = g.Cout;
-    a.taps = g.k * g.k; a.cblocks = g.Cin / BLOCK_K; a.rows_per_tap = cout_pad;
-    for (int t = 0; t < a.taps; ++t) {
-        a.tap_dy[t] = (signed char)((t / g.k) * g.dil - g.pad_t); a.tap_dx[t] = (signed char)((t % g.k) * g.dil - g.pad_l); a.tap_w[t] = (unsigned char)t;
-    }
+    SSDB_REQUIRE(g.k <= 3, "tcgen05 path supports 1x1 and 3x3 filters");
+    a.cblocks = g.Cin / BLOCK_K; a.rows_per_tap = cout_pad;
+    int tdy[9], tdx[9];
+    for (int t = 0; t < g.k * g.k; ++t) { tdy[t] = (t / g.k) * g.dil - g.pad_t; tdx[t] = (t % g.k) * g.dil - g.pad_l; }
     a.sstride = g.stride; a.dscale = 1; a.dpy = a.dpx = 0; a.mode = 0; a.mtu = tc_mtu(a.block_n);
+    int wth = 0, wtn = 0;
+    const bool rw = want_row_window(g, a.block_n, g.B, g.Ho, g.Wo, t.eff, &wth, &wtn);
+    if (rw) {
+        t.TW = 8; t.TH = wth; t.TN = wtn; a.TW = 8; a.TH = wth; a.TN = wtn;
+        a.tiles_x = (g.Wo + 7) / 8; a.tiles_y = (g.Ho + wth - 1) / wth; a.tiles_n = (g.B + wtn - 1) / wtn;
+        if (a.block_n > 64) a.mtu = 1;                        // 2 x 20 KB + 3 x 16 KB would leave only two stages
+    }
+    fill_groups(a, g.k, tdy, tdx, rw);
     SSDB_REQUIRE(g.pad_t == g.pad_l, "tcgen05 path assumes equal top/left padding");
     a.dst = y; a.bias = ep.bias; a.mask = nullptr; a.relu = ep.relu; a.beta = 0; a.round_out = ep.round_tf32;
     a.scatter = ep.scatter; a.V = ep.V; a.n_valid = ep.n_valid; a.anchor_base = ep.anchor_base; a.A = ep.A;
     CUtensorMap ms, mw;
-    int rc = encode_act_map(&ms, x, g.B, g.H, g.W, g.Cin, t.TW, t.TH, t.TN, CU_TENSOR_MAP_SWIZZLE_128B, g.stride); if (rc) return rc;
-    rc = encode_w_map(&mw, w_t, (long long)a.taps * cout_pad, g.Cin, a.block_n); if (rc) return rc;
+    int rc = encode_act_map(&ms, x, g.B, g.H, g.W, g.Cin, rw ? t.TW + g.k - 1 : t.TW, t.TH, t.TN, CU_TENSOR_MAP_SWIZZLE_128B, g.stride); if (rc) return rc;
+    rc = encode_w_map(&mw, w_t, (long long)g.k * g.k * cout_pad, g.Cin, a.block_n); if (rc) return rc;
     return launch_tc(ms, mw, a, st);
 }
 
@@ -761,23 +833,40 @@ int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, const
             a.block_n = block_n_for(g.Cin); a.n_tiles = (g.Cin + a.block_n - 1) / a.block_n;
             a.Hd = g.H; a.Wd = g.W; a.Bn = g.B; a.Cd = g.Cin; a.cd_valid = g.Cin;
             a.cblocks = g.Cout / BLOCK_K; a.rows_per_tap = g.Cin;
-            a.taps = 0;
-            for (int kh = 0; kh < g.k; ++kh) {
-                int ny = py + g.pad_t - kh * g.dil;
-                if (((ny % s) + s) % s) continue;
-                for (int kw = 0; kw < g.k; ++kw) {
-                    int nx = px + g.pad_l - kw * g.dil;
-                    if (((nx % s) + s) % s) continue;
-                    // floor division: ny, nx are multiples of s here
-                    a.tap_dy[a.taps] = (signed char)(ny / s); a.tap_dx[a.taps] = (signed char)(nx / s);
-                    a.tap_w[a.taps] = (unsigned char)(kh * g.k + kw); ++a.taps;
-                }
-            }
-            SSDB_REQUIRE(a.taps > 0, "tcgen05 dgrad: a destination parity class without any filter tap");
             a.sstride = 1; a.dscale = s; a.dpy = py; a.dpx = px; a.mode = 1; a.mtu = tc_mtu(a.block_n);
+            SSDB_REQUIRE(g.k <= 3, "tcgen05 path supports 1x1 and 3x3 filters");
+            int wth = 0, wtn = 0;
+            const bool rw = s == 1 && want_row_window(g, a.block_n, g.B, Hc, Wc, t.eff, &wth, &wtn);
+            if (rw) {
+                t.TW = 8; t.TH = wth; t.TN = wtn; a.TW = 8; a.TH = wth; a.TN = wtn;
+                a.tiles_x = (Wc + 7) / 8; a.tiles_y = (Hc + wth - 1) / wth; a.tiles_n = (g.B + wtn - 1) / wtn;
+                if (a.block_n > 64) a.mtu = 1;
+                int tdy[9], tdx[9];
+                for (int tt = 0; tt < g.k * g.k; ++tt) { tdy[tt] = g.pad_t - (tt / g.k) * g.dil; tdx[tt] = g.pad_l - (tt % g.k) * g.dil; }
+                fill_groups(a, g.k, tdy, tdx, true);
+            } else {
+                int ntap = 0;
+                a.ngroups = 0;
+                for (int kh = 0; kh < g.k; ++kh) {
+                    int ny = py + g.pad_t - kh * g.dil;
+                    if (((ny % s) + s) % s) continue;
+                    for (int kw = 0; kw < g.k; ++kw) {
+                        int nx = px + g.pad_l - kw * g.dil;
+                        if (((nx % s) + s) % s) continue;
+                        // floor division: ny, nx are multiples of s here
+                        a.g_dy[ntap] = (signed char)(ny / s); a.g_dx[ntap] = (signed char)(nx / s); a.g_nt[ntap] = 1;
+                        a.g_win[ntap][0] = 0; a.g_w[ntap][0] = (unsigned char)(kh * g.k + kw); ++ntap;
+                    }
+                }
+                SSDB_REQUIRE(ntap > 0, "tcgen05 dgrad: a destination parity class without any filter tap");
+                a.ngroups = ntap;
+                a.a_rows = a.TW * a.TH * a.TN; a.a_slot = A_BYTES; a.a_sbo = 1024; a.b_tiles = 1;
+                a.stage_bytes = a.mtu * a.a_slot + a.block_n * 128; a.stage_bytes = (a.stage_bytes + 1023) / 1024 * 1024;
+                a.stages = RING_BYTES / a.stage_bytes; if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
+            }
             a.dst = dx; a.bias = nullptr; a.mask = mask_x; a.relu = 0; a.beta = beta; a.round_out = round_out;
             CUtensorMap ms, mw;
-            int rc = encode_act_map(&ms, dz, g.B, g.Ho, g.Wo, g.Cout, t.TW, t.TH, t.TN); if (rc) return rc;
+            int rc = encode_act_map(&ms, dz, g.B, g.Ho, g.Wo, g.Cout, rw ? t.TW + g.k - 1 : t.TW, t.TH, t.TN); if (rc) return rc;
             rc = encode_w_map(&mw, w_hwio, (long long)g.k * g.k * g.Cin, g.Cout, a.block_n); if (rc) return rc;
             rc = launch_tc(ms, mw, a, st); if (rc) return rc;
         }
