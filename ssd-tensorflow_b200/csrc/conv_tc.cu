@@ -118,13 +118,13 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
 // 8-row groups 1024 B apart (SBO), rows 128 B apart, 16-byte units.
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t sbo_bytes = 1024) {
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t sbo_bytes = 1024, int use_base_offset = 1) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
     d |= (uint64_t)1 << 16;                      // leading byte offset (unused for swizzled K-major)
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;   // stride byte offset between 8-row groups
     d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
-    d |= (uint64_t)((smem_addr >> 7) & 7) << 49; // base offset: swizzle phase of a start that is not 1024-byte aligned
+    if (use_base_offset) d |= (uint64_t)((smem_addr >> 7) & 7) << 49; // base offset: swizzle phase of a start that is not 1024-byte aligned
     d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
     return d;
 }
@@ -151,6 +151,7 @@ struct TcArgs {
     int a_sbo;                      // bytes between 8-row groups of the A operand
     int b_tiles;                    // B tiles per stage = max taps per group
     int stage_bytes, stages;
+    int use_bo;                     // bring-up: set the descriptor base-offset field for unaligned window starts
     int sstride;                    // fprop with stride s: source pixel = dst pixel * s + shift
     int dscale, dpy, dpx;           // dgrad of a strided conv: this launch writes dst pixels (i*dscale+dpy, j*dscale+dpx)
     int cblocks;                    // source channels / 32
@@ -327,8 +328,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
                         const uint32_t sa = base + stage * STAGE_BYTES;
                         for (int t = 0; t < ntap; ++t) {
                             const uint32_t woff = (uint32_t)p.g_win[gi][t] * 128u;
-                            const uint64_t a0 = make_kmajor_desc(sa + woff, (uint32_t)p.a_sbo);
-                            const uint64_t a1 = make_kmajor_desc(sa + (uint32_t)p.a_slot + woff, (uint32_t)p.a_sbo);
+                            const uint64_t a0 = make_kmajor_desc(sa + woff, (uint32_t)p.a_sbo, p.use_bo);
+                            const uint64_t a1 = make_kmajor_desc(sa + (uint32_t)p.a_slot + woff, (uint32_t)p.a_sbo, p.use_bo);
                             const uint64_t bd = make_kmajor_desc(sa + b_off + (uint32_t)t * b_bytes);
 #pragma unroll
                             for (int k = 0; k < BLOCK_K / 8; ++k) {
@@ -717,8 +718,12 @@ void fill_groups(TcArgs& a, int k, const int* dy, const int* dx, bool row_window
             a.g_dy[kh] = (signed char)dy[kh * k]; a.g_dx[kh] = (signed char)dmin; a.g_nt[kh] = (unsigned char)k;
             for (int kw = 0; kw < k; ++kw) { a.g_win[kh][kw] = (unsigned char)(dx[kh * k + kw] - dmin); a.g_w[kh][kw] = (unsigned char)(kh * k + kw); }
         }
-        a.a_rows = (a.TW + k - 1) * a.TH * a.TN; a.a_slot = (a.a_rows * 128 + 1023) / 1024 * 1024; a.a_sbo = (a.TW + k - 1) * 128; a.b_tiles = k;
+        int boxw = a.TW + k - 1;
+        if (const char* ov = getenv("SSDB_KW3_BOXW")) { int v = atoi(ov); if (v >= boxw && v <= 32) boxw = v; }
+        a.a_rows = boxw * a.TH * a.TN; a.a_slot = (a.a_rows * 128 + 1023) / 1024 * 1024; a.a_sbo = boxw * 128; a.b_tiles = k;
     }
+    a.use_bo = 1;
+    if (const char* ov = getenv("SSDB_KW3_BO")) a.use_bo = atoi(ov) ? 1 : 0;
     a.stage_bytes = a.mtu * a.a_slot + a.b_tiles * a.block_n * 128;
     a.stage_bytes = (a.stage_bytes + 1023) / 1024 * 1024;
     a.stages = RING_BYTES / a.stage_bytes; if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
@@ -812,7 +817,7 @@ int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_
     a.dst = y; a.bias = ep.bias; a.mask = nullptr; a.relu = ep.relu; a.beta = 0; a.round_out = ep.round_tf32;
     a.scatter = ep.scatter; a.V = ep.V; a.n_valid = ep.n_valid; a.anchor_base = ep.anchor_base; a.A = ep.A;
     CUtensorMap ms, mw;
-    int rc = encode_act_map(&ms, x, g.B, g.H, g.W, g.Cin, rw ? t.TW + g.k - 1 : t.TW, t.TH, t.TN, CU_TENSOR_MAP_SWIZZLE_128B, g.stride); if (rc) return rc;
+    int rc = encode_act_map(&ms, x, g.B, g.H, g.W, g.Cin, rw ? a.a_sbo / 128 : t.TW, t.TH, t.TN, CU_TENSOR_MAP_SWIZZLE_128B, g.stride); if (rc) return rc;
     rc = encode_w_map(&mw, w_t, (long long)g.k * g.k * cout_pad, g.Cin, a.block_n); if (rc) return rc;
     return launch_tc(ms, mw, a, st);
 }
@@ -860,13 +865,13 @@ int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, const
                 }
                 SSDB_REQUIRE(ntap > 0, "tcgen05 dgrad: a destination parity class without any filter tap");
                 a.ngroups = ntap;
-                a.a_rows = a.TW * a.TH * a.TN; a.a_slot = A_BYTES; a.a_sbo = 1024; a.b_tiles = 1;
+                a.a_rows = a.TW * a.TH * a.TN; a.a_slot = A_BYTES; a.a_sbo = 1024; a.b_tiles = 1; a.use_bo = 1;
                 a.stage_bytes = a.mtu * a.a_slot + a.block_n * 128; a.stage_bytes = (a.stage_bytes + 1023) / 1024 * 1024;
                 a.stages = RING_BYTES / a.stage_bytes; if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
             }
             a.dst = dx; a.bias = nullptr; a.mask = mask_x; a.relu = 0; a.beta = beta; a.round_out = round_out;
             CUtensorMap ms, mw;
-            int rc = encode_act_map(&ms, dz, g.B, g.Ho, g.Wo, g.Cout, rw ? t.TW + g.k - 1 : t.TW, t.TH, t.TN); if (rc) return rc;
+            int rc = encode_act_map(&ms, dz, g.B, g.Ho, g.Wo, g.Cout, rw ? a.a_sbo / 128 : t.TW, t.TH, t.TN); if (rc) return rc;
             rc = encode_w_map(&mw, w_hwio, (long long)g.k * g.k * g.Cin, g.Cout, a.block_n); if (rc) return rc;
             rc = launch_tc(ms, mw, a, st); if (rc) return rc;
         }
