@@ -118,7 +118,10 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
 // 8-row groups 1024 B apart (SBO), rows 128 B apart, 16-byte units.
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t sbo_bytes = 1024, int use_base_offset = 1) {
+// Measured on B200 (tools/kw3_probe.py): the 128-byte swizzle is applied to the ABSOLUTE shared-memory address, so a
+// descriptor may start at any 128-byte row of a TMA-written box and use any row-multiple SBO; the base-offset field must
+// stay 0 (setting it to the start's row phase gives garbage).
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t sbo_bytes = 1024, int use_base_offset = 0) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
     d |= (uint64_t)1 << 16;                      // leading byte offset (unused for swizzled K-major)
@@ -722,7 +725,7 @@ void fill_groups(TcArgs& a, int k, const int* dy, const int* dx, bool row_window
         if (const char* ov = getenv("SSDB_KW3_BOXW")) { int v = atoi(ov); if (v >= boxw && v <= 32) boxw = v; }
         a.a_rows = boxw * a.TH * a.TN; a.a_slot = (a.a_rows * 128 + 1023) / 1024 * 1024; a.a_sbo = boxw * 128; a.b_tiles = k;
     }
-    a.use_bo = 1;
+    a.use_bo = 0;
     if (const char* ov = getenv("SSDB_KW3_BO")) a.use_bo = atoi(ov) ? 1 : 0;
     a.stage_bytes = a.mtu * a.a_slot + a.b_tiles * a.block_n * 128;
     a.stage_bytes = (a.stage_bytes + 1023) / 1024 * 1024;
@@ -865,7 +868,7 @@ int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, const
                 }
                 SSDB_REQUIRE(ntap > 0, "tcgen05 dgrad: a destination parity class without any filter tap");
                 a.ngroups = ntap;
-                a.a_rows = a.TW * a.TH * a.TN; a.a_slot = A_BYTES; a.a_sbo = 1024; a.b_tiles = 1; a.use_bo = 1;
+                a.a_rows = a.TW * a.TH * a.TN; a.a_slot = A_BYTES; a.a_sbo = 1024; a.b_tiles = 1; a.use_bo = 0;
                 a.stage_bytes = a.mtu * a.a_slot + a.block_n * 128; a.stage_bytes = (a.stage_bytes + 1023) / 1024 * 1024;
                 a.stages = RING_BYTES / a.stage_bytes; if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
             }
