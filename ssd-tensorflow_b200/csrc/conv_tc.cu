@@ -46,7 +46,8 @@ constexpr int B_BYTES = MAX_N * BLOCK_K * 4;     // 32 KB
 // wgrad kernel for N >= 128 (long units), not in fprop / dgrad, whose mid layers already run at ~88% of the tf32 peak.
 constexpr int RING_BYTES = 204 * 1024;           // 4 x 48 KB, 3 x 64 KB, or 3 x 68 KB (row-window mode, N = 128)
 constexpr int ACC_STRIDE = 256;                  // TMEM columns per accumulator buffer
-constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_STAGE_BYTES = 4 * 32 * 128;         // per-warp 32 x 32 fp32 transpose buffers of the epilogue
+constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 __host__ __device__ constexpr int stage_bytes_for(int mtu) { return mtu * A_BYTES + B_BYTES; }
 __host__ __device__ constexpr int stages_for(int mtu) { return mtu == 1 ? 4 : 3; }
 constexpr int NUM_THREADS = 192;
@@ -168,8 +169,13 @@ struct TcArgs {
     int scatter, V, n_valid, anchor_base, A;
 };
 
-// epilogue of one 128-row tile: TMEM -> registers -> bias / ReLU / tf32 rounding (fprop) or beta / mask (dgrad) -> global
-__device__ __forceinline__ void epilogue_tile(const TcArgs& p, int mt, int nt, uint32_t t_row, int row, int lane) {
+// epilogue of one 128-row tile: TMEM -> registers -> (per-warp shared-memory transpose) -> global.
+// A thread owns one TMEM lane = one destination pixel; writing its 32 channels directly would make every store
+// instruction touch 32 different cache lines in 16-byte pieces (measured: 32 sectors per request, partial-sector writes,
+// the bottleneck of the short-K layers).  Each warp therefore stages its 32 pixel x 32 channel chunk in 4 KB of shared
+// memory (16-byte slots XOR-swizzled by row) and writes it back with 8 lanes per pixel: every instruction moves four
+// complete 128-byte rows, and the bias / ReLU / tf32 rounding (fprop) or beta / ReLU-mask (dgrad) reads are coalesced too.
+__device__ __forceinline__ void epilogue_tile(const TcArgs& p, int mt, int nt, uint32_t t_row, int row, int lane, float4* stage) {
     const int rows_valid = p.TW * p.TH * p.TN;
     const int tx = mt % p.tiles_x; const int r1 = mt / p.tiles_x;
     const int ty = r1 % p.tiles_y; const int tn = r1 / p.tiles_y;
@@ -178,17 +184,15 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& p, int mt, int nt, u
     const int xi = tx * p.TW + lx, yi = ty * p.TH + ly, n = tn * p.TN + ln;       // tile-grid coordinates
     const int x = xi * p.dscale + p.dpx, y = yi * p.dscale + p.dpy;              // destination pixel
     const bool ok = row < rows_valid && x < p.Wd && y < p.Hd && n < p.Bn;
-    const long long pix = ((long long)n * p.Hd + y) * p.Wd + x;
+    const long long pix = ok ? ((long long)n * p.Hd + y) * p.Wd + x : -1;
     for (int c0 = 0; c0 < p.block_n; c0 += 32) {
         uint32_t r[32];
         __syncwarp();
         tc_ld32(t_row + (uint32_t)c0, r);
         tc_wait_ld();
         const int ch0 = nt * p.block_n + c0;
-        if (!ok) {
-            // rows outside the destination: nothing to store
-        } else if (p.mode == 0) {
-            if (p.scatter) {
+        if (p.mode == 0 && p.scatter) {
+            if (ok) {
                 const int hw = p.Hd * p.Wd;
                 const int pimg = y * p.Wd + x;
 #pragma unroll
@@ -200,42 +204,43 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& p, int mt, int nt, u
                         p.dst[((long long)n * p.A + p.anchor_base + (long long)bt * hw + pimg) * p.V + v] = val;
                     }
                 }
+            }
+            continue;
+        }
+        // stage: row = lane, eight 16-byte slots, slot index XOR (lane & 7)
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+            stage[lane * 8 + (j4 ^ (lane & 7))] = make_float4(__uint_as_float(r[j4 * 4]), __uint_as_float(r[j4 * 4 + 1]),
+                                                              __uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3]));
+        __syncwarp();
+        const int c4 = lane & 7, sub = lane >> 3;
+        const int ch = ch0 + c4 * 4;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.mode == 0 && p.bias && ch < p.cd_valid) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
+        long long prs[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) prs[it] = __shfl_sync(0xffffffffu, pix, it * 4 + sub);   // all lanes, before any divergence
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + sub;
+            const long long pr = prs[it];
+            float4 v = stage[rr * 8 + (c4 ^ (rr & 7))];
+            if (pr < 0 || ch >= p.cd_valid) continue;
+            float* d = p.dst + pr * p.Cd + ch;
+            if (p.mode == 0) {
+                v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+                if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
             } else {
-                float* d = p.dst + pix * p.Cd + ch0;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    if (ch0 + j < p.cd_valid) {
-                        float v[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            v[q] = __uint_as_float(r[j + q]) + (p.bias ? __ldg(p.bias + ch0 + j + q) : 0.f);
-                            if (p.relu) v[q] = fmaxf(v[q], 0.f);
-                            if (p.round_out) v[q] = tf32_rn(v[q]);
-                        }
-                        *reinterpret_cast<float4*>(d + j) = make_float4(v[0], v[1], v[2], v[3]);
-                    }
+                if (p.beta) { float4 o = *reinterpret_cast<const float4*>(d); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                if (p.mask) {
+                    float4 m4 = __ldg(reinterpret_cast<const float4*>(p.mask + pr * p.Cd + ch));
+                    v.x = m4.x > 0.f ? v.x : 0.f; v.y = m4.y > 0.f ? v.y : 0.f; v.z = m4.z > 0.f ? v.z : 0.f; v.w = m4.w > 0.f ? v.w : 0.f;
                 }
             }
-        } else {
-            float* d = p.dst + pix * p.Cd + ch0;
-            const float* mk = p.mask ? p.mask + pix * p.Cd + ch0 : nullptr;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                if (ch0 + j < p.cd_valid) {
-                    float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])};
-                    if (p.beta) { float4 o = *reinterpret_cast<const float4*>(d + j); v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w; }
-                    if (mk) {
-                        float4 m4 = *reinterpret_cast<const float4*>(mk + j);
-                        v[0] = m4.x > 0.f ? v[0] : 0.f; v[1] = m4.y > 0.f ? v[1] : 0.f;
-                        v[2] = m4.z > 0.f ? v[2] : 0.f; v[3] = m4.w > 0.f ? v[3] : 0.f;
-                    }
-                    if (p.round_out) { v[0] = tf32_rn(v[0]); v[1] = tf32_rn(v[1]); v[2] = tf32_rn(v[2]); v[3] = tf32_rn(v[3]); }
-                    *reinterpret_cast<float4*>(d + j) = make_float4(v[0], v[1], v[2], v[3]);
-                }
-            }
+            if (p.round_out) { v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w); }
+            *reinterpret_cast<float4*>(d) = v;
         }
     }
-    (void)lane;
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -354,6 +359,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
         // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
+        float4* stage = reinterpret_cast<float4*>(smem_raw + (bars + 256 - raw)) + quarter * 256;
         int acc = 0; uint32_t acc_phase = 0;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
             const int mp = u / p.n_tiles, nt = u - mp * p.n_tiles;
@@ -361,8 +367,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t)(acc * ACC_STRIDE) + ((uint32_t)(quarter * 32) << 16);
-            epilogue_tile(p, p.mtu * mp, nt, t_row, row, lane);
-            if (two) epilogue_tile(p, 2 * mp + 1, nt, t_row + (uint32_t)noff, row, lane);
+            epilogue_tile(p, p.mtu * mp, nt, t_row, row, lane, stage);
+            if (two) epilogue_tile(p, 2 * mp + 1, nt, t_row + (uint32_t)noff, row, lane, stage);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
