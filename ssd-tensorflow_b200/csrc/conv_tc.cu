@@ -220,25 +220,38 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& p, int mt, int nt, u
         long long prs[8];
 #pragma unroll
         for (int it = 0; it < 8; ++it) prs[it] = __shfl_sync(0xffffffffu, pix, it * 4 + sub);   // all lanes, before any divergence
+        const bool chok = ch < p.cd_valid;
+        if (p.mode == 0) {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + sub;
-            const long long pr = prs[it];
-            float4 v = stage[rr * 8 + (c4 ^ (rr & 7))];
-            if (pr < 0 || ch >= p.cd_valid) continue;
-            float* d = p.dst + pr * p.Cd + ch;
-            if (p.mode == 0) {
+            for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + sub;
+                float4 v = stage[rr * 8 + (c4 ^ (rr & 7))];
+                if (prs[it] < 0 || !chok) continue;
                 v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
                 if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            } else {
-                if (p.beta) { float4 o = *reinterpret_cast<const float4*>(d); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-                if (p.mask) {
-                    float4 m4 = __ldg(reinterpret_cast<const float4*>(p.mask + pr * p.Cd + ch));
-                    v.x = m4.x > 0.f ? v.x : 0.f; v.y = m4.y > 0.f ? v.y : 0.f; v.z = m4.z > 0.f ? v.z : 0.f; v.w = m4.w > 0.f ? v.w : 0.f;
-                }
+                if (p.round_out) { v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w); }
+                *reinterpret_cast<float4*>(p.dst + prs[it] * p.Cd + ch) = v;
             }
-            if (p.round_out) { v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w); }
-            *reinterpret_cast<float4*>(d) = v;
+        } else {
+            // dgrad: issue every mask / old-value load of the chunk first (8 independent cache lines per lane in flight),
+            // then combine -- a load -> use chain per row would expose the memory latency eight times
+            float4 m4[8], o4[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const bool okr = prs[it] >= 0 && chok;
+                m4[it] = (p.mask && okr) ? __ldg(reinterpret_cast<const float4*>(p.mask + prs[it] * p.Cd + ch)) : make_float4(1.f, 1.f, 1.f, 1.f);
+                o4[it] = (p.beta && okr) ? *reinterpret_cast<const float4*>(p.dst + prs[it] * p.Cd + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + sub;
+                float4 v = stage[rr * 8 + (c4 ^ (rr & 7))];
+                if (prs[it] < 0 || !chok) continue;
+                v.x += o4[it].x; v.y += o4[it].y; v.z += o4[it].z; v.w += o4[it].w;
+                v.x = m4[it].x > 0.f ? v.x : 0.f; v.y = m4[it].y > 0.f ? v.y : 0.f; v.z = m4[it].z > 0.f ? v.z : 0.f; v.w = m4[it].w > 0.f ? v.w : 0.f;
+                if (p.round_out) { v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w); }
+                *reinterpret_cast<float4*>(p.dst + prs[it] * p.Cd + ch) = v;
+            }
         }
     }
 }

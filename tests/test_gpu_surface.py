@@ -70,7 +70,7 @@ def test_session_run_train_eval_infer():
             sess.run(net.result, feed_dict={net.image_input: np.zeros((1, 300, 300, 3), np.float32)})
         net.build_from_vgg(None, 20)
         step = GlobalStep(0)
-        net.build_optimizer(learning_rate=piecewise_constant(step, [2, 4], [0.00075, 0.0001, 0.00001]), weight_decay=0.0005,
+        net.build_optimizer(learning_rate=piecewise_constant(step, [2, 4], [1e-5, 1e-6, 1e-7]), weight_decay=0.0005,
                             momentum=0.9, global_step=step)
         x = synth.images(0, 2, 300)
         gts = [synth.gt_boxes(i) for i in range(2)]
