@@ -119,3 +119,16 @@ def test_tcgen05_stride2_matches_simt(case):
     d_s = run_dgrad(ssdb.CONV_SIMT, dz, w, None, x.shape, k, stride, dil, pad, beta=1, dx0=old)
     d_t = run_dgrad(ssdb.CONV_TC, dz, w, None, x.shape, k, stride, dil, pad, beta=1, dx0=old)
     assert rel_err(d_t, d_s) < TF32_TOL, ('dgrad s2 beta', case, rel_err(d_t, d_s))
+
+
+@pytest.mark.parametrize('case', [(2, 64, 64, 64), (3, 40, 128, 128), (2, 38, 512, 128), (4, 19, 64, 96), (2, 150, 64, 128)])
+def test_tcgen05_row_window_wgrad_matches_simt(case):
+    """3x3 SAME layers with <= 128 output channels take the row-window wgrad kernel (one x box per filter row)."""
+    B, H, Cin, Cout = case
+    x, w, b, pad, Ho = conv_case(B, H, Cin, Cout, 3, 1, 1, 'SAME', seed=H + Cout)
+    rng = np.random.default_rng(9)
+    dz = rng.standard_normal((B, Ho, Ho, Cout), dtype=np.float32)
+    w_s, b_s = run_wgrad(ssdb.CONV_SIMT, x, dz, 3, 1, 1, pad)
+    w_t, b_t = run_wgrad(ssdb.CONV_TC, x, dz, 3, 1, 1, pad)
+    assert rel_err(w_t, w_s) < TF32_TOL, ('wgrad rw', case, rel_err(w_t, w_s))
+    assert rel_err(b_t, b_s) < TF32_TOL, ('bias rw', case, rel_err(b_t, b_s))
