@@ -493,8 +493,10 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const int sp = u % p.splits; const int r1 = u / p.splits;
-                const int nt = r1 % p.n_tiles; const int mt = r1 / p.n_tiles;
+                // units that share a pixel range are neighbours (m tile fastest): the CTAs running at the same time stream
+                // the same x / dz region, which is then read from HBM once and served from L2 to the others
+                const int mt = u % p.m_tiles; const int r1 = u / p.m_tiles;
+                const int nt = r1 % p.n_tiles; const int sp = r1 / p.n_tiles;
                 const int q0 = sp * p.tiles_per_split;
                 const int q1 = min(pix_tiles, q0 + p.tiles_per_split);
                 int na = p.slots - mt * spu; na = na > spu ? spu : na;      // valid A blocks of this unit
@@ -527,7 +529,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const int sp = u % p.splits; const int mt = (u / p.splits) / p.n_tiles;
+                const int mt = u % p.m_tiles; const int sp = (u / p.m_tiles) / p.n_tiles;
                 const int q0 = sp * p.tiles_per_split;
                 const int q1 = min(pix_tiles, q0 + p.tiles_per_split);
                 const bool two = p.mtu == 2 && p.slots - mt * 8 > 4;     // the second 128-row tile has at least one valid slot
@@ -558,8 +560,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         int acc = 0; uint32_t acc_phase = 0;
         const long long wsize = (long long)p.taps * p.Cin * p.Cout;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            const int sp = u % p.splits; const int r1 = u / p.splits;
-            const int nt = r1 % p.n_tiles; const int mt = r1 / p.n_tiles;
+            const int mt = u % p.m_tiles; const int r1 = u / p.m_tiles;
+            const int nt = r1 % p.n_tiles; const int sp = r1 / p.n_tiles;
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
             for (int half = 0; half < 2; ++half) {
@@ -665,8 +667,10 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const int sp = u % p.splits; const int r1 = u / p.splits;
-                const int nt = r1 % p.n_tiles; const int ut = r1 / p.n_tiles;
+                // unit type fastest: the filter rows / channel groups / bias unit of ONE pixel range run side by side, so
+                // x and dz come from HBM once and from L2 for the other unit types
+                const int ut = u % utypes; const int r1 = u / utypes;
+                const int nt = r1 % p.n_tiles; const int sp = r1 / p.n_tiles;
                 const bool is_bias = ut >= 3 * p.cgroups;
                 const int kh = is_bias ? 0 : ut / p.cgroups, cg = is_bias ? 0 : ut - kh * p.cgroups;
                 int ncb = p.cblocks - cg * p.cpu; ncb = ncb > p.cpu ? p.cpu : ncb;
@@ -699,7 +703,7 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                                    ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
             int stage = 0; uint32_t phase = 0; uint32_t acc_phase = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const int sp = u % p.splits; const int ut = (u / p.splits) / p.n_tiles;
+                const int ut = u % utypes; const int sp = (u / utypes) / p.n_tiles;
                 const bool is_bias = ut >= 3 * p.cgroups;
                 const int cg = is_bias ? 0 : ut % p.cgroups;
                 int ncb = is_bias ? 1 : p.cblocks - cg * p.cpu; ncb = ncb > p.cpu ? p.cpu : ncb;
@@ -734,8 +738,8 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         uint32_t acc_phase = 0;
         const long long wsize = 9LL * p.Cin * p.Cout;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            const int sp = u % p.splits; const int r1 = u / p.splits;
-            const int nt = r1 % p.n_tiles; const int ut = r1 / p.n_tiles;
+            const int ut = u % utypes; const int r1 = u / utypes;
+            const int nt = r1 % p.n_tiles; const int sp = r1 / p.n_tiles;
             const bool is_bias = ut >= 3 * p.cgroups;
             const int kh = is_bias ? 0 : ut / p.cgroups, cg = is_bias ? 0 : ut - kh * p.cgroups;
             int ncb = is_bias ? 1 : p.cblocks - cg * p.cpu; ncb = ncb > p.cpu ? p.cpu : ncb;
