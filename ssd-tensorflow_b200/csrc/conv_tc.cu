@@ -299,8 +299,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        {   // the whole warp runs the loop so that addresses / descriptors stay on the uniform datapath; lane 0 issues
-            const bool leader = lane == 0;
+        if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
                 const int mp = u / p.n_tiles, nt = u - mp * p.n_tiles;
@@ -317,12 +316,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
                     for (int cb = 0; cb < p.cblocks; ++cb) {
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
                         const uint32_t fb = full0 + 8 * stage;
-                        if (leader) mbar_expect_tx(fb, (two ? 2u : 1u) * a_bytes + (uint32_t)ntap * b_bytes);
+                        mbar_expect_tx(fb, (two ? 2u : 1u) * a_bytes + (uint32_t)ntap * b_bytes);
                         const uint32_t sa = base + stage * STAGE_BYTES;
-                        if (leader) tma_load_4d(sa, &map_src, fb, cb * BLOCK_K, x0[0] * p.sstride + dx, y0[0] * p.sstride + dy, n0[0]);
-                        if (leader && two) tma_load_4d(sa + p.a_slot, &map_src, fb, cb * BLOCK_K, x0[1] * p.sstride + dx, y0[1] * p.sstride + dy, n0[1]);
+                        tma_load_4d(sa, &map_src, fb, cb * BLOCK_K, x0[0] * p.sstride + dx, y0[0] * p.sstride + dy, n0[0]);
+                        if (two) tma_load_4d(sa + p.a_slot, &map_src, fb, cb * BLOCK_K, x0[1] * p.sstride + dx, y0[1] * p.sstride + dy, n0[1]);
                         for (int t = 0; t < ntap; ++t)
-                            if (leader) tma_load_2d(sa + b_off + (uint32_t)t * b_bytes, &map_w, fb, cb * BLOCK_K, (int)p.g_w[gi][t] * p.rows_per_tap + nt * p.block_n);
+                            tma_load_2d(sa + b_off + (uint32_t)t * b_bytes, &map_w, fb, cb * BLOCK_K, (int)p.g_w[gi][t] * p.rows_per_tap + nt * p.block_n);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -330,8 +329,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        {   // the whole warp runs the loop so that addresses / descriptors stay on the uniform datapath; lane 0 issues
-            const bool leader = lane == 0;
+        if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -357,16 +355,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
 #pragma unroll
                             for (int k = 0; k < BLOCK_K / 8; ++k) {
                                 // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
-                                if (leader) tc_mma_tf32(d0, a0 + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, started);
-                                if (leader && two) tc_mma_tf32(d1, a1 + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, started);
+                                tc_mma_tf32(d0, a0 + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, started);
+                                if (two) tc_mma_tf32(d1, a1 + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, started);
                                 started = 1;
                             }
                         }
-                        if (leader) tc_commit(empty0 + 8 * stage);  // frees the smem slot when these MMAs retire
+                        tc_commit(empty0 + 8 * stage);              // frees the smem slot when these MMAs retire
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
-                if (leader) tc_commit(tfull0 + 8 * acc);        // accumulators complete -> epilogue
+                tc_commit(tfull0 + 8 * acc);                    // accumulators complete -> epilogue
                 if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -492,8 +490,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const uint32_t b_off = (uint32_t)spu * blk_bytes;          // B blocks follow the mtu x 4 A blocks
 
     if (warp == 0) {
-        {   // the whole warp runs the loop so that addresses / descriptors stay on the uniform datapath; lane 0 issues
-            const bool leader = lane == 0;
+        if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
                 // units that share a pixel range are neighbours (m tile fastest): the CTAs running at the same time stream
@@ -510,24 +507,23 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t fb = full0 + 8 * stage;
                     const uint32_t ea = (p.debug & 1) ? 0u : (uint32_t)na * blk_bytes, eb = (p.debug & 2) ? 0u : (uint32_t)nblk_b * blk_bytes;
-                    if (leader) { if (ea + eb) mbar_expect_tx(fb, ea + eb); else mbar_arrive(fb); }
+                    if (ea + eb) mbar_expect_tx(fb, ea + eb); else mbar_arrive(fb);
                     const uint32_t sa = base + stage * STAGE_BYTES;
                     for (int j = 0; j < na && !(p.debug & 1); j += p.load_blocks) {
                         const int slot = mt * spu + j;
-                        if (slot == p.bias_slot) { if (leader) bulk_load_1d(sa + (uint32_t)j * blk_bytes, p.ones, blk_bytes, fb); break; }
+                        if (slot == p.bias_slot) { bulk_load_1d(sa + (uint32_t)j * blk_bytes, p.ones, blk_bytes, fb); break; }
                         const int tap = slot / p.cblocks, cb = slot - tap * p.cblocks;
                         const int kh = tap / p.kdim, kw = tap - kh * p.kdim;
-                        if (leader) tma_load_5d(sa + (uint32_t)j * blk_bytes, &map_x, fb, 0, x0 * p.sstride + p.off0 + kw * p.offstep,
+                        tma_load_5d(sa + (uint32_t)j * blk_bytes, &map_x, fb, 0, x0 * p.sstride + p.off0 + kw * p.offstep,
                                     y0 * p.sstride + p.off0 + kh * p.offstep, n0, cb);
                     }
-                    if (leader && !(p.debug & 2)) tma_load_5d(sa + b_off, &map_dz, fb, 0, x0, y0, n0, nt * nblk_b);
+                    if (!(p.debug & 2)) tma_load_5d(sa + b_off, &map_dz, fb, 0, x0, y0, n0, nt * nblk_b);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        {   // the whole warp runs the loop so that addresses / descriptors stay on the uniform datapath; lane 0 issues
-            const bool leader = lane == 0;
+        if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
@@ -549,13 +545,13 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     const uint64_t bd = make_mnmajor_desc(sa + b_off, blk_bytes);
                     const int ksteps = p.P / 8;
                     for (int k = 0; k < ksteps && !(p.debug & 4); ++k) {     // 8 pixel rows = 1024 bytes = +64 in 16-byte units
-                        if (leader) tc_mma_tf32(d0, a0 + (uint64_t)(k * 64), bd + (uint64_t)(k * 64), idesc, (q > q0 || k > 0) ? 1u : 0u);
-                        if (leader && two) tc_mma_tf32(d1, a1 + (uint64_t)(k * 64), bd + (uint64_t)(k * 64), idesc, (q > q0 || k > 0) ? 1u : 0u);
+                        tc_mma_tf32(d0, a0 + (uint64_t)(k * 64), bd + (uint64_t)(k * 64), idesc, (q > q0 || k > 0) ? 1u : 0u);
+                        if (two) tc_mma_tf32(d1, a1 + (uint64_t)(k * 64), bd + (uint64_t)(k * 64), idesc, (q > q0 || k > 0) ? 1u : 0u);
                     }
-                    if (leader) tc_commit(empty0 + 8 * stage);
+                    tc_commit(empty0 + 8 * stage);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (leader) tc_commit(tfull0 + 8 * acc);
+                tc_commit(tfull0 + 8 * acc);
                 acc_phase ^= 1;
             }
         }
@@ -668,8 +664,7 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     const int noff = (p.block_n + 31) & ~31;
 
     if (warp == 0) {
-        {   // the whole warp runs the loop so that addresses / descriptors stay on the uniform datapath; lane 0 issues
-            const bool leader = lane == 0;
+        if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
                 // unit type fastest: the filter rows / channel groups / bias unit of ONE pixel range run side by side, so
@@ -689,21 +684,21 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                     const uint32_t fb = full0 + 8 * stage;
                     const uint32_t sa = base + stage * p.stage_bytes;
                     if (is_bias) {
-                        if (leader) { mbar_expect_tx(fb, zblk_bytes + (uint32_t)nblk_b * zblk_bytes); bulk_load_1d(sa, p.ones, zblk_bytes, fb); }
+                        mbar_expect_tx(fb, zblk_bytes + (uint32_t)nblk_b * zblk_bytes);
+                        bulk_load_1d(sa, p.ones, zblk_bytes, fb);
                     } else {
-                        if (leader) mbar_expect_tx(fb, (uint32_t)p.cpu * xbox_bytes + (uint32_t)nblk_b * zblk_bytes);
+                        mbar_expect_tx(fb, (uint32_t)p.cpu * xbox_bytes + (uint32_t)nblk_b * zblk_bytes);
                         // the box always spans cpu channel blocks; blocks past Cin are zero-filled by TMA and never read back
-                        if (leader) tma_load_5d(sa, &map_x, fb, 0, x0 - p.pad, y0 + kh - p.pad, n0, cg * p.cpu);
+                        tma_load_5d(sa, &map_x, fb, 0, x0 - p.pad, y0 + kh - p.pad, n0, cg * p.cpu);
                     }
-                    if (leader) tma_load_5d(sa + z_off, &map_dz, fb, 0, x0, y0, n0, nt * nblk_b);
+                    tma_load_5d(sa + z_off, &map_dz, fb, 0, x0, y0, n0, nt * nblk_b);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 (void)ncb;
             }
         }
     } else if (warp == 1) {
-        {   // the whole warp runs the loop so that addresses / descriptors stay on the uniform datapath; lane 0 issues
-            const bool leader = lane == 0;
+        if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
             int stage = 0; uint32_t phase = 0; uint32_t acc_phase = 0;
@@ -720,21 +715,21 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                     mbar_wait(full0 + 8 * stage, phase);
                     tc_fence_after();
                     const uint32_t sa = base + stage * p.stage_bytes;
-                    // descriptors differ only in the start-address field (16-byte units): one 8-pixel line = one K = 8 MMA per M tile
-                    const uint64_t b0 = make_mnmajor_desc(sa + z_off, zblk_bytes);
-                    const uint64_t a0 = is_bias ? make_mnmajor_desc(sa, 0u) : make_mnmajor_desc(sa, 128u);   // windows kw = 0..3 are 128 bytes apart
-                    const uint32_t a_line = is_bias ? 64u : 88u;          // bytes/16 between lines: 8 rows (ones block) or 11 rows (x box)
-                    const uint32_t a_blk = xbox_bytes >> 4;
-                    for (int j = 0; j < p.L; ++j) {
-                        const uint64_t bd = b0 + (uint64_t)(j * 64);
+                    for (int j = 0; j < p.L; ++j) {                       // one 8-pixel line = one K = 8 MMA per M tile
+                        const uint64_t bd = make_mnmajor_desc(sa + z_off + (uint32_t)j * 1024u, zblk_bytes);
                         const uint32_t accum = (q > q0 || j > 0) ? 1u : 0u;
-                        for (int t = 0; t < ncb; ++t)
-                            if (leader) tc_mma_tf32(tmem_base + (uint32_t)(t * noff), a0 + (uint64_t)(t * a_blk + j * a_line), bd, idesc, accum);
+                        if (is_bias) {
+                            tc_mma_tf32(tmem_base, make_mnmajor_desc(sa + (uint32_t)j * 1024u, 0u), bd, idesc, accum);
+                        } else {
+                            for (int t = 0; t < ncb; ++t)                  // windows kw = 0..3 are 128 bytes apart
+                                tc_mma_tf32(tmem_base + (uint32_t)(t * noff),
+                                            make_mnmajor_desc(sa + (uint32_t)t * xbox_bytes + (uint32_t)j * 1408u, 128u), bd, idesc, accum);
+                        }
                     }
-                    if (leader) tc_commit(empty0 + 8 * stage);
+                    tc_commit(empty0 + 8 * stage);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (leader) tc_commit(tfull0);
+                tc_commit(tfull0);
                 acc_phase ^= 1;
             }
         }
