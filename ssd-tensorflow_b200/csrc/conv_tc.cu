@@ -715,16 +715,16 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                     mbar_wait(full0 + 8 * stage, phase);
                     tc_fence_after();
                     const uint32_t sa = base + stage * p.stage_bytes;
-                    for (int j = 0; j < p.L; ++j) {                       // one 8-pixel line = one K = 8 MMA per M tile
-                        const uint64_t bd = make_mnmajor_desc(sa + z_off + (uint32_t)j * 1024u, zblk_bytes);
+                    // descriptors differ only in the start-address field (16-byte units): one 8-pixel line = one K = 8 MMA per M tile
+                    const uint64_t b0 = make_mnmajor_desc(sa + z_off, zblk_bytes);
+                    const uint64_t a0 = is_bias ? make_mnmajor_desc(sa, 0u) : make_mnmajor_desc(sa, 128u);   // windows kw = 0..3 are 128 bytes apart
+                    const uint32_t a_line = is_bias ? 64u : 88u;          // bytes/16 between lines: 8 rows (ones block) or 11 rows (x box)
+                    const uint32_t a_blk = xbox_bytes >> 4;
+                    for (int j = 0; j < p.L; ++j) {
+                        const uint64_t bd = b0 + (uint64_t)(j * 64);
                         const uint32_t accum = (q > q0 || j > 0) ? 1u : 0u;
-                        if (is_bias) {
-                            tc_mma_tf32(tmem_base, make_mnmajor_desc(sa + (uint32_t)j * 1024u, 0u), bd, idesc, accum);
-                        } else {
-                            for (int t = 0; t < ncb; ++t)                  // windows kw = 0..3 are 128 bytes apart
-                                tc_mma_tf32(tmem_base + (uint32_t)(t * noff),
-                                            make_mnmajor_desc(sa + (uint32_t)t * xbox_bytes + (uint32_t)j * 1408u, 128u), bd, idesc, accum);
-                        }
+                        for (int t = 0; t < ncb; ++t)
+                            tc_mma_tf32(tmem_base + (uint32_t)(t * noff), a0 + (uint64_t)(t * a_blk + j * a_line), bd, idesc, accum);
                     }
                     tc_commit(empty0 + 8 * stage);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
