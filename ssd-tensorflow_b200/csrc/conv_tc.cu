@@ -92,6 +92,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// one lane of a converged warp; the compiler knows the branch is taken by a single thread (no per-lane serialisation
+// loop around the uniform-datapath instructions UTMALDG / UTCHMMA that `lane == 0` would get)
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xFFFFFFFF;\n\t@P1 mov.s32 %0, 1;\n\t}" : "+r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -299,7 +306,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             int stage = 0; uint32_t phase = 0;
             for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
                 const int mp = u / p.n_tiles, nt = u - mp * p.n_tiles;
@@ -329,7 +336,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -490,7 +497,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const uint32_t b_off = (uint32_t)spu * blk_bytes;          // B blocks follow the mtu x 4 A blocks
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             int stage = 0; uint32_t phase = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
                 // units that share a pixel range are neighbours (m tile fastest): the CTAs running at the same time stream
@@ -523,7 +530,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
@@ -664,7 +671,7 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     const int noff = (p.block_n + 31) & ~31;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             int stage = 0; uint32_t phase = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
                 // unit type fastest: the filter rows / channel groups / bias unit of ONE pixel range run side by side, so
@@ -698,7 +705,7 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
             int stage = 0; uint32_t phase = 0; uint32_t acc_phase = 0;
