@@ -610,27 +610,26 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     }
 }
 
-// ------------------------------------------------------------------ row-window wgrad kernel (3x3, dilation 1, stride 1, N <= 128)
+// ------------------------------------------------------------------ window wgrad kernel (3x3, dilation 1, stride 1, SAME, N <= 128)
 // The layers with few output channels make the plain wgrad kernel L2-bound: every (tap, channel block) slot reloads a
-// shifted copy of the same x pixels, 48 KB per ~256 tensor cycles.  Here a unit is one filter ROW kh and up to four
-// 32-channel blocks; per pipeline stage it loads, per channel block, ONE x box that is 11 pixels wide for 8 output pixels,
-// and the MMA reads the taps kw = 0..2 as row windows of that box: the A descriptor of a 128-row M tile = 4 windows x 32
-// channels with a leading-dimension offset of ONE ROW (128 bytes) -- overlapping windows, no extra traffic (the 4th window
-// is a dummy whose rows are dropped).  One K = 8 MMA consumes one 8-pixel line; lines are 11 rows apart in the x box and
-// 8 rows apart in the dz box.  x traffic drops 3x, dz is shared by 3 taps x cpu channel blocks.
-// The bias gradient is a separate unit type of the same launch: A = a block of ones (leading offset 0), B = dz.
+// shifted copy of the same x pixels.  Here ONE x box per channel block -- 11 pixels wide and PH + 2 lines tall for an
+// 8 x PH block of output pixels -- serves all nine taps: the MMA reads tap (kh, kw) as the row window that starts kw
+// pixels into line j + kh of the box.  The A descriptor of a 128-row M tile = 4 windows x 32 channels with a
+// leading-dimension offset of ONE ROW (128 bytes): overlapping windows, no extra traffic (the 4th window is a dummy whose
+// rows are dropped).  One K = 8 MMA consumes one 8-pixel line; lines are 11 rows apart in the x box and 8 rows apart in
+// the dz box.  All 3 x cpu accumulators of a unit (+1 for the bias gradient: A = a resident block of ones with leading
+// offset 0) live in TMEM at once; dz is read once per channel group, x once per pixel.
 struct WgRwArgs {
-    int PH, PN, L;                  // lines per stage L = PH*PN (8 pixels each)
-    int ptx, pty, ptn;              // pixel tiling of the dz map (x in steps of 8)
-    int cblocks, cpu, cgroups;      // Cin/32, channel blocks per unit, ceil(cblocks/cpu)
-    int n_tiles, block_n;
+    int PH;                         // output lines per stage (8 pixels each); the x box has PH + 2 lines
+    int ptx, pty, ptn;              // pixel tiling of the dz map (x in steps of 8, one image per box)
+    int cblocks, cpu, cgroups;      // Cin/32, channel blocks per unit, cblocks/cpu
+    int block_n;
     int Cin, Cout, pad;
     int splits, tiles_per_split;
-    int bias_units;                 // 1 when db is wanted
+    int want_bias;
     int stage_bytes, stages;
     long long psize;
     float* partial;
-    const float* ones;
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -642,6 +641,7 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
     const uint32_t tmem_slot = tempty0 + 16;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+    const uint32_t ones_addr = bars + 1024u;                                  // 8 KB of 1.0f inside the epilogue staging area
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -650,6 +650,11 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dz) : "memory");
+    }
+    {   // resident block of ones (the bias-gradient A operand); made visible to the tensor core's async proxy
+        float* ones = reinterpret_cast<float*>(smem_raw + (ones_addr - raw));
+        for (int i = threadIdx.x; i < 2048; i += NUM_THREADS) ones[i] = 1.0f;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
@@ -660,12 +665,11 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    const int utypes = 3 * p.cgroups + p.bias_units;                 // (kh, channel group) units, then the bias unit
-    const int units = utypes * p.n_tiles * p.splits;
+    const int units = p.cgroups * p.splits;
     const int pix_tiles = p.ptx * p.pty * p.ptn;
     const int nblk_b = p.block_n / 32;
-    const uint32_t xbox_bytes = (uint32_t)(11 * p.L) * 128u;          // one channel block of x: L lines of 11 pixels
-    const uint32_t zblk_bytes = (uint32_t)(8 * p.L) * 128u;           // one channel block of dz: L lines of 8 pixels
+    const uint32_t xbox_bytes = (uint32_t)(11 * (p.PH + 2)) * 128u;   // one channel block of x: PH + 2 lines of 11 pixels
+    const uint32_t zblk_bytes = (uint32_t)(8 * p.PH) * 128u;          // one channel block of dz: PH lines of 8 pixels
     const uint32_t z_off = ((uint32_t)p.cpu * xbox_bytes + 1023u) & ~1023u;   // dz blocks follow the x boxes (1 KB aligned)
     const int STAGES = p.stages;
     const int noff = (p.block_n + 31) & ~31;
@@ -674,34 +678,22 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         if (elect_one_sync()) {
             int stage = 0; uint32_t phase = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                // unit type fastest: the filter rows / channel groups / bias unit of ONE pixel range run side by side, so
-                // x and dz come from HBM once and from L2 for the other unit types
-                const int ut = u % utypes; const int r1 = u / utypes;
-                const int nt = r1 % p.n_tiles; const int sp = r1 / p.n_tiles;
-                const bool is_bias = ut >= 3 * p.cgroups;
-                const int kh = is_bias ? 0 : ut / p.cgroups, cg = is_bias ? 0 : ut - kh * p.cgroups;
-                int ncb = p.cblocks - cg * p.cpu; ncb = ncb > p.cpu ? p.cpu : ncb;
+                // channel group fastest: the groups of ONE pixel range run side by side and share x / dz through L2
+                const int cg = u % p.cgroups, sp = u / p.cgroups;
                 const int q0 = sp * p.tiles_per_split;
                 const int q1 = min(pix_tiles, q0 + p.tiles_per_split);
                 for (int q = q0; q < q1; ++q) {
                     const int qx = q % p.ptx; const int r2 = q / p.ptx;
-                    const int qy = r2 % p.pty; const int qn = r2 / p.pty;
-                    const int x0 = qx * 8, y0 = qy * p.PH, n0 = qn * p.PN;
+                    const int qy = r2 % p.pty; const int n0 = r2 / p.pty;
+                    const int x0 = qx * 8, y0 = qy * p.PH;
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t fb = full0 + 8 * stage;
                     const uint32_t sa = base + stage * p.stage_bytes;
-                    if (is_bias) {
-                        mbar_expect_tx(fb, zblk_bytes + (uint32_t)nblk_b * zblk_bytes);
-                        bulk_load_1d(sa, p.ones, zblk_bytes, fb);
-                    } else {
-                        mbar_expect_tx(fb, (uint32_t)p.cpu * xbox_bytes + (uint32_t)nblk_b * zblk_bytes);
-                        // the box always spans cpu channel blocks; blocks past Cin are zero-filled by TMA and never read back
-                        tma_load_5d(sa, &map_x, fb, 0, x0 - p.pad, y0 + kh - p.pad, n0, cg * p.cpu);
-                    }
-                    tma_load_5d(sa + z_off, &map_dz, fb, 0, x0, y0, n0, nt * nblk_b);
+                    mbar_expect_tx(fb, (uint32_t)p.cpu * xbox_bytes + (uint32_t)nblk_b * zblk_bytes);
+                    tma_load_5d(sa, &map_x, fb, 0, x0 - p.pad, y0 - p.pad, n0, cg * p.cpu);
+                    tma_load_5d(sa + z_off, &map_dz, fb, 0, x0, y0, n0, 0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                (void)ncb;
             }
         }
     } else if (warp == 1) {
@@ -709,11 +701,11 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
             int stage = 0; uint32_t phase = 0; uint32_t acc_phase = 0;
+            const uint64_t ones_desc = make_mnmajor_desc(ones_addr, 0u);
+            const uint32_t a_blk = xbox_bytes >> 4;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const int ut = u % utypes; const int sp = (u / utypes) / p.n_tiles;
-                const bool is_bias = ut >= 3 * p.cgroups;
-                const int cg = is_bias ? 0 : ut % p.cgroups;
-                int ncb = is_bias ? 1 : p.cblocks - cg * p.cpu; ncb = ncb > p.cpu ? p.cpu : ncb;
+                const int cg = u % p.cgroups, sp = u / p.cgroups;
+                const bool do_bias = p.want_bias && cg == 0;
                 const int q0 = sp * p.tiles_per_split;
                 const int q1 = min(pix_tiles, q0 + p.tiles_per_split);
                 mbar_wait(tempty0, acc_phase ^ 1);
@@ -722,16 +714,17 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                     mbar_wait(full0 + 8 * stage, phase);
                     tc_fence_after();
                     const uint32_t sa = base + stage * p.stage_bytes;
-                    // descriptors differ only in the start-address field (16-byte units): one 8-pixel line = one K = 8 MMA per M tile
+                    // descriptors differ only in the start-address field (16-byte units)
                     const uint64_t b0 = make_mnmajor_desc(sa + z_off, zblk_bytes);
-                    const uint64_t a0 = is_bias ? make_mnmajor_desc(sa, 0u) : make_mnmajor_desc(sa, 128u);   // windows kw = 0..3 are 128 bytes apart
-                    const uint32_t a_line = is_bias ? 64u : 88u;          // bytes/16 between lines: 8 rows (ones block) or 11 rows (x box)
-                    const uint32_t a_blk = xbox_bytes >> 4;
-                    for (int j = 0; j < p.L; ++j) {
+                    const uint64_t a0 = make_mnmajor_desc(sa, 128u);             // windows kw = 0..3 are 128 bytes apart
+                    for (int j = 0; j < p.PH; ++j) {                             // one 8-pixel line = one K = 8 MMA per accumulator
                         const uint64_t bd = b0 + (uint64_t)(j * 64);
                         const uint32_t accum = (q > q0 || j > 0) ? 1u : 0u;
-                        for (int t = 0; t < ncb; ++t)
-                            tc_mma_tf32(tmem_base + (uint32_t)(t * noff), a0 + (uint64_t)(t * a_blk + j * a_line), bd, idesc, accum);
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh)
+                            for (int t = 0; t < p.cpu; ++t)                      // x line j + kh, 11 rows (88 x 16 B) per line
+                                tc_mma_tf32(tmem_base + (uint32_t)((kh * p.cpu + t) * noff), a0 + (uint64_t)(t * a_blk + (j + kh) * 88), bd, idesc, accum);
+                        if (do_bias) tc_mma_tf32(tmem_base + (uint32_t)(3 * p.cpu * noff), ones_desc + (uint64_t)(j * 64), bd, idesc, accum);
                     }
                     tc_commit(empty0 + 8 * stage);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -745,31 +738,30 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         uint32_t acc_phase = 0;
         const long long wsize = 9LL * p.Cin * p.Cout;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            const int ut = u % utypes; const int r1 = u / utypes;
-            const int nt = r1 % p.n_tiles; const int sp = r1 / p.n_tiles;
-            const bool is_bias = ut >= 3 * p.cgroups;
-            const int kh = is_bias ? 0 : ut / p.cgroups, cg = is_bias ? 0 : ut - kh * p.cgroups;
-            int ncb = is_bias ? 1 : p.cblocks - cg * p.cpu; ncb = ncb > p.cpu ? p.cpu : ncb;
+            const int cg = u % p.cgroups, sp = u / p.cgroups;
+            const bool do_bias = p.want_bias && cg == 0;
             mbar_wait(tfull0, acc_phase);
             tc_fence_after();
-            for (int t = 0; t < ncb; ++t) {
-                // lane quarter = window kw (3 = dummy); bias unit: all rows equal, lane 0 of quarter 0 writes
+            const int nacc = 3 * p.cpu + (do_bias ? 1 : 0);
+            for (int ai = 0; ai < nacc; ++ai) {
+                const bool is_bias = ai == 3 * p.cpu;
+                const int kh = ai / p.cpu, t = ai - kh * p.cpu;
+                // lane quarter = window kw (3 = dummy); bias accumulator: all rows equal, lane 0 of quarter 0 writes
                 const bool ok = is_bias ? (quarter == 0 && lane == 0) : (quarter < 3);
                 const int c = (cg * p.cpu + t) * 32 + lane;
                 float* drow = p.partial + (long long)sp * p.psize +
                               (is_bias ? wsize : ((long long)(kh * 3 + quarter) * p.Cin + c) * p.Cout);
-                const uint32_t t_row = tmem_base + (uint32_t)(t * noff) + ((uint32_t)(quarter * 32) << 16);
+                const uint32_t t_row = tmem_base + (uint32_t)(ai * noff) + ((uint32_t)(quarter * 32) << 16);
                 for (int c0 = 0; c0 < p.block_n; c0 += 32) {
                     uint32_t r[32];
                     __syncwarp();
                     tc_ld32(t_row + (uint32_t)c0, r);
                     tc_wait_ld();
-                    const int ch0 = nt * p.block_n + c0;
                     if (ok) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
-                            if (ch0 + j < p.Cout)
-                                *reinterpret_cast<float4*>(drow + ch0 + j) =
+                            if (c0 + j < p.Cout)
+                                *reinterpret_cast<float4*>(drow + c0 + j) =
                                     make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
                     }
                 }
@@ -1146,54 +1138,45 @@ const float* ones_buffer() {
 
 struct WgRwPlan { WgRwArgs a; bool ok; };
 
-// row-window plan: 3x3, dilation 1, stride 1, symmetric padding, few output channels
+// window plan: 3x3, dilation 1, stride 1, SAME, few output channels
 WgRwPlan plan_wgrad_rw(const ConvGeom& g) {
     WgRwPlan pl{}; pl.ok = false;
     if (const char* ov = getenv("SSDB_WG_RW")) { if (atoi(ov) == 0) return pl; }
-    if (g.k != 3 || g.dil != 1 || g.stride != 1 || g.pad_t != g.pad_l || g.Cin % 32 != 0 || g.Cout % 32 != 0 || g.Cout > 128) return pl;
-    if (g.Ho != g.H || g.Wo != g.W) return pl;                // SAME 3x3 only (pad 1); the VALID tails use the plain kernel
+    if (g.k != 3 || g.dil != 1 || g.stride != 1 || g.pad_t != 1 || g.pad_l != 1 || g.Cin % 32 != 0 || g.Cout % 32 != 0 || g.Cout > 128) return pl;
+    if (g.Ho != g.H || g.Wo != g.W) return pl;                // SAME 3x3 only; the VALID tails use the plain kernel
     WgRwArgs& a = pl.a;
-    a.block_n = g.Cout; a.n_tiles = 1;
+    a.block_n = g.Cout;
     a.Cin = g.Cin; a.Cout = g.Cout; a.pad = g.pad_t;
     a.cblocks = g.Cin / 32;
-    a.cpu = a.cblocks < 4 ? a.cblocks : 4;
     const int noff = (a.block_n + 31) & ~31;
-    while (a.cpu * noff > TMEM_COLS) --a.cpu;
-    a.cgroups = (a.cblocks + a.cpu - 1) / a.cpu;
-    if (a.cblocks % a.cpu) return pl;                        // keep every x box fully inside the channel range
-    // lines per stage: as many as fit (<= 8), at least 3 stages in the ring
-    int L = 8;
-    for (;; L >>= 1) {
-        int sb = (a.cpu * 11 * L * 128 + 1023) / 1024 * 1024 + (a.block_n / 32) * 8 * L * 128;
+    a.cpu = a.cblocks < 4 ? a.cblocks : 4;
+    while (a.cpu > 1 && ((3 * a.cpu + 1) * noff > TMEM_COLS || a.cblocks % a.cpu)) --a.cpu;   // 3 x cpu taps-rows + the bias accumulator
+    if ((3 * a.cpu + 1) * noff > TMEM_COLS) return pl;
+    a.cgroups = a.cblocks / a.cpu;
+    // output lines per stage: as many as fit (<= 8) with at least 3 stages in the ring
+    int PH = g.H < 8 ? g.H : 8;
+    for (;; --PH) {
+        int sb = (a.cpu * 11 * (PH + 2) * 128 + 1023) / 1024 * 1024 + (a.block_n / 32) * 8 * PH * 128;
         sb = (sb + 1023) / 1024 * 1024;
-        if (RING_BYTES / sb >= 3 || L == 1) { a.stage_bytes = sb; break; }
+        if (RING_BYTES / sb >= 3 || PH == 1) { a.stage_bytes = sb; break; }
     }
-    if (L < 2) return pl;
-    a.L = L;
+    if (PH < 2) return pl;
+    a.PH = PH;
     a.stages = RING_BYTES / a.stage_bytes; if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
-    // PH x PN = L with the least waste, at most 4 images per box
-    double best = -1.0; a.PH = L; a.PN = 1;
-    for (int pn = 1; pn <= 4 && pn <= L; pn <<= 1) {
-        int ph = L / pn;
-        if (pn > g.B) continue;
-        long long tiles = (long long)((g.W + 7) / 8) * ((g.H + ph - 1) / ph) * ((g.B + pn - 1) / pn);
-        double eff = (double)g.B * g.H * g.W / ((double)tiles * 8 * L);
-        if (eff > best) { best = eff; a.PH = ph; a.PN = pn; }
-    }
-    if (best < 0.5) return pl;
-    a.ptx = (g.W + 7) / 8; a.pty = (g.H + a.PH - 1) / a.PH; a.ptn = (g.B + a.PN - 1) / a.PN;
+    a.ptx = (g.W + 7) / 8; a.pty = (g.H + PH - 1) / PH; a.ptn = g.B;
+    double eff = (double)g.H * g.W / ((double)a.ptx * a.pty * 8 * PH);
+    if (eff < 0.5) return pl;
     a.psize = 9LL * g.Cin * g.Cout + g.Cout;
-    a.bias_units = 1;
+    a.want_bias = 1;
     long long pix_tiles = (long long)a.ptx * a.pty * a.ptn;
-    long long base_units = 3LL * a.cgroups + 1;
-    long long want = (2LL * num_sms() + base_units - 1) / base_units;
+    long long want = (2LL * num_sms() + a.cgroups - 1) / a.cgroups;
     long long max_splits = (pix_tiles + 7) / 8;
     if (want > max_splits) want = max_splits;
     if (want < 1) want = 1;
-    if (want > 256) want = 256;
+    if (want > 512) want = 512;
     a.tiles_per_split = (int)((pix_tiles + want - 1) / want);
     a.splits = (int)((pix_tiles + a.tiles_per_split - 1) / a.tiles_per_split);
-    a.partial = nullptr; a.ones = nullptr;
+    a.partial = nullptr;
     pl.ok = true;
     return pl;
 }
@@ -1278,15 +1261,14 @@ int conv_tc_wgrad(const ConvGeom& g, const float* x, const float* dz, float* dw,
     WgRwPlan rw = plan_wgrad_rw(g);
     if (rw.ok) {
         WgRwArgs a = rw.a;
-        a.partial = partial; a.ones = ones_buffer();
-        SSDB_REQUIRE(a.ones != nullptr, "could not allocate the ones buffer");
-        a.bias_units = db ? 1 : 0;
+        a.partial = partial;
+        a.want_bias = db ? 1 : 0;
         CUtensorMap mx, mz;
-        int rc = encode_rw_map(&mx, x, g.B, g.H, g.W, g.Cin, 11, a.PH, a.PN, a.cpu); if (rc) return rc;
-        rc = encode_rw_map(&mz, dz, g.B, g.Ho, g.Wo, g.Cout, 8, a.PH, a.PN, a.block_n / 32); if (rc) return rc;
+        int rc = encode_rw_map(&mx, x, g.B, g.H, g.W, g.Cin, 11, a.PH + 2, 1, a.cpu); if (rc) return rc;
+        rc = encode_rw_map(&mz, dz, g.B, g.Ho, g.Wo, g.Cout, 8, a.PH, 1, a.block_n / 32); if (rc) return rc;
         static bool attr_rw = false;
         if (!attr_rw) { SSDB_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_rw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_rw = true; }
-        long long units = (3LL * a.cgroups + a.bias_units) * a.n_tiles * a.splits;
+        long long units = (long long)a.cgroups * a.splits;
         int grid = (int)(units < num_sms() ? units : num_sms());
         conv_tc_wgrad_rw_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mx, mz, a);
         SSDB_LAUNCH_CHECK();
