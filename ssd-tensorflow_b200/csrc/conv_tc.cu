@@ -896,11 +896,13 @@ int launch_tc(const CUtensorMap& ms, const CUtensorMap& mw, const TcArgs& a, cud
     return SSDB_OK;
 }
 
-// measured on B200 (tools/ab_probe.sh): two tiles per unit win for N <= 128 (short units are TMA-issue bound; the shared
-// B tile halves the barrier traffic per FLOP and TMEM still double-buffers), one tile per unit wins for N = 256
+// measured on B200 (tools/ab_probe.sh, after the elect.sync fix): two M tiles per unit sharing one B tile win for every
+// N (17-20% on the N = 256 layers: 1.5x less L2 -> smem traffic per FLOP; with N = 256 both accumulators fill TMEM and the
+// epilogue is exposed, but it is ~2-4% of a unit)
 int tc_mtu(int block_n) {
     if (const char* ov = getenv("SSDB_TC_MTU")) { int v = atoi(ov); if (v == 1 || v == 2) return v; }
-    return block_n <= 128 ? 2 : 1;
+    (void)block_n;
+    return 2;
 }
 
 // fill the tap-group table: plain (one tap per group) or row-window (3 taps of a filter row per group, TW must be 8)
