@@ -111,6 +111,11 @@ int maxpool_fwd(const float* x, int B, int H, int W, int C, int k, int stride, i
 // dx = (beta*dx + routed dy) * (x > 0)
 int maxpool_bwd(const float* x, const float* dy, int B, int H, int W, int C, int k, int stride,
                 int pad_t, int pad_l, int Ho, int Wo, int beta, int relu_mask, int round_out, float* dx, cudaStream_t st);
+// overlapping pools (3x3 stride 1): forward records the winning window cell (1 byte per element), backward routes by it
+int maxpool_fwd_arg(const float* x, int B, int H, int W, int C, int k, int stride, int pad_t, int pad_l, int Ho, int Wo,
+                    float* y, unsigned char* arg, cudaStream_t st);
+int maxpool_bwd_arg(const float* x, const float* dy, const unsigned char* arg, int B, int H, int W, int C, int k, int stride, int pad_t,
+                    int pad_l, int Ho, int Wo, int beta, int relu_mask, int round_out, float* dx, cudaStream_t st);
 int l2norm_fwd(const float* x, const float* scale, long long pixels, int C, int round_out, float* y, cudaStream_t st);
 int l2norm_bwd(const float* x, const float* scale, const float* dy, long long pixels, int C, int beta,
                int round_out, float* dx, float* dscale, float* partial, cudaStream_t st);

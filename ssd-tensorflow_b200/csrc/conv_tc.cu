@@ -896,13 +896,18 @@ int launch_tc(const CUtensorMap& ms, const CUtensorMap& mw, const TcArgs& a, cud
     return SSDB_OK;
 }
 
-// measured on B200 (tools/ab_probe.sh, after the elect.sync fix): two M tiles per unit sharing one B tile win for every
-// N (17-20% on the N = 256 layers: 1.5x less L2 -> smem traffic per FLOP; with N = 256 both accumulators fill TMEM and the
-// epilogue is exposed, but it is ~2-4% of a unit)
-int tc_mtu(int block_n) {
+// One or two M tiles per unit?  Two tiles share one B tile (1.5x less L2 -> smem traffic per FLOP, measured 15-20% on
+// long-K layers), but halve the number of units (wave quantisation on the small maps) and, when both accumulators fill
+// TMEM (N = 256), expose the epilogue -- heavier in dgrad (mask / old-value reads).  Cost model fitted to B200 timings.
+int tc_mtu(int block_n, long long m_tiles, int n_tiles, int kblocks, bool dgrad) {
     if (const char* ov = getenv("SSDB_TC_MTU")) { int v = atoi(ov); if (v == 1 || v == 2) return v; }
-    (void)block_n;
-    return 2;
+    const int sms = num_sms();
+    const long long w1 = (m_tiles * n_tiles + sms - 1) / sms;
+    const long long w2 = (((m_tiles + 1) / 2) * n_tiles + sms - 1) / sms;
+    const int noff = (block_n + 31) & ~31;
+    const double e = (2 * noff <= ACC_STRIDE) ? 0.0 : (dgrad ? 15.0 : 4.0);
+    const double c2 = 2.0 * (0.85 + e / (double)(kblocks > 0 ? kblocks : 1));
+    return (double)w2 * c2 < (double)w1 ? 2 : 1;
 }
 
 // fill the tap-group table: plain (one tap per group) or row-window (3 taps of a filter row per group, TW must be 8)
@@ -1008,7 +1013,8 @@ int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_
     a.cblocks = g.Cin / BLOCK_K; a.rows_per_tap = cout_pad;
     int tdy[9], tdx[9];
     for (int t = 0; t < g.k * g.k; ++t) { tdy[t] = (t / g.k) * g.dil - g.pad_t; tdx[t] = (t % g.k) * g.dil - g.pad_l; }
-    a.sstride = g.stride; a.dscale = 1; a.dpy = a.dpx = 0; a.mode = 0; a.mtu = tc_mtu(a.block_n);
+    a.sstride = g.stride; a.dscale = 1; a.dpy = a.dpx = 0; a.mode = 0;
+    a.mtu = tc_mtu(a.block_n, (long long)a.tiles_x * a.tiles_y * a.tiles_n, a.n_tiles, g.k * g.k * a.cblocks, false);
     int wth = 0, wtn = 0;
     const bool rw = want_row_window(g, a.block_n, g.B, g.Ho, g.Wo, t.eff, &wth, &wtn);
     if (rw) {
@@ -1042,7 +1048,8 @@ int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, const
             a.block_n = block_n_for(g.Cin); a.n_tiles = (g.Cin + a.block_n - 1) / a.block_n;
             a.Hd = g.H; a.Wd = g.W; a.Bn = g.B; a.Cd = g.Cin; a.cd_valid = g.Cin;
             a.cblocks = g.Cout / BLOCK_K; a.rows_per_tap = g.Cin;
-            a.sstride = 1; a.dscale = s; a.dpy = py; a.dpx = px; a.mode = 1; a.mtu = tc_mtu(a.block_n);
+            a.sstride = 1; a.dscale = s; a.dpy = py; a.dpx = px; a.mode = 1;
+            a.mtu = tc_mtu(a.block_n, (long long)a.tiles_x * a.tiles_y * a.tiles_n, a.n_tiles, g.k * g.k * a.cblocks / (s * s), true);
             SSDB_REQUIRE(g.k <= 3, "tcgen05 path supports 1x1 and 3x3 filters");
             int wth = 0, wtn = 0;
             const bool rw = s == 1 && want_row_window(g, a.block_n, g.B, Hc, Wc, t.eff, &wth, &wtn);

@@ -30,6 +30,72 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ x, int B, int H, in
     reinterpret_cast<float4*>(y)[i] = m;
 }
 
+// forward of a pool that also records, per output element, which window cell won (first maximum, row-major): 4 bytes per
+// float4 group.  The backward of overlapping windows (mod_pool5, 3x3 stride 1) then tests 9 bytes per input element
+// instead of re-scanning 81 neighbours.
+__global__ void maxpool_fwd_arg_kernel(const float* __restrict__ x, int B, int H, int W, int C4, int k, int s,
+                                       int pt, int pl, int Ho, int Wo, float* __restrict__ y, uchar4* __restrict__ arg) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)B * Ho * Wo * C4;
+    if (i >= total) return;
+    int c = (int)(i % C4); long long r = i / C4;
+    int ox = (int)(r % Wo); r /= Wo;
+    int oy = (int)(r % Ho); int b = (int)(r / Ho);
+    float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    unsigned char a[4] = {255, 255, 255, 255};
+    for (int dy = 0; dy < k; ++dy) {
+        int iy = oy * s + dy - pt;
+        if (iy < 0 || iy >= H) continue;
+        for (int dx = 0; dx < k; ++dx) {
+            int ix = ox * s + dx - pl;
+            if (ix < 0 || ix >= W) continue;
+            float4 v = reinterpret_cast<const float4*>(x)[(((long long)b * H + iy) * W + ix) * C4 + c];
+            float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (vv[q] > m[q] || a[q] == 255) { m[q] = vv[q]; a[q] = (unsigned char)(dy * k + dx); }
+        }
+    }
+    reinterpret_cast<float4*>(y)[i] = make_float4(m[0], m[1], m[2], m[3]);
+    arg[i] = make_uchar4(a[0], a[1], a[2], a[3]);
+}
+
+__global__ void maxpool_bwd_arg_kernel(const float* __restrict__ x, const float* __restrict__ dy, const uchar4* __restrict__ arg, int B,
+                                       int H, int W, int C4, int k, int s, int pt, int pl, int Ho, int Wo, int beta, int relu_mask,
+                                       int round_out, float* __restrict__ dx) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)B * H * W * C4;
+    if (i >= total) return;
+    int c = (int)(i % C4); long long r = i / C4;
+    int ix = (int)(r % W); r /= W;
+    int iy = (int)(r % H); int b = (int)(r / H);
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int wy = 0; wy < k; ++wy) {
+        int ny = iy + pt - wy;                       // window row oy with oy*s + wy - pt == iy
+        if (ny < 0 || ny % s) continue;
+        int oy = ny / s; if (oy >= Ho) continue;
+        for (int wx = 0; wx < k; ++wx) {
+            int nx = ix + pl - wx;
+            if (nx < 0 || nx % s) continue;
+            int ox = nx / s; if (ox >= Wo) continue;
+            long long o = (((long long)b * Ho + oy) * Wo + ox) * C4 + c;
+            uchar4 a = arg[o];
+            float4 gy = reinterpret_cast<const float4*>(dy)[o];
+            unsigned char cell = (unsigned char)(wy * k + wx);
+            if (a.x == cell) g[0] += gy.x;
+            if (a.y == cell) g[1] += gy.y;
+            if (a.z == cell) g[2] += gy.z;
+            if (a.w == cell) g[3] += gy.w;
+        }
+    }
+    if (beta) { float4 o = reinterpret_cast<const float4*>(dx)[i]; g[0] += o.x; g[1] += o.y; g[2] += o.z; g[3] += o.w; }
+    if (relu_mask) {
+        float4 me = reinterpret_cast<const float4*>(x)[i];
+        g[0] = me.x > 0.f ? g[0] : 0.f; g[1] = me.y > 0.f ? g[1] : 0.f; g[2] = me.z > 0.f ? g[2] : 0.f; g[3] = me.w > 0.f ? g[3] : 0.f;
+    }
+    if (round_out) { g[0] = tf32_rn(g[0]); g[1] = tf32_rn(g[1]); g[2] = tf32_rn(g[2]); g[3] = tf32_rn(g[3]); }
+    reinterpret_cast<float4*>(dx)[i] = make_float4(g[0], g[1], g[2], g[3]);
+}
+
 // one thread per input element group (float4 of channels): sum dy over the windows whose
 // first maximum (row-major scan) is this element
 __global__ void maxpool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, int B, int H, int W,
@@ -336,6 +402,26 @@ int maxpool_fwd(const float* x, int B, int H, int W, int C, int k, int stride, i
     SSDB_REQUIRE(C % 4 == 0, "channels must be a multiple of 4");
     long long total = (long long)B * Ho * Wo * (C / 4);
     maxpool_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, B, H, W, C / 4, k, stride, pad_t, pad_l, Ho, Wo, y);
+    SSDB_LAUNCH_CHECK();
+    return SSDB_OK;
+}
+
+int maxpool_fwd_arg(const float* x, int B, int H, int W, int C, int k, int stride, int pad_t, int pad_l, int Ho, int Wo,
+                    float* y, unsigned char* arg, cudaStream_t st) {
+    SSDB_REQUIRE(C % 4 == 0 && k * k < 255, "unsupported pool");
+    long long total = (long long)B * Ho * Wo * (C / 4);
+    maxpool_fwd_arg_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, B, H, W, C / 4, k, stride, pad_t, pad_l, Ho, Wo, y,
+                                                                               reinterpret_cast<uchar4*>(arg));
+    SSDB_LAUNCH_CHECK();
+    return SSDB_OK;
+}
+
+int maxpool_bwd_arg(const float* x, const float* dy, const unsigned char* arg, int B, int H, int W, int C, int k, int stride, int pad_t,
+                    int pad_l, int Ho, int Wo, int beta, int relu_mask, int round_out, float* dx, cudaStream_t st) {
+    SSDB_REQUIRE(C % 4 == 0, "channels must be a multiple of 4");
+    long long total = (long long)B * H * W * (C / 4);
+    maxpool_bwd_arg_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, dy, reinterpret_cast<const uchar4*>(arg), B, H, W, C / 4, k,
+                                                                               stride, pad_t, pad_l, Ho, Wo, beta, relu_mask, round_out, dx);
     SSDB_LAUNCH_CHECK();
     return SSDB_OK;
 }

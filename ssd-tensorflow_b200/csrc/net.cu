@@ -92,6 +92,7 @@ struct ssdb_net {
     float *wr = nullptr;               // tf32-rounded copy of the parameters (dgrad B operand)
     // conv1_1 as a 1x1 tensor-core conv over an explicit 3x3x3 patch matrix (Cin = 3 cannot feed the MMA directly)
     float *patches = nullptr, *c1_w32 = nullptr, *c1_wt = nullptr, *c1_dw32 = nullptr;
+    unsigned char* pool5_arg = nullptr;   // winning window cell of mod_pool5 (3x3 stride 1), one byte per output element
     bool round = true;                 // activations / gradients are stored tf32-rounded (off in pure-SIMT mode)
     float *acts = nullptr, *gacts = nullptr;
     float *out = nullptr, *out_grad = nullptr, *result = nullptr, *dz_head = nullptr;
@@ -338,7 +339,10 @@ int run_forward(ssdb_net* n, const float* images, int B, cudaStream_t st) {
                 rc = conv_simt_fprop(g, x, n->params + n->masters[op.w].off, ep, y, st);
         } else if (op.type == OP_POOL) {
             const Buf& bi = n->bufs[op.in]; const Buf& bo = n->bufs[op.out];
-            rc = maxpool_fwd(n->act(op.in, B), B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W, n->act(op.out, B), st);
+            if (op.stride == 1 && n->pool5_arg)
+                rc = maxpool_fwd_arg(n->act(op.in, B), B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W, n->act(op.out, B), n->pool5_arg, st);
+            else
+                rc = maxpool_fwd(n->act(op.in, B), B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W, n->act(op.out, B), st);
         } else {
             const Buf& bi = n->bufs[op.in];
             rc = l2norm_fwd(n->act(op.in, B), n->params + n->masters[op.w].off, (long long)B * bi.H * bi.W, bi.C, n->round ? 1 : 0, n->act(op.out, B), st);
@@ -404,6 +408,10 @@ int run_backward(ssdb_net* n, int B, cudaStream_t st) {
             ProfScope ps(n, st, std::string("bwd:") + op.name);
             SSDB_REQUIRE(written[op.out], "internal: gradient of a pool output was never produced");
             const Buf& bi = n->bufs[op.in]; const Buf& bo = n->bufs[op.out];
+            if (op.stride == 1 && n->pool5_arg)
+                rc = maxpool_bwd_arg(n->act(op.in, B), n->gact(op.out, B), n->pool5_arg, B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W,
+                                     written[op.in] ? 1 : 0, bi.relu_out ? 1 : 0, n->round ? 1 : 0, n->gact(op.in, B), st);
+            else
             rc = maxpool_bwd(n->act(op.in, B), n->gact(op.out, B), B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W,
                              written[op.in] ? 1 : 0, bi.relu_out ? 1 : 0, n->round ? 1 : 0, n->gact(op.in, B), st);
             written[op.in] = 1;
@@ -500,6 +508,8 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
     ALLOC(n->partial, partial, float); ALLOC(n->small_ws, 4096 + 2 * (size_t)max_batch, float);
     ALLOC(n->counter, 1, unsigned int); ALLOC(n->decay_mask, n->n_flat / OPT_BLOCK, unsigned char);
     ALLOC(n->anchors, (size_t)n->A * 4, double);
+    for (const Op& op : n->ops)
+        if (op.type == OP_POOL && op.stride == 1) { const Buf& bo = n->bufs[op.out]; ALLOC(n->pool5_arg, (size_t)max_batch * bo.H * bo.W * bo.C, unsigned char); }
     if (n->round) {
         const Op& c1 = n->ops[0];
         ConvGeom g1 = geom_of(n, c1, max_batch); g1.Cin = 32; g1.k = 1; g1.pad_t = g1.pad_l = 0;
@@ -536,7 +546,7 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
 int ssdb_destroy(ssdb_net* n) {
     if (!n) return SSDB_OK;
     cudaDeviceSynchronize();
-    void* ptrs[] = {n->patches, n->c1_w32, n->c1_wt, n->c1_dw32, n->wr, n->params, n->grads, n->moms, n->wt, n->acts, n->gacts, n->out, n->out_grad, n->result, n->labels_stage,
+    void* ptrs[] = {n->pool5_arg, n->patches, n->c1_w32, n->c1_wt, n->c1_dw32, n->wr, n->params, n->grads, n->moms, n->wt, n->acts, n->gacts, n->out, n->out_grad, n->result, n->labels_stage,
                     n->dz_head, n->images_stage, n->partial, n->small_ws, n->counter, n->decay_mask, n->anchors};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (n->host_small) cudaFreeHost(n->host_small);
