@@ -623,7 +623,7 @@ struct WgRwArgs {
     int PH;                         // output lines per stage (8 pixels each); the x box has PH + 2 lines
     int ptx, pty, ptn;              // pixel tiling of the dz map (x in steps of 8, one image per box)
     int cblocks, cpu, cgroups;      // Cin/32, channel blocks per unit, cblocks/cpu
-    int block_n;
+    int block_n, n_tiles;           // output channels per unit (<= 128) and Cout / block_n
     int Cin, Cout, pad;
     int splits, tiles_per_split;
     int want_bias;
@@ -665,7 +665,8 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    const int units = p.cgroups * p.splits;
+    const int utypes = p.cgroups * p.n_tiles;                     // (channel group, N tile) pairs of one pixel range run side by side
+    const int units = utypes * p.splits;
     const int pix_tiles = p.ptx * p.pty * p.ptn;
     const int nblk_b = p.block_n / 32;
     const uint32_t xbox_bytes = (uint32_t)(11 * (p.PH + 2)) * 128u;   // one channel block of x: PH + 2 lines of 11 pixels
@@ -678,8 +679,9 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         if (elect_one_sync()) {
             int stage = 0; uint32_t phase = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                // channel group fastest: the groups of ONE pixel range run side by side and share x / dz through L2
-                const int cg = u % p.cgroups, sp = u / p.cgroups;
+                // unit type fastest: the units of ONE pixel range run side by side and share x / dz through L2
+                const int ut = u % utypes, sp = u / utypes;
+                const int cg = ut % p.cgroups, nt = ut / p.cgroups;
                 const int q0 = sp * p.tiles_per_split;
                 const int q1 = min(pix_tiles, q0 + p.tiles_per_split);
                 for (int q = q0; q < q1; ++q) {
@@ -691,7 +693,7 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                     const uint32_t sa = base + stage * p.stage_bytes;
                     mbar_expect_tx(fb, (uint32_t)p.cpu * xbox_bytes + (uint32_t)nblk_b * zblk_bytes);
                     tma_load_5d(sa, &map_x, fb, 0, x0 - p.pad, y0 - p.pad, n0, cg * p.cpu);
-                    tma_load_5d(sa + z_off, &map_dz, fb, 0, x0, y0, n0, 0);
+                    tma_load_5d(sa + z_off, &map_dz, fb, 0, x0, y0, n0, nt * nblk_b);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -704,7 +706,8 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             const uint64_t ones_desc = make_mnmajor_desc(ones_addr, 0u);
             const uint32_t a_blk = xbox_bytes >> 4;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const int cg = u % p.cgroups, sp = u / p.cgroups;
+                const int ut = u % utypes, sp = u / utypes;
+                const int cg = ut % p.cgroups;
                 const bool do_bias = p.want_bias && cg == 0;
                 const int q0 = sp * p.tiles_per_split;
                 const int q1 = min(pix_tiles, q0 + p.tiles_per_split);
@@ -738,7 +741,8 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         uint32_t acc_phase = 0;
         const long long wsize = 9LL * p.Cin * p.Cout;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            const int cg = u % p.cgroups, sp = u / p.cgroups;
+            const int ut = u % utypes, sp = u / utypes;
+            const int cg = ut % p.cgroups, nt = ut / p.cgroups;
             const bool do_bias = p.want_bias && cg == 0;
             mbar_wait(tfull0, acc_phase);
             tc_fence_after();
@@ -757,11 +761,12 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                     __syncwarp();
                     tc_ld32(t_row + (uint32_t)c0, r);
                     tc_wait_ld();
+                    const int ch0 = nt * p.block_n + c0;
                     if (ok) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
-                            if (c0 + j < p.Cout)
-                                *reinterpret_cast<float4*>(drow + c0 + j) =
+                            if (ch0 + j < p.Cout)
+                                *reinterpret_cast<float4*>(drow + ch0 + j) =
                                     make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
                     }
                 }
@@ -1151,10 +1156,11 @@ struct WgRwPlan { WgRwArgs a; bool ok; };
 WgRwPlan plan_wgrad_rw(const ConvGeom& g) {
     WgRwPlan pl{}; pl.ok = false;
     if (const char* ov = getenv("SSDB_WG_RW")) { if (atoi(ov) == 0) return pl; }
-    if (g.k != 3 || g.dil != 1 || g.stride != 1 || g.pad_t != 1 || g.pad_l != 1 || g.Cin % 32 != 0 || g.Cout % 32 != 0 || g.Cout > 128) return pl;
+    if (g.k != 3 || g.dil != 1 || g.stride != 1 || g.pad_t != 1 || g.pad_l != 1 || g.Cin % 32 != 0 || g.Cout % 32 != 0) return pl;
+    if (g.Cout > 128 && g.Cout % 128 != 0) return pl;
     if (g.Ho != g.H || g.Wo != g.W) return pl;                // SAME 3x3 only; the VALID tails use the plain kernel
     WgRwArgs& a = pl.a;
-    a.block_n = g.Cout;
+    a.block_n = g.Cout > 128 ? 128 : g.Cout; a.n_tiles = g.Cout / a.block_n;
     a.Cin = g.Cin; a.Cout = g.Cout; a.pad = g.pad_t;
     a.cblocks = g.Cin / 32;
     const int noff = (a.block_n + 31) & ~31;
@@ -1178,7 +1184,8 @@ WgRwPlan plan_wgrad_rw(const ConvGeom& g) {
     a.psize = 9LL * g.Cin * g.Cout + g.Cout;
     a.want_bias = 1;
     long long pix_tiles = (long long)a.ptx * a.pty * a.ptn;
-    long long want = (2LL * num_sms() + a.cgroups - 1) / a.cgroups;
+    long long ut = (long long)a.cgroups * a.n_tiles;
+    long long want = (2LL * num_sms() + ut - 1) / ut;
     long long max_splits = (pix_tiles + 7) / 8;
     if (want > max_splits) want = max_splits;
     if (want < 1) want = 1;
@@ -1277,7 +1284,7 @@ int conv_tc_wgrad(const ConvGeom& g, const float* x, const float* dz, float* dw,
         rc = encode_rw_map(&mz, dz, g.B, g.Ho, g.Wo, g.Cout, 8, a.PH, 1, a.block_n / 32); if (rc) return rc;
         static bool attr_rw = false;
         if (!attr_rw) { SSDB_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_rw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_rw = true; }
-        long long units = (long long)a.cgroups * a.splits;
+        long long units = (long long)a.cgroups * a.n_tiles * a.splits;
         int grid = (int)(units < num_sms() ? units : num_sms());
         conv_tc_wgrad_rw_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mx, mz, a);
         SSDB_LAUNCH_CHECK();

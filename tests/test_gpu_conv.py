@@ -121,7 +121,7 @@ def test_tcgen05_stride2_matches_simt(case):
     assert rel_err(d_t, d_s) < TF32_TOL, ('dgrad s2 beta', case, rel_err(d_t, d_s))
 
 
-@pytest.mark.parametrize('case', [(2, 64, 64, 64), (3, 40, 128, 128), (2, 38, 512, 128), (4, 19, 64, 96), (2, 150, 64, 128)])
+@pytest.mark.parametrize('case', [(2, 64, 64, 64), (3, 40, 128, 128), (2, 38, 512, 128), (4, 19, 64, 96), (2, 150, 64, 128), (2, 38, 256, 512), (4, 19, 512, 1024), (2, 75, 128, 256)])
 def test_tcgen05_row_window_wgrad_matches_simt(case):
     """3x3 SAME layers with <= 128 output channels take the row-window wgrad kernel (one x box per filter row)."""
     B, H, Cin, Cout = case
