@@ -1157,6 +1157,10 @@ WgRwPlan plan_wgrad_rw(const ConvGeom& g) {
     WgRwPlan pl{}; pl.ok = false;
     if (const char* ov = getenv("SSDB_WG_RW")) { if (atoi(ov) == 0) return pl; }
     if (g.k != 3 || g.dil != 1 || g.stride != 1 || g.pad_t != 1 || g.pad_l != 1 || g.Cin % 32 != 0 || g.Cout % 32 != 0) return pl;
+    // Measured on B200: MN-major tf32 MMAs issue at about half the K-major rate (a 128x256x8 MMA takes ~260 cycles), and the
+    // plain wgrad kernel already runs the N = 256 layers at that limit; the window kernel pays 25% dummy-window MMAs for its
+    // lower L2 traffic, which only wins where the plain kernel is traffic-bound: N <= 128 (SSDB_WG_RW_MAXN to experiment).
+    { int maxn = 128; if (const char* ov = getenv("SSDB_WG_RW_MAXN")) maxn = atoi(ov); if (g.Cout > maxn) return pl; }
     if (g.Cout > 128 && g.Cout % 128 != 0) return pl;
     if (g.Ho != g.H || g.Wo != g.W) return pl;                // SAME 3x3 only; the VALID tails use the plain kernel
     WgRwArgs& a = pl.a;

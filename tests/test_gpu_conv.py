@@ -1,5 +1,7 @@
 """GPU parity of the convolution kernels (SIMT and tcgen05) against a float64 torch-CPU
 restatement of tf.nn.conv2d / atrous_conv2d + bias + relu and its gradients."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -129,6 +131,10 @@ def test_tcgen05_row_window_wgrad_matches_simt(case):
     rng = np.random.default_rng(9)
     dz = rng.standard_normal((B, Ho, Ho, Cout), dtype=np.float32)
     w_s, b_s = run_wgrad(ssdb.CONV_SIMT, x, dz, 3, 1, 1, pad)
-    w_t, b_t = run_wgrad(ssdb.CONV_TC, x, dz, 3, 1, 1, pad)
+    os.environ['SSDB_WG_RW_MAXN'] = '1024'          # exercise the window kernel on the wide layers too (N tiles of 128)
+    try:
+        w_t, b_t = run_wgrad(ssdb.CONV_TC, x, dz, 3, 1, 1, pad)
+    finally:
+        os.environ.pop('SSDB_WG_RW_MAXN', None)
     assert rel_err(w_t, w_s) < TF32_TOL, ('wgrad rw', case, rel_err(w_t, w_s))
     assert rel_err(b_t, b_s) < TF32_TOL, ('bias rw', case, rel_err(b_t, b_s))
