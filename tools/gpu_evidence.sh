@@ -12,3 +12,5 @@ timeout 1200 ncu --set full --clock-control none --import-source on -k regex:con
 tail -1 gpurun_out/ncu_full_$R.log
 timeout 600 ncu --set full --clock-control none -k regex:"multibox_loss|decode_nms" -c 2 -o gpurun_out/prof_loss_$R python tools/ncu_target.py 64 1 > gpurun_out/ncu_loss_$R.log 2>&1
 ls -la gpurun_out | grep $R
+python bench.py --preset vgg512 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_vgg512_$R.json 2> gpurun_out/bench_vgg512_$R.err
+cut -c1-700 gpurun_out/bench_vgg512_$R.json; tail -3 gpurun_out/bench_vgg512_$R.err
