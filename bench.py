@@ -90,6 +90,21 @@ class ClockSampler(threading.Thread):
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': reasons, 'samples': len(self.rows)}
 
 
+def ncu_traffic():
+    """Average DRAM bytes per conv launch from the committed `ncu --set full` summary (profiles/), or None."""
+    path = os.path.join(ROOT, 'profiles', 'r1_ncu_conv_tc_b64.txt')
+    if not os.path.exists(path):
+        return None, None
+    mult = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    tot, n = 0.0, 0
+    for line in open(path):
+        parts = line.split()
+        if len(parts) >= 3 and parts[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum') and parts[2] in mult:
+            tot += float(parts[1]) * mult[parts[2]]
+            n += parts[0] == 'dram__bytes_read.sum'
+    return (tot / n, n) if n else (None, None)
+
+
 def labels_for(first, count, preset_name, anchors):
     """Dense labels for the synthetic GT boxes, built by the GPU matcher (product path)."""
     import ssdb
@@ -237,10 +252,7 @@ def main():
             # the reference-facing call: sess.run([net.result, net.losses, net.optimizer], feed_dict) (train.py:262-266)
             sess.run([model.result, model.losses, model.optimizer], feed_dict={model.image_input: x_np, model.labels: y_np})
         else:
-            x_dev.copy_(x_host, non_blocking=True); y_dev.copy_(y_host, non_blocking=True)
-            dev_step()
-            res_host.copy_(result_dev, non_blocking=True)
-            losses_dev.cpu()
+            trainer.step_host(x_np, y_np, lr, mu, wd)
     if world == 1:
         r, l = sess.run([model.result, model.losses, model.optimizer], feed_dict={model.image_input: x_np, model.labels: y_np})[:2]
         assert r.shape == (B, A, 25) and np.isfinite(l['total'])
@@ -273,8 +285,10 @@ def main():
         by_phase = {}
         for lab, ms_, _ in prof:
             by_phase[lab.split(':')[0]] = by_phase.get(lab.split(':')[0], 0.0) + ms_
+        traffic, ncap = ncu_traffic()
         roof = {'bound': 'tensor', 'achieved': achieved, 'peak': tensor_peak, 'unit': 'TFLOP/s', 'frac': achieved / tensor_peak,
-                'traffic': None, 'kernel': 'conv_tc_kernel + conv_tc_wgrad_kernel (tcgen05 kind::tf32 implicit GEMM), all conv launches of one step',
+                'traffic': traffic, 'traffic_note': 'mean dram__bytes_read+write per launch over the %s conv launches of profiles/r1_ncu_conv_tc_b64.txt '
+                                                    '(ncu --set full, batch 64)' % ncap if traffic else None, 'kernel': 'conv_tc_kernel + conv_tc_wgrad_kernel (tcgen05 kind::tf32 implicit GEMM), all conv launches of one step',
                 'launches': conv_launch, 'ms_per_step_in_kernel': conv_ms,
                 'peak_source': '%s bf16 dense / 2 (tf32 runs at half the bf16 rate)' % pk_kind,
                 'step_breakdown_ms': by_phase}
@@ -332,7 +346,7 @@ def main():
             'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                     'ms_per_step': e2e_ms / args.steps,
                     'call': 'Session.run([net.result, net.losses, net.optimizer], feed_dict) -> ssdb_train_step_host' if world == 1
-                            else 'pinned H2D + DataParallelTrainer.step + D2H'},
+                            else 'DataParallelTrainer.step_host (ssdb_train_step_host_noupdate -> NCCL all-reduce -> ssdb_apply_update)'},
             'gpu_launches': int(launches), 'losses': final_losses,
             'roofline': roof, 'cpu_baseline': cpu, 'nms': nms,
         }

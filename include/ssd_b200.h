@@ -190,6 +190,10 @@ int ssdb_train_step(ssdb_net* net, const float* images_dev, const float* labels_
 int ssdb_train_step_host(ssdb_net* net, const float* images_host, const float* labels_host,
                          int B, float lr, float momentum, float weight_decay,
                          float* losses_out_host, float* result_host);
+/* Data-parallel flavour of ssdb_train_step_host: forward + loss + backward with the same overlapped host copies, but NO
+ * update -- the caller all-reduces ssdb_flat_buffer(net, 1) across ranks and then calls ssdb_apply_update(1/world). */
+int ssdb_train_step_host_noupdate(ssdb_net* net, const float* images_host, const float* labels_host, int B,
+                                  float weight_decay, float* losses_out_host, float* result_host);
 /* validation pass (train.py:291-294): forward + loss, no backward */
 int ssdb_eval_step(ssdb_net* net, const float* images_dev, const float* labels_dev, int B,
                    float weight_decay, float* losses_out_dev, float* result_dev, void* stream);

@@ -668,8 +668,8 @@ int ssdb_train_step(ssdb_net* n, const float* images_dev, const float* labels_de
     return rc;
 }
 
-int ssdb_train_step_host(ssdb_net* n, const float* images_host, const float* labels_host, int B, float lr, float momentum,
-                         float weight_decay, float* losses_out_host, float* result_host) {
+static int train_step_host_impl(ssdb_net* n, const float* images_host, const float* labels_host, int B, float lr, float momentum,
+                                float weight_decay, int apply_update, float* losses_out_host, float* result_host) {
     SSDB_REQUIRE(n && images_host && labels_host && B >= 1 && B <= n->max_batch, "bad arguments");
     // copies ride a second stream: the labels arrive while the forward runs (they are first needed by the loss) and the
     // result leaves while the backward runs; only the image upload is on the critical path
@@ -690,12 +690,22 @@ int ssdb_train_step_host(ssdb_net* n, const float* images_host, const float* lab
         SSDB_CUDA(cudaMemcpyAsync(result_host, n->result, bav, cudaMemcpyDeviceToHost, cs));
     }
     rc = run_backward(n, B, st); if (rc) return rc;
-    rc = ssdb_apply_update(n, lr, momentum, weight_decay, 1.0f, st); if (rc) return rc;
+    if (apply_update) { rc = ssdb_apply_update(n, lr, momentum, weight_decay, 1.0f, st); if (rc) return rc; }
     SSDB_CUDA(cudaMemcpyAsync(n->host_small, n->small_ws, 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
     SSDB_CUDA(cudaStreamSynchronize(st));
     SSDB_CUDA(cudaStreamSynchronize(cs));
     if (losses_out_host) memcpy(losses_out_host, n->host_small, 4 * sizeof(float));
     return SSDB_OK;
+}
+
+int ssdb_train_step_host(ssdb_net* n, const float* images_host, const float* labels_host, int B, float lr, float momentum,
+                         float weight_decay, float* losses_out_host, float* result_host) {
+    return train_step_host_impl(n, images_host, labels_host, B, lr, momentum, weight_decay, 1, losses_out_host, result_host);
+}
+
+int ssdb_train_step_host_noupdate(ssdb_net* n, const float* images_host, const float* labels_host, int B, float weight_decay,
+                                  float* losses_out_host, float* result_host) {
+    return train_step_host_impl(n, images_host, labels_host, B, 0.f, 0.f, weight_decay, 0, losses_out_host, result_host);
 }
 
 int ssdb_eval_step(ssdb_net* n, const float* images_dev, const float* labels_dev, int B, float weight_decay, float* losses_out_dev,

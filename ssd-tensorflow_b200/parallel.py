@@ -53,6 +53,17 @@ class DataParallelTrainer:
         if self.world > 1:
             dist.broadcast(self.params, src=src, group=self.group)
 
+    def step_host(self, images, labels, lr, momentum, weight_decay):
+        """The data-parallel equivalent of sess.run([net.result, net.losses, net.optimizer], feed_dict): host arrays in,
+        (result, losses) out; copies overlap the compute inside the library, then one all-reduce and the fused update."""
+        import torch
+        res, losses = self.net.train_step_host_noupdate(images, labels, weight_decay)
+        scale = average_gradients(self.grads, self.world, self.group)
+        st = torch.cuda.current_stream().cuda_stream
+        self.net.apply_update(lr, momentum, weight_decay, grad_post_scale=scale, stream=st)
+        torch.cuda.current_stream().synchronize()
+        return res, losses
+
     def step(self, images_ptr, labels_ptr, local_batch, lr, momentum, weight_decay, losses_ptr=None, result_ptr=None,
              gt_ptr=None, gt_count_ptr=None, G=0):
         import torch

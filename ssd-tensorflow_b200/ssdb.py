@@ -70,6 +70,7 @@ SIGNATURES = {
     'ssdb_forward_host': (_i, [_p, _p, _i, _p]),
     'ssdb_train_step': (_i, [_p, _p, _p, _p, _p, _i, _i, _f, _f, _f, _f, _i, _p, _p, _p]),
     'ssdb_train_step_host': (_i, [_p, _p, _p, _i, _f, _f, _f, _p, _p]),
+    'ssdb_train_step_host_noupdate': (_i, [_p, _p, _p, _i, _f, _p, _p]),
     'ssdb_eval_step': (_i, [_p, _p, _p, _i, _f, _p, _p, _p]),
     'ssdb_apply_update': (_i, [_p, _f, _f, _f, _f, _p]),
     'ssdb_pinned_alloc': (_i, [_ll, C.POINTER(_p)]),
@@ -239,6 +240,16 @@ class Net:
         losses = np.empty(4, np.float32)
         check(lib().ssdb_train_step_host(self._h, px, py, B, lr, momentum, weight_decay, losses.ctypes.data_as(_p),
                                          res.ctypes.data_as(_p) if res is not None else None))
+        return res, losses
+
+    def train_step_host_noupdate(self, images, labels, weight_decay, result_out=None):
+        """forward + loss + backward from host buffers (overlapped copies), gradients left in the flat buffer."""
+        x, px = _np(images, np.float32)
+        y, py = _np(labels, np.float32)
+        B = x.shape[0]
+        res = result_out if result_out is not None else self.result_buffer(B)
+        losses = np.empty(4, np.float32)
+        check(lib().ssdb_train_step_host_noupdate(self._h, px, py, B, weight_decay, losses.ctypes.data_as(_p), res.ctypes.data_as(_p)))
         return res, losses
 
     # device-pointer calls
