@@ -148,7 +148,9 @@ constexpr int OPT_BLOCK = 1024;   // elements per decay-mask entry (tensors are 
 int multibox_loss_launch(const float* output, const float* labels, const double* gt, const int* gt_count,
                          int G, const double* anchors_prop, int B, int A, int C, float grad_scale,
                          float* losses_out, float* grad_out, float* result_out, int* match_out,
-                         float* per_image_ws, unsigned int* counter_ws, cudaStream_t st);
+                         void* ws, cudaStream_t st);
+// workspace of multibox_loss_launch: zero it once when allocated
+size_t multibox_loss_ws_bytes(int B, int A);
 int match_anchors_launch(const double* gt, const int* gt_count, int B, int G, const double* anchors_prop,
                          int A, int C, int* match_out, float* labels_out, cudaStream_t st);
 int decode_nms_launch(const float* pred, int B, int A, int C, const double* anchors_prop, float conf_thr,

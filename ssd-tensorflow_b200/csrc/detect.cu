@@ -1,4 +1,4 @@
-// Fused decode_boxes + class-wise greedy NMS, one CTA per image.
+// Fused decode_boxes + class-wise greedy NMS.
 //
 // Restates on the GPU, bit-exactly, what the reference does per image in Python:
 //   ssdutils.decode_boxes (ssdutils.py:192-229): arg-max over the C object classes,
@@ -13,16 +13,27 @@
 //     per class with inclusive-pixel IoU > thr in float64, output grouped by class in
 //     order of first appearance.
 //
-// Pipeline inside the CTA: arg-max/confidence pass (HBM read of the image's [A, C+5]
-// block, the only large traffic) -> exact radix select of the cap-th largest
-// confidence -> compaction -> bitonic sort of <= cap 64-bit keys (confidence desc,
-// anchor index asc) -> decode -> greedy sweep -> rank -> write.
+// Two kernels (default; SSDB_NMS=v1 keeps everything in the per-image kernel as the cross-check):
+//   decode_scan_kernel (grid = anchor tiles x images): the only large traffic, the HBM read of
+//     pred [B, A, C+5].  A contiguous tile of 256 anchor rows comes into shared memory with one TMA
+//     bulk copy; thread-per-row arg-max out of shared memory (stride 25 words: conflict free);
+//     one ordered confidence key per anchor goes to a 4-byte/anchor workspace.
+//   decode_nms_kernel (one CTA per image): keys -> exact radix select of the cap-th largest
+//     confidence -> compaction -> bitonic sort of <= cap 64-bit keys (confidence desc, anchor index
+//     asc) -> decode -> greedy NMS -> rank -> write.  For cap <= 256 the greedy pass is a
+//     suppression bit matrix built by all threads + one warp walking it (no per-box CTA barrier).
+#include <cstdlib>
+
+#include "bulk.cuh"
 #include "common.cuh"
 
 namespace ssdb {
 namespace {
 
 constexpr int DT = 1024;
+constexpr int RT = 256;              // anchor rows per tile / threads per CTA of the scan kernel
+constexpr int MAXV = 72;             // C <= 64
+constexpr int BITS_P_MAX = 256;      // suppression bit matrix up to this many candidates
 constexpr int SMEM_P_MAX = 1024;     // candidate lists up to this size live in shared memory
 constexpr int CAND_WORDS = 11;       // cls, box[4], nms[4], conf bits, anchor
 
@@ -41,7 +52,35 @@ struct DetArgs {
     int* dets; int* counts;
     unsigned long long* g_keys; int* g_cand; int P;   // global scratch when P > SMEM_P_MAX
     int cap_eff;
+    const unsigned int* ckey_in;                      // [B*A] keys from decode_scan_kernel, or null (v1: scan in this kernel)
 };
+
+// VT = compile-time row width (C + 5), 0 = generic
+template <int VT>
+__global__ void __launch_bounds__(RT) decode_scan_kernel(const float* __restrict__ pred, int A, int C, float conf_thr, int use_bulk,
+                                                          unsigned int* __restrict__ ckey_out) {
+    extern __shared__ __align__(128) unsigned char dyn[];
+    float* zt = reinterpret_cast<float*>(dyn);
+    __shared__ __align__(8) unsigned long long bar;
+    const int V = VT ? VT : C + 5;
+    const int tid = threadIdx.x, s = blockIdx.x, b = blockIdx.y;
+    const int a0 = s * RT, rows = min(RT, A - a0), nfl = rows * V;
+    const long long tile_off = ((long long)b * A + a0) * V;
+    bulk::tile_load<RT>(zt, pred + tile_off, nullptr, nullptr, nfl, use_bulk, &bar);
+    bulk::tile_load_wait(use_bulk, &bar);
+    if (tid < rows) {
+        const float* r = zt + tid * V;
+        float best = r[0];
+        if (VT) {
+#pragma unroll
+            for (int c = 1; c < (VT ? VT - 5 : 1); ++c) { float v = r[c]; if (v > best) best = v; }
+        } else {
+            for (int c = 1; c < C; ++c) { float v = r[c]; if (v > best) best = v; }
+        }
+        const bool ok = !(best < conf_thr);
+        ckey_out[(long long)b * A + a0 + tid] = ok ? okey(best) : 0u;
+    }
+}
 
 __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
     extern __shared__ __align__(16) unsigned char dyn[];
@@ -69,6 +108,10 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
 
     // ---- pass 1: arg-max class and confidence per anchor ----
     int nvalid = 0;
+    if (p.ckey_in) {
+        const unsigned int* gk = p.ckey_in + (size_t)b * A;
+        for (int a = tid; a < A; a += DT) { unsigned int k = gk[a]; ckey[a] = k; nvalid += k != 0u; }
+    } else
     for (int a = tid; a < A; a += DT) {
         const float* r = pb + (size_t)a * V;
         float best = r[0];
@@ -190,8 +233,46 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
             if (cls < 64) atomicMin(&first_pos[cls], i);
         }
         __syncthreads();
-        // ---- greedy sweep in confidence order; alive flags reuse ckey[] ----
+        // ---- greedy NMS in confidence order; alive flags reuse ckey[] ----
         unsigned int* alive = ckey;
+        if (P <= BITS_P_MAX && P <= SMEM_P_MAX) {
+            // suppression matrix: bit j of row i <=> j > i, same class, IoU(i, j) > thr; then ONE warp walks the rows in
+            // confidence order keeping the removed set in registers (lane w = candidates 32w .. 32w+31)
+            const int W = (P + 31) / 32;
+            unsigned int* sup = reinterpret_cast<unsigned int*>(cand + CAND_WORDS * P);
+            for (int t = tid; t < n * W; t += DT) {
+                const int i = t / W, w = t - i * W;
+                unsigned int bits = 0u;
+                if (w * 32 + 31 > i) {
+                    const int ci = cand[0 * P + i];
+                    const int ix0 = cand[5 * P + i], ix1 = cand[6 * P + i], iy0 = cand[7 * P + i], iy1 = cand[8 * P + i];
+                    const long long area_i = (long long)(ix1 - ix0 + 1) * (iy1 - iy0 + 1);
+                    for (int jj = 0; jj < 32; ++jj) {
+                        const int j = w * 32 + jj;
+                        if (j <= i || j >= n || cand[0 * P + j] != ci) continue;
+                        int jx0 = cand[5 * P + j], jx1 = cand[6 * P + j], jy0 = cand[7 * P + j], jy1 = cand[8 * P + j];
+                        int iw = min(ix1, jx1) - max(ix0, jx0) + 1; iw = iw < 0 ? 0 : iw;
+                        int ih = min(iy1, jy1) - max(iy0, jy0) + 1; ih = ih < 0 ? 0 : ih;
+                        long long inter = (long long)iw * ih;
+                        long long uni = area_i + (long long)(jx1 - jx0 + 1) * (jy1 - jy0 + 1) - inter;
+                        if (__ddiv_rn((double)inter, (double)uni) > p.iou_thr) bits |= 1u << jj;
+                    }
+                }
+                sup[t] = bits;
+            }
+            __syncthreads();
+            if (tid < 32) {
+                unsigned int removed = 0u;
+                for (int i = 0; i < n; ++i) {
+                    const unsigned int row = tid < W ? sup[i * W + tid] : 0u;
+                    const unsigned int r = __shfl_sync(0xffffffffu, removed, i >> 5);
+                    if (!((r >> (i & 31)) & 1u)) removed |= row;
+                }
+                if (tid < W)
+                    for (int jj = 0; jj < 32; ++jj) { const int j = tid * 32 + jj; if (j < n) alive[j] = ((removed >> jj) & 1u) ? 0u : 1u; }
+            }
+            __syncthreads();
+        } else {
         for (int i = tid; i < n; i += DT) alive[i] = 1u;
         __syncthreads();
         for (int i = 0; i < n; ++i) {
@@ -209,6 +290,7 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
                 if (__ddiv_rn((double)inter, (double)uni) > p.iou_thr) alive[j] = 0u;
             }
             __syncthreads();
+        }
         }
         // ---- output rank: classes by first appearance, confidence order inside a class ----
         int kept = 0;
@@ -314,34 +396,60 @@ __global__ void __launch_bounds__(DT) nms_only_kernel(const int* __restrict__ bo
 
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
+bool nms_v1() {        // read per call so that a test can run both implementations in one process
+    const char* e = getenv("SSDB_NMS");
+    return e && e[0] == 'v' && e[1] == '1';
+}
+
+size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
 }  // namespace
 
+// scratch = [B*A] u32 confidence keys, then (cap > 1024 only) sort keys + candidate records in global memory
 size_t decode_nms_scratch_bytes(int B, int A, int cap) {
     int cap_eff = (cap > 0 && cap < A) ? cap : A;
     int P = next_pow2(cap_eff);
-    if (P <= SMEM_P_MAX) return 0;
-    return (size_t)B * P * (8 + 4 * CAND_WORDS);
+    size_t keys = align256((size_t)B * A * 4);
+    if (P <= SMEM_P_MAX) return keys;
+    return keys + (size_t)B * P * (8 + 4 * CAND_WORDS);
 }
 
 int decode_nms_launch(const float* pred, int B, int A, int C, const double* anchors_prop, float conf_thr, int cap,
                       double iou_thr, int* dets_out, int* counts_out, void* scratch, size_t scratch_bytes, cudaStream_t st) {
     SSDB_REQUIRE(B >= 1 && A >= 1 && C >= 1 && C <= 64, "bad sizes");
+    SSDB_REQUIRE(scratch && scratch_bytes >= decode_nms_scratch_bytes(B, A, cap), "scratch too small");
     DetArgs p;
     p.pred = pred; p.anchors = anchors_prop; p.B = B; p.A = A; p.C = C; p.conf_thr = conf_thr; p.cap = cap; p.iou_thr = iou_thr;
     p.dets = dets_out; p.counts = counts_out;
     p.cap_eff = (cap > 0 && cap < A) ? cap : A;
     p.P = next_pow2(p.cap_eff);
     size_t sh = ((size_t)A * 4 + 15) / 16 * 16;
-    p.g_keys = nullptr; p.g_cand = nullptr;
-    if (p.P <= SMEM_P_MAX) sh += (size_t)p.P * (8 + 4 * CAND_WORDS);
-    else {
-        SSDB_REQUIRE(scratch && scratch_bytes >= decode_nms_scratch_bytes(B, A, cap), "scratch too small");
-        p.g_keys = reinterpret_cast<unsigned long long*>(scratch);
-        p.g_cand = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(scratch) + (size_t)B * p.P * 8);
+    p.g_keys = nullptr; p.g_cand = nullptr; p.ckey_in = nullptr;
+    unsigned char* sc = reinterpret_cast<unsigned char*>(scratch);
+    const size_t keys_bytes = align256((size_t)B * A * 4);
+    if (p.P <= SMEM_P_MAX) {
+        sh += (size_t)p.P * (8 + 4 * CAND_WORDS);
+        if (p.P <= BITS_P_MAX) sh += (size_t)p.P * ((p.P + 31) / 32) * 4;
+    } else {
+        p.g_keys = reinterpret_cast<unsigned long long*>(sc + keys_bytes);
+        p.g_cand = reinterpret_cast<int*>(sc + keys_bytes + (size_t)B * p.P * 8);
     }
     SSDB_REQUIRE(sh <= 200 * 1024, "anchor count too large for one CTA");
     static bool attr = false;
-    if (!attr) { SSDB_CUDA(cudaFuncSetAttribute(decode_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+    if (!attr) {
+        SSDB_CUDA(cudaFuncSetAttribute(decode_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SSDB_CUDA(cudaFuncSetAttribute(decode_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT * MAXV * 4));
+        attr = true;
+    }
+    if (!nms_v1()) {
+        const int V = C + 5, S = (A + RT - 1) / RT;
+        const int use_bulk = ((size_t)A * V * 4) % 16 == 0 && bulk::aligned16(pred);
+        unsigned int* ckey = reinterpret_cast<unsigned int*>(sc);
+        if (C == 20) decode_scan_kernel<25><<<dim3(S, B), RT, (size_t)RT * V * 4, st>>>(pred, A, C, conf_thr, use_bulk, ckey);
+        else decode_scan_kernel<0><<<dim3(S, B), RT, (size_t)RT * V * 4, st>>>(pred, A, C, conf_thr, use_bulk, ckey);
+        SSDB_LAUNCH_CHECK();
+        p.ckey_in = ckey;
+    }
     decode_nms_kernel<<<B, DT, sh, st>>>(p);
     SSDB_LAUNCH_CHECK();
     return SSDB_OK;

@@ -8,9 +8,22 @@
 //         hard-negative mining (top_k replaced by an exact radix select of the
 //         k-th largest negative CE), per-image normalisation, batch mean.
 //
-// One CTA per image.  All box arithmetic uses explicit round-to-nearest
-// intrinsics (no FMA contraction) so the integer grid coordinates and IoU
-// comparisons are bit-identical to the reference's float64 NumPy arithmetic.
+// Two implementations of the loss live here:
+//   v2 (default): three streaming kernels.  `loss_rows_kernel` (grid = anchor tiles x images) pulls a
+//       contiguous tile of 256 anchor rows of the head output (and of the dense labels) into shared
+//       memory with one TMA bulk copy each, computes CE / smooth-L1 / softmax thread-per-row out of
+//       shared memory (row stride 25 words: conflict free), writes `net.result` back with a bulk
+//       store and leaves per-anchor CE + kind and per-tile partial sums in a workspace;
+//       `loss_select_kernel` (one CTA per image) does the exact radix select of the k-th largest
+//       negative CE on that 44 KB workspace slice; `loss_grad_kernel` (tiles x images) writes the
+//       gradient tile by tile (zeros for unselected negatives, recomputed rows for the rest).
+//       HBM traffic = the algorithmic bytes: read output + labels once, write result + gradient once.
+//   v1 (SSDB_LOSS=v1): the original one-CTA-per-image kernel, kept as the on-device cross-check.
+// All box arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction) so the integer grid
+// coordinates and IoU comparisons are bit-identical to the reference's float64 NumPy arithmetic.
+#include <cstdlib>
+
+#include "bulk.cuh"
 #include "common.cuh"
 
 namespace ssdb {
@@ -93,8 +106,7 @@ __device__ void match_prepare(MatchShared& ms, const double* gt, int G, const do
 
 // owner GT of anchor a (-1 = background): pass 1 over all IoU > 0.5 (strictly higher wins,
 // earlier GT keeps ties), then pass 2 with a fresh score table over the GTs whose arg-max is a.
-__device__ __forceinline__ int match_one(const MatchShared& ms, int G, const double* anchors, int a) {
-    IBox ab = prop2abs_1000(anchors[a * 4 + 0], anchors[a * 4 + 1], anchors[a * 4 + 2], anchors[a * 4 + 3]);
+__device__ __forceinline__ int match_one_box(const MatchShared& ms, int G, const IBox& ab, int a) {
     int owner = -1; double score = -1.0;
     for (int g = 0; g < G; ++g) {
         double v = iou_incl(ms.gt[g], ab);
@@ -107,6 +119,10 @@ __device__ __forceinline__ int match_one(const MatchShared& ms, int G, const dou
         any2 = true; score2 = ms.best_iou[g]; owner = g;
     }
     return owner;
+}
+__device__ __forceinline__ int match_one(const MatchShared& ms, int G, const double* anchors, int a) {
+    IBox ab = prop2abs_1000(anchors[a * 4 + 0], anchors[a * 4 + 1], anchors[a * 4 + 2], anchors[a * 4 + 3]);
+    return match_one_box(ms, G, ab, a);
 }
 
 __global__ void __launch_bounds__(LT) match_kernel(const double* __restrict__ gt, const int* __restrict__ gt_count, int G,
@@ -367,6 +383,383 @@ __global__ void __launch_bounds__(LT) multibox_loss_kernel(
     }
 }
 
+
+// =====================================================================================
+// v2: tiled streaming implementation
+// =====================================================================================
+constexpr int RT = 256;            // anchor rows per tile = threads per CTA of the streaming kernels
+
+struct TilePart { float pos_sum, loc_sum; int pos_cnt, neg_cnt; };
+
+struct LossWs {
+    float* ce;               // [B*A]  per-anchor cross entropy
+    unsigned char* kind;     // [B*A]  0 positive, 1 negative, 2 selected negative
+    signed char* own;        // [B*A]  owner GT (fused-match mode)
+    TilePart* part;          // [B*S]
+    float* gs;               // [B]    gradient scale of the image: grad_scale / (B * pos_num)
+    float* per_image;        // [B*2]
+    unsigned int* counter;   // [1]    self-resetting
+    double* best_iou;        // [B*MAX_G]
+    int* best_idx;           // [B*MAX_G]
+    IBox* anc_abs;           // [A]
+};
+
+__host__ __device__ inline size_t ws_align(size_t v) { return (v + 255) / 256 * 256; }
+
+// anchors on the 1000x1000 grid, once per launch instead of once per (GT, anchor) pair
+__global__ void __launch_bounds__(256) anchor_abs_kernel(const double* __restrict__ anchors, int A, IBox* __restrict__ out) {
+    int a = blockIdx.x * 256 + threadIdx.x;
+    if (a < A) out[a] = prop2abs_1000(anchors[a * 4 + 0], anchors[a * 4 + 1], anchors[a * 4 + 2], anchors[a * 4 + 3]);
+}
+
+// arg-max anchor of every GT box (first maximum = lowest anchor index), one CTA per (GT, image)
+__global__ void __launch_bounds__(RT) match_best_kernel(const double* __restrict__ gt, const int* __restrict__ gt_count, int G,
+                                                         const IBox* __restrict__ anc_abs, int A, double* __restrict__ best_iou,
+                                                         int* __restrict__ best_idx) {
+    const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    if (g >= min(gt_count[b], G)) return;
+    __shared__ double red_iou[RT / 32];
+    __shared__ int red_idx[RT / 32];
+    const double* r = gt + ((long long)b * G + g) * 5;
+    const IBox gb = prop2abs_1000(r[1], r[2], r[3], r[4]);
+    double bi = -1.0; int bx = 0x7fffffff;
+    for (int a = tid; a < A; a += RT) {
+        double v = iou_incl(gb, anc_abs[a]);
+        if (v > bi) { bi = v; bx = a; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        double oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        int ox = __shfl_xor_sync(0xffffffffu, bx, o);
+        if (oi > bi || (oi == bi && ox < bx)) { bi = oi; bx = ox; }
+    }
+    if ((tid & 31) == 0) { red_iou[tid >> 5] = bi; red_idx[tid >> 5] = bx; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < RT / 32; ++w)
+            if (red_iou[w] > bi || (red_iou[w] == bi && red_idx[w] < bx)) { bi = red_iou[w]; bx = red_idx[w]; }
+        best_iou[b * MAX_G + g] = bi; best_idx[b * MAX_G + g] = bx;
+    }
+}
+
+using bulk::tile_load_wait;
+
+// VT = compile-time row width (C + 5), 0 = generic (<= MAXV)
+template <bool GT_MODE, int VT>
+__global__ void __launch_bounds__(RT) loss_rows_kernel(
+    const float* __restrict__ output, const float* __restrict__ labels, const double* __restrict__ gt,
+    const int* __restrict__ gt_count, int G, const double* __restrict__ anchors, int A, int C, int S, int use_bulk, LossWs ws,
+    float* __restrict__ result_out, int* __restrict__ match_out) {
+    extern __shared__ __align__(128) unsigned char dyn[];
+    constexpr int VMAX = VT ? VT : MAXV;
+    const int V = VT ? VT : C + 5, NC = V - 4;
+    float* zt = reinterpret_cast<float*>(dyn);        // [RT*V] head output tile, becomes the result tile
+    float* yt = zt + RT * V;                          // [RT*V] dense label tile (not in fused-match mode)
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ MatchShared ms;
+    __shared__ float red[RT / 32][4];
+
+    const int tid = threadIdx.x, s = blockIdx.x, b = blockIdx.y;
+    const int a0 = s * RT, rows = min(RT, A - a0), nfl = rows * V;
+    const long long tile_off = ((long long)b * A + a0) * V;
+    bulk::tile_load<RT>(zt, output + tile_off, yt, GT_MODE ? nullptr : labels + tile_off, nfl, use_bulk, &bar);
+    const double* gtb = GT_MODE ? gt + (long long)b * G * 5 : nullptr;
+    int g_n = 0;
+    if (GT_MODE) {
+        g_n = min(gt_count[b], G);
+        if (tid < g_n) {
+            ms.gt[tid] = prop2abs_1000(gtb[tid * 5 + 1], gtb[tid * 5 + 2], gtb[tid * 5 + 3], gtb[tid * 5 + 4]);
+            ms.best_iou[tid] = ws.best_iou[b * MAX_G + tid];
+            ms.best_idx[tid] = ws.best_idx[b * MAX_G + tid];
+        }
+    }
+    tile_load_wait(use_bulk, &bar);
+
+    float pos_sum = 0.f, loc_sum = 0.f; int pos_cnt = 0, neg_cnt = 0;
+    if (tid < rows) {
+        const int a = a0 + tid;
+        float* zr = zt + tid * V;
+        float z[VMAX];
+#pragma unroll
+        for (int c = 0; c < VMAX; ++c) z[c] = c < V ? zr[c] : 0.f;
+        float m = z[0];
+#pragma unroll
+        for (int c = 1; c < VMAX; ++c) if (c < NC) m = fmaxf(m, z[c]);
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < VMAX; ++c) if (c < NC) sum += expf(z[c] - m);
+        const float lse = m + logf(sum);
+        const float inv = 1.f / sum;
+        float cev, l1 = 0.f; bool pos;
+        if (GT_MODE) {
+            const int owner = match_one_box(ms, g_n, ws.anc_abs[a], a);
+            ws.own[(long long)b * A + a] = (signed char)owner;
+            if (match_out) match_out[(long long)b * A + a] = owner;
+            pos = owner >= 0;
+            const int cls = pos ? (int)gtb[owner * 5] : C;
+            cev = lse - zr[cls];
+            if (pos) {
+                float t[4]; encode_loc(gtb + owner * 5, anchors + a * 4, t);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { float d = zr[NC + i] - t[i]; float ad = fabsf(d); l1 += ad < 1.f ? 0.5f * d * d : ad - 0.5f; }
+            }
+        } else {
+            const float* yr = yt + tid * V;
+            float dot = 0.f, sy = 0.f;
+#pragma unroll
+            for (int c = 0; c < VMAX; ++c) if (c < NC) { float y = yr[c]; dot += y * z[c]; sy += y; }
+            cev = sy * lse - dot;
+            pos = yr[C] == 0.f;
+            if (pos) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { float d = zr[NC + i] - yr[NC + i]; float ad = fabsf(d); l1 += ad < 1.f ? 0.5f * d * d : ad - 0.5f; }
+            }
+        }
+        ws.ce[(long long)b * A + a] = cev;
+        ws.kind[(long long)b * A + a] = pos ? 0 : 1;
+        if (pos) { pos_sum = cev; loc_sum = l1; pos_cnt = 1; } else neg_cnt = 1;
+        // the tile becomes net.result: softmax over the class columns, offsets unchanged (ssdvgg.py:365-372)
+#pragma unroll
+        for (int c = 0; c < VMAX; ++c) if (c < NC) zr[c] = expf(z[c] - m) * inv;
+    }
+    // per-tile partial sums (fixed order: deterministic)
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        pos_sum += __shfl_xor_sync(0xffffffffu, pos_sum, o); loc_sum += __shfl_xor_sync(0xffffffffu, loc_sum, o);
+        pos_cnt += __shfl_xor_sync(0xffffffffu, pos_cnt, o); neg_cnt += __shfl_xor_sync(0xffffffffu, neg_cnt, o);
+    }
+    if ((tid & 31) == 0) { red[tid >> 5][0] = pos_sum; red[tid >> 5][1] = loc_sum; red[tid >> 5][2] = __int_as_float(pos_cnt); red[tid >> 5][3] = __int_as_float(neg_cnt); }
+    if (result_out) bulk::tile_store<RT>(result_out + tile_off, zt, nfl, use_bulk); else __syncthreads();
+    if (tid == 0) {
+        TilePart tp{0.f, 0.f, 0, 0};
+        for (int w = 0; w < RT / 32; ++w) { tp.pos_sum += red[w][0]; tp.loc_sum += red[w][1]; tp.pos_cnt += __float_as_int(red[w][2]); tp.neg_cnt += __float_as_int(red[w][3]); }
+        ws.part[b * S + s] = tp;
+    }
+}
+
+// one CTA per image: exact k-th largest negative CE, marks the selected negatives, per-image losses, batch mean
+__global__ void __launch_bounds__(LT) loss_select_kernel(LossWs ws, int B, int A, int S, float grad_scale, float* __restrict__ losses_out) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    float* ce = reinterpret_cast<float*>(dyn);
+    signed char* kind = reinterpret_cast<signed char*>(ce + A);
+    __shared__ float redf[LT / 32];
+    __shared__ int hist[256];
+    __shared__ int sel_bin, sel_rem;
+    __shared__ int scan[LT];
+    __shared__ TilePart tot;
+    const int tid = threadIdx.x, b = blockIdx.x;
+    const float* gce = ws.ce + (long long)b * A;
+    unsigned char* gkind = ws.kind + (long long)b * A;
+    for (int a = tid; a < A; a += LT) { ce[a] = gce[a]; kind[a] = (signed char)gkind[a]; }
+    if (tid == 0) {
+        TilePart t{0.f, 0.f, 0, 0};
+        for (int s = 0; s < S; ++s) { const TilePart p = ws.part[b * S + s]; t.pos_sum += p.pos_sum; t.loc_sum += p.loc_sum; t.pos_cnt += p.pos_cnt; t.neg_cnt += p.neg_cnt; }
+        tot = t;
+    }
+    __syncthreads();
+    const float pos_sum = tot.pos_sum, loc_sum = tot.loc_sum; const int pos_cnt = tot.pos_cnt, neg_cnt = tot.neg_cnt;
+    const int k = min(neg_cnt, 3 * pos_cnt);
+    float neg_sum = 0.f;
+    if (k > 0) {
+        unsigned int prefix = 0, mask = 0; int remaining = k;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            for (int i = tid; i < 256; i += LT) hist[i] = 0;
+            __syncthreads();
+            for (int a = tid; a < A; a += LT) {
+                if (kind[a] != 1) continue;
+                unsigned int key = order_key(ce[a]);
+                if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int cum = 0, bin = 255;
+                for (; bin >= 0; --bin) { if (cum + hist[bin] >= remaining) break; cum += hist[bin]; }
+                sel_bin = bin; sel_rem = remaining - cum;
+            }
+            __syncthreads();
+            prefix |= ((unsigned int)sel_bin) << shift; mask |= 255u << shift; remaining = sel_rem;
+            __syncthreads();
+        }
+        // prefix = key of the k-th largest; `remaining` ties (key == prefix) are taken, lowest index first (tf.nn.top_k order)
+        const int per = (A + LT - 1) / LT;
+        const int a_lo = tid * per, a_hi = min(A, a_lo + per);
+        int ties = 0;
+        for (int a = a_lo; a < a_hi; ++a) if (kind[a] == 1 && order_key(ce[a]) == prefix) ++ties;
+        scan[tid] = ties;
+        __syncthreads();
+        for (int o = 1; o < LT; o <<= 1) {
+            int v = tid >= o ? scan[tid - o] : 0;
+            __syncthreads();
+            scan[tid] += v;
+            __syncthreads();
+        }
+        int rank = scan[tid] - ties;
+        float part = 0.f;
+        for (int a = a_lo; a < a_hi; ++a) {
+            if (kind[a] != 1) continue;
+            unsigned int key = order_key(ce[a]);
+            bool take = key > prefix;
+            if (key == prefix) { take = rank < remaining; ++rank; }
+            if (take) { gkind[a] = 2; part += ce[a]; }
+        }
+        neg_sum = block_sum(part, redf);
+    }
+    if (tid == 0) {
+        ws.per_image[b * 2 + 0] = pos_cnt > 0 ? (pos_sum + neg_sum) / (float)pos_cnt : 0.f;
+        ws.per_image[b * 2 + 1] = pos_cnt > 0 ? loc_sum / (float)pos_cnt : 0.f;
+        ws.gs[b] = grad_scale * (pos_cnt > 0 ? 1.f / (float)pos_cnt : 0.f) / (float)B;
+    }
+    // ---- batch mean by the last CTA, summed in image order (deterministic) ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int done = atomicAdd(ws.counter, 1u);
+        if (done == (unsigned int)B - 1) {
+            __threadfence();
+            float c = 0.f, l = 0.f;
+            const volatile float* pi = ws.per_image;
+            for (int i = 0; i < B; ++i) { c += pi[i * 2]; l += pi[i * 2 + 1]; }
+            losses_out[0] = c / (float)B;
+            losses_out[1] = l / (float)B;
+            *ws.counter = 0;
+        }
+    }
+}
+
+// gradient w.r.t. the head output, tile by tile: zeros for unselected negatives, recomputed rows for the rest
+template <bool GT_MODE, int VT>
+__global__ void __launch_bounds__(RT) loss_grad_kernel(
+    const float* __restrict__ output, const float* __restrict__ labels, const double* __restrict__ gt, int G,
+    const double* __restrict__ anchors, int A, int C, int use_bulk, LossWs ws, float* __restrict__ grad_out) {
+    extern __shared__ __align__(128) unsigned char dyn[];
+    constexpr int VMAX = VT ? VT : MAXV;
+    const int V = VT ? VT : C + 5, NC = V - 4;
+    float* gtile = reinterpret_cast<float*>(dyn);     // [RT*V]
+    const int tid = threadIdx.x, s = blockIdx.x, b = blockIdx.y;
+    const int a0 = s * RT, rows = min(RT, A - a0), nfl = rows * V;
+    const long long tile_off = ((long long)b * A + a0) * V;
+    if (tid < rows) {
+        const int a = a0 + tid;
+        float* gr = gtile + tid * V;
+        const int kd = ws.kind[(long long)b * A + a];
+        if (kd == 1) {
+#pragma unroll
+            for (int c = 0; c < VMAX; ++c) if (c < V) gr[c] = 0.f;
+        } else {
+            const float gs = ws.gs[b];
+            const float* zr = output + tile_off + (long long)tid * V;
+            float z[VMAX];
+#pragma unroll
+            for (int c = 0; c < VMAX; ++c) z[c] = c < V ? zr[c] : 0.f;
+            float m = z[0];
+#pragma unroll
+            for (int c = 1; c < VMAX; ++c) if (c < NC) m = fmaxf(m, z[c]);
+            float sum = 0.f;
+#pragma unroll
+            for (int c = 0; c < VMAX; ++c) if (c < NC) sum += expf(z[c] - m);
+            const float inv = 1.f / sum;
+            if (GT_MODE) {
+                const int owner = ws.own[(long long)b * A + a];
+                const double* gtb = gt + (long long)b * G * 5;
+                const int cls = owner >= 0 ? (int)gtb[owner * 5] : C;
+#pragma unroll
+                for (int c = 0; c < VMAX; ++c) if (c < NC) gr[c] = (expf(z[c] - m) * inv - (c == cls ? 1.f : 0.f)) * gs;
+                if (owner >= 0) {
+                    float t[4]; encode_loc(gtb + owner * 5, anchors + a * 4, t);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { float d = zr[NC + i] - t[i]; gr[NC + i] = (fabsf(d) < 1.f ? d : (d > 0.f ? 1.f : -1.f)) * gs; }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) gr[NC + i] = 0.f;
+                }
+            } else {
+                const float* yr = labels + tile_off + (long long)tid * V;
+                float y[VMAX];
+#pragma unroll
+                for (int c = 0; c < VMAX; ++c) y[c] = c < V ? yr[c] : 0.f;
+                float sy = 0.f;
+#pragma unroll
+                for (int c = 0; c < VMAX; ++c) if (c < NC) sy += y[c];
+#pragma unroll
+                for (int c = 0; c < VMAX; ++c) if (c < NC) gr[c] = (sy * (expf(z[c] - m) * inv) - y[c]) * gs;
+                if (kd == 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { float d = zr[NC + i] - yr[NC + i]; gr[NC + i] = (fabsf(d) < 1.f ? d : (d > 0.f ? 1.f : -1.f)) * gs; }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) gr[NC + i] = 0.f;
+                }
+            }
+        }
+    }
+    bulk::tile_store<RT>(grad_out + tile_off, gtile, nfl, use_bulk);
+}
+
+template <typename K>
+int opt_in_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) SSDB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return SSDB_OK;
+}
+
+LossWs carve_ws(void* base, int B, int A) {
+    const int S = (A + RT - 1) / RT;
+    unsigned char* p = reinterpret_cast<unsigned char*>(base);
+    LossWs w;
+    auto take = [&](size_t bytes) { unsigned char* r = p; p += ws_align(bytes); return r; };
+    w.counter = reinterpret_cast<unsigned int*>(take(256));
+    w.ce = reinterpret_cast<float*>(take((size_t)B * A * 4));
+    w.kind = reinterpret_cast<unsigned char*>(take((size_t)B * A));
+    w.own = reinterpret_cast<signed char*>(take((size_t)B * A));
+    w.part = reinterpret_cast<TilePart*>(take((size_t)B * S * sizeof(TilePart)));
+    w.gs = reinterpret_cast<float*>(take((size_t)B * 4));
+    w.per_image = reinterpret_cast<float*>(take((size_t)B * 8));
+    w.best_iou = reinterpret_cast<double*>(take((size_t)B * MAX_G * 8));
+    w.best_idx = reinterpret_cast<int*>(take((size_t)B * MAX_G * 4));
+    w.anc_abs = reinterpret_cast<IBox*>(take((size_t)A * sizeof(IBox)));
+    return w;
+}
+
+template <bool GT_MODE, int VT>
+int loss_v2(const float* output, const float* labels, const double* gt, const int* gt_count, int G, const double* anchors, int B, int A,
+            int C, float grad_scale, float* losses_out, float* grad_out, float* result_out, int* match_out, void* ws_base, cudaStream_t st) {
+    const int V = C + 5, S = (A + RT - 1) / RT;
+    LossWs ws = carve_ws(ws_base, B, A);
+    const bool row_ok = ((size_t)A * V * 4) % 16 == 0;
+    const int bulk_rows = row_ok && bulk::aligned16(output) && (GT_MODE || bulk::aligned16(labels)) && (!result_out || bulk::aligned16(result_out));
+    const int bulk_grad = row_ok && (!grad_out || bulk::aligned16(grad_out));
+    if (GT_MODE) {
+        anchor_abs_kernel<<<(A + 255) / 256, 256, 0, st>>>(anchors, A, ws.anc_abs);
+        SSDB_LAUNCH_CHECK();
+        match_best_kernel<<<dim3(G, B), RT, 0, st>>>(gt, gt_count, G, ws.anc_abs, A, ws.best_iou, ws.best_idx);
+        SSDB_LAUNCH_CHECK();
+    }
+    const size_t sh_rows = (size_t)RT * V * 4 * (GT_MODE ? 1 : 2), sh_sel = (size_t)A * 5 + 16, sh_grad = (size_t)RT * V * 4;
+    SSDB_REQUIRE(sh_sel <= 200 * 1024, "anchor count too large for the select kernel");
+    static bool attr = false;     // per template instantiation
+    if (!attr) {
+        int rc = opt_in_smem(loss_rows_kernel<GT_MODE, VT>, (size_t)RT * MAXV * 8); if (rc) return rc;
+        rc = opt_in_smem(loss_select_kernel, 200 * 1024); if (rc) return rc;
+        rc = opt_in_smem(loss_grad_kernel<GT_MODE, VT>, sh_grad); if (rc) return rc;
+        attr = true;
+    }
+    loss_rows_kernel<GT_MODE, VT><<<dim3(S, B), RT, sh_rows, st>>>(output, labels, gt, gt_count, G, anchors, A, C, S, bulk_rows, ws,
+                                                                   result_out, match_out);
+    SSDB_LAUNCH_CHECK();
+    loss_select_kernel<<<B, LT, sh_sel, st>>>(ws, B, A, S, grad_scale, losses_out);
+    SSDB_LAUNCH_CHECK();
+    if (grad_out) {
+        loss_grad_kernel<GT_MODE, VT><<<dim3(S, B), RT, sh_grad, st>>>(output, labels, gt, G, anchors, A, C, bulk_grad, ws, grad_out);
+        SSDB_LAUNCH_CHECK();
+    }
+    return SSDB_OK;
+}
+
+bool use_v1() {       // read per call so that a test can run both implementations in one process
+    const char* e = getenv("SSDB_LOSS");
+    return e && e[0] == 'v' && e[1] == '1';
+}
+
 }  // namespace
 
 int match_anchors_launch(const double* gt, const int* gt_count, int B, int G, const double* anchors_prop, int A, int C,
@@ -378,24 +771,37 @@ int match_anchors_launch(const double* gt, const int* gt_count, int B, int G, co
     return SSDB_OK;
 }
 
+size_t multibox_loss_ws_bytes(int B, int A) {
+    const int S = (A + RT - 1) / RT;
+    return 256 + ws_align((size_t)B * A * 4) + 2 * ws_align((size_t)B * A) + ws_align((size_t)B * S * sizeof(TilePart)) + ws_align((size_t)B * 4) +
+           ws_align((size_t)B * 8) + ws_align((size_t)B * MAX_G * 8) + ws_align((size_t)B * MAX_G * 4) + ws_align((size_t)A * sizeof(IBox));
+}
+
+// ws: multibox_loss_ws_bytes(B, A) bytes, zeroed once when allocated (the batch counter resets itself)
 int multibox_loss_launch(const float* output, const float* labels, const double* gt, const int* gt_count, int G,
                          const double* anchors_prop, int B, int A, int C, float grad_scale, float* losses_out,
-                         float* grad_out, float* result_out, int* match_out, float* per_image_ws,
-                         unsigned int* counter_ws, cudaStream_t st) {
+                         float* grad_out, float* result_out, int* match_out, void* ws, cudaStream_t st) {
     SSDB_REQUIRE(C + 5 <= MAXV, "too many classes");
-    SSDB_REQUIRE(B >= 1 && A >= 1, "bad sizes");
+    SSDB_REQUIRE(B >= 1 && A >= 1 && ws, "bad sizes");
+    if (!labels) SSDB_REQUIRE(gt && gt_count && anchors_prop && G >= 1 && G <= MAX_G, "ground truth required");
+    if (!use_v1()) {
+        if (labels) return C == 20 ? loss_v2<false, 25>(output, labels, nullptr, nullptr, 0, nullptr, B, A, C, grad_scale, losses_out, grad_out, result_out, nullptr, ws, st)
+                                   : loss_v2<false, 0>(output, labels, nullptr, nullptr, 0, nullptr, B, A, C, grad_scale, losses_out, grad_out, result_out, nullptr, ws, st);
+        return C == 20 ? loss_v2<true, 25>(output, nullptr, gt, gt_count, G, anchors_prop, B, A, C, grad_scale, losses_out, grad_out, result_out, match_out, ws, st)
+                       : loss_v2<true, 0>(output, nullptr, gt, gt_count, G, anchors_prop, B, A, C, grad_scale, losses_out, grad_out, result_out, match_out, ws, st);
+    }
+    LossWs w = carve_ws(ws, B, A);
     size_t sh = (size_t)A * 4 + (size_t)A * 2 + 16;
     if (labels) {
         static bool attr0 = false;
         if (!attr0) { SSDB_CUDA(cudaFuncSetAttribute(multibox_loss_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr0 = true; }
         multibox_loss_kernel<false><<<B, LT, sh, st>>>(output, labels, nullptr, nullptr, 0, nullptr, B, A, C, grad_scale,
-                                                        losses_out, grad_out, result_out, nullptr, per_image_ws, counter_ws);
+                                                        losses_out, grad_out, result_out, nullptr, w.per_image, w.counter);
     } else {
-        SSDB_REQUIRE(gt && gt_count && anchors_prop && G >= 1 && G <= MAX_G, "ground truth required");
         static bool attr1 = false;
         if (!attr1) { SSDB_CUDA(cudaFuncSetAttribute(multibox_loss_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr1 = true; }
         multibox_loss_kernel<true><<<B, LT, sh, st>>>(output, nullptr, gt, gt_count, G, anchors_prop, B, A, C, grad_scale,
-                                                       losses_out, grad_out, result_out, match_out, per_image_ws, counter_ws);
+                                                       losses_out, grad_out, result_out, match_out, w.per_image, w.counter);
     }
     SSDB_LAUNCH_CHECK();
     return SSDB_OK;

@@ -100,6 +100,8 @@ struct ssdb_net {
     float *partial = nullptr; size_t partial_floats = 0;
     float *small_ws = nullptr;         // [0..3] losses, [4..5] conf/loc, [6] l2 sum, then per-image + partials
     unsigned int* counter = nullptr;
+    void* loss_ws = nullptr;           // workspace of the multibox loss kernels (multibox_loss_ws_bytes)
+    void* det_ws = nullptr;            // workspace of ssdb_decode_nms_net (decode_nms_scratch_bytes at max_batch)
     unsigned char* decay_mask = nullptr;
     double* anchors = nullptr;
     float* host_small = nullptr;       // pinned
@@ -508,6 +510,8 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
     ALLOC(n->partial, partial, float); ALLOC(n->small_ws, 4096 + 2 * (size_t)max_batch, float);
     ALLOC(n->counter, 1, unsigned int); ALLOC(n->decay_mask, n->n_flat / OPT_BLOCK, unsigned char);
     ALLOC(n->anchors, (size_t)n->A * 4, double);
+    ALLOC(n->loss_ws, multibox_loss_ws_bytes(max_batch, n->A), unsigned char);
+    SSDB_CUDA(cudaMemset(n->loss_ws, 0, multibox_loss_ws_bytes(max_batch, n->A)));
     for (const Op& op : n->ops)
         if (op.type == OP_POOL && op.stride == 1) { const Buf& bo = n->bufs[op.out]; ALLOC(n->pool5_arg, (size_t)max_batch * bo.H * bo.W * bo.C, unsigned char); }
     if (n->round) {
@@ -547,7 +551,7 @@ int ssdb_destroy(ssdb_net* n) {
     if (!n) return SSDB_OK;
     cudaDeviceSynchronize();
     void* ptrs[] = {n->pool5_arg, n->patches, n->c1_w32, n->c1_wt, n->c1_dw32, n->wr, n->params, n->grads, n->moms, n->wt, n->acts, n->gacts, n->out, n->out_grad, n->result, n->labels_stage,
-                    n->dz_head, n->images_stage, n->partial, n->small_ws, n->counter, n->decay_mask, n->anchors};
+                    n->dz_head, n->images_stage, n->partial, n->small_ws, n->counter, n->decay_mask, n->anchors, n->loss_ws, n->det_ws};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (n->host_small) cudaFreeHost(n->host_small);
     if (n->own_stream) cudaStreamDestroy(n->own_stream);
@@ -635,10 +639,9 @@ static int loss_and_finalize(ssdb_net* n, const float* labels_dev, const double*
                              float weight_decay, float grad_scale, bool want_grad, float* losses_out_dev, float* result_dev, cudaStream_t st) {
     float* conf_loc = n->small_ws + 4;
     float* l2s = n->small_ws + 6;
-    float* per_image = n->small_ws + 4096;
     ProfScope ps(n, st, "loss");
     int rc = multibox_loss_launch(n->out, labels_dev, gt_dev, gt_count_dev, G, n->anchors, B, n->A, n->C, grad_scale, conf_loc,
-                                  want_grad ? n->out_grad : nullptr, result_dev ? result_dev : n->result, nullptr, per_image, n->counter, st);
+                                  want_grad ? n->out_grad : nullptr, result_dev ? result_dev : n->result, nullptr, n->loss_ws, st);
     if (rc) return rc;
     rc = l2_sum(n->params, (long long)n->n_flat, n->decay_mask, n->small_ws + 8, l2s, st); if (rc) return rc;
     finalize_losses_kernel<<<1, 32, 0, st>>>(conf_loc, l2s, weight_decay, losses_out_dev ? losses_out_dev : n->small_ws);
@@ -777,32 +780,34 @@ int ssdb_nms_host(const int* boxes, const int* labelid, const float* conf, int n
     return nms_only_host(boxes, labelid, conf, n, nclass, iou_thr, keep_out, count_out);
 }
 
-static int loss_ws(int B, float** per_image, unsigned int** counter) {
-    static float* ws = nullptr; static unsigned int* cnt = nullptr; static int cap = 0;
-    if (B > cap) {
-        if (ws) cudaFree(ws);
-        SSDB_CUDA(cudaMalloc(&ws, (size_t)B * 2 * sizeof(float))); cap = B;
+// grow-only workspace of the stateless loss entry points (one caller thread per process, like the reference)
+static int loss_ws(int B, int A, void** ws_out) {
+    static void* ws = nullptr; static size_t cap = 0;
+    const size_t need = multibox_loss_ws_bytes(B, A);
+    if (need > cap) {
+        if (ws) { SSDB_CUDA(cudaDeviceSynchronize()); cudaFree(ws); ws = nullptr; cap = 0; }
+        SSDB_CUDA(cudaMalloc(&ws, need)); cap = need;
+        SSDB_CUDA(cudaMemset(ws, 0, need));
     }
-    if (!cnt) { SSDB_CUDA(cudaMalloc(&cnt, sizeof(unsigned int))); SSDB_CUDA(cudaMemset(cnt, 0, sizeof(unsigned int))); }
-    *per_image = ws; *counter = cnt;
+    *ws_out = ws;
     return SSDB_OK;
 }
 
 int ssdb_multibox_loss(const float* output_dev, const float* labels_dev, int B, int A, int C, float grad_scale, float* losses_out_dev,
                        float* grad_out_dev, float* result_out_dev, void* stream) {
     SSDB_REQUIRE(output_dev && labels_dev && losses_out_dev, "bad arguments");
-    float* pi; unsigned int* cnt; int rc = loss_ws(B, &pi, &cnt); if (rc) return rc;
+    void* ws; int rc = loss_ws(B, A, &ws); if (rc) return rc;
     return multibox_loss_launch(output_dev, labels_dev, nullptr, nullptr, 0, nullptr, B, A, C, grad_scale, losses_out_dev, grad_out_dev,
-                                result_out_dev, nullptr, pi, cnt, (cudaStream_t)stream);
+                                result_out_dev, nullptr, ws, (cudaStream_t)stream);
 }
 
 int ssdb_multibox_loss_gt(const float* output_dev, const double* gt_dev, const int* gt_count_dev, int B, int G, const double* anchors_prop_dev,
                           int A, int C, float grad_scale, float* losses_out_dev, float* grad_out_dev, float* result_out_dev,
                           int* match_out_dev, void* stream) {
     SSDB_REQUIRE(output_dev && gt_dev && gt_count_dev && anchors_prop_dev && losses_out_dev, "bad arguments");
-    float* pi; unsigned int* cnt; int rc = loss_ws(B, &pi, &cnt); if (rc) return rc;
+    void* ws; int rc = loss_ws(B, A, &ws); if (rc) return rc;
     return multibox_loss_launch(output_dev, nullptr, gt_dev, gt_count_dev, G, anchors_prop_dev, B, A, C, grad_scale, losses_out_dev,
-                                grad_out_dev, result_out_dev, match_out_dev, pi, cnt, (cudaStream_t)stream);
+                                grad_out_dev, result_out_dev, match_out_dev, ws, (cudaStream_t)stream);
 }
 
 static ConvGeom make_geom(int B, int H, int W, int Cin, int Cout, int k, int stride, int dil, int pad_t, int pad_l, int Ho, int Wo) {

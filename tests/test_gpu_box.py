@@ -12,6 +12,13 @@ import synth
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=['v2', 'v1'], autouse=True)
+def nms_impl(request, monkeypatch):
+    """Decode + NMS runs as scan kernel + per-image kernel (default) and as the single per-image kernel."""
+    monkeypatch.setenv('SSDB_NMS', request.param)
+    return request.param
+
+
 def _labels_equal(got, want):
     """classes / background flag / linear offsets exact; log offsets within 1 float32 ulp
     (device log() vs libm log() may differ in the last float64 bit before rounding)."""
@@ -71,7 +78,8 @@ def _rows_from_dets(dets, counts, i):
 
 @pytest.mark.parametrize('preset,dist,thr,cap', [
     ('vgg300', 'U', 0.01, 200), ('vgg300', 'C', 0.01, 200), ('vgg300', 'C', 0.5, 200), ('vgg300', 'C', 0.3, None),
-    ('vgg300', 'U', 0.97, None), ('vgg300', 'C', 0.01, 50), ('vgg512', 'C', 0.01, 200), ('vgg512', 'U', 0.01, 200)])
+    ('vgg300', 'U', 0.97, None), ('vgg300', 'C', 0.01, 50), ('vgg512', 'C', 0.01, 200), ('vgg512', 'U', 0.01, 200),
+    ('vgg300', 'C', 0.01, 256), ('vgg300', 'C', 0.01, 300), ('vgg300', 'C', 0.01, 7), ('vgg300', 'U', 0.01, 33)])
 def test_decode_nms_vs_oracle(preset, dist, thr, cap):
     anc = bo.anchors(preset)
     B = 4 if preset == 'vgg300' else 2
@@ -112,3 +120,22 @@ def test_decode_nms_nothing_above_threshold():
     pred = synth.pred_uniform(1, anc.shape[0])[None]
     dets, counts = ssdb.decode_nms_host(pred, anc, 2.0, 200, 0.45)
     assert counts[0, 0] == 0 and counts[0, 1] == 0
+
+
+def test_decode_nms_batch_128_property():
+    """BASELINE.json configs[4] size (128 images): a sample of images is compared with the oracle row by row; every
+    image satisfies the size-independent properties (kept <= candidates <= cap, confidence-descending inside a class)."""
+    anc = bo.anchors('vgg300')
+    preds = np.stack([synth.pred_clustered(3000 + i, anc) for i in range(128)])
+    dets, counts = ssdb.decode_nms_host(preds, anc, 0.01, 200, 0.45)
+    for i in range(0, 128, 9):
+        rows, cand = bo.detect(preds[i], anc, 0.01, 200)
+        got = _rows_from_dets(dets, counts, i)
+        assert got.shape == rows.shape and np.array_equal(got, rows), i
+    for i in range(128):
+        n = counts[i, 0]
+        assert 0 < n <= counts[i, 1] <= 200
+        conf = dets[i, :n, 0].astype(np.uint32).view(np.float32)
+        cls = dets[i, :n, 1]
+        for c in np.unique(cls):
+            assert np.all(np.diff(conf[cls == c]) <= 0), 'confidence order inside a class'
