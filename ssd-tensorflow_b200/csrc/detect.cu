@@ -26,6 +26,7 @@
 
 #include "bulk.cuh"
 #include "common.cuh"
+#include "select.cuh"
 
 namespace ssdb {
 namespace {
@@ -53,6 +54,12 @@ struct DetArgs {
     unsigned long long* g_keys; int* g_cand; int P;   // global scratch when P > SMEM_P_MAX
     int cap_eff;
     const unsigned int* ckey_in;                      // [B*A] keys from decode_scan_kernel, or null (v1: scan in this kernel)
+    int fast;                                         // 1: private-histogram select, shuffle scan, rank sort, bit-matrix NMS
+};
+
+struct ConfKey {         // participants of the top-cap selection: anchors at or above the confidence threshold
+    const unsigned int* ckey;
+    __device__ __forceinline__ bool operator()(int a, unsigned& key) const { key = ckey[a]; return key != 0u; }
 };
 
 // VT = compile-time row width (C + 5), 0 = generic
@@ -91,8 +98,8 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
     const int b = blockIdx.x, tid = threadIdx.x;
     if (P <= SMEM_P_MAX) {
         size_t off = ((size_t)p.A * 4 + 15) / 16 * 16;
-        keys = reinterpret_cast<unsigned long long*>(dyn + off);
-        cand = reinterpret_cast<int*>(dyn + off + (size_t)P * 8);
+        keys = reinterpret_cast<unsigned long long*>(dyn + off);                // [P] (+ [P] sorted copy when P <= BITS_P_MAX)
+        cand = reinterpret_cast<int*>(dyn + off + (size_t)P * 8 * (P <= BITS_P_MAX ? 2 : 1));
     } else {
         keys = p.g_keys + (size_t)b * P;
         cand = p.g_cand + (size_t)b * P * CAND_WORDS;
@@ -102,6 +109,9 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
     __shared__ int scan[DT];
     __shared__ int redi[DT / 32];
     __shared__ int first_pos[64];
+    __shared__ int whist[(DT / 32) * 256];
+    __shared__ int sel[2];
+    __shared__ int wsum[32];
 
     const int V = p.C + 5, A = p.A, C = p.C;
     const float* pb = p.pred + (size_t)b * A * V;
@@ -134,6 +144,8 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
     if (n > 0) {
         // ---- exact n-th largest confidence key (radix select, 4 x 8 bits) ----
         unsigned int prefix = 0, mask = 0; int remaining = n;
+        if (p.fast) radix_select_kth<DT>(A, n, ConfKey{ckey}, whist, hist, sel, prefix, remaining);
+        else
         for (int pass = 0; pass < 4; ++pass) {
             const int shift = 24 - 8 * pass;
             for (int i = tid; i < 256; i += DT) hist[i] = 0;
@@ -160,15 +172,19 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
         const int a_lo = tid * per, a_hi = min(A, a_lo + per);
         int ties = 0;
         for (int a = a_lo; a < a_hi; ++a) if (ckey[a] == prefix) ++ties;
-        scan[tid] = ties;
-        __syncthreads();
-        for (int o = 1; o < DT; o <<= 1) {
-            int v = tid >= o ? scan[tid - o] : 0;
+        int rank;
+        if (p.fast) rank = block_excl_scan<DT>(ties, wsum);
+        else {
+            scan[tid] = ties;
             __syncthreads();
-            scan[tid] += v;
-            __syncthreads();
+            for (int o = 1; o < DT; o <<= 1) {
+                int v = tid >= o ? scan[tid - o] : 0;
+                __syncthreads();
+                scan[tid] += v;
+                __syncthreads();
+            }
+            rank = scan[tid] - ties;
         }
-        int rank = scan[tid] - ties;
         const int base_ties = n - remaining;       // number of keys strictly above the pivot
         for (int a = a_lo; a < a_hi; ++a) {
             unsigned int k = ckey[a];
@@ -179,6 +195,19 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
             if (slot >= 0) keys[slot] = ((unsigned long long)k << 32) | (unsigned long long)(0xffffffffu - (unsigned int)a);
         }
         __syncthreads();
+        if (p.fast && P <= BITS_P_MAX) {
+            // ---- rank sort: keys are unique (they carry the anchor index), so #greater = final position; 4 lanes per key ----
+            unsigned long long* sorted = keys + P;
+            const int i = tid >> 2, q = tid & 3;
+            const unsigned long long me = i < n ? keys[i] : 0ull;
+            int cnt = 0;
+            if (i < n) for (int j = q; j < n; j += 4) cnt += keys[j] > me;
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+            if (i < n && q == 0) sorted[cnt] = me;
+            __syncthreads();
+            keys = sorted;
+        } else
         // ---- bitonic sort, descending ----
         for (int k2 = 2; k2 <= P; k2 <<= 1) {
             for (int j = k2 >> 1; j > 0; j >>= 1) {
@@ -235,9 +264,8 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
         __syncthreads();
         // ---- greedy NMS in confidence order; alive flags reuse ckey[] ----
         unsigned int* alive = ckey;
-        if (P <= BITS_P_MAX && P <= SMEM_P_MAX) {
-            // suppression matrix: bit j of row i <=> j > i, same class, IoU(i, j) > thr; then ONE warp walks the rows in
-            // confidence order keeping the removed set in registers (lane w = candidates 32w .. 32w+31)
+        if (p.fast && P <= BITS_P_MAX) {
+            // suppression matrix: bit j of row i <=> j > i, same class, IoU(i, j) > thr (built by all threads)
             const int W = (P + 31) / 32;
             unsigned int* sup = reinterpret_cast<unsigned int*>(cand + CAND_WORDS * P);
             for (int t = tid; t < n * W; t += DT) {
@@ -255,21 +283,36 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
                         int ih = min(iy1, jy1) - max(iy0, jy0) + 1; ih = ih < 0 ? 0 : ih;
                         long long inter = (long long)iw * ih;
                         long long uni = area_i + (long long)(jx1 - jx0 + 1) * (jy1 - jy0 + 1) - inter;
-                        if (__ddiv_rn((double)inter, (double)uni) > p.iou_thr) bits |= 1u << jj;
+                        const double v = inter == 0 ? 0.0 : __ddiv_rn((double)inter, (double)uni);     // 0 / uni == 0.0 exactly
+                        if (v > p.iou_thr) bits |= 1u << jj;
                     }
                 }
                 sup[t] = bits;
             }
             __syncthreads();
-            if (tid < 32) {
-                unsigned int removed = 0u;
-                for (int i = 0; i < n; ++i) {
-                    const unsigned int row = tid < W ? sup[i * W + tid] : 0u;
-                    const unsigned int r = __shfl_sync(0xffffffffu, removed, i >> 5);
-                    if (!((r >> (i & 31)) & 1u)) removed |= row;
+            // classes never interact: warp c walks only the candidates of class c (in confidence order) with its removed
+            // set in registers (lane w = candidates 32w .. 32w+31); serial depth = largest class, not n
+            {
+                const int lane = tid & 31;
+                for (int c = tid >> 5; c < C; c += DT / 32) {
+                    unsigned int removed = 0u;
+                    for (int chunk = 0; chunk < W; ++chunk) {
+                        const int j = chunk * 32 + lane;
+                        unsigned int m = __ballot_sync(0xffffffffu, j < n && cand[0 * P + j] == c);
+                        while (m) {
+                            const int bit = __ffs(m) - 1; m &= m - 1;
+                            const int i = chunk * 32 + bit;
+                            const unsigned int row = lane < W ? sup[i * W + lane] : 0u;
+                            const unsigned int r = __shfl_sync(0xffffffffu, removed, chunk);
+                            if (!((r >> bit) & 1u)) removed |= row;
+                        }
+                    }
+                    for (int chunk = 0; chunk < W; ++chunk) {
+                        const int j = chunk * 32 + lane;
+                        const unsigned int r = __shfl_sync(0xffffffffu, removed, chunk);
+                        if (j < n && cand[0 * P + j] == c) alive[j] = ((r >> lane) & 1u) ? 0u : 1u;
+                    }
                 }
-                if (tid < W)
-                    for (int jj = 0; jj < 32; ++jj) { const int j = tid * 32 + jj; if (j < n) alive[j] = ((removed >> jj) & 1u) ? 0u : 1u; }
             }
             __syncthreads();
         } else {
@@ -301,6 +344,29 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
         if ((tid & 31) == 0) redi[tid >> 5] = kept;
         __syncthreads();
         if (tid == 0) { int t = 0; for (int i = 0; i < DT / 32; ++i) t += redi[i]; p.counts[b * 2] = t; p.counts[b * 2 + 1] = n; }
+        if (p.fast && P <= BITS_P_MAX) {
+            // 4 lanes per candidate split the count of kept boxes that come earlier in the reference's output order
+            const int i = tid >> 2, q = tid & 3;
+            const bool live = i < n && alive[i];
+            const int ci = live ? cand[0 * P + i] : 0;
+            const int fi = ci < 64 ? first_pos[ci] : 0;
+            int rnk = 0;
+            if (live)
+                for (int j = q; j < n; j += 4) {
+                    if (!alive[j]) continue;
+                    const int cj = cand[0 * P + j];
+                    const int fj = cj < 64 ? first_pos[cj] : 0;
+                    if (fj < fi || (fj == fi && j < i)) ++rnk;
+                }
+            rnk += __shfl_xor_sync(0xffffffffu, rnk, 1);
+            rnk += __shfl_xor_sync(0xffffffffu, rnk, 2);
+            if (live && q == 0) {
+                int* o = p.dets + ((size_t)b * p.cap_eff + rnk) * 8;
+                o[0] = cand[9 * P + i]; o[1] = ci;
+                o[2] = cand[1 * P + i]; o[3] = cand[2 * P + i]; o[4] = cand[3 * P + i]; o[5] = cand[4 * P + i];
+                o[6] = cand[10 * P + i]; o[7] = i;
+            }
+        } else
         for (int i = tid; i < n; i += DT) {
             if (!alive[i]) continue;
             const int ci = cand[0 * P + i];
@@ -424,23 +490,26 @@ int decode_nms_launch(const float* pred, int B, int A, int C, const double* anch
     p.cap_eff = (cap > 0 && cap < A) ? cap : A;
     p.P = next_pow2(p.cap_eff);
     size_t sh = ((size_t)A * 4 + 15) / 16 * 16;
-    p.g_keys = nullptr; p.g_cand = nullptr; p.ckey_in = nullptr;
+    p.g_keys = nullptr; p.g_cand = nullptr; p.ckey_in = nullptr; p.fast = nms_v1() ? 0 : 1;
     unsigned char* sc = reinterpret_cast<unsigned char*>(scratch);
     const size_t keys_bytes = align256((size_t)B * A * 4);
     if (p.P <= SMEM_P_MAX) {
         sh += (size_t)p.P * (8 + 4 * CAND_WORDS);
-        if (p.P <= BITS_P_MAX) sh += (size_t)p.P * ((p.P + 31) / 32) * 4;
+        if (p.P <= BITS_P_MAX) sh += (size_t)p.P * 8 + (size_t)p.P * ((p.P + 31) / 32) * 4;
     } else {
         p.g_keys = reinterpret_cast<unsigned long long*>(sc + keys_bytes);
         p.g_cand = reinterpret_cast<int*>(sc + keys_bytes + (size_t)B * p.P * 8);
     }
-    SSDB_REQUIRE(sh <= 200 * 1024, "anchor count too large for one CTA");
-    static bool attr = false;
-    if (!attr) {
-        SSDB_CUDA(cudaFuncSetAttribute(decode_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    static size_t dyn_max = 0;          // 227 KB per CTA minus the kernel's static shared memory
+    if (!dyn_max) {
+        cudaFuncAttributes fa;
+        SSDB_CUDA(cudaFuncGetAttributes(&fa, decode_nms_kernel));
+        size_t m = 232448 - fa.sharedSizeBytes;
+        SSDB_CUDA(cudaFuncSetAttribute(decode_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m));
         SSDB_CUDA(cudaFuncSetAttribute(decode_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT * MAXV * 4));
-        attr = true;
+        dyn_max = m;
     }
+    SSDB_REQUIRE(sh <= dyn_max, "anchor count too large for one CTA");
     if (!nms_v1()) {
         const int V = C + 5, S = (A + RT - 1) / RT;
         const int use_bulk = ((size_t)A * V * 4) % 16 == 0 && bulk::aligned16(pred);

@@ -25,6 +25,7 @@
 
 #include "bulk.cuh"
 #include "common.cuh"
+#include "select.cuh"
 
 namespace ssdb {
 namespace {
@@ -53,6 +54,7 @@ __device__ __forceinline__ double iou_incl(const IBox& a, const IBox& b) {
     int iw = min(a.x1, b.x1) - max(a.x0, b.x0) + 1; iw = iw < 0 ? 0 : iw;
     int ih = min(a.y1, b.y1) - max(a.y0, b.y0) + 1; ih = ih < 0 ? 0 : ih;
     long long inter = (long long)iw * ih;
+    if (inter == 0) return 0.0;                       // 0 / uni == 0.0 exactly: skip the float64 division for disjoint boxes
     long long uni = area_a + area_b - inter;
     return __ddiv_rn((double)inter, (double)uni);
 }
@@ -537,64 +539,50 @@ __global__ void __launch_bounds__(RT) loss_rows_kernel(
     }
 }
 
+struct NegKey {          // participants of the hard-negative selection: negatives, ordered by cross entropy
+    const float* ce; const signed char* kind;
+    __device__ __forceinline__ bool operator()(int a, unsigned& key) const { key = order_key(ce[a]); return kind[a] == 1; }
+};
+
 // one CTA per image: exact k-th largest negative CE, marks the selected negatives, per-image losses, batch mean
 __global__ void __launch_bounds__(LT) loss_select_kernel(LossWs ws, int B, int A, int S, float grad_scale, float* __restrict__ losses_out) {
     extern __shared__ __align__(16) unsigned char dyn[];
     float* ce = reinterpret_cast<float*>(dyn);
     signed char* kind = reinterpret_cast<signed char*>(ce + A);
     __shared__ float redf[LT / 32];
-    __shared__ int hist[256];
-    __shared__ int sel_bin, sel_rem;
-    __shared__ int scan[LT];
+    __shared__ int whist[(LT / 32) * 256];
+    __shared__ int tot_bins[256];
+    __shared__ int sel[2];
+    __shared__ int wsum[32];
     __shared__ TilePart tot;
     const int tid = threadIdx.x, b = blockIdx.x;
     const float* gce = ws.ce + (long long)b * A;
     unsigned char* gkind = ws.kind + (long long)b * A;
     for (int a = tid; a < A; a += LT) { ce[a] = gce[a]; kind[a] = (signed char)gkind[a]; }
-    if (tid == 0) {
+    if (tid < 32) {
+        // per-tile partial sums in tile order (lane-strided, then a fixed shuffle tree: deterministic)
         TilePart t{0.f, 0.f, 0, 0};
-        for (int s = 0; s < S; ++s) { const TilePart p = ws.part[b * S + s]; t.pos_sum += p.pos_sum; t.loc_sum += p.loc_sum; t.pos_cnt += p.pos_cnt; t.neg_cnt += p.neg_cnt; }
-        tot = t;
+        for (int s = tid; s < S; s += 32) { const TilePart p = ws.part[b * S + s]; t.pos_sum += p.pos_sum; t.loc_sum += p.loc_sum; t.pos_cnt += p.pos_cnt; t.neg_cnt += p.neg_cnt; }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            t.pos_sum += __shfl_xor_sync(0xffffffffu, t.pos_sum, o); t.loc_sum += __shfl_xor_sync(0xffffffffu, t.loc_sum, o);
+            t.pos_cnt += __shfl_xor_sync(0xffffffffu, t.pos_cnt, o); t.neg_cnt += __shfl_xor_sync(0xffffffffu, t.neg_cnt, o);
+        }
+        if (tid == 0) tot = t;
     }
     __syncthreads();
     const float pos_sum = tot.pos_sum, loc_sum = tot.loc_sum; const int pos_cnt = tot.pos_cnt, neg_cnt = tot.neg_cnt;
     const int k = min(neg_cnt, 3 * pos_cnt);
     float neg_sum = 0.f;
     if (k > 0) {
-        unsigned int prefix = 0, mask = 0; int remaining = k;
-        for (int pass = 0; pass < 4; ++pass) {
-            const int shift = 24 - 8 * pass;
-            for (int i = tid; i < 256; i += LT) hist[i] = 0;
-            __syncthreads();
-            for (int a = tid; a < A; a += LT) {
-                if (kind[a] != 1) continue;
-                unsigned int key = order_key(ce[a]);
-                if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
-            }
-            __syncthreads();
-            if (tid == 0) {
-                int cum = 0, bin = 255;
-                for (; bin >= 0; --bin) { if (cum + hist[bin] >= remaining) break; cum += hist[bin]; }
-                sel_bin = bin; sel_rem = remaining - cum;
-            }
-            __syncthreads();
-            prefix |= ((unsigned int)sel_bin) << shift; mask |= 255u << shift; remaining = sel_rem;
-            __syncthreads();
-        }
+        unsigned int prefix; int remaining;
+        radix_select_kth<LT>(A, k, NegKey{ce, kind}, whist, tot_bins, sel, prefix, remaining);
         // prefix = key of the k-th largest; `remaining` ties (key == prefix) are taken, lowest index first (tf.nn.top_k order)
         const int per = (A + LT - 1) / LT;
         const int a_lo = tid * per, a_hi = min(A, a_lo + per);
         int ties = 0;
         for (int a = a_lo; a < a_hi; ++a) if (kind[a] == 1 && order_key(ce[a]) == prefix) ++ties;
-        scan[tid] = ties;
-        __syncthreads();
-        for (int o = 1; o < LT; o <<= 1) {
-            int v = tid >= o ? scan[tid - o] : 0;
-            __syncthreads();
-            scan[tid] += v;
-            __syncthreads();
-        }
-        int rank = scan[tid] - ties;
+        int rank = block_excl_scan<LT>(ties, wsum);
         float part = 0.f;
         for (int a = a_lo; a < a_hi; ++a) {
             if (kind[a] != 1) continue;
@@ -735,14 +723,16 @@ int loss_v2(const float* output, const float* labels, const double* gt, const in
         SSDB_LAUNCH_CHECK();
     }
     const size_t sh_rows = (size_t)RT * V * 4 * (GT_MODE ? 1 : 2), sh_sel = (size_t)A * 5 + 16, sh_grad = (size_t)RT * V * 4;
-    SSDB_REQUIRE(sh_sel <= 200 * 1024, "anchor count too large for the select kernel");
-    static bool attr = false;     // per template instantiation
-    if (!attr) {
+    static size_t sel_max = 0;    // per template instantiation; 227 KB per CTA minus the select kernel's static shared memory
+    if (!sel_max) {
         int rc = opt_in_smem(loss_rows_kernel<GT_MODE, VT>, (size_t)RT * MAXV * 8); if (rc) return rc;
-        rc = opt_in_smem(loss_select_kernel, 200 * 1024); if (rc) return rc;
-        rc = opt_in_smem(loss_grad_kernel<GT_MODE, VT>, sh_grad); if (rc) return rc;
-        attr = true;
+        cudaFuncAttributes fa;
+        SSDB_CUDA(cudaFuncGetAttributes(&fa, loss_select_kernel));
+        size_t m = 232448 - fa.sharedSizeBytes;
+        SSDB_CUDA(cudaFuncSetAttribute(loss_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m));
+        sel_max = m;
     }
+    SSDB_REQUIRE(sh_sel <= sel_max, "anchor count too large for the select kernel");
     loss_rows_kernel<GT_MODE, VT><<<dim3(S, B), RT, sh_rows, st>>>(output, labels, gt, gt_count, G, anchors, A, C, S, bulk_rows, ws,
                                                                    result_out, match_out);
     SSDB_LAUNCH_CHECK();

@@ -1,0 +1,91 @@
+// Block-wide exact selection primitives shared by the multibox loss (k-th largest negative cross entropy,
+// tf.nn.top_k(k=A) in ssdvgg.py:463) and decode_boxes (cap-th largest confidence, np.argsort in ssdutils.py:203).
+//
+// 4-pass, 8-bit radix select over 32-bit order-preserving keys.  Confidence / CE keys of one image share
+// their top byte almost everywhere, so a plain shared-memory atomicAdd histogram serialises ~A same-address
+// atomics per pass (measured on B200: 39 us for 8732 keys).  Here every warp owns a private 256-bin histogram
+// and aggregates equal bins with match.any before touching it: no atomics, no cross-warp contention.
+#pragma once
+#include <cstdint>
+
+namespace ssdb {
+
+// KeyAt: __device__ bool operator()(int a, unsigned& key) const  -- false: element a does not take part
+// whist: [NT/32][256] ints, tot: [256] ints, sel: [2] ints (all shared memory)
+// On return `prefix` is the key of the k-th largest participant and `remaining` (>= 1) says how many elements whose
+// key == prefix belong to the top k (the caller takes them in index order).  Every thread of the CTA must call.
+template <int NT, typename KeyAt>
+__device__ __forceinline__ void radix_select_kth(int A, int k, const KeyAt& key_at, int* whist, int* tot, int* sel,
+                                                 unsigned& prefix, int& remaining) {
+    static_assert(NT >= 256 && NT % 32 == 0, "one thread per bin in the reduction");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int* mine = whist + warp * 256;
+    prefix = 0u; unsigned mask = 0u; remaining = k;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = tid; i < (NT / 32) * 256; i += NT) whist[i] = 0;
+        __syncthreads();
+        for (int a0 = 0; a0 < A; a0 += NT) {
+            const int a = a0 + tid;
+            unsigned key = 0u;
+            const bool valid = a < A && key_at(a, key) && (key & mask) == prefix;
+            const int bin = (int)((key >> shift) & 255u);
+            const unsigned act = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                const unsigned m = __match_any_sync(act, bin);
+                if (__ffs(m) - 1 == lane) mine[bin] += __popc(m);     // one lane per distinct bin: plain add is race free
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        if (tid < 256) {
+            int s = 0;
+#pragma unroll 8
+            for (int w = 0; w < NT / 32; ++w) s += whist[w * 256 + tid];
+            tot[tid] = s;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            // lane l owns bins 255-8l .. 248-8l (descending); find the bin where the running count reaches `remaining`
+            int loc[8]; int s = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { loc[q] = tot[255 - 8 * lane - q]; s += loc[q]; }
+            int inc = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            const int exc = inc - s;
+            if (exc < remaining && remaining <= inc) {
+                int cum = exc;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (cum + loc[q] >= remaining) { sel[0] = 255 - 8 * lane - q; sel[1] = remaining - cum; break; }
+                    cum += loc[q];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= ((unsigned)sel[0]) << shift; mask |= 255u << shift; remaining = sel[1];
+    }
+}
+
+// exclusive prefix sum of one int per thread in thread order; wsum: [32] ints of shared memory; contains two CTA barriers
+template <int NT>
+__device__ __forceinline__ int block_excl_scan(int v, int* wsum) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const int s = lane < NT / 32 ? wsum[lane] : 0;
+        int si = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, si, o); if (lane >= o) si += t; }
+        wsum[lane] = si - s;
+    }
+    __syncthreads();
+    return inc - v + wsum[warp];
+}
+
+}  // namespace ssdb
