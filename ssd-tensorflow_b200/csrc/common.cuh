@@ -116,6 +116,10 @@ int maxpool_fwd_arg(const float* x, int B, int H, int W, int C, int k, int strid
                     float* y, unsigned char* arg, cudaStream_t st);
 int maxpool_bwd_arg(const float* x, const float* dy, const unsigned char* arg, int B, int H, int W, int C, int k, int stride, int pad_t,
                     int pad_l, int Ho, int Wo, int beta, int relu_mask, int round_out, float* dx, cudaStream_t st);
+// non-overlapping 2x2/s2 pools: one code byte per output element (winning cell + "winner > 0"), so the backward reads no activations
+int maxpool2x2_fwd_code(const float* x, int B, int H, int W, int C, int Ho, int Wo, float* y, unsigned char* code, cudaStream_t st);
+int maxpool2x2_bwd_code(const float* dy, const unsigned char* code, int B, int H, int W, int C, int Ho, int Wo, int relu_mask,
+                        int round_out, float* dx, cudaStream_t st);
 int l2norm_fwd(const float* x, const float* scale, long long pixels, int C, int round_out, float* y, cudaStream_t st);
 int l2norm_bwd(const float* x, const float* scale, const float* dy, long long pixels, int C, int beta,
                int round_out, float* dx, float* dscale, float* partial, cudaStream_t st);

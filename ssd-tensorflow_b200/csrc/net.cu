@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -93,6 +94,7 @@ struct ssdb_net {
     // conv1_1 as a 1x1 tensor-core conv over an explicit 3x3x3 patch matrix (Cin = 3 cannot feed the MMA directly)
     float *patches = nullptr, *c1_w32 = nullptr, *c1_wt = nullptr, *c1_dw32 = nullptr;
     unsigned char* pool5_arg = nullptr;   // winning window cell of mod_pool5 (3x3 stride 1), one byte per output element
+    std::vector<unsigned char*> pool_code; // per op: code bytes of the 2x2/s2 pools (null for every other op)
     bool round = true;                 // activations / gradients are stored tf32-rounded (off in pure-SIMT mode)
     float *acts = nullptr, *gacts = nullptr;
     float *out = nullptr, *out_grad = nullptr, *result = nullptr, *dz_head = nullptr;
@@ -343,6 +345,8 @@ int run_forward(ssdb_net* n, const float* images, int B, cudaStream_t st) {
             const Buf& bi = n->bufs[op.in]; const Buf& bo = n->bufs[op.out];
             if (op.stride == 1 && n->pool5_arg)
                 rc = maxpool_fwd_arg(n->act(op.in, B), B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W, n->act(op.out, B), n->pool5_arg, st);
+            else if (n->pool_code[&op - n->ops.data()])
+                rc = maxpool2x2_fwd_code(n->act(op.in, B), B, bi.H, bi.W, bi.C, bo.H, bo.W, n->act(op.out, B), n->pool_code[&op - n->ops.data()], st);
             else
                 rc = maxpool_fwd(n->act(op.in, B), B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W, n->act(op.out, B), st);
         } else {
@@ -413,6 +417,9 @@ int run_backward(ssdb_net* n, int B, cudaStream_t st) {
             if (op.stride == 1 && n->pool5_arg)
                 rc = maxpool_bwd_arg(n->act(op.in, B), n->gact(op.out, B), n->pool5_arg, B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W,
                                      written[op.in] ? 1 : 0, bi.relu_out ? 1 : 0, n->round ? 1 : 0, n->gact(op.in, B), st);
+            else if (n->pool_code[&op - n->ops.data()] && !written[op.in])
+                rc = maxpool2x2_bwd_code(n->gact(op.out, B), n->pool_code[&op - n->ops.data()], B, bi.H, bi.W, bi.C, bo.H, bo.W, bi.relu_out ? 1 : 0,
+                                         n->round ? 1 : 0, n->gact(op.in, B), st);
             else
             rc = maxpool_bwd(n->act(op.in, B), n->gact(op.out, B), B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W,
                              written[op.in] ? 1 : 0, bi.relu_out ? 1 : 0, n->round ? 1 : 0, n->gact(op.in, B), st);
@@ -514,6 +521,14 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
     SSDB_CUDA(cudaMemset(n->loss_ws, 0, multibox_loss_ws_bytes(max_batch, n->A)));
     for (const Op& op : n->ops)
         if (op.type == OP_POOL && op.stride == 1) { const Buf& bo = n->bufs[op.out]; ALLOC(n->pool5_arg, (size_t)max_batch * bo.H * bo.W * bo.C, unsigned char); }
+    n->pool_code.assign(n->ops.size(), nullptr);
+    if (!getenv("SSDB_POOL_CODE") || atoi(getenv("SSDB_POOL_CODE")))
+        for (size_t i = 0; i < n->ops.size(); ++i) {
+            const Op& op = n->ops[i];
+            if (op.type != OP_POOL || op.k != 2 || op.stride != 2 || op.pad != 0) continue;
+            const Buf& bo = n->bufs[op.out];
+            ALLOC(n->pool_code[i], (size_t)max_batch * bo.H * bo.W * bo.C, unsigned char);
+        }
     if (n->round) {
         const Op& c1 = n->ops[0];
         ConvGeom g1 = geom_of(n, c1, max_batch); g1.Cin = 32; g1.k = 1; g1.pad_t = g1.pad_l = 0;
@@ -553,6 +568,7 @@ int ssdb_destroy(ssdb_net* n) {
     void* ptrs[] = {n->pool5_arg, n->patches, n->c1_w32, n->c1_wt, n->c1_dw32, n->wr, n->params, n->grads, n->moms, n->wt, n->acts, n->gacts, n->out, n->out_grad, n->result, n->labels_stage,
                     n->dz_head, n->images_stage, n->partial, n->small_ws, n->counter, n->decay_mask, n->anchors, n->loss_ws, n->det_ws};
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (unsigned char* p : n->pool_code) if (p) cudaFree(p);
     if (n->host_small) cudaFreeHost(n->host_small);
     if (n->own_stream) cudaStreamDestroy(n->own_stream);
     if (n->copy_stream) cudaStreamDestroy(n->copy_stream);
@@ -746,15 +762,28 @@ int ssdb_match_anchors_host(const double* gt, const int* gt_count, int B, int G,
     return rc;
 }
 
+// grow-only scratch per stream: calls on one stream are ordered, calls on different streams never share a buffer
+static int decode_scratch(cudaStream_t st, size_t need, void** out) {
+    struct Scratch { void* p = nullptr; size_t cap = 0; };
+    static std::map<cudaStream_t, Scratch> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    Scratch& s = cache[st];
+    if (need > s.cap) {
+        if (s.p) { SSDB_CUDA(cudaStreamSynchronize(st)); cudaFree(s.p); s.p = nullptr; s.cap = 0; }
+        SSDB_CUDA(cudaMalloc(&s.p, need)); s.cap = need;
+    }
+    *out = s.p;
+    return SSDB_OK;
+}
+
 int ssdb_decode_nms(const float* pred_dev, int B, int A, int C, const double* anchors_prop_dev, float conf_thr, int cap, double iou_thr,
                     int* dets_out_dev, int* counts_out_dev, void* stream) {
     SSDB_REQUIRE(pred_dev && anchors_prop_dev && dets_out_dev && counts_out_dev, "bad arguments");
     size_t sb = decode_nms_scratch_bytes(B, A, cap);
     void* scratch = nullptr;
-    if (sb) SSDB_CUDA(cudaMallocAsync(&scratch, sb, (cudaStream_t)stream));
-    int rc = decode_nms_launch(pred_dev, B, A, C, anchors_prop_dev, conf_thr, cap, iou_thr, dets_out_dev, counts_out_dev, scratch, sb, (cudaStream_t)stream);
-    if (scratch) cudaFreeAsync(scratch, (cudaStream_t)stream);
-    return rc;
+    int rc = decode_scratch((cudaStream_t)stream, sb, &scratch); if (rc) return rc;
+    return decode_nms_launch(pred_dev, B, A, C, anchors_prop_dev, conf_thr, cap, iou_thr, dets_out_dev, counts_out_dev, scratch, sb, (cudaStream_t)stream);
 }
 
 int ssdb_decode_nms_host(const float* pred, int B, int A, int C, const double* anchors, float conf_thr, int cap, double iou_thr,
