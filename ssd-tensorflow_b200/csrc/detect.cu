@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
     __shared__ int whist[(DT / 32) * 256];
     __shared__ int sel[2];
     __shared__ int wsum[32];
+    __shared__ unsigned int cmask[64 * 8];       // per class: which of the (<= 256) sorted candidates belong to it
+    __shared__ unsigned int rmask[64 * 8];       // per class: candidates removed by the greedy pass
 
     const int V = p.C + 5, A = p.A, C = p.C;
     const float* pb = p.pred + (size_t)b * A * V;
@@ -224,6 +226,7 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
         }
         // ---- decode the n candidates ----
         for (int i = tid; i < C && i < 64; i += DT) first_pos[i] = 0x7fffffff;
+        for (int i = tid; i < 64 * 8; i += DT) cmask[i] = 0u;
         __syncthreads();
         for (int i = tid; i < n; i += DT) {
             unsigned long long kk = keys[i];
@@ -260,60 +263,62 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
             cand[9 * P + i] = (int)__float_as_uint(okey_inv((unsigned int)(kk >> 32)));
             cand[10 * P + i] = a;
             if (cls < 64) atomicMin(&first_pos[cls], i);
+            if (P <= BITS_P_MAX) atomicOr(&cmask[cls * 8 + (i >> 5)], 1u << (i & 31));
         }
         __syncthreads();
         // ---- greedy NMS in confidence order; alive flags reuse ckey[] ----
         unsigned int* alive = ckey;
         if (p.fast && P <= BITS_P_MAX) {
-            // suppression matrix: bit j of row i <=> j > i, same class, IoU(i, j) > thr (built by all threads)
-            const int W = (P + 31) / 32;
+            // suppression matrix sup[i][8 words]: bit j of row i <=> j > i, same class, IoU(i, j) > thr.  One (i, j) pair per
+            // thread and step, so the same-class pairs (the only ones that cost arithmetic) spread evenly over the CTA.
+            // IoU > thr is decided by one float64 multiply when inter is clearly off thr * union; only a pair within 1e-9
+            // (relative) of the threshold takes the reference's rounded float64 division.
             unsigned int* sup = reinterpret_cast<unsigned int*>(cand + CAND_WORDS * P);
-            for (int t = tid; t < n * W; t += DT) {
-                const int i = t / W, w = t - i * W;
-                unsigned int bits = 0u;
-                if (w * 32 + 31 > i) {
-                    const int ci = cand[0 * P + i];
-                    const int ix0 = cand[5 * P + i], ix1 = cand[6 * P + i], iy0 = cand[7 * P + i], iy1 = cand[8 * P + i];
-                    const long long area_i = (long long)(ix1 - ix0 + 1) * (iy1 - iy0 + 1);
-                    for (int jj = 0; jj < 32; ++jj) {
-                        const int j = w * 32 + jj;
-                        if (j <= i || j >= n || cand[0 * P + j] != ci) continue;
-                        int jx0 = cand[5 * P + j], jx1 = cand[6 * P + j], jy0 = cand[7 * P + j], jy1 = cand[8 * P + j];
-                        int iw = min(ix1, jx1) - max(ix0, jx0) + 1; iw = iw < 0 ? 0 : iw;
-                        int ih = min(iy1, jy1) - max(iy0, jy0) + 1; ih = ih < 0 ? 0 : ih;
-                        long long inter = (long long)iw * ih;
-                        long long uni = area_i + (long long)(jx1 - jx0 + 1) * (jy1 - jy0 + 1) - inter;
-                        const double v = inter == 0 ? 0.0 : __ddiv_rn((double)inter, (double)uni);     // 0 / uni == 0.0 exactly
-                        if (v > p.iou_thr) bits |= 1u << jj;
-                    }
-                }
-                sup[t] = bits;
+            for (int t = tid; t < P * 8; t += DT) sup[t] = 0u;
+            __syncthreads();
+            const int lp = 31 - __clz(P);                       // P is a power of two
+            for (int t = tid; t < (n << lp); t += DT) {
+                const int i = t >> lp, j = t & (P - 1);
+                if (j <= i || j >= n) continue;
+                const int ci = cand[0 * P + i];
+                if (cand[0 * P + j] != ci) continue;
+                const int ix0 = cand[5 * P + i], ix1 = cand[6 * P + i], iy0 = cand[7 * P + i], iy1 = cand[8 * P + i];
+                const int jx0 = cand[5 * P + j], jx1 = cand[6 * P + j], jy0 = cand[7 * P + j], jy1 = cand[8 * P + j];
+                int iw = min(ix1, jx1) - max(ix0, jx0) + 1; iw = iw < 0 ? 0 : iw;
+                int ih = min(iy1, jy1) - max(iy0, jy0) + 1; ih = ih < 0 ? 0 : ih;
+                const long long inter = (long long)iw * ih;
+                const long long uni = (long long)(ix1 - ix0 + 1) * (iy1 - iy0 + 1) + (long long)(jx1 - jx0 + 1) * (jy1 - jy0 + 1) - inter;
+                const double di = (double)inter, lim = __dmul_rn(p.iou_thr, (double)uni);
+                bool hit;
+                if (di > __dmul_rn(lim, 1.000000001)) hit = true;
+                else if (di < __dmul_rn(lim, 0.999999999) || inter == 0) hit = (inter == 0) ? (0.0 > p.iou_thr) : false;
+                else hit = __ddiv_rn(di, (double)uni) > p.iou_thr;
+                if (hit) atomicOr(&sup[i * 8 + (j >> 5)], 1u << (j & 31));
             }
             __syncthreads();
-            // classes never interact: warp c walks only the candidates of class c (in confidence order) with its removed
-            // set in registers (lane w = candidates 32w .. 32w+31); serial depth = largest class, not n
-            {
-                const int lane = tid & 31;
+            // classes never interact: ONE THREAD per class walks that class's candidates in confidence order with the removed
+            // set (256 bits) in registers; a kept candidate ORs its matrix row in (two 16-byte shared loads)
+            if ((tid & 31) == 0) {
                 for (int c = tid >> 5; c < C; c += DT / 32) {
-                    unsigned int removed = 0u;
-                    for (int chunk = 0; chunk < W; ++chunk) {
-                        const int j = chunk * 32 + lane;
-                        unsigned int m = __ballot_sync(0xffffffffu, j < n && cand[0 * P + j] == c);
+                    unsigned int removed[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) {
+                        unsigned int m = cmask[c * 8 + w];
                         while (m) {
                             const int bit = __ffs(m) - 1; m &= m - 1;
-                            const int i = chunk * 32 + bit;
-                            const unsigned int row = lane < W ? sup[i * W + lane] : 0u;
-                            const unsigned int r = __shfl_sync(0xffffffffu, removed, chunk);
-                            if (!((r >> bit) & 1u)) removed |= row;
+                            if ((removed[w] >> bit) & 1u) continue;
+                            const uint4* row = reinterpret_cast<const uint4*>(sup + (w * 32 + bit) * 8);
+                            const uint4 r0 = row[0], r1 = row[1];
+                            removed[0] |= r0.x; removed[1] |= r0.y; removed[2] |= r0.z; removed[3] |= r0.w;
+                            removed[4] |= r1.x; removed[5] |= r1.y; removed[6] |= r1.z; removed[7] |= r1.w;
                         }
                     }
-                    for (int chunk = 0; chunk < W; ++chunk) {
-                        const int j = chunk * 32 + lane;
-                        const unsigned int r = __shfl_sync(0xffffffffu, removed, chunk);
-                        if (j < n && cand[0 * P + j] == c) alive[j] = ((r >> lane) & 1u) ? 0u : 1u;
-                    }
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) rmask[c * 8 + w] = removed[w];
                 }
             }
+            __syncthreads();
+            for (int j = tid; j < n; j += DT) alive[j] = ((rmask[cand[0 * P + j] * 8 + (j >> 5)] >> (j & 31)) & 1u) ? 0u : 1u;
             __syncthreads();
         } else {
         for (int i = tid; i < n; i += DT) alive[i] = 1u;
@@ -495,7 +500,7 @@ int decode_nms_launch(const float* pred, int B, int A, int C, const double* anch
     const size_t keys_bytes = align256((size_t)B * A * 4);
     if (p.P <= SMEM_P_MAX) {
         sh += (size_t)p.P * (8 + 4 * CAND_WORDS);
-        if (p.P <= BITS_P_MAX) sh += (size_t)p.P * 8 + (size_t)p.P * ((p.P + 31) / 32) * 4;
+        if (p.P <= BITS_P_MAX) sh += (size_t)p.P * 8 + (size_t)p.P * 8 * 4;      // sorted keys + suppression matrix rows of 8 words
     } else {
         p.g_keys = reinterpret_cast<unsigned long long*>(sc + keys_bytes);
         p.g_cand = reinterpret_cast<int*>(sc + keys_bytes + (size_t)B * p.P * 8);

@@ -4,7 +4,7 @@
 // 4-pass, 8-bit radix select over 32-bit order-preserving keys.  Confidence / CE keys of one image share
 // their top byte almost everywhere, so a plain shared-memory atomicAdd histogram serialises ~A same-address
 // atomics per pass (measured on B200: 39 us for 8732 keys).  Here every warp owns a private 256-bin histogram
-// and aggregates equal bins with match.any before touching it: no atomics, no cross-warp contention.
+// and aggregates the dominant bin with a ballot before touching it: no cross-warp contention, few atomics.
 #pragma once
 #include <cstdint>
 
@@ -30,10 +30,15 @@ __device__ __forceinline__ void radix_select_kth(int A, int k, const KeyAt& key_
             unsigned key = 0u;
             const bool valid = a < A && key_at(a, key) && (key & mask) == prefix;
             const int bin = (int)((key >> shift) & 255u);
+            // warp-aggregated update of the warp-private histogram: the lanes that share the first valid lane's bin (in
+            // the early passes nearly all of them) are counted with one ballot; the others add individually
             const unsigned act = __ballot_sync(0xffffffffu, valid);
-            if (valid) {
-                const unsigned m = __match_any_sync(act, bin);
-                if (__ffs(m) - 1 == lane) mine[bin] += __popc(m);     // one lane per distinct bin: plain add is race free
+            if (act) {
+                const int leader = __ffs(act) - 1;
+                const int b0 = __shfl_sync(0xffffffffu, bin, leader);
+                const unsigned same = __ballot_sync(0xffffffffu, valid && bin == b0);
+                if (lane == leader) mine[b0] += __popc(same);
+                else if (valid && bin != b0) atomicAdd(&mine[bin], 1);
             }
             __syncwarp();
         }
