@@ -55,7 +55,9 @@ struct DetArgs {
     int cap_eff;
     const unsigned int* ckey_in;                      // [B*A] keys from decode_scan_kernel, or null (v1: scan in this kernel)
     int fast;                                         // 1: private-histogram select, shuffle scan, rank sort, bit-matrix NMS
+    long long* trace;                                 // SSDB_TRACE=1: clock64() of CTA 0 at the phase boundaries (bring-up only)
 };
+#define SSDB_TRACE_PT(k) do { if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[k] = clock64(); } while (0)
 
 struct ConfKey {         // participants of the top-cap selection: anchors at or above the confidence threshold
     const unsigned int* ckey;
@@ -114,8 +116,11 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
     __shared__ int wsum[32];
     __shared__ unsigned int cmask[64 * 8];       // per class: which of the (<= 256) sorted candidates belong to it
     __shared__ unsigned int rmask[64 * 8];       // per class: candidates removed by the greedy pass
+    __shared__ __align__(4) unsigned char ccls[BITS_P_MAX];   // class of each sorted candidate (255 = empty slot)
+    __shared__ int kcnt[64], kbase[64];          // per class: kept boxes, and kept boxes of the classes that come earlier in the output
 
     const int V = p.C + 5, A = p.A, C = p.C;
+    SSDB_TRACE_PT(0);
     const float* pb = p.pred + (size_t)b * A * V;
 
     // ---- pass 1: arg-max class and confidence per anchor ----
@@ -141,6 +146,7 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
     __syncthreads();
     nvalid = redi[0];
     const int n = min(nvalid, p.cap_eff);
+    SSDB_TRACE_PT(1);
     __syncthreads();
 
     if (n > 0) {
@@ -166,6 +172,7 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
             prefix |= ((unsigned int)sel_bin) << shift; mask |= 255u << shift; remaining = sel_rem;
             __syncthreads();
         }
+        SSDB_TRACE_PT(2);
         // ---- compaction: keys above the pivot anywhere, `remaining` ties by lowest anchor index ----
         if (tid == 0) n_gt = 0;
         for (int i = tid; i < P; i += DT) keys[i] = 0ull;
@@ -197,6 +204,7 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
             if (slot >= 0) keys[slot] = ((unsigned long long)k << 32) | (unsigned long long)(0xffffffffu - (unsigned int)a);
         }
         __syncthreads();
+        SSDB_TRACE_PT(3);
         if (p.fast && P <= BITS_P_MAX) {
             // ---- rank sort: keys are unique (they carry the anchor index), so #greater = final position; 4 lanes per key ----
             unsigned long long* sorted = keys + P;
@@ -224,9 +232,11 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
                 __syncthreads();
             }
         }
+        SSDB_TRACE_PT(4);
         // ---- decode the n candidates ----
         for (int i = tid; i < C && i < 64; i += DT) first_pos[i] = 0x7fffffff;
         for (int i = tid; i < 64 * 8; i += DT) cmask[i] = 0u;
+        for (int i = tid; i < BITS_P_MAX; i += DT) ccls[i] = 255;
         __syncthreads();
         for (int i = tid; i < n; i += DT) {
             unsigned long long kk = keys[i];
@@ -263,9 +273,10 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
             cand[9 * P + i] = (int)__float_as_uint(okey_inv((unsigned int)(kk >> 32)));
             cand[10 * P + i] = a;
             if (cls < 64) atomicMin(&first_pos[cls], i);
-            if (P <= BITS_P_MAX) atomicOr(&cmask[cls * 8 + (i >> 5)], 1u << (i & 31));
+            if (P <= BITS_P_MAX) { atomicOr(&cmask[cls * 8 + (i >> 5)], 1u << (i & 31)); ccls[i] = (unsigned char)cls; }
         }
         __syncthreads();
+        SSDB_TRACE_PT(5);
         // ---- greedy NMS in confidence order; alive flags reuse ckey[] ----
         unsigned int* alive = ckey;
         if (p.fast && P <= BITS_P_MAX) {
@@ -276,41 +287,53 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
             unsigned int* sup = reinterpret_cast<unsigned int*>(cand + CAND_WORDS * P);
             for (int t = tid; t < P * 8; t += DT) sup[t] = 0u;
             __syncthreads();
-            const int lp = 31 - __clz(P);                       // P is a power of two
-            for (int t = tid; t < (n << lp); t += DT) {
-                const int i = t >> lp, j = t & (P - 1);
-                if (j <= i || j >= n) continue;
-                const int ci = cand[0 * P + i];
-                if (cand[0 * P + j] != ci) continue;
+        SSDB_TRACE_PT(6);
+            // four candidates j per step: their class bytes come as one word and are compared with class(i) at once, so the
+            // (majority of) pairs of different classes cost a handful of instructions
+            const int G = (P < 4 ? 4 : P) >> 2, lg = 31 - __clz(G);      // P is a power of two
+            for (int t = tid; t < (n << lg); t += DT) {
+                const int i = t >> lg, g = t & (G - 1);
+                if (g * 4 + 3 <= i) continue;
+                const unsigned int ci = ccls[i];
+                const unsigned int eq = __vcmpeq4(*reinterpret_cast<const unsigned int*>(ccls + g * 4), ci * 0x01010101u);
+                if (!eq) continue;
                 const int ix0 = cand[5 * P + i], ix1 = cand[6 * P + i], iy0 = cand[7 * P + i], iy1 = cand[8 * P + i];
-                const int jx0 = cand[5 * P + j], jx1 = cand[6 * P + j], jy0 = cand[7 * P + j], jy1 = cand[8 * P + j];
-                int iw = min(ix1, jx1) - max(ix0, jx0) + 1; iw = iw < 0 ? 0 : iw;
-                int ih = min(iy1, jy1) - max(iy0, jy0) + 1; ih = ih < 0 ? 0 : ih;
-                const long long inter = (long long)iw * ih;
-                const long long uni = (long long)(ix1 - ix0 + 1) * (iy1 - iy0 + 1) + (long long)(jx1 - jx0 + 1) * (jy1 - jy0 + 1) - inter;
-                const double di = (double)inter, lim = __dmul_rn(p.iou_thr, (double)uni);
-                bool hit;
-                if (di > __dmul_rn(lim, 1.000000001)) hit = true;
-                else if (di < __dmul_rn(lim, 0.999999999) || inter == 0) hit = (inter == 0) ? (0.0 > p.iou_thr) : false;
-                else hit = __ddiv_rn(di, (double)uni) > p.iou_thr;
-                if (hit) atomicOr(&sup[i * 8 + (j >> 5)], 1u << (j & 31));
+                const long long area_i = (long long)(ix1 - ix0 + 1) * (iy1 - iy0 + 1);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = g * 4 + q;
+                    if (!((eq >> (8 * q)) & 0xffu) || j <= i) continue;        // slots >= n carry class 255: never equal
+                    const int jx0 = cand[5 * P + j], jx1 = cand[6 * P + j], jy0 = cand[7 * P + j], jy1 = cand[8 * P + j];
+                    int iw = min(ix1, jx1) - max(ix0, jx0) + 1; iw = iw < 0 ? 0 : iw;
+                    int ih = min(iy1, jy1) - max(iy0, jy0) + 1; ih = ih < 0 ? 0 : ih;
+                    const long long inter = (long long)iw * ih;
+                    const long long uni = area_i + (long long)(jx1 - jx0 + 1) * (jy1 - jy0 + 1) - inter;
+                    const double di = (double)inter, lim = __dmul_rn(p.iou_thr, (double)uni);
+                    bool hit;
+                    if (di > __dmul_rn(lim, 1.000000001)) hit = true;
+                    else if (di < __dmul_rn(lim, 0.999999999) || inter == 0) hit = (inter == 0) ? (0.0 > p.iou_thr) : false;
+                    else hit = __ddiv_rn(di, (double)uni) > p.iou_thr;
+                    if (hit) atomicOr(&sup[i * 8 + (j >> 5)], 1u << (j & 31));
+                }
             }
             __syncthreads();
             // classes never interact: ONE THREAD per class walks that class's candidates in confidence order with the removed
-            // set (256 bits) in registers; a kept candidate ORs its matrix row in (two 16-byte shared loads)
+            // set (256 bits) in registers.  Only KEPT candidates cost an iteration: the next one is the lowest set bit of
+            // (class members & ~removed); it ORs its matrix row in (two 16-byte shared loads).
             if ((tid & 31) == 0) {
                 for (int c = tid >> 5; c < C; c += DT / 32) {
                     unsigned int removed[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll
                     for (int w = 0; w < 8; ++w) {
-                        unsigned int m = cmask[c * 8 + w];
+                        const unsigned int members = cmask[c * 8 + w];
+                        unsigned int m = members & ~removed[w];
                         while (m) {
-                            const int bit = __ffs(m) - 1; m &= m - 1;
-                            if ((removed[w] >> bit) & 1u) continue;
+                            const int bit = __ffs(m) - 1;
                             const uint4* row = reinterpret_cast<const uint4*>(sup + (w * 32 + bit) * 8);
                             const uint4 r0 = row[0], r1 = row[1];
                             removed[0] |= r0.x; removed[1] |= r0.y; removed[2] |= r0.z; removed[3] |= r0.w;
                             removed[4] |= r1.x; removed[5] |= r1.y; removed[6] |= r1.z; removed[7] |= r1.w;
+                            m &= ~removed[w] & (0xfffffffeu << bit);       // later members of this word that are still alive
                         }
                     }
 #pragma unroll
@@ -318,8 +341,36 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
                 }
             }
             __syncthreads();
-            for (int j = tid; j < n; j += DT) alive[j] = ((rmask[cand[0 * P + j] * 8 + (j >> 5)] >> (j & 31)) & 1u) ? 0u : 1u;
+            SSDB_TRACE_PT(8);
+            // ---- output order = classes by first appearance, confidence order inside a class: with the per-class kept
+            //      masks this is a handful of popcounts per candidate (no pass over the other candidates) ----
+            if (tid < 64) {
+                int sk = 0;
+                if (tid < C)
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) sk += __popc(cmask[tid * 8 + w] & ~rmask[tid * 8 + w]);
+                kcnt[tid] = sk;
+            }
             __syncthreads();
+            if (tid < 64) {
+                int base = 0;
+                if (tid < C) { const int fp = first_pos[tid]; for (int c2 = 0; c2 < C; ++c2) if (first_pos[c2] < fp) base += kcnt[c2]; }
+                kbase[tid] = base;
+            }
+            if (tid == 0) { int t = 0; for (int c2 = 0; c2 < C; ++c2) t += kcnt[c2]; p.counts[b * 2] = t; p.counts[b * 2 + 1] = n; }
+            __syncthreads();
+            SSDB_TRACE_PT(9);
+            for (int i = tid; i < n; i += DT) {
+                const int ci = ccls[i], w = i >> 5;
+                const unsigned int aw = cmask[ci * 8 + w] & ~rmask[ci * 8 + w];
+                if (!((aw >> (i & 31)) & 1u)) continue;
+                int rnk = kbase[ci] + __popc(aw & ((1u << (i & 31)) - 1u));
+                for (int w2 = 0; w2 < w; ++w2) rnk += __popc(cmask[ci * 8 + w2] & ~rmask[ci * 8 + w2]);
+                int* o = p.dets + ((size_t)b * p.cap_eff + rnk) * 8;
+                o[0] = cand[9 * P + i]; o[1] = ci;
+                o[2] = cand[1 * P + i]; o[3] = cand[2 * P + i]; o[4] = cand[3 * P + i]; o[5] = cand[4 * P + i];
+                o[6] = cand[10 * P + i]; o[7] = i;
+            }
         } else {
         for (int i = tid; i < n; i += DT) alive[i] = 1u;
         __syncthreads();
@@ -339,7 +390,7 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
             }
             __syncthreads();
         }
-        }
+        SSDB_TRACE_PT(9);
         // ---- output rank: classes by first appearance, confidence order inside a class ----
         int kept = 0;
         for (int i = tid; i < n; i += DT) kept += alive[i] ? 1 : 0;
@@ -349,29 +400,6 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
         if ((tid & 31) == 0) redi[tid >> 5] = kept;
         __syncthreads();
         if (tid == 0) { int t = 0; for (int i = 0; i < DT / 32; ++i) t += redi[i]; p.counts[b * 2] = t; p.counts[b * 2 + 1] = n; }
-        if (p.fast && P <= BITS_P_MAX) {
-            // 4 lanes per candidate split the count of kept boxes that come earlier in the reference's output order
-            const int i = tid >> 2, q = tid & 3;
-            const bool live = i < n && alive[i];
-            const int ci = live ? cand[0 * P + i] : 0;
-            const int fi = ci < 64 ? first_pos[ci] : 0;
-            int rnk = 0;
-            if (live)
-                for (int j = q; j < n; j += 4) {
-                    if (!alive[j]) continue;
-                    const int cj = cand[0 * P + j];
-                    const int fj = cj < 64 ? first_pos[cj] : 0;
-                    if (fj < fi || (fj == fi && j < i)) ++rnk;
-                }
-            rnk += __shfl_xor_sync(0xffffffffu, rnk, 1);
-            rnk += __shfl_xor_sync(0xffffffffu, rnk, 2);
-            if (live && q == 0) {
-                int* o = p.dets + ((size_t)b * p.cap_eff + rnk) * 8;
-                o[0] = cand[9 * P + i]; o[1] = ci;
-                o[2] = cand[1 * P + i]; o[3] = cand[2 * P + i]; o[4] = cand[3 * P + i]; o[5] = cand[4 * P + i];
-                o[6] = cand[10 * P + i]; o[7] = i;
-            }
-        } else
         for (int i = tid; i < n; i += DT) {
             if (!alive[i]) continue;
             const int ci = cand[0 * P + i];
@@ -388,9 +416,12 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
             o[2] = cand[1 * P + i]; o[3] = cand[2 * P + i]; o[4] = cand[3 * P + i]; o[5] = cand[4 * P + i];
             o[6] = cand[10 * P + i]; o[7] = i;
         }
+        }
     } else {
         if (tid == 0) { p.counts[b * 2] = 0; p.counts[b * 2 + 1] = 0; }
     }
+    __syncthreads();
+    SSDB_TRACE_PT(10);
 }
 
 
@@ -524,8 +555,24 @@ int decode_nms_launch(const float* pred, int B, int A, int C, const double* anch
         SSDB_LAUNCH_CHECK();
         p.ckey_in = ckey;
     }
+    static long long* trace_dev = nullptr;
+    const bool tracing = getenv("SSDB_TRACE") != nullptr;
+    p.trace = nullptr;
+    if (tracing) {
+        if (!trace_dev) SSDB_CUDA(cudaMalloc(&trace_dev, 16 * sizeof(long long)));
+        SSDB_CUDA(cudaMemsetAsync(trace_dev, 0, 16 * sizeof(long long), st));
+        p.trace = trace_dev;
+    }
     decode_nms_kernel<<<B, DT, sh, st>>>(p);
     SSDB_LAUNCH_CHECK();
+    if (tracing) {
+        long long h[16];
+        SSDB_CUDA(cudaStreamSynchronize(st));
+        SSDB_CUDA(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "ssdb trace decode_nms_kernel (cycles since entry):");
+        for (int k = 1; k <= 10; ++k) fprintf(stderr, " p%d=%lld", k, h[k] ? h[k] - h[0] : -1);
+        fprintf(stderr, "\n");
+    }
     return SSDB_OK;
 }
 

@@ -545,7 +545,9 @@ struct NegKey {          // participants of the hard-negative selection: negativ
 };
 
 // one CTA per image: exact k-th largest negative CE, marks the selected negatives, per-image losses, batch mean
-__global__ void __launch_bounds__(LT) loss_select_kernel(LossWs ws, int B, int A, int S, float grad_scale, float* __restrict__ losses_out) {
+#define SSDB_TRACE_PT(k) do { if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[k] = clock64(); } while (0)
+__global__ void __launch_bounds__(LT) loss_select_kernel(LossWs ws, int B, int A, int S, float grad_scale, float* __restrict__ losses_out,
+                                                         long long* __restrict__ trace) {
     extern __shared__ __align__(16) unsigned char dyn[];
     float* ce = reinterpret_cast<float*>(dyn);
     signed char* kind = reinterpret_cast<signed char*>(ce + A);
@@ -558,6 +560,7 @@ __global__ void __launch_bounds__(LT) loss_select_kernel(LossWs ws, int B, int A
     const int tid = threadIdx.x, b = blockIdx.x;
     const float* gce = ws.ce + (long long)b * A;
     unsigned char* gkind = ws.kind + (long long)b * A;
+    SSDB_TRACE_PT(0);
     for (int a = tid; a < A; a += LT) { ce[a] = gce[a]; kind[a] = (signed char)gkind[a]; }
     if (tid < 32) {
         // per-tile partial sums in tile order (lane-strided, then a fixed shuffle tree: deterministic)
@@ -574,15 +577,18 @@ __global__ void __launch_bounds__(LT) loss_select_kernel(LossWs ws, int B, int A
     const float pos_sum = tot.pos_sum, loc_sum = tot.loc_sum; const int pos_cnt = tot.pos_cnt, neg_cnt = tot.neg_cnt;
     const int k = min(neg_cnt, 3 * pos_cnt);
     float neg_sum = 0.f;
+    SSDB_TRACE_PT(1);
     if (k > 0) {
         unsigned int prefix; int remaining;
         radix_select_kth<LT>(A, k, NegKey{ce, kind}, whist, tot_bins, sel, prefix, remaining);
+        SSDB_TRACE_PT(2);
         // prefix = key of the k-th largest; `remaining` ties (key == prefix) are taken, lowest index first (tf.nn.top_k order)
         const int per = (A + LT - 1) / LT;
         const int a_lo = tid * per, a_hi = min(A, a_lo + per);
         int ties = 0;
         for (int a = a_lo; a < a_hi; ++a) if (kind[a] == 1 && order_key(ce[a]) == prefix) ++ties;
         int rank = block_excl_scan<LT>(ties, wsum);
+        SSDB_TRACE_PT(3);
         float part = 0.f;
         for (int a = a_lo; a < a_hi; ++a) {
             if (kind[a] != 1) continue;
@@ -593,6 +599,7 @@ __global__ void __launch_bounds__(LT) loss_select_kernel(LossWs ws, int B, int A
         }
         neg_sum = block_sum(part, redf);
     }
+    SSDB_TRACE_PT(4);
     if (tid == 0) {
         ws.per_image[b * 2 + 0] = pos_cnt > 0 ? (pos_sum + neg_sum) / (float)pos_cnt : 0.f;
         ws.per_image[b * 2 + 1] = pos_cnt > 0 ? loc_sum / (float)pos_cnt : 0.f;
@@ -613,6 +620,7 @@ __global__ void __launch_bounds__(LT) loss_select_kernel(LossWs ws, int B, int A
             *ws.counter = 0;
         }
     }
+    SSDB_TRACE_PT(5);
 }
 
 // gradient w.r.t. the head output, tile by tile: zeros for unselected negatives, recomputed rows for the rest
@@ -736,8 +744,22 @@ int loss_v2(const float* output, const float* labels, const double* gt, const in
     loss_rows_kernel<GT_MODE, VT><<<dim3(S, B), RT, sh_rows, st>>>(output, labels, gt, gt_count, G, anchors, A, C, S, bulk_rows, ws,
                                                                    result_out, match_out);
     SSDB_LAUNCH_CHECK();
-    loss_select_kernel<<<B, LT, sh_sel, st>>>(ws, B, A, S, grad_scale, losses_out);
+    static long long* trace_dev = nullptr;
+    const bool tracing = getenv("SSDB_TRACE") != nullptr;
+    if (tracing) {
+        if (!trace_dev) SSDB_CUDA(cudaMalloc(&trace_dev, 16 * sizeof(long long)));
+        SSDB_CUDA(cudaMemsetAsync(trace_dev, 0, 16 * sizeof(long long), st));
+    }
+    loss_select_kernel<<<B, LT, sh_sel, st>>>(ws, B, A, S, grad_scale, losses_out, tracing ? trace_dev : nullptr);
     SSDB_LAUNCH_CHECK();
+    if (tracing) {
+        long long h[16];
+        SSDB_CUDA(cudaStreamSynchronize(st));
+        SSDB_CUDA(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "ssdb trace loss_select_kernel (cycles since entry):");
+        for (int k = 1; k <= 5; ++k) fprintf(stderr, " p%d=%lld", k, h[k] ? h[k] - h[0] : -1);
+        fprintf(stderr, "\n");
+    }
     if (grad_out) {
         loss_grad_kernel<GT_MODE, VT><<<dim3(S, B), RT, sh_grad, st>>>(output, labels, gt, G, anchors, A, C, bulk_grad, ws, grad_out);
         SSDB_LAUNCH_CHECK();

@@ -22,6 +22,43 @@ __device__ __forceinline__ void radix_select_kth(int A, int k, const KeyAt& key_
     int* mine = whist + warp * 256;
     prefix = 0u; unsigned mask = 0u; remaining = k;
     for (int pass = 0; pass < 4; ++pass) {
+        if (pass == 2) {
+            // 16 bits are fixed: normally only a few dozen keys still match.  Gather them (warp-aggregated slots) and, if they
+            // are at most NT/4, finish by counting: the wanted key is the one with #greater < remaining <= #greater + #equal.
+            unsigned* surv = reinterpret_cast<unsigned*>(whist);
+            int* nsurv = tot;
+            if (tid == 0) *nsurv = 0;
+            __syncthreads();
+            for (int a0 = 0; a0 < A; a0 += NT) {
+                const int a = a0 + tid;
+                unsigned key = 0u;
+                const bool valid = a < A && key_at(a, key) && (key & mask) == prefix;
+                const unsigned act = __ballot_sync(0xffffffffu, valid);
+                if (act) {
+                    const int leader = __ffs(act) - 1;
+                    int base = 0;
+                    if (lane == leader) base = atomicAdd(nsurv, __popc(act));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    const int slot = base + __popc(act & ((1u << lane) - 1u));
+                    if (valid && slot < NT / 4) surv[slot] = key;
+                }
+            }
+            __syncthreads();
+            const int m = *nsurv;
+            if (m <= NT / 4) {                               // CTA-uniform
+                const int i = tid >> 2, q = tid & 3;
+                const unsigned me = i < m ? surv[i] : 0u;
+                int gt = 0, eq = 0;
+                if (i < m) for (int j = q; j < m; j += 4) { const unsigned o = surv[j]; gt += o > me; eq += o == me; }
+                gt += __shfl_xor_sync(0xffffffffu, gt, 1); eq += __shfl_xor_sync(0xffffffffu, eq, 1);
+                gt += __shfl_xor_sync(0xffffffffu, gt, 2); eq += __shfl_xor_sync(0xffffffffu, eq, 2);
+                __syncthreads();                             // everyone has read *nsurv (= tot[0]) and surv before sel is written
+                if (i < m && q == 0 && gt < remaining && remaining <= gt + eq) { sel[0] = (int)me; sel[1] = remaining - gt; }
+                __syncthreads();
+                prefix = (unsigned)sel[0]; remaining = sel[1];
+                return;
+            }
+        }
         const int shift = 24 - 8 * pass;
         for (int i = tid; i < (NT / 32) * 256; i += NT) whist[i] = 0;
         __syncthreads();
