@@ -23,6 +23,7 @@
 //     asc) -> decode -> greedy NMS -> rank -> write.  For cap <= 256 the greedy pass is a
 //     suppression bit matrix built by all threads + one warp walking it (no per-box CTA barrier).
 #include <cstdlib>
+#include <vector>
 
 #include "bulk.cuh"
 #include "common.cuh"
@@ -55,9 +56,10 @@ struct DetArgs {
     int cap_eff;
     const unsigned int* ckey_in;                      // [B*A] keys from decode_scan_kernel, or null (v1: scan in this kernel)
     int fast;                                         // 1: private-histogram select, shuffle scan, rank sort, bit-matrix NMS
-    long long* trace;                                 // SSDB_TRACE=1: clock64() of CTA 0 at the phase boundaries (bring-up only)
+    const double* half_over_1000;                     // [2000] (k / 2) / 1000, or null (v1: divide in the kernel)
+    long long* trace; int trace_block;                // SSDB_TRACE=1: clock64() of CTA SSDB_TRACE_BLOCK at the phase boundaries (bring-up only)
 };
-#define SSDB_TRACE_PT(k) do { if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[k] = clock64(); } while (0)
+#define SSDB_TRACE_PT(k) do { if (p.trace && blockIdx.x == p.trace_block && threadIdx.x == 0) p.trace[k] = clock64(); } while (0)
 
 struct ConfKey {         // participants of the top-cap selection: anchors at or above the confidence threshold
     const unsigned int* ckey;
@@ -253,18 +255,26 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
             double w = __dmul_rn(exp((double)__fdiv_rn(o2, 5.f)), aw);
             double h = __dmul_rn(exp((double)__fdiv_rn(o3, 5.f)), ah);
             float px = __fmul_rn(x, 1000.f), py = __fmul_rn(y, 1000.f);
-            float hw = (float)__ddiv_rn(__dmul_rn(w, 1000.0), 2.0);
-            float hh = (float)__ddiv_rn(__dmul_rn(h, 1000.0), 2.0);
+            float hw = (float)__dmul_rn(__dmul_rn(w, 1000.0), 0.5);          // x * 0.5 == x / 2 exactly
+            float hh = (float)__dmul_rn(__dmul_rn(h, 1000.0), 0.5);
             int x0 = (int)__fsub_rn(px, hw), x1 = (int)__fadd_rn(px, hw);
             int y0 = (int)__fsub_rn(py, hh), y1 = (int)__fadd_rn(py, hh);
             x0 = max(x0, 0); x1 = min(x1, 999); y0 = max(y0, 0); y1 = min(y1, 999);
             x0 = min(x0, x1); y0 = min(y0, y1);
             // abs2prop (float64) then the NMS stage's prop2abs (float64)
             double bw = (double)(x1 - x0), bh = (double)(y1 - y0);
-            double pcx = __ddiv_rn(__dadd_rn((double)x0, __ddiv_rn(bw, 2.0)), 1000.0);
-            double pcy = __ddiv_rn(__dadd_rn((double)y0, __ddiv_rn(bh, 2.0)), 1000.0);
-            double sw = __ddiv_rn(bw, 1000.0), sh = __ddiv_rn(bh, 1000.0);
-            double hw2 = __ddiv_rn(__dmul_rn(sw, 1000.0), 2.0), hh2 = __ddiv_rn(__dmul_rn(sh, 1000.0), 2.0);
+            // (x0 + bw/2) / 1000 and bw / 1000: the numerators are half-integers in [0, 999.5], so the four float64 divisions
+            // come from a 2000-entry table of (k / 2) / 1000 computed on the host with the same IEEE division
+            double pcx, pcy, sw, sh;
+            if (p.half_over_1000) {
+                pcx = __ldg(p.half_over_1000 + (x0 + x1)); pcy = __ldg(p.half_over_1000 + (y0 + y1));
+                sw = __ldg(p.half_over_1000 + 2 * (x1 - x0)); sh = __ldg(p.half_over_1000 + 2 * (y1 - y0));
+            } else {
+                pcx = __ddiv_rn(__dadd_rn((double)x0, __ddiv_rn(bw, 2.0)), 1000.0);
+                pcy = __ddiv_rn(__dadd_rn((double)y0, __ddiv_rn(bh, 2.0)), 1000.0);
+                sw = __ddiv_rn(bw, 1000.0); sh = __ddiv_rn(bh, 1000.0);
+            }
+            double hw2 = __dmul_rn(__dmul_rn(sw, 1000.0), 0.5), hh2 = __dmul_rn(__dmul_rn(sh, 1000.0), 0.5);
             double cx2 = __dmul_rn(pcx, 1000.0), cy2 = __dmul_rn(pcy, 1000.0);
             cand[0 * P + i] = cls;
             cand[1 * P + i] = x0; cand[2 * P + i] = x1; cand[3 * P + i] = y0; cand[4 * P + i] = y1;
@@ -291,6 +301,7 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
             // four candidates j per step: their class bytes come as one word and are compared with class(i) at once, so the
             // (majority of) pairs of different classes cost a handful of instructions
             const int G = (P < 4 ? 4 : P) >> 2, lg = 31 - __clz(G);      // P is a power of two
+            const float thr_f = (float)p.iou_thr;
             for (int t = tid; t < (n << lg); t += DT) {
                 const int i = t >> lg, g = t & (G - 1);
                 if (g * 4 + 3 <= i) continue;
@@ -298,7 +309,7 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
                 const unsigned int eq = __vcmpeq4(*reinterpret_cast<const unsigned int*>(ccls + g * 4), ci * 0x01010101u);
                 if (!eq) continue;
                 const int ix0 = cand[5 * P + i], ix1 = cand[6 * P + i], iy0 = cand[7 * P + i], iy1 = cand[8 * P + i];
-                const long long area_i = (long long)(ix1 - ix0 + 1) * (iy1 - iy0 + 1);
+                const int area_i = (ix1 - ix0 + 1) * (iy1 - iy0 + 1);          // <= 10^6: everything fits 32 bits
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int j = g * 4 + q;
@@ -306,22 +317,30 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
                     const int jx0 = cand[5 * P + j], jx1 = cand[6 * P + j], jy0 = cand[7 * P + j], jy1 = cand[8 * P + j];
                     int iw = min(ix1, jx1) - max(ix0, jx0) + 1; iw = iw < 0 ? 0 : iw;
                     int ih = min(iy1, jy1) - max(iy0, jy0) + 1; ih = ih < 0 ? 0 : ih;
-                    const long long inter = (long long)iw * ih;
-                    const long long uni = area_i + (long long)(jx1 - jx0 + 1) * (jy1 - jy0 + 1) - inter;
-                    const double di = (double)inter, lim = __dmul_rn(p.iou_thr, (double)uni);
+                    const int inter = iw * ih;
+                    const int uni = area_i + (jx1 - jx0 + 1) * (jy1 - jy0 + 1) - inter;
+                    // float32 filter (inter, uni < 2^24 convert exactly; thr_f * uni is within 1.2e-7 relative of thr * uni):
+                    // decisive unless inter / uni is within 1e-6 of the threshold, where the reference's rounded float64
+                    // division decides.  (float64 arithmetic issues at a fraction of the fp32 rate: keep it off the common path.)
+                    const float fi = (float)inter, lim = thr_f * (float)uni;
                     bool hit;
-                    if (di > __dmul_rn(lim, 1.000000001)) hit = true;
-                    else if (di < __dmul_rn(lim, 0.999999999) || inter == 0) hit = (inter == 0) ? (0.0 > p.iou_thr) : false;
-                    else hit = __ddiv_rn(di, (double)uni) > p.iou_thr;
+                    if (inter == 0) hit = 0.0 > p.iou_thr;
+                    else if (fi > lim * 1.000001f && lim >= 0.f) hit = true;
+                    else if (fi < lim * 0.999999f) hit = false;
+                    else hit = __ddiv_rn((double)inter, (double)uni) > p.iou_thr;
                     if (hit) atomicOr(&sup[i * 8 + (j >> 5)], 1u << (j & 31));
                 }
             }
+            SSDB_TRACE_PT(11);
             __syncthreads();
+            SSDB_TRACE_PT(7);
             // classes never interact: ONE THREAD per class walks that class's candidates in confidence order with the removed
             // set (256 bits) in registers.  Only KEPT candidates cost an iteration: the next one is the lowest set bit of
             // (class members & ~removed); it ORs its matrix row in (two 16-byte shared loads).
             if ((tid & 31) == 0) {
                 for (int c = tid >> 5; c < C; c += DT / 32) {
+                    const long long t_walk0 = (p.trace && blockIdx.x == p.trace_block) ? clock64() : 0;
+                    int walk_iters = 0;
                     unsigned int removed[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll
                     for (int w = 0; w < 8; ++w) {
@@ -329,6 +348,7 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
                         unsigned int m = members & ~removed[w];
                         while (m) {
                             const int bit = __ffs(m) - 1;
+                            ++walk_iters;
                             const uint4* row = reinterpret_cast<const uint4*>(sup + (w * 32 + bit) * 8);
                             const uint4 r0 = row[0], r1 = row[1];
                             removed[0] |= r0.x; removed[1] |= r0.y; removed[2] |= r0.z; removed[3] |= r0.w;
@@ -338,6 +358,7 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
                     }
 #pragma unroll
                     for (int w = 0; w < 8; ++w) rmask[c * 8 + w] = removed[w];
+                    if (p.trace && blockIdx.x == p.trace_block && c < 24) { p.trace[16 + c] = clock64() - t_walk0; p.trace[40 + c] = walk_iters; }
                 }
             }
             __syncthreads();
@@ -527,6 +548,14 @@ int decode_nms_launch(const float* pred, int B, int A, int C, const double* anch
     p.P = next_pow2(p.cap_eff);
     size_t sh = ((size_t)A * 4 + 15) / 16 * 16;
     p.g_keys = nullptr; p.g_cand = nullptr; p.ckey_in = nullptr; p.fast = nms_v1() ? 0 : 1;
+    static double* table_dev = nullptr;
+    if (!table_dev) {
+        std::vector<double> t(2000);
+        for (int k = 0; k < 2000; ++k) { volatile double half = (double)k / 2.0; t[k] = half / 1000.0; }
+        SSDB_CUDA(cudaMalloc(&table_dev, t.size() * sizeof(double)));
+        SSDB_CUDA(cudaMemcpy(table_dev, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    p.half_over_1000 = p.fast ? table_dev : nullptr;
     unsigned char* sc = reinterpret_cast<unsigned char*>(scratch);
     const size_t keys_bytes = align256((size_t)B * A * 4);
     if (p.P <= SMEM_P_MAX) {
@@ -557,20 +586,22 @@ int decode_nms_launch(const float* pred, int B, int A, int C, const double* anch
     }
     static long long* trace_dev = nullptr;
     const bool tracing = getenv("SSDB_TRACE") != nullptr;
-    p.trace = nullptr;
+    p.trace = nullptr; p.trace_block = getenv("SSDB_TRACE_BLOCK") ? atoi(getenv("SSDB_TRACE_BLOCK")) : 0;
     if (tracing) {
-        if (!trace_dev) SSDB_CUDA(cudaMalloc(&trace_dev, 16 * sizeof(long long)));
-        SSDB_CUDA(cudaMemsetAsync(trace_dev, 0, 16 * sizeof(long long), st));
+        if (!trace_dev) SSDB_CUDA(cudaMalloc(&trace_dev, 64 * sizeof(long long)));
+        SSDB_CUDA(cudaMemsetAsync(trace_dev, 0, 64 * sizeof(long long), st));
         p.trace = trace_dev;
     }
     decode_nms_kernel<<<B, DT, sh, st>>>(p);
     SSDB_LAUNCH_CHECK();
     if (tracing) {
-        long long h[16];
+        long long h[64];
         SSDB_CUDA(cudaStreamSynchronize(st));
         SSDB_CUDA(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
         fprintf(stderr, "ssdb trace decode_nms_kernel (cycles since entry):");
-        for (int k = 1; k <= 10; ++k) fprintf(stderr, " p%d=%lld", k, h[k] ? h[k] - h[0] : -1);
+        for (int k = 1; k <= 11; ++k) fprintf(stderr, " p%d=%lld", k, h[k] ? h[k] - h[0] : -1);
+        fprintf(stderr, "\n  walk cycles/kept per class:");
+        for (int c = 0; c < 24; ++c) if (h[16 + c]) fprintf(stderr, " c%d=%lld/%lld", c, h[16 + c], h[40 + c]);
         fprintf(stderr, "\n");
     }
     return SSDB_OK;
