@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
         SSDB_TRACE_PT(4);
         // ---- decode the n candidates ----
         for (int i = tid; i < C && i < 64; i += DT) first_pos[i] = 0x7fffffff;
-        for (int i = tid; i < 64 * 8; i += DT) cmask[i] = 0u;
+        for (int i = tid; i < 64 * 8; i += DT) { cmask[i] = 0u; rmask[i] = 0u; }
         for (int i = tid; i < BITS_P_MAX; i += DT) ccls[i] = 255;
         __syncthreads();
         for (int i = tid; i < n; i += DT) {
@@ -246,6 +246,8 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
             const float* r = pb + (size_t)a * V;
             int cls = 0; float best = r[0];
             for (int c = 1; c < C; ++c) { float v = r[c]; if (v > best) { best = v; cls = c; } }
+            if (p.trace && best > 1e30f) p.trace[63] = 1;      // (keeps the trace point below after the class loop)
+            SSDB_TRACE_PT(12);
             float o0 = r[C + 1], o1 = r[C + 2], o2 = r[C + 3], o3 = r[C + 4];
             o0 = o0 > 100.f ? 100.f : o0; o1 = o1 > 100.f ? 100.f : o1;
             o2 = o2 > 100.f ? 100.f : o2; o3 = o3 > 100.f ? 100.f : o3;
@@ -261,6 +263,8 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
             int y0 = (int)__fsub_rn(py, hh), y1 = (int)__fadd_rn(py, hh);
             x0 = max(x0, 0); x1 = min(x1, 999); y0 = max(y0, 0); y1 = min(y1, 999);
             x0 = min(x0, x1); y0 = min(y0, y1);
+            if (p.trace && x0 + y0 > 100000) p.trace[63] = 2;
+            SSDB_TRACE_PT(13);
             // abs2prop (float64) then the NMS stage's prop2abs (float64)
             double bw = (double)(x1 - x0), bh = (double)(y1 - y0);
             // (x0 + bw/2) / 1000 and bw / 1000: the numerators are half-integers in [0, 999.5], so the four float64 divisions
@@ -282,6 +286,7 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
             cand[7 * P + i] = (int)__dsub_rn(cy2, hh2); cand[8 * P + i] = (int)__dadd_rn(cy2, hh2);
             cand[9 * P + i] = (int)__float_as_uint(okey_inv((unsigned int)(kk >> 32)));
             cand[10 * P + i] = a;
+            SSDB_TRACE_PT(14);
             if (cls < 64) atomicMin(&first_pos[cls], i);
             if (P <= BITS_P_MAX) { atomicOr(&cmask[cls * 8 + (i >> 5)], 1u << (i & 31)); ccls[i] = (unsigned char)cls; }
         }
@@ -290,75 +295,47 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
         // ---- greedy NMS in confidence order; alive flags reuse ckey[] ----
         unsigned int* alive = ckey;
         if (p.fast && P <= BITS_P_MAX) {
-            // suppression matrix sup[i][8 words]: bit j of row i <=> j > i, same class, IoU(i, j) > thr.  One (i, j) pair per
-            // thread and step, so the same-class pairs (the only ones that cost arithmetic) spread evenly over the CTA.
-            // IoU > thr is decided by one float64 multiply when inter is clearly off thr * union; only a pair within 1e-9
-            // (relative) of the threshold takes the reference's rounded float64 division.
-            unsigned int* sup = reinterpret_cast<unsigned int*>(cand + CAND_WORDS * P);
-            for (int t = tid; t < P * 8; t += DT) sup[t] = 0u;
-            __syncthreads();
-        SSDB_TRACE_PT(6);
-            // four candidates j per step: their class bytes come as one word and are compared with class(i) at once, so the
-            // (majority of) pairs of different classes cost a handful of instructions
-            const int G = (P < 4 ? 4 : P) >> 2, lg = 31 - __clz(G);      // P is a power of two
-            const float thr_f = (float)p.iou_thr;
-            for (int t = tid; t < (n << lg); t += DT) {
-                const int i = t >> lg, g = t & (G - 1);
-                if (g * 4 + 3 <= i) continue;
-                const unsigned int ci = ccls[i];
-                const unsigned int eq = __vcmpeq4(*reinterpret_cast<const unsigned int*>(ccls + g * 4), ci * 0x01010101u);
-                if (!eq) continue;
-                const int ix0 = cand[5 * P + i], ix1 = cand[6 * P + i], iy0 = cand[7 * P + i], iy1 = cand[8 * P + i];
-                const int area_i = (ix1 - ix0 + 1) * (iy1 - iy0 + 1);          // <= 10^6: everything fits 32 bits
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int j = g * 4 + q;
-                    if (!((eq >> (8 * q)) & 0xffu) || j <= i) continue;        // slots >= n carry class 255: never equal
-                    const int jx0 = cand[5 * P + j], jx1 = cand[6 * P + j], jy0 = cand[7 * P + j], jy1 = cand[8 * P + j];
-                    int iw = min(ix1, jx1) - max(ix0, jx0) + 1; iw = iw < 0 ? 0 : iw;
-                    int ih = min(iy1, jy1) - max(iy0, jy0) + 1; ih = ih < 0 ? 0 : ih;
-                    const int inter = iw * ih;
-                    const int uni = area_i + (jx1 - jx0 + 1) * (jy1 - jy0 + 1) - inter;
-                    // float32 filter (inter, uni < 2^24 convert exactly; thr_f * uni is within 1.2e-7 relative of thr * uni):
-                    // decisive unless inter / uni is within 1e-6 of the threshold, where the reference's rounded float64
-                    // division decides.  (float64 arithmetic issues at a fraction of the fp32 rate: keep it off the common path.)
-                    const float fi = (float)inter, lim = thr_f * (float)uni;
-                    bool hit;
-                    if (inter == 0) hit = 0.0 > p.iou_thr;
-                    else if (fi > lim * 1.000001f && lim >= 0.f) hit = true;
-                    else if (fi < lim * 0.999999f) hit = false;
-                    else hit = __ddiv_rn((double)inter, (double)uni) > p.iou_thr;
-                    if (hit) atomicOr(&sup[i * 8 + (j >> 5)], 1u << (j & 31));
-                }
-            }
-            SSDB_TRACE_PT(11);
-            __syncthreads();
-            SSDB_TRACE_PT(7);
-            // classes never interact: ONE THREAD per class walks that class's candidates in confidence order with the removed
-            // set (256 bits) in registers.  Only KEPT candidates cost an iteration: the next one is the lowest set bit of
-            // (class members & ~removed); it ORs its matrix row in (two 16-byte shared loads).
-            if ((tid & 31) == 0) {
+            // Lazy greedy NMS, one WARP per class (classes never interact).  Only a KEPT box ever suppresses anything, and
+            // only ~6% of the candidates are kept, so no suppression matrix is built: the warp finds its class's next alive
+            // candidate i (lowest set bit of members & ~removed), then its lanes test the later alive members of the class
+            // against i (one 32-candidate word per step, skipping empty words) and a ballot extends the removed set.
+            // IoU > thr without float64 on the common path: areas fit 32 bits, inter / uni converts exactly to fp32 and
+            // thr_f * uni is within 1.2e-7 (relative) of thr * uni; only a pair within 1e-6 of the threshold takes the
+            // reference's rounded float64 division.
+            {
+                const int lane = tid & 31;
+                const float thr_f = (float)p.iou_thr;
                 for (int c = tid >> 5; c < C; c += DT / 32) {
-                    const long long t_walk0 = (p.trace && blockIdx.x == p.trace_block) ? clock64() : 0;
-                    int walk_iters = 0;
-                    unsigned int removed[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-#pragma unroll
                     for (int w = 0; w < 8; ++w) {
-                        const unsigned int members = cmask[c * 8 + w];
-                        unsigned int m = members & ~removed[w];
-                        while (m) {
-                            const int bit = __ffs(m) - 1;
-                            ++walk_iters;
-                            const uint4* row = reinterpret_cast<const uint4*>(sup + (w * 32 + bit) * 8);
-                            const uint4 r0 = row[0], r1 = row[1];
-                            removed[0] |= r0.x; removed[1] |= r0.y; removed[2] |= r0.z; removed[3] |= r0.w;
-                            removed[4] |= r1.x; removed[5] |= r1.y; removed[6] |= r1.z; removed[7] |= r1.w;
-                            m &= ~removed[w] & (0xfffffffeu << bit);       // later members of this word that are still alive
+                        unsigned int m = cmask[c * 8 + w];
+                        while (m) {                                                    // warp-uniform
+                            const int bit = __ffs(m) - 1, i = w * 32 + bit;
+                            const int ix0 = cand[5 * P + i], ix1 = cand[6 * P + i], iy0 = cand[7 * P + i], iy1 = cand[8 * P + i];
+                            const int area_i = (ix1 - ix0 + 1) * (iy1 - iy0 + 1);     // <= 10^6
+                            for (int w2 = w; w2 < 8; ++w2) {
+                                unsigned int cm = cmask[c * 8 + w2] & ~rmask[c * 8 + w2];
+                                if (w2 == w) cm &= 0xfffffffeu << bit;
+                                if (!cm) continue;
+                                bool hit = false;
+                                if ((cm >> lane) & 1u) {
+                                    const int j = w2 * 32 + lane;
+                                    const int jx0 = cand[5 * P + j], jx1 = cand[6 * P + j], jy0 = cand[7 * P + j], jy1 = cand[8 * P + j];
+                                    int iw = min(ix1, jx1) - max(ix0, jx0) + 1; iw = iw < 0 ? 0 : iw;
+                                    int ih = min(iy1, jy1) - max(iy0, jy0) + 1; ih = ih < 0 ? 0 : ih;
+                                    const int inter = iw * ih;
+                                    const int uni = area_i + (jx1 - jx0 + 1) * (jy1 - jy0 + 1) - inter;
+                                    const float fi = (float)inter, lim = thr_f * (float)uni;
+                                    if (inter == 0) hit = 0.0 > p.iou_thr;
+                                    else if (fi > lim * 1.000001f && lim >= 0.f) hit = true;
+                                    else if (fi < lim * 0.999999f) hit = false;
+                                    else hit = __ddiv_rn((double)inter, (double)uni) > p.iou_thr;
+                                }
+                                const unsigned int h = __ballot_sync(0xffffffffu, hit);
+                                if (h) { if (lane == 0) rmask[c * 8 + w2] |= h; __syncwarp(); }
+                            }
+                            m = cmask[c * 8 + w] & ~rmask[c * 8 + w] & (0xfffffffeu << bit);
                         }
                     }
-#pragma unroll
-                    for (int w = 0; w < 8; ++w) rmask[c * 8 + w] = removed[w];
-                    if (p.trace && blockIdx.x == p.trace_block && c < 24) { p.trace[16 + c] = clock64() - t_walk0; p.trace[40 + c] = walk_iters; }
                 }
             }
             __syncthreads();
@@ -599,7 +576,7 @@ int decode_nms_launch(const float* pred, int B, int A, int C, const double* anch
         SSDB_CUDA(cudaStreamSynchronize(st));
         SSDB_CUDA(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
         fprintf(stderr, "ssdb trace decode_nms_kernel (cycles since entry):");
-        for (int k = 1; k <= 11; ++k) fprintf(stderr, " p%d=%lld", k, h[k] ? h[k] - h[0] : -1);
+        for (int k = 1; k <= 14; ++k) fprintf(stderr, " p%d=%lld", k, h[k] ? h[k] - h[0] : -1);
         fprintf(stderr, "\n  walk cycles/kept per class:");
         for (int c = 0; c < 24; ++c) if (h[16 + c]) fprintf(stderr, " c%d=%lld/%lld", c, h[16 + c], h[40 + c]);
         fprintf(stderr, "\n");
