@@ -55,6 +55,7 @@ struct DetArgs {
     unsigned long long* g_keys; int* g_cand; int P;   // global scratch when P > SMEM_P_MAX
     int cap_eff;
     const unsigned int* ckey_in;                      // [B*A] keys from decode_scan_kernel, or null (v1: scan in this kernel)
+    const unsigned char* cls_in;                      // [B*A] arg-max class from decode_scan_kernel (with ckey_in)
     int fast;                                         // 1: private-histogram select, shuffle scan, rank sort, bit-matrix NMS
     const double* half_over_1000;                     // [2000] (k / 2) / 1000, or null (v1: divide in the kernel)
     long long* trace; int trace_block;                // SSDB_TRACE=1: clock64() of CTA SSDB_TRACE_BLOCK at the phase boundaries (bring-up only)
@@ -69,7 +70,7 @@ struct ConfKey {         // participants of the top-cap selection: anchors at or
 // VT = compile-time row width (C + 5), 0 = generic
 template <int VT>
 __global__ void __launch_bounds__(RT) decode_scan_kernel(const float* __restrict__ pred, int A, int C, float conf_thr, int use_bulk,
-                                                          unsigned int* __restrict__ ckey_out) {
+                                                          unsigned int* __restrict__ ckey_out, unsigned char* __restrict__ cls_out) {
     extern __shared__ __align__(128) unsigned char dyn[];
     float* zt = reinterpret_cast<float*>(dyn);
     __shared__ __align__(8) unsigned long long bar;
@@ -81,15 +82,16 @@ __global__ void __launch_bounds__(RT) decode_scan_kernel(const float* __restrict
     bulk::tile_load_wait(use_bulk, &bar);
     if (tid < rows) {
         const float* r = zt + tid * V;
-        float best = r[0];
+        float best = r[0]; int cls = 0;
         if (VT) {
 #pragma unroll
-            for (int c = 1; c < (VT ? VT - 5 : 1); ++c) { float v = r[c]; if (v > best) best = v; }
+            for (int c = 1; c < (VT ? VT - 5 : 1); ++c) { float v = r[c]; if (v > best) { best = v; cls = c; } }
         } else {
-            for (int c = 1; c < C; ++c) { float v = r[c]; if (v > best) best = v; }
+            for (int c = 1; c < C; ++c) { float v = r[c]; if (v > best) { best = v; cls = c; } }
         }
         const bool ok = !(best < conf_thr);
         ckey_out[(long long)b * A + a0 + tid] = ok ? okey(best) : 0u;
+        cls_out[(long long)b * A + a0 + tid] = (unsigned char)cls;      // np.argmax: first maximum
     }
 }
 
@@ -244,11 +246,12 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
             unsigned long long kk = keys[i];
             int a = (int)(0xffffffffu - (unsigned int)(kk & 0xffffffffull));
             const float* r = pb + (size_t)a * V;
-            int cls = 0; float best = r[0];
-            for (int c = 1; c < C; ++c) { float v = r[c]; if (v > best) { best = v; cls = c; } }
-            if (p.trace && best > 1e30f) p.trace[63] = 1;      // (keeps the trace point below after the class loop)
-            SSDB_TRACE_PT(12);
             float o0 = r[C + 1], o1 = r[C + 2], o2 = r[C + 3], o3 = r[C + 4];
+            int cls = 0;
+            if (p.cls_in) cls = p.cls_in[(size_t)b * A + a];
+            else { float best = r[0]; for (int c = 1; c < C; ++c) { float v = r[c]; if (v > best) { best = v; cls = c; } } }
+            if (p.trace && o0 > 1e30f) p.trace[63] = 1;        // (keeps the trace point below after the loads)
+            SSDB_TRACE_PT(12);
             o0 = o0 > 100.f ? 100.f : o0; o1 = o1 > 100.f ? 100.f : o1;
             o2 = o2 > 100.f ? 100.f : o2; o3 = o3 > 100.f ? 100.f : o3;
             const double ax = p.anchors[a * 4 + 0], ay = p.anchors[a * 4 + 1], aw = p.anchors[a * 4 + 2], ah = p.anchors[a * 4 + 3];
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
                 const float thr_f = (float)p.iou_thr;
                 for (int c = tid >> 5; c < C; c += DT / 32) {
                     for (int w = 0; w < 8; ++w) {
-                        unsigned int m = cmask[c * 8 + w];
+                        unsigned int m = cmask[c * 8 + w] & ~rmask[c * 8 + w];
                         while (m) {                                                    // warp-uniform
                             const int bit = __ffs(m) - 1, i = w * 32 + bit;
                             const int ix0 = cand[5 * P + i], ix1 = cand[6 * P + i], iy0 = cand[7 * P + i], iy1 = cand[8 * P + i];
@@ -509,7 +512,7 @@ size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 size_t decode_nms_scratch_bytes(int B, int A, int cap) {
     int cap_eff = (cap > 0 && cap < A) ? cap : A;
     int P = next_pow2(cap_eff);
-    size_t keys = align256((size_t)B * A * 4);
+    size_t keys = align256((size_t)B * A * 4) + align256((size_t)B * A);
     if (P <= SMEM_P_MAX) return keys;
     return keys + (size_t)B * P * (8 + 4 * CAND_WORDS);
 }
@@ -524,7 +527,7 @@ int decode_nms_launch(const float* pred, int B, int A, int C, const double* anch
     p.cap_eff = (cap > 0 && cap < A) ? cap : A;
     p.P = next_pow2(p.cap_eff);
     size_t sh = ((size_t)A * 4 + 15) / 16 * 16;
-    p.g_keys = nullptr; p.g_cand = nullptr; p.ckey_in = nullptr; p.fast = nms_v1() ? 0 : 1;
+    p.g_keys = nullptr; p.g_cand = nullptr; p.ckey_in = nullptr; p.cls_in = nullptr; p.fast = nms_v1() ? 0 : 1;
     static double* table_dev = nullptr;
     if (!table_dev) {
         std::vector<double> t(2000);
@@ -534,7 +537,7 @@ int decode_nms_launch(const float* pred, int B, int A, int C, const double* anch
     }
     p.half_over_1000 = p.fast ? table_dev : nullptr;
     unsigned char* sc = reinterpret_cast<unsigned char*>(scratch);
-    const size_t keys_bytes = align256((size_t)B * A * 4);
+    const size_t keys_bytes = align256((size_t)B * A * 4) + align256((size_t)B * A);
     if (p.P <= SMEM_P_MAX) {
         sh += (size_t)p.P * (8 + 4 * CAND_WORDS);
         if (p.P <= BITS_P_MAX) sh += (size_t)p.P * 8 + (size_t)p.P * 8 * 4;      // sorted keys + suppression matrix rows of 8 words
@@ -556,10 +559,11 @@ int decode_nms_launch(const float* pred, int B, int A, int C, const double* anch
         const int V = C + 5, S = (A + RT - 1) / RT;
         const int use_bulk = ((size_t)A * V * 4) % 16 == 0 && bulk::aligned16(pred);
         unsigned int* ckey = reinterpret_cast<unsigned int*>(sc);
-        if (C == 20) decode_scan_kernel<25><<<dim3(S, B), RT, (size_t)RT * V * 4, st>>>(pred, A, C, conf_thr, use_bulk, ckey);
-        else decode_scan_kernel<0><<<dim3(S, B), RT, (size_t)RT * V * 4, st>>>(pred, A, C, conf_thr, use_bulk, ckey);
+        unsigned char* ccls = sc + align256((size_t)B * A * 4);
+        if (C == 20) decode_scan_kernel<25><<<dim3(S, B), RT, (size_t)RT * V * 4, st>>>(pred, A, C, conf_thr, use_bulk, ckey, ccls);
+        else decode_scan_kernel<0><<<dim3(S, B), RT, (size_t)RT * V * 4, st>>>(pred, A, C, conf_thr, use_bulk, ckey, ccls);
         SSDB_LAUNCH_CHECK();
-        p.ckey_in = ckey;
+        p.ckey_in = ckey; p.cls_in = ccls;
     }
     static long long* trace_dev = nullptr;
     const bool tracing = getenv("SSDB_TRACE") != nullptr;
