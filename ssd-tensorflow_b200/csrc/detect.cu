@@ -299,46 +299,61 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
         unsigned int* alive = ckey;
         if (p.fast && P <= BITS_P_MAX) {
             // Lazy greedy NMS, one WARP per class (classes never interact).  Only a KEPT box ever suppresses anything, and
-            // only ~6% of the candidates are kept, so no suppression matrix is built: the warp finds its class's next alive
-            // candidate i (lowest set bit of members & ~removed), then its lanes test the later alive members of the class
-            // against i (one 32-candidate word per step, skipping empty words) and a ballot extends the removed set.
+            // only ~6% of the candidates are kept, so no suppression matrix is built: the warp compacts its class's members
+            // (confidence order) into a list, one position per lane and 32-step; the next alive position is kept, the lanes
+            // test their own later alive positions against it and mark them dead in a private bit mask.
             // IoU > thr without float64 on the common path: areas fit 32 bits, inter / uni converts exactly to fp32 and
             // thr_f * uni is within 1.2e-7 (relative) of thr * uni; only a pair within 1e-6 of the threshold takes the
             // reference's rounded float64 division.
             {
                 const int lane = tid & 31;
                 const float thr_f = (float)p.iou_thr;
+                unsigned char* ml = reinterpret_cast<unsigned char*>(cand + CAND_WORDS * P) + (tid >> 5) * P;   // this warp's member list (P bytes)
                 for (int c = tid >> 5; c < C; c += DT / 32) {
+                    // the class's candidates in confidence order, compacted: position q of the list lives in lane q % 32
+                    int cnt = 0;
                     for (int w = 0; w < 8; ++w) {
-                        unsigned int m = cmask[c * 8 + w] & ~rmask[c * 8 + w];
-                        while (m) {                                                    // warp-uniform
-                            const int bit = __ffs(m) - 1, i = w * 32 + bit;
+                        const unsigned int m = cmask[c * 8 + w];
+                        if ((m >> lane) & 1u) ml[cnt + __popc(m & ((1u << lane) - 1u))] = (unsigned char)(w * 32 + lane);
+                        cnt += __popc(m);
+                    }
+                    __syncwarp();
+                    const int K = (cnt + 31) >> 5;
+                    unsigned int dead = 0u;                       // bit k: list position lane + 32k was suppressed
+                    for (int k = 0; k < K; ++k) {
+                        unsigned int todo = __ballot_sync(0xffffffffu, lane + 32 * k < cnt);
+                        while (true) {                                                 // warp-uniform
+                            todo &= ~__ballot_sync(0xffffffffu, (dead >> k) & 1u);
+                            if (!todo) break;
+                            const int src = __ffs(todo) - 1;                           // next alive member: it is kept
+                            todo &= 0xfffffffeu << src;
+                            const int pos = 32 * k + src, i = ml[pos];
                             const int ix0 = cand[5 * P + i], ix1 = cand[6 * P + i], iy0 = cand[7 * P + i], iy1 = cand[8 * P + i];
                             const int area_i = (ix1 - ix0 + 1) * (iy1 - iy0 + 1);     // <= 10^6
-                            for (int w2 = w; w2 < 8; ++w2) {
-                                unsigned int cm = cmask[c * 8 + w2] & ~rmask[c * 8 + w2];
-                                if (w2 == w) cm &= 0xfffffffeu << bit;
-                                if (!cm) continue;
-                                bool hit = false;
-                                if ((cm >> lane) & 1u) {
-                                    const int j = w2 * 32 + lane;
-                                    const int jx0 = cand[5 * P + j], jx1 = cand[6 * P + j], jy0 = cand[7 * P + j], jy1 = cand[8 * P + j];
-                                    int iw = min(ix1, jx1) - max(ix0, jx0) + 1; iw = iw < 0 ? 0 : iw;
-                                    int ih = min(iy1, jy1) - max(iy0, jy0) + 1; ih = ih < 0 ? 0 : ih;
-                                    const int inter = iw * ih;
-                                    const int uni = area_i + (jx1 - jx0 + 1) * (jy1 - jy0 + 1) - inter;
-                                    const float fi = (float)inter, lim = thr_f * (float)uni;
-                                    if (inter == 0) hit = 0.0 > p.iou_thr;
-                                    else if (fi > lim * 1.000001f && lim >= 0.f) hit = true;
-                                    else if (fi < lim * 0.999999f) hit = false;
-                                    else hit = __ddiv_rn((double)inter, (double)uni) > p.iou_thr;
-                                }
-                                const unsigned int h = __ballot_sync(0xffffffffu, hit);
-                                if (h) { if (lane == 0) rmask[c * 8 + w2] |= h; __syncwarp(); }
+                            for (int k2 = k; k2 < K; ++k2) {
+                                const int q = lane + 32 * k2;
+                                if (q <= pos || q >= cnt || ((dead >> k2) & 1u)) continue;
+                                const int j = ml[q];
+                                const int jx0 = cand[5 * P + j], jx1 = cand[6 * P + j], jy0 = cand[7 * P + j], jy1 = cand[8 * P + j];
+                                int iw = min(ix1, jx1) - max(ix0, jx0) + 1; iw = iw < 0 ? 0 : iw;
+                                int ih = min(iy1, jy1) - max(iy0, jy0) + 1; ih = ih < 0 ? 0 : ih;
+                                const int inter = iw * ih;
+                                const int uni = area_i + (jx1 - jx0 + 1) * (jy1 - jy0 + 1) - inter;
+                                const float fi = (float)inter, lim = thr_f * (float)uni;
+                                bool hit;
+                                if (inter == 0) hit = 0.0 > p.iou_thr;
+                                else if (fi > lim * 1.000001f && lim >= 0.f) hit = true;
+                                else if (fi < lim * 0.999999f) hit = false;
+                                else hit = __ddiv_rn((double)inter, (double)uni) > p.iou_thr;
+                                if (hit) dead |= 1u << k2;
                             }
-                            m = cmask[c * 8 + w] & ~rmask[c * 8 + w] & (0xfffffffeu << bit);
                         }
                     }
+                    for (int k = 0; k < K; ++k) {
+                        const int q = lane + 32 * k;
+                        if (q < cnt && ((dead >> k) & 1u)) { const int j = ml[q]; atomicOr(&rmask[c * 8 + (j >> 5)], 1u << (j & 31)); }
+                    }
+                    __syncwarp();
                 }
             }
             __syncthreads();

@@ -386,6 +386,47 @@ __global__ void __launch_bounds__(LT) multibox_loss_kernel(
 }
 
 
+// ---- exact integer form of the matching (v2) ----
+// Coordinates live on the 1000x1000 grid, so intersection I and union U are integers below 2^21.  Two IoUs compare
+// exactly by cross-multiplication (products < 2^42), and I/U > 0.5 <=> 2I > U: distinct rationals with such small
+// denominators are more than 2^-42 apart, far more than the rounding of the reference's float64 division, so every
+// comparison below decides exactly like the reference's `iou > threshold` / `score > stored` on rounded float64 values
+//  -- without a single float64 instruction.
+struct IU { int i, u; };
+__device__ __forceinline__ IU iou_int(const IBox& a, const IBox& b) {
+    const int area_a = (a.x1 - a.x0 + 1) * (a.y1 - a.y0 + 1), area_b = (b.x1 - b.x0 + 1) * (b.y1 - b.y0 + 1);
+    int iw = min(a.x1, b.x1) - max(a.x0, b.x0) + 1; iw = iw < 0 ? 0 : iw;
+    int ih = min(a.y1, b.y1) - max(a.y0, b.y0) + 1; ih = ih < 0 ? 0 : ih;
+    IU r; r.i = iw * ih; r.u = area_a + area_b - r.i;
+    return r;
+}
+__device__ __forceinline__ bool iu_greater(const IU& a, const IU& b) {      // a.i/a.u > b.i/b.u   (u > 0)
+    return (long long)a.i * b.u > (long long)b.i * a.u;
+}
+
+struct MatchSharedInt {
+    IBox gt[MAX_G];
+    IU best[MAX_G];          // IoU of each GT with its arg-max anchor
+    int best_idx[MAX_G];
+};
+
+// owner GT of anchor a (-1 = background), same two-pass rule as match_one_box
+__device__ __forceinline__ int match_one_int(const MatchSharedInt& ms, int G, const IBox& ab, int a) {
+    int owner = -1; IU score{-1, 1};
+    for (int g = 0; g < G; ++g) {
+        const IU v = iou_int(ms.gt[g], ab);
+        if (2 * v.i > v.u && iu_greater(v, score)) { score = v; owner = g; }
+    }
+    bool any2 = false; IU score2{-1, 1};
+    for (int g = 0; g < G; ++g) {
+        const IU bg = ms.best[g];
+        if (ms.best_idx[g] != a || !(2 * bg.i > bg.u)) continue;
+        if (any2 && !iu_greater(bg, score2)) continue;
+        any2 = true; score2 = bg; owner = g;
+    }
+    return owner;
+}
+
 // =====================================================================================
 // v2: tiled streaming implementation
 // =====================================================================================
@@ -401,7 +442,7 @@ struct LossWs {
     float* gs;               // [B]    gradient scale of the image: grad_scale / (B * pos_num)
     float* per_image;        // [B*2]
     unsigned int* counter;   // [1]    self-resetting
-    double* best_iou;        // [B*MAX_G]
+    IU* best_iou;            // [B*MAX_G] (intersection, union) of each GT with its arg-max anchor
     int* best_idx;           // [B*MAX_G]
     IBox* anc_abs;           // [A]
 };
@@ -414,32 +455,34 @@ __global__ void __launch_bounds__(256) anchor_abs_kernel(const double* __restric
     if (a < A) out[a] = prop2abs_1000(anchors[a * 4 + 0], anchors[a * 4 + 1], anchors[a * 4 + 2], anchors[a * 4 + 3]);
 }
 
-// arg-max anchor of every GT box (first maximum = lowest anchor index), one CTA per (GT, image)
+// arg-max anchor of every GT box (first maximum = lowest anchor index), one CTA per (GT, image); integer-exact
 __global__ void __launch_bounds__(RT) match_best_kernel(const double* __restrict__ gt, const int* __restrict__ gt_count, int G,
-                                                         const IBox* __restrict__ anc_abs, int A, double* __restrict__ best_iou,
+                                                         const IBox* __restrict__ anc_abs, int A, IU* __restrict__ best_iou,
                                                          int* __restrict__ best_idx) {
     const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     if (g >= min(gt_count[b], G)) return;
-    __shared__ double red_iou[RT / 32];
+    __shared__ IU red_iou[RT / 32];
     __shared__ int red_idx[RT / 32];
     const double* r = gt + ((long long)b * G + g) * 5;
     const IBox gb = prop2abs_1000(r[1], r[2], r[3], r[4]);
-    double bi = -1.0; int bx = 0x7fffffff;
+    IU bi{-1, 1}; int bx = 0x7fffffff;
     for (int a = tid; a < A; a += RT) {
-        double v = iou_incl(gb, anc_abs[a]);
-        if (v > bi) { bi = v; bx = a; }
+        const IU v = iou_int(gb, anc_abs[a]);
+        if (iu_greater(v, bi)) { bi = v; bx = a; }        // ascending a per thread: first maximum kept
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
-        double oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        int ox = __shfl_xor_sync(0xffffffffu, bx, o);
-        if (oi > bi || (oi == bi && ox < bx)) { bi = oi; bx = ox; }
+        IU oi; oi.i = __shfl_xor_sync(0xffffffffu, bi.i, o); oi.u = __shfl_xor_sync(0xffffffffu, bi.u, o);
+        const int ox = __shfl_xor_sync(0xffffffffu, bx, o);
+        if (iu_greater(oi, bi) || (!iu_greater(bi, oi) && ox < bx)) { bi = oi; bx = ox; }
     }
     if ((tid & 31) == 0) { red_iou[tid >> 5] = bi; red_idx[tid >> 5] = bx; }
     __syncthreads();
     if (tid == 0) {
-        for (int w = 1; w < RT / 32; ++w)
-            if (red_iou[w] > bi || (red_iou[w] == bi && red_idx[w] < bx)) { bi = red_iou[w]; bx = red_idx[w]; }
+        for (int w = 1; w < RT / 32; ++w) {
+            const IU oi = red_iou[w]; const int ox = red_idx[w];
+            if (iu_greater(oi, bi) || (!iu_greater(bi, oi) && ox < bx)) { bi = oi; bx = ox; }
+        }
         best_iou[b * MAX_G + g] = bi; best_idx[b * MAX_G + g] = bx;
     }
 }
@@ -458,7 +501,7 @@ __global__ void __launch_bounds__(RT) loss_rows_kernel(
     float* zt = reinterpret_cast<float*>(dyn);        // [RT*V] head output tile, becomes the result tile
     float* yt = zt + RT * V;                          // [RT*V] dense label tile (not in fused-match mode)
     __shared__ __align__(8) unsigned long long bar;
-    __shared__ MatchShared ms;
+    __shared__ MatchSharedInt ms;
     __shared__ float red[RT / 32][4];
 
     const int tid = threadIdx.x, s = blockIdx.x, b = blockIdx.y;
@@ -471,7 +514,7 @@ __global__ void __launch_bounds__(RT) loss_rows_kernel(
         g_n = min(gt_count[b], G);
         if (tid < g_n) {
             ms.gt[tid] = prop2abs_1000(gtb[tid * 5 + 1], gtb[tid * 5 + 2], gtb[tid * 5 + 3], gtb[tid * 5 + 4]);
-            ms.best_iou[tid] = ws.best_iou[b * MAX_G + tid];
+            ms.best[tid] = ws.best_iou[b * MAX_G + tid];
             ms.best_idx[tid] = ws.best_idx[b * MAX_G + tid];
         }
     }
@@ -494,7 +537,7 @@ __global__ void __launch_bounds__(RT) loss_rows_kernel(
         const float inv = 1.f / sum;
         float cev, l1 = 0.f; bool pos;
         if (GT_MODE) {
-            const int owner = match_one_box(ms, g_n, ws.anc_abs[a], a);
+            const int owner = match_one_int(ms, g_n, ws.anc_abs[a], a);
             ws.own[(long long)b * A + a] = (signed char)owner;
             if (match_out) match_out[(long long)b * A + a] = owner;
             pos = owner >= 0;
@@ -710,7 +753,7 @@ LossWs carve_ws(void* base, int B, int A) {
     w.part = reinterpret_cast<TilePart*>(take((size_t)B * S * sizeof(TilePart)));
     w.gs = reinterpret_cast<float*>(take((size_t)B * 4));
     w.per_image = reinterpret_cast<float*>(take((size_t)B * 8));
-    w.best_iou = reinterpret_cast<double*>(take((size_t)B * MAX_G * 8));
+    w.best_iou = reinterpret_cast<IU*>(take((size_t)B * MAX_G * 8));
     w.best_idx = reinterpret_cast<int*>(take((size_t)B * MAX_G * 4));
     w.anc_abs = reinterpret_cast<IBox*>(take((size_t)A * sizeof(IBox)));
     return w;
