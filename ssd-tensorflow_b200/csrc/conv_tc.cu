@@ -169,6 +169,7 @@ struct TcArgs {
     int rows_per_tap;               // rows of the B tensor map per tap
     int mode;                       // 0 fprop, 1 dgrad
     int mtu;                        // M tiles per unit (1 or 2)
+    int ring_bytes, tmem_cols, acc_stride;   // RING_BYTES / 512 / 256, or the two-CTAs-per-SM configuration (launch_tc)
     float* dst;
     const float* bias;              // fprop
     const float* mask;              // dgrad: ReLU mask source (same shape as dst) or null
@@ -268,7 +269,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B needs 1024-byte alignment
-    const uint32_t bars = base + RING_BYTES;
+    const uint32_t bars = base + (uint32_t)p.ring_bytes;
     // barrier layout: full[MAX_STAGES] empty[MAX_STAGES] tfull[2] tempty[2] then tmem pointer
     const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
     const uint32_t tmem_slot = tempty0 + 16;
@@ -287,7 +288,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -302,7 +303,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
     const uint32_t a_bytes = (uint32_t)p.a_rows * 128u;
     const uint32_t b_bytes = (uint32_t)p.block_n * 128u;
     const int noff = (p.block_n + 31) & ~31;                       // TMEM column offset of the second tile's accumulator
-    const int acc_stages = (p.mtu * noff <= ACC_STRIDE) ? 2 : 1;   // two accumulator buffers when a unit fits in 256 columns
+    const int acc_stages = (p.mtu * noff <= p.acc_stride) ? 2 : 1;   // two accumulator buffers when a unit fits in one of them
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -345,7 +346,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
                 const bool two = p.mtu == 2 && 2 * mp + 1 < m_tiles;
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d0 = tmem_base + (uint32_t)(acc * ACC_STRIDE);
+                const uint32_t d0 = tmem_base + (uint32_t)(acc * p.acc_stride);
                 const uint32_t d1 = d0 + (uint32_t)noff;
                 uint32_t started = 0;
                 for (int gi = 0; gi < p.ngroups; ++gi) {
@@ -386,7 +387,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
             const bool two = p.mtu == 2 && 2 * mp + 1 < m_tiles;
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + (uint32_t)(acc * ACC_STRIDE) + ((uint32_t)(quarter * 32) << 16);
+            const uint32_t t_row = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
             epilogue_tile(p, p.mtu * mp, nt, t_row, row, lane, stage);
             if (two) epilogue_tile(p, 2 * mp + 1, nt, t_row + (uint32_t)noff, row, lane, stage);
             tc_fence_before();
@@ -400,7 +401,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
     }
 }
 
@@ -890,13 +891,35 @@ int num_sms() {
     return n;
 }
 
-int launch_tc(const CUtensorMap& ms, const CUtensorMap& mw, const TcArgs& a, cudaStream_t st) {
+// Two CTAs per SM for the short-K, narrow-N layers (conv1_1 / conv1_2 / conv2_1 dgrad: N tile <= 64).  Their units are
+// dominated by the epilogue (128 x 64 outputs per ~0.6 us of MMA), and one CTA's four epilogue warps cannot keep enough
+// bytes in flight; a second resident CTA doubles the epilogue / TMA parallelism.  Each CTA then gets half the ring (2-3
+// stages), a 256-column TMEM allocation (two 128-column accumulator buffers) and one M tile per unit.
+constexpr int DUAL_RING_BYTES = 92 * 1024;
+constexpr int DUAL_SMEM_BYTES = DUAL_RING_BYTES + 1024 + 256 + EPI_STAGE_BYTES;      // 109.25 KB: two fit in 227 KB
+
+int launch_tc(const CUtensorMap& ms, const CUtensorMap& mw, const TcArgs& a_in, cudaStream_t st) {
     static bool attr = false;
     if (!attr) { SSDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr = true; }
+    TcArgs a = a_in;
+    a.ring_bytes = RING_BYTES; a.tmem_cols = TMEM_COLS; a.acc_stride = ACC_STRIDE;
     long long m_tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_n;
+    int smem = SMEM_BYTES, ctas_per_sm = 1;
+    static int dual_mode = -1;
+    if (dual_mode < 0) { const char* ov = getenv("SSDB_TC_DUAL"); dual_mode = ov ? atoi(ov) : 0; }
+    if (dual_mode && a.block_n <= 64 && !a.scatter) {
+        const int sb1 = (a.a_slot + a.b_tiles * a.block_n * 128 + 1023) / 1024 * 1024;     // stage with one M tile per unit
+        if (2 * sb1 <= DUAL_RING_BYTES && m_tiles * a.n_tiles >= 4LL * num_sms()) {
+            a.mtu = 1; a.stage_bytes = sb1;
+            a.stages = DUAL_RING_BYTES / sb1; if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
+            a.ring_bytes = DUAL_RING_BYTES; a.tmem_cols = 256; a.acc_stride = 128;
+            smem = DUAL_SMEM_BYTES; ctas_per_sm = 2;
+        }
+    }
     long long total = ((m_tiles + a.mtu - 1) / a.mtu) * a.n_tiles;
-    int grid = (int)(total < num_sms() ? total : num_sms());
-    conv_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ms, mw, a);
+    const long long slots = (long long)num_sms() * ctas_per_sm;
+    int grid = (int)(total < slots ? total : slots);
+    conv_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(ms, mw, a);
     SSDB_LAUNCH_CHECK();
     return SSDB_OK;
 }
