@@ -905,9 +905,16 @@ int launch_tc(const CUtensorMap& ms, const CUtensorMap& mw, const TcArgs& a_in, 
     a.ring_bytes = RING_BYTES; a.tmem_cols = TMEM_COLS; a.acc_stride = ACC_STRIDE;
     long long m_tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_n;
     int smem = SMEM_BYTES, ctas_per_sm = 1;
+    // measured on B200 (vgg300, batch 64; SSDB_TC_DUAL=1 forces it for every N <= 64 layer, =0 disables it):
+    //   conv1_1 fprop 0.92 -> 0.67 ms, conv1_2 dgrad 1.74 -> 1.00 ms   (epilogue-bound: K blocks per unit <= 2, or a dgrad
+    //   with its mask read and <= 18 K blocks);   conv1_2 fprop 0.87 -> 0.97, conv2_1 dgrad 0.43 -> 0.48 (MMA-heavier units
+    //   miss the deeper ring more than they gain from the second CTA) -> those keep one CTA per SM.
     static int dual_mode = -1;
-    if (dual_mode < 0) { const char* ov = getenv("SSDB_TC_DUAL"); dual_mode = ov ? atoi(ov) : 0; }
-    if (dual_mode && a.block_n <= 64 && !a.scatter) {
+    if (dual_mode < 0) { const char* ov = getenv("SSDB_TC_DUAL"); dual_mode = ov ? (atoi(ov) ? 1 : 0) : 2; }
+    int kblocks = 0;
+    for (int g = 0; g < a.ngroups; ++g) kblocks += a.g_nt[g] * a.cblocks;
+    const bool dual_wanted = dual_mode == 1 || (dual_mode == 2 && (kblocks <= 2 || (a.mode == 1 && a.mask && kblocks <= 18)));
+    if (dual_wanted && a.block_n <= 64 && !a.scatter) {
         const int sb1 = (a.a_slot + a.b_tiles * a.block_n * 128 + 1023) / 1024 * 1024;     // stage with one M tile per unit
         if (2 * sb1 <= DUAL_RING_BYTES && m_tiles * a.n_tiles >= 4LL * num_sms()) {
             a.mtu = 1; a.stage_bytes = sb1;
