@@ -258,8 +258,6 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
             int cls = 0;
             if (p.cls_in) cls = p.cls_in[(size_t)b * A + a];
             else { float best = r[0]; for (int c = 1; c < C; ++c) { float v = r[c]; if (v > best) { best = v; cls = c; } } }
-            if (p.trace && o0 > 1e30f) p.trace[63] = 1;        // (keeps the trace point below after the loads)
-            SSDB_TRACE_PT(12);
             o0 = o0 > 100.f ? 100.f : o0; o1 = o1 > 100.f ? 100.f : o1;
             o2 = o2 > 100.f ? 100.f : o2; o3 = o3 > 100.f ? 100.f : o3;
             const double ax = p.anchors[a * 4 + 0], ay = p.anchors[a * 4 + 1], aw = p.anchors[a * 4 + 2], ah = p.anchors[a * 4 + 3];
@@ -274,8 +272,6 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
             int y0 = (int)__fsub_rn(py, hh), y1 = (int)__fadd_rn(py, hh);
             x0 = max(x0, 0); x1 = min(x1, 999); y0 = max(y0, 0); y1 = min(y1, 999);
             x0 = min(x0, x1); y0 = min(y0, y1);
-            if (p.trace && x0 + y0 > 100000) p.trace[63] = 2;
-            SSDB_TRACE_PT(13);
             // abs2prop (float64) then the NMS stage's prop2abs (float64)
             double bw = (double)(x1 - x0), bh = (double)(y1 - y0);
             // (x0 + bw/2) / 1000 and bw / 1000: the numerators are half-integers in [0, 999.5], so the four float64 divisions
@@ -297,7 +293,6 @@ __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
             cand[7 * P + i] = (int)__dsub_rn(cy2, hh2); cand[8 * P + i] = (int)__dadd_rn(cy2, hh2);
             cand[9 * P + i] = (int)__float_as_uint(okey_inv((unsigned int)(kk >> 32)));
             cand[10 * P + i] = a;
-            SSDB_TRACE_PT(14);
             if (cls < 64) atomicMin(&first_pos[cls], i);
             if (P <= BITS_P_MAX) { atomicOr(&cmask[cls * 8 + (i >> 5)], 1u << (i & 31)); ccls[i] = (unsigned char)cls; }
         }
@@ -603,7 +598,7 @@ int decode_nms_launch(const float* pred, int B, int A, int C, const double* anch
         SSDB_CUDA(cudaStreamSynchronize(st));
         SSDB_CUDA(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
         fprintf(stderr, "ssdb trace decode_nms_kernel (cycles since entry):");
-        for (int k = 1; k <= 14; ++k) fprintf(stderr, " p%d=%lld", k, h[k] ? h[k] - h[0] : -1);
+        for (int k = 1; k <= 10; ++k) fprintf(stderr, " p%d=%lld", k, h[k] ? h[k] - h[0] : -1);
         fprintf(stderr, "\n");
     }
     return SSDB_OK;
