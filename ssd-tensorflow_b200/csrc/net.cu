@@ -112,6 +112,7 @@ struct ssdb_net {
     int swap_rb = 1; float mean[3] = {103.939f, 116.779f, 123.68f};
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_labels = nullptr, ev_result = nullptr, ev_images = nullptr;
+    cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};   // image chunks of the host entry points
     int last_B = 0;
     // per-op device timing (ssdb_profile_step)
     bool prof = false;
@@ -317,11 +318,27 @@ struct ProfScope {
 
 double conv_flops(const ConvGeom& g) { return 2.0 * g.B * g.Ho * g.Wo * (double)g.k * g.k * g.Cin * g.Cout; }
 
-int run_forward(ssdb_net* n, const float* images, int B, cudaStream_t st) {
+// conv1_1 (patch matrix + 1x1 tensor-core conv) of images [b0, b0 + Bc) only: every output pixel depends on its own image,
+// so the host entry points run it chunk by chunk while the rest of the batch is still on its way over PCIe
+int run_first_conv_chunk(ssdb_net* n, const float* images, int b0, int Bc, cudaStream_t st) {
+    const Op& op = n->ops[0];
+    SSDB_REQUIRE(op.type == OP_CONV && op.in < 0 && n->patches, "internal: chunked conv1_1 needs the tensor-core first layer");
+    ConvGeom g = geom_of(n, op, Bc);
+    ConvEpilogue ep;
+    ep.bias = n->params + n->masters[op.b].off; ep.relu = op.relu ? 1 : 0; ep.round_tf32 = n->round ? 1 : 0;
+    const size_t px = (size_t)b0 * n->S * n->S;
+    float* patches = n->patches + px * 32;
+    int rc = conv1_im2col(images + px * 3, Bc, n->S, n->swap_rb, n->mean, patches, st); if (rc) return rc;
+    ConvGeom g1 = g; g1.Cin = 32; g1.k = 1; g1.pad_t = g1.pad_l = 0; g1.dil = 1;
+    return conv_tc_fprop(g1, patches, n->c1_wt, op.cout, ep, n->act(op.out, n->max_batch) + px * op.cout, st);
+}
+
+int run_forward(ssdb_net* n, const float* images, int B, cudaStream_t st, bool skip_first = false) {
     SSDB_REQUIRE(B >= 1 && B <= n->max_batch, "batch size out of range");
     if (n->wt_dirty) { ProfScope ps(n, st, "repack"); int rc = repack_filters(n, st); if (rc) return rc; }
     for (const Op& op : n->ops) {
         int rc = SSDB_OK;
+        if (skip_first && &op == &n->ops[0]) continue;
         ProfScope ps(n, st, std::string("fwd:") + op.name, op.type == OP_CONV ? conv_flops(geom_of(n, op, B)) : 0.0);
         if (op.type == OP_CONV) {
             ConvGeom g = geom_of(n, op, B);
@@ -558,6 +575,7 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
     SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_labels, cudaEventDisableTiming));
     SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_result, cudaEventDisableTiming));
     SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_images, cudaEventDisableTiming));
+    for (int c = 0; c < 4; ++c) SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_chunk[c], cudaEventDisableTiming));
     *out = n;
     return SSDB_OK;
 }
@@ -575,6 +593,7 @@ int ssdb_destroy(ssdb_net* n) {
     if (n->ev_labels) cudaEventDestroy(n->ev_labels);
     if (n->ev_result) cudaEventDestroy(n->ev_result);
     if (n->ev_images) cudaEventDestroy(n->ev_images);
+    for (int c = 0; c < 4; ++c) if (n->ev_chunk[c]) cudaEventDestroy(n->ev_chunk[c]);
     delete n;
     return SSDB_OK;
 }
@@ -641,11 +660,42 @@ int ssdb_forward(ssdb_net* n, const float* images_dev, int B, float* result_dev,
     return rc;
 }
 
+// Host entry points: the image batch goes up in (up to) four chunks on the copy stream and conv1_1 runs chunk by chunk
+// behind it on the compute stream, so only the first chunk's transfer (not the whole 69 MB at batch 64) is exposed.
+// *first_done tells the caller to skip conv1_1 in run_forward.
+static int upload_images_chunked(ssdb_net* n, const float* images_host, int B, cudaStream_t st, cudaStream_t cs, bool* first_done) {
+    const size_t img = (size_t)n->S * n->S * 3;
+    const char* ov = getenv("SSDB_CHUNKED_UPLOAD");
+    const bool chunked = n->patches && B >= 8 && !(ov && atoi(ov) == 0);
+    *first_done = false;
+    if (!chunked) {
+        SSDB_CUDA(cudaMemcpyAsync(n->images_stage, images_host, (size_t)B * img * sizeof(float), cudaMemcpyHostToDevice, cs));
+        SSDB_CUDA(cudaEventRecord(n->ev_images, cs));
+        SSDB_CUDA(cudaStreamWaitEvent(st, n->ev_images, 0));
+        return SSDB_OK;
+    }
+    if (n->wt_dirty) { int rc = repack_filters(n, st); if (rc) return rc; }
+    const int per = (B + 3) / 4;
+    for (int c = 0; c < 4; ++c) {
+        const int b0 = c * per, bc = B - b0 < per ? B - b0 : per;
+        if (bc <= 0) break;
+        SSDB_CUDA(cudaMemcpyAsync(n->images_stage + (size_t)b0 * img, images_host + (size_t)b0 * img, (size_t)bc * img * sizeof(float),
+                                  cudaMemcpyHostToDevice, cs));
+        SSDB_CUDA(cudaEventRecord(n->ev_chunk[c], cs));
+        SSDB_CUDA(cudaStreamWaitEvent(st, n->ev_chunk[c], 0));
+        int rc = run_first_conv_chunk(n, n->images_stage, b0, bc, st); if (rc) return rc;
+    }
+    *first_done = true;
+    return SSDB_OK;
+}
+
 int ssdb_forward_host(ssdb_net* n, const float* images_host, int B, float* result_host) {
     SSDB_REQUIRE(n && images_host && result_host && B >= 1 && B <= n->max_batch, "bad arguments");
     cudaStream_t st = n->own_stream;
-    SSDB_CUDA(cudaMemcpyAsync(n->images_stage, images_host, (size_t)B * n->S * n->S * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
-    int rc = ssdb_forward(n, n->images_stage, B, n->result, st); if (rc) return rc;
+    bool first_done = false;
+    int rc = upload_images_chunked(n, images_host, B, st, n->copy_stream, &first_done); if (rc) return rc;
+    rc = run_forward(n, n->images_stage, B, st, first_done); if (rc) return rc;
+    rc = softmax_result(n->out, (long long)B * n->A, n->C, n->result, st); if (rc) return rc;
     SSDB_CUDA(cudaMemcpyAsync(result_host, n->result, (size_t)B * n->A * n->V * sizeof(float), cudaMemcpyDeviceToHost, st));
     SSDB_CUDA(cudaStreamSynchronize(st));
     return SSDB_OK;
@@ -694,13 +744,13 @@ static int train_step_host_impl(ssdb_net* n, const float* images_host, const flo
     // result leaves while the backward runs; only the image upload is on the critical path
     cudaStream_t st = n->own_stream, cs = n->copy_stream;
     const size_t bav = (size_t)B * n->A * n->V * sizeof(float);
-    // both uploads share one DMA direction: images first (critical path), labels behind them
-    SSDB_CUDA(cudaMemcpyAsync(n->images_stage, images_host, (size_t)B * n->S * n->S * 3 * sizeof(float), cudaMemcpyHostToDevice, cs));
-    SSDB_CUDA(cudaEventRecord(n->ev_images, cs));
+    // both uploads share one DMA direction: images first (critical path, chunked so that conv1_1 starts after the first
+    // quarter), labels behind them
+    bool first_done = false;
+    int rc = upload_images_chunked(n, images_host, B, st, cs, &first_done); if (rc) return rc;
     SSDB_CUDA(cudaMemcpyAsync(n->labels_stage, labels_host, bav, cudaMemcpyHostToDevice, cs));
     SSDB_CUDA(cudaEventRecord(n->ev_labels, cs));
-    SSDB_CUDA(cudaStreamWaitEvent(st, n->ev_images, 0));
-    int rc = run_forward(n, n->images_stage, B, st); if (rc) return rc;
+    rc = run_forward(n, n->images_stage, B, st, first_done); if (rc) return rc;
     SSDB_CUDA(cudaStreamWaitEvent(st, n->ev_labels, 0));
     rc = loss_and_finalize(n, n->labels_stage, nullptr, nullptr, 0, B, weight_decay, 1.0f, true, n->small_ws, n->result, st); if (rc) return rc;
     if (result_host) {
