@@ -8,6 +8,7 @@ seeded synthetic inputs (ssd-tensorflow_b200/synth.py).  Outputs:
   anchors.npz   G1: default boxes of both presets (+ 1000-grid integer bounds)
   match.npz     G2: LabelCreatorTransform label tensors, stored sparsely
   detect.npz    G3: decode_boxes + suppress_overlaps results
+  ap.npz        G7: APCalculator.compute_aps of the reference on decode + NMS output of 24 clustered images
 Inputs whose result would depend on NumPy's unspecified argsort tie order
 (duplicate confidences inside the candidate set) are skipped, as SURVEY 8c asks.
 """
@@ -97,8 +98,46 @@ def main():
         print(key, 'candidates', ncand, 'kept', len(dets))
     g3['cases'] = np.array(kept_cases)
     np.savez_compressed(os.path.join(OUT, 'detect.npz'), **g3)
+    make_ap(ru, rs, anchors, g1)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+AP_IMAGES = 24
+
+
+def make_ap(ru, rs, anchors, g1):
+    """G7: the reference's APCalculator fed with the reference's own decode_boxes + suppress_overlaps output; ground truth =
+    the objects the clustered prediction generator planted.  Stored: per image the GT rows, the detection rows
+    (conf, labelid, cx, cy, w, h) and the resulting per-class APs."""
+    rap = ref_loader.load_ap()
+    p, ra = anchors['vgg300']
+    prop = g1['vgg300_prop']
+    lid2name = {i: 'c%d' % i for i in range(20)}
+    out = {}
+    for minoverlap, tag in ((0.5, 'm50'), (0.7, 'm70')):
+        calc = rap.APCalculator(minoverlap)
+        all_conf = []
+        for i in range(AP_IMAGES):
+            pred, objs = synth.pred_clustered(5000 + i, prop, return_objects=True)
+            if i % 3 == 2:        # every third image: detections unrelated to the ground truth (false positives at all confidences)
+                pred = synth.pred_clustered(9000 + i, prop)
+            gt_boxes = [ru.Box(lid2name[int(o[0])], int(o[0]), ru.Point(o[1], o[2]), ru.Size(o[3], o[4])) for o in objs]
+            dets = rs.suppress_overlaps(rs.decode_boxes(pred.copy(), ra, 0.01, lid2name, 200))
+            calc.add_detections(gt_boxes, dets)
+            rows = np.array([(float(c), b.labelid, b.center.x, b.center.y, b.size.w, b.size.h) for c, b in dets], np.float64).reshape(-1, 6)
+            out['img%d_gt' % i] = objs
+            out['img%d_det' % i] = rows
+            out['img%d_conf32' % i] = np.array([c for c, _ in dets], np.float32)
+            all_conf.extend((b.labelid, np.float32(c)) for c, b in dets)
+        assert len(set(all_conf)) == len(all_conf), 'duplicate (class, confidence): argsort tie order would matter'
+        aps = calc.compute_aps()
+        ids = sorted(int(k[1:]) for k in aps)
+        out['aps_%s_ids' % tag] = np.array(ids, np.int32)
+        out['aps_%s' % tag] = np.array([aps['c%d' % k] for k in ids], np.float64)
+        out['map_%s' % tag] = np.array([rap.APs2mAP(aps)], np.float64)
+        print('AP fixture', tag, 'classes', len(ids), 'mAP', rap.APs2mAP(aps))
+    np.savez_compressed(os.path.join(OUT, 'ap.npz'), **out)
 
 
 if __name__ == '__main__':

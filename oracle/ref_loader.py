@@ -50,3 +50,30 @@ def load():
         sys.modules[name] = m
     _cache['mods'] = tuple(mods)
     return _cache['mods']
+
+
+def load_ap():
+    """The reference's average_precision module (needs the NumPy-1 alias ``np.int``, removed in NumPy 1.24: supplied here,
+    in the test process only, because the reference file cannot be edited)."""
+    if 'ap' in _cache:
+        return _cache['ap']
+    import numpy as np
+    ru, rs, _ = load()
+    if not hasattr(np, 'int'):
+        np.int = int
+    if not hasattr(np, 'bool'):
+        np.bool = bool
+    saved = {k: sys.modules.get(k) for k in ('utils', 'ssdutils')}
+    sys.modules['utils'] = ru; sys.modules['ssdutils'] = rs
+    try:
+        spec = importlib.util.spec_from_file_location('_ref_average_precision', os.path.join(REF_DIR, 'average_precision.py'))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _cache['ap'] = m
+    return m

@@ -172,6 +172,16 @@ def detect_batch(pred, anchors, confidence_threshold=0.01, lid2name={}, detectio
     return [_boxes_from_rows(dets[i, :counts[i, 0]], lid2name) for i in range(pred.shape[0])]
 
 
+def detect_batch_rows(pred, anchors, confidence_threshold=0.01, detections_cap=200, overlap_threshold=0.45):
+    """decode_boxes + suppress_overlaps for a batch, as the kernels' integer rows: (dets [B,cap,8] int32, counts [B,2])
+    with row = (confidence bits, labelid, xmin, xmax, ymin, ymax on the 1000 grid, anchor, confidence rank) --
+    what ``average_precision.APCalculator.add_detections_batch`` consumes without building Box tuples."""
+    pred = np.asarray(pred, np.float32)
+    if pred.ndim == 2:
+        pred = pred[None]
+    return ssdb.decode_nms_host(pred, anchors_as_array(anchors), confidence_threshold, detections_cap, overlap_threshold)
+
+
 def decode_boxes(pred, anchors, confidence_threshold=0.01, lid2name={}, detections_cap=200):
     """Decode boxes from one image's predictions (ssdutils.py:192-229), on the GPU.
 

@@ -62,10 +62,11 @@ def pred_uniform(image_index, num_anchors, num_classes=20):
     return np.concatenate([_softmax(z), loc], axis=1)
 
 
-def pred_clustered(image_index, anchors, num_classes=20, objects=8):
+def pred_clustered(image_index, anchors, num_classes=20, objects=8, return_objects=False):
     """Distribution C: `objects` boxes per image; anchors with IoU > 0.4 to an
     object get logit +6 on its class and offsets = encode(object) + N(0, 0.3^2);
-    all others logit +6 on background.  anchors: [A,4] float64 (cx,cy,w,h)."""
+    all others logit +6 on background.  anchors: [A,4] float64 (cx,cy,w,h).
+    return_objects: also the [objects,5] (labelid, cx, cy, w, h) rows -- the ground truth of the image for AP evaluation."""
     r = np.random.default_rng(BASE_SEED + 15485863 * 100 + int(image_index))
     a = anchors
     n = a.shape[0]
@@ -74,11 +75,13 @@ def pred_clustered(image_index, anchors, num_classes=20, objects=8):
     z[:, num_classes] += 6
     ax0, ax1 = a[:, 0] - a[:, 2] / 2, a[:, 0] + a[:, 2] / 2
     ay0, ay1 = a[:, 1] - a[:, 3] / 2, a[:, 1] + a[:, 3] / 2
-    for _ in range(objects):
+    objs = np.zeros((objects, 5), np.float64)
+    for k in range(objects):
         w, h = r.uniform(0.1, 0.6, 2)
         cx = r.uniform(w / 2, 1 - w / 2)
         cy = r.uniform(h / 2, 1 - h / 2)
         c = int(r.integers(0, num_classes))
+        objs[k] = (c, cx, cy, w, h)
         iw = np.maximum(0, np.minimum(ax1, cx + w / 2) - np.maximum(ax0, cx - w / 2))
         ih = np.maximum(0, np.minimum(ay1, cy + h / 2) - np.maximum(ay0, cy - h / 2))
         inter = iw * ih
@@ -90,4 +93,5 @@ def pred_clustered(image_index, anchors, num_classes=20, objects=8):
         loc[hit, 1] += (cy - a[hit, 1]) / a[hit, 3] * 10
         loc[hit, 2] += np.log(w / a[hit, 2]) * 5
         loc[hit, 3] += np.log(h / a[hit, 3]) * 5
-    return np.concatenate([_softmax(z), loc.astype(np.float32)], axis=1)
+    pred = np.concatenate([_softmax(z), loc.astype(np.float32)], axis=1)
+    return (pred, objs) if return_objects else pred

@@ -4,7 +4,7 @@
 The reference's data pipeline (training_data.py, transforms.py, multiprocessing workers) is out of scope
 (SURVEY.md section 2); this driver feeds seeded synthetic batches (--synthetic, the default) through the same
 call sequence as train.py:166-343: build_from_vgg -> build_optimizer -> sess.run([result, losses, optimizer])
-per batch -> decode + NMS of the predictions."""
+per batch -> decode + NMS of the predictions -> APCalculator (train.py:275-281: from the second epoch on)."""
 import argparse
 import os
 import sys
@@ -14,6 +14,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import ssdutils   # noqa: E402
+from average_precision import APCalculator, APs2mAP   # noqa: E402
 import synth      # noqa: E402
 from ssdvgg import SSDVGG, GlobalStep, Session, piecewise_constant   # noqa: E402
 from utils import str2bool   # noqa: E402
@@ -56,8 +57,11 @@ def main():
         net.build_optimizer(learning_rate=piecewise_constant(step, lr_boundaries, lr_values),
                             weight_decay=args.weight_decay, momentum=args.momentum, global_step=step)
         side = preset.image_size.w
+        lid2name = {i: 'class%d' % i for i in range(20)}
+        ap_calc = APCalculator()
         for e in range(args.epochs):
             t0 = time.time()
+            ap_calc.clear()
             for b in range(args.batches_per_epoch):
                 first = (e * args.batches_per_epoch + b) * args.batch_size
                 x = synth.images(first, args.batch_size, side)
@@ -68,10 +72,15 @@ def main():
                                              feed_dict={net.image_input: x, net.labels: y})
                 if np.isnan(losses['confidence']):
                     print('[!] Confidence loss is NaN.')
-            dets = ssdutils.detect_batch(result, anchors, 0.5, {}, 200)
-            print('[i] epoch %d: total %.4f loc %.4f conf %.4f l2 %.4f | %d detections in the last batch | %.2fs' %
+                if e == 0:
+                    continue
+                # train.py:275-278: decode + NMS of every sample, fed to the AP calculator -- one batched launch here
+                dets, counts = ssdutils.detect_batch_rows(result, anchors, 0.5, 200)
+                ap_calc.add_detections_batch(gts, dets, counts, lid2name)
+            aps = ap_calc.compute_aps() if e > 0 else {}
+            print('[i] epoch %d: total %.4f loc %.4f conf %.4f l2 %.4f | mAP %.4f over %d classes | %.2fs' %
                   (e, losses['total'], losses['localization'], losses['confidence'], losses['l2'],
-                   sum(len(d) for d in dets), time.time() - t0))
+                   APs2mAP(aps), len(aps), time.time() - t0))
             if (e + 1) % args.checkpoint_interval == 0:
                 os.makedirs(args.name, exist_ok=True)
                 net.save(os.path.join(args.name, 'e%d' % (e + 1)))

@@ -103,3 +103,26 @@ def test_session_run_train_eval_infer():
         net2.build_from_metagraph(None, os.path.join(d, 'final.npz'))
         res_rest = np.array(sess2.run(net2.result, feed_dict={net2.image_input: x}))
         assert np.array_equal(res_rest, res_after)
+
+
+def test_ap_from_gpu_detections_equals_reference_fixture(golden_dir):
+    """decode + NMS on the GPU -> APCalculator.add_detections_batch == the APs the REAL reference computed from its own
+    decode_boxes / suppress_overlaps / APCalculator chain (tests/golden/ap.npz)."""
+    import average_precision as ap
+    g = np.load(os.path.join(golden_dir, 'ap.npz'))
+    anc = bo.anchors('vgg300')
+    lid2name = {i: 'c%d' % i for i in range(20)}
+    preds, gts = [], []
+    for i in range(24):
+        pred, objs = synth.pred_clustered(5000 + i, anc, return_objects=True)
+        if i % 3 == 2:
+            pred = synth.pred_clustered(9000 + i, anc)
+        preds.append(pred); gts.append(objs)
+    dets, counts = ssdutils.detect_batch_rows(np.stack(preds), ssdutils.get_anchors_for_preset(ssdutils.get_preset_by_name('vgg300')), 0.01, 200)
+    for tag, mo in (('m50', 0.5), ('m70', 0.7)):
+        calc = ap.APCalculator(mo)
+        calc.add_detections_batch(gts, dets, counts, lid2name)
+        aps = calc.compute_aps()
+        ids = [int(k) for k in g['aps_%s_ids' % tag]]
+        assert np.array_equal(np.array([aps[lid2name[k]] for k in ids]), g['aps_' + tag])
+        assert ap.APs2mAP(aps) == g['map_' + tag][0]
