@@ -82,7 +82,9 @@ int ssdb_match_anchors_host(const double* gt_host, const int* gt_count_host, int
  *              classes by first appearance, confidence-descending inside a class.
  *   counts_out [B, 2] int32: (kept detections, candidates that entered NMS)
  * conf_thr is compared in float32 and iou_thr in float64, as NumPy does in the reference.
- * Ties in confidence are broken by lower anchor index (NumPy leaves it unspecified). */
+ * Ties in confidence are broken by lower anchor index (NumPy leaves it unspecified).
+ * Two launches (anchor-tile scan, then one CTA per image); the 5-byte-per-anchor workspace between them is a
+ * grow-only buffer kept per stream by the library (allocated on first use / when B*A grows, never per call). */
 int ssdb_decode_nms(const float* pred_dev, int B, int A, int C, const double* anchors_prop_dev,
                     float conf_thr, int cap, double iou_thr,
                     int* dets_out_dev, int* counts_out_dev, void* stream);
@@ -111,7 +113,10 @@ int ssdb_nms_host(const int* boxes_abs_host, const int* labelid_host, const floa
  *   grad_out   [B, A, C+5] d(conf+loc)/d(output) * grad_scale      (may be NULL)
  *   result_out [B, A, C+5] softmax(logits) | offsets = net.result (:368-372) (may be NULL)
  * ssdb_multibox_loss_gt is the fused variant: anchor matching happens inside the
- * same kernel from raw ground truth (no dense label tensor in HBM). */
+ * loss kernels from raw ground truth (no dense label tensor in HBM), in exact integer arithmetic.
+ * Three streaming launches (anchor tiles, per-image selection, gradient tiles; the fused variant adds two small
+ * matching launches); their ~6-byte-per-anchor workspace is a grow-only buffer kept by the library (one caller
+ * thread per process, like the reference's single session). */
 int ssdb_multibox_loss(const float* output_dev, const float* labels_dev, int B, int A, int C,
                        float grad_scale, float* losses_out_dev, float* grad_out_dev,
                        float* result_out_dev, void* stream);
