@@ -105,6 +105,27 @@ def ncu_traffic():
     return (tot / n, n) if n else (None, None)
 
 
+def ncu_box_traffic(kernel_prefixes):
+    """Sum of dram__bytes_read + dram__bytes_write of the FIRST launch of each named kernel in the committed `ncu --set full`
+    summary of the loss / decode+NMS kernels (profiles/r1_ncu_box_kernels.txt: 64 images for the loss, 128 for NMS), or None."""
+    path = os.path.join(ROOT, 'profiles', 'r1_ncu_box_kernels.txt')
+    if not os.path.exists(path):
+        return None
+    mult = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    seen, cur, tot = set(), None, 0.0
+    for line in open(path):
+        if line.startswith('---'):
+            name = line.split('::')[-1].strip()
+            cur = next((k for k in kernel_prefixes if name.startswith(k) and k not in seen), None)
+            if cur:
+                seen.add(cur)
+            continue
+        parts = line.split()
+        if cur and len(parts) >= 3 and parts[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum') and parts[2] in mult:
+            tot += float(parts[1]) * mult[parts[2]]
+    return tot if len(seen) == len(kernel_prefixes) else None
+
+
 def labels_for(first, count, preset_name, anchors):
     """Dense labels for the synthetic GT boxes, built by the GPU matcher (product path)."""
     import ssdb
@@ -317,7 +338,11 @@ def main():
         loss_info = {'kernel': 'loss_rows_kernel + loss_select_kernel + loss_grad_kernel (dense-label multibox loss, batch %d)' % B,
                      'ms': t_ms, 'launches_per_call': (ssdb.launch_count() - l0) // 20,
                      'roofline': {'bound': 'hbm', 'achieved': bytes_alg / (t_ms * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
-                                  'frac': bytes_alg / (t_ms * 1e-3) / 1e9 / hbm, 'traffic': None, 'peak_source': pk_kind,
+                                  'frac': bytes_alg / (t_ms * 1e-3) / 1e9 / hbm,
+                                  'traffic': ncu_box_traffic(['loss_rows_kernel<0', 'loss_select_kernel', 'loss_grad_kernel<0']) if B == 64 else None,
+                                  'traffic_note': 'dram bytes of the three kernels of one call, profiles/r1_ncu_box_kernels.txt (ncu --set full, 64 images; '
+                                                  'writes still in the L2 when a kernel ends are not counted by ncu)',
+                                  'peak_source': pk_kind,
                                   'note': 'algorithmic bytes = 4 x [B,A,25] f32 = %.1f MB (3.49 MB/img); the four tensors (%.0f MB) exceed the L2' % (bytes_alg / 1e6, bytes_alg / 1e6)}}
         del out_d, g_d, r_d
 
@@ -373,7 +398,9 @@ def main():
                        'h2d_bytes_per_step': int(pred.nbytes + anchors.nbytes), 'd2h_bytes_per_step': int(NB * 200 * 8 * 4 + NB * 8),
                        'call': 'ssdb.decode_nms_host(pred, anchors, 0.01, 200, 0.45) -> ssdb_decode_nms_host (pageable host buffers)'},
                'cpu_baseline': nms_cpu,
-               'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': gbs / hbm, 'traffic': None,
+               'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': gbs / hbm,
+                            'traffic': ncu_box_traffic(['decode_scan_kernel', 'decode_nms_kernel']),
+                            'traffic_note': 'dram bytes of the two kernels of one call, profiles/r1_ncu_box_kernels.txt (ncu --set full, 128 images)',
                             'note': 'algorithmic bytes = read of pred [128,8732,25] f32 (112 MB) by decode_scan_kernel; the per-image '
                                     'select / sort / greedy-NMS kernel that follows is latency-bound and is inside the timed region',
                             'peak_source': pk_kind}}

@@ -118,3 +118,39 @@ def test_oracle_and_package_vs_live_reference_random():
         assert {int(k[1:]): v for k, v in want.items()} == got_o
         assert want == got_p
         assert rap.APs2mAP(want) == ap.APs2mAP(got_p) == ap_oracle.aps2map(got_o)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree not present (GPU box)')
+def test_pascal_summary_files_equal_the_reference(tmp_path):
+    import importlib.util
+    import sys
+    import cv2
+    import pascal_summary as ps
+    ru, rs, _ = ref_loader.load()
+    saved = sys.modules.get('utils')
+    sys.modules['utils'] = ru
+    try:
+        spec = importlib.util.spec_from_file_location('_ref_pascal_summary', os.path.join(ref_loader.REF_DIR, 'pascal_summary.py'))
+        rps = importlib.util.module_from_spec(spec); spec.loader.exec_module(rps)
+    finally:
+        if saved is None:
+            sys.modules.pop('utils', None)
+        else:
+            sys.modules['utils'] = saved
+    rng = np.random.default_rng(5)
+    ref, got = rps.PascalSummary(), ps.PascalSummary()
+    for k, (w, h) in enumerate([(500, 375), (333, 500), (64, 48)]):
+        fn = str(tmp_path / ('img_%d.x.jpg' % k))
+        cv2.imwrite(fn, np.zeros((h, w, 3), np.uint8))
+        rows = [(np.float32(rng.random()), 'c%d' % int(rng.integers(0, 3)), *rng.uniform(-0.1, 1.1, 2), *rng.uniform(0.01, 0.9, 2)) for _ in range(20)]
+        ref.add_detections(fn, [(c, ru.Box(l, 0, ru.Point(cx, cy), ru.Size(bw, bh))) for (c, l, cx, cy, bw, bh) in rows])
+        if k == 1:
+            got.add_detections(fn, [(c, Box(l, 0, Point(cx, cy), Size(bw, bh))) for (c, l, cx, cy, bw, bh) in rows])       # via cv2
+        else:
+            got.add_detections(fn, [(c, Box(l, 0, Point(cx, cy), Size(bw, bh))) for (c, l, cx, cy, bw, bh) in rows], Size(w, h))
+    (tmp_path / 'ref').mkdir(); (tmp_path / 'got').mkdir()
+    ref.write_summary(str(tmp_path / 'ref')); got.write_summary(str(tmp_path / 'got'))
+    names = sorted(os.listdir(tmp_path / 'ref'))
+    assert names == sorted(os.listdir(tmp_path / 'got')) and len(names) == 3
+    for n in names:
+        assert (tmp_path / 'ref' / n).read_text() == (tmp_path / 'got' / n).read_text()
