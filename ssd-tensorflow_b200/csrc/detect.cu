@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(RT) decode_scan_kernel(const float* __restrict
 }
 
 __global__ void __launch_bounds__(DT) decode_nms_kernel(DetArgs p) {
-    extern __shared__ __align__(16) unsigned char dyn[];
+    extern __shared__ __align__(128) unsigned char dyn[];
     unsigned int* ckey = reinterpret_cast<unsigned int*>(dyn);                 // [A] ordered confidence keys (0 = not a candidate)
     unsigned long long* keys;                                                  // [P] sort keys
     int* cand;                                                                 // [CAND_WORDS][P]

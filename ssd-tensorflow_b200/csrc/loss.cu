@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(LT) multibox_loss_kernel(
     const int* __restrict__ gt_count, int G, const double* __restrict__ anchors, int B, int A, int C, float grad_scale,
     float* __restrict__ losses_out, float* __restrict__ grad_out, float* __restrict__ result_out, int* __restrict__ match_out,
     float* __restrict__ per_image, unsigned int* __restrict__ counter) {
-    extern __shared__ __align__(16) unsigned char dyn[];
+    extern __shared__ __align__(128) unsigned char dyn[];
     float* ce = reinterpret_cast<float*>(dyn);
     signed char* kind = reinterpret_cast<signed char*>(ce + A);
     signed char* own = kind + A;
@@ -591,7 +591,7 @@ struct NegKey {          // participants of the hard-negative selection: negativ
 #define SSDB_TRACE_PT(k) do { if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[k] = clock64(); } while (0)
 __global__ void __launch_bounds__(LT) loss_select_kernel(LossWs ws, int B, int A, int S, float grad_scale, float* __restrict__ losses_out,
                                                          long long* __restrict__ trace) {
-    extern __shared__ __align__(16) unsigned char dyn[];
+    extern __shared__ __align__(128) unsigned char dyn[];
     float* ce = reinterpret_cast<float*>(dyn);
     signed char* kind = reinterpret_cast<signed char*>(ce + A);
     __shared__ float redf[LT / 32];
