@@ -163,3 +163,64 @@ def test_radix_select_model_finds_kth_largest_with_ties(seed):
         srt = np.sort(keys[valid])[::-1]
         assert prefix == srt[k - 1]
         assert remaining == k - int((keys[valid] > prefix).sum()) and remaining >= 1
+
+
+def _lazy_nms_model(cls, nms_boxes, thr, P=256):
+    """Python model of the fast path of csrc/detect.cu decode_nms_kernel after the sort: per-class member masks (cmask),
+    lazy greedy pass over compacted member lists with the fp32-filtered IoU test (rmask), then the popcount ranking
+    (kcnt / kbase).  Returns the candidate positions in output order."""
+    n = len(cls)
+    W = 8
+    cmask = np.zeros((64, W), np.uint32); rmask = np.zeros((64, W), np.uint32)
+    first_pos = np.full(64, 0x7fffffff, np.int64)
+    for i, c in enumerate(cls):
+        cmask[c, i >> 5] |= np.uint32(1 << (i & 31)); first_pos[c] = min(first_pos[c], i)
+    def hit(i, j):
+        a, b = nms_boxes[i], nms_boxes[j]
+        iw = max(int(min(a[1], b[1]) - max(a[0], b[0]) + 1), 0); ih = max(int(min(a[3], b[3]) - max(a[2], b[2]) + 1), 0)
+        inter = iw * ih
+        uni = int((a[1] - a[0] + 1) * (a[3] - a[2] + 1) + (b[1] - b[0] + 1) * (b[3] - b[2] + 1)) - inter
+        return bool(_filter_decision(np.array([inter]), np.array([uni]), thr)[0][0])
+    for c in range(64):
+        ml = [w * 32 + k for w in range(W) for k in range(32) if (int(cmask[c, w]) >> k) & 1]
+        dead = [False] * len(ml)
+        for pos in range(len(ml)):
+            if dead[pos]:
+                continue                                  # only alive (= kept) members test their later class mates
+            for q in range(pos + 1, len(ml)):
+                if not dead[q] and hit(ml[pos], ml[q]):
+                    dead[q] = True
+        for q, j in enumerate(ml):
+            if dead[q]:
+                rmask[c, j >> 5] |= np.uint32(1 << (j & 31))
+    alive = cmask & ~rmask
+    kcnt = np.array([sum(bin(int(v)).count('1') for v in alive[c]) for c in range(64)])
+    kbase = np.array([sum(kcnt[c2] for c2 in range(64) if first_pos[c2] < first_pos[c]) for c in range(64)])
+    out = [None] * int(kcnt.sum())
+    for i in range(n):
+        c, w = cls[i], i >> 5
+        if not (int(alive[c, w]) >> (i & 31)) & 1:
+            continue
+        rnk = kbase[c] + bin(int(alive[c, w]) & ((1 << (i & 31)) - 1)).count('1') + sum(bin(int(alive[c, w2])).count('1') for w2 in range(w))
+        out[rnk] = i
+    return out
+
+
+@pytest.mark.parametrize('seed', range(5))
+def test_lazy_per_class_nms_model_equals_reference_order(seed):
+    """The lazy per-class pass + popcount ranking produce the reference's kept set AND output order
+    (ssdutils.py:232-318: classes by first appearance, confidence-descending inside a class)."""
+    import box_oracle as bo
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(1, 201))
+    centers = rng.uniform(100, 900, (6, 2))
+    which = rng.integers(0, 6, n)
+    cxy = centers[which] + rng.normal(0, 25, (n, 2))
+    wh = rng.uniform(40, 300, (n, 2))
+    box = np.stack([cxy[:, 0] - wh[:, 0] / 2, cxy[:, 0] + wh[:, 0] / 2, cxy[:, 1] - wh[:, 1] / 2, cxy[:, 1] + wh[:, 1] / 2], axis=1)
+    box = np.clip(np.trunc(box), 0, 999).astype(np.int64)
+    cls = rng.integers(0, 1 + seed * 4, n)                  # seed 0: a single class holds every candidate
+    cand = dict(idx=np.arange(n), cls=cls, nms=box)
+    want = bo.nms_classwise(cand, 0.45)
+    got = _lazy_nms_model(cls, box, 0.45)
+    assert list(want) == got
