@@ -25,6 +25,8 @@
 #ifndef SSD_B200_H
 #define SSD_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -209,6 +211,12 @@ int ssdb_apply_update(ssdb_net* net, float lr, float momentum, float weight_deca
 /* page-locked host memory for feeds / fetches (cudaHostAlloc): makes the host entry points' copies asynchronous DMA */
 int ssdb_pinned_alloc(long long bytes, void** host_ptr_out);
 int ssdb_pinned_free(void* host_ptr);
+
+/* CRC32C (Castagnoli) of a HOST buffer, continuing from `crc` (0 to start).  Not on the compute path: it is the
+ * checksum TensorFlow's checkpoint-V2 "tensor bundle" files carry per table block and per tensor
+ * (tf.train.Saver, train.py:208,336-343; the VGG saved-model, ssdvgg.py:190-207), used by tf_bundle.py to read / write
+ * those files without TensorFlow when payloads are hundreds of megabytes. */
+unsigned int ssdb_crc32c(unsigned int crc, const void* data_host, size_t bytes);
 
 /* number of kernels this library launched since load (bench.py's gpu_launches) */
 long long ssdb_launch_count(void);

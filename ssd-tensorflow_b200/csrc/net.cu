@@ -978,6 +978,32 @@ int ssdb_pinned_free(void* host_ptr) {
     return SSDB_OK;
 }
 
+unsigned int ssdb_crc32c(unsigned int crc, const void* data_host, size_t bytes) {
+    static uint32_t table[8][256];
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1) ? 0x82f63b78u : 0u);
+            table[0][i] = c;
+        }
+        for (uint32_t i = 0; i < 256; ++i)
+            for (int t = 1; t < 8; ++t) table[t][i] = (table[t - 1][i] >> 8) ^ table[0][table[t - 1][i] & 0xff];
+    });
+    const unsigned char* p = static_cast<const unsigned char*>(data_host);
+    uint32_t c = crc ^ 0xffffffffu;
+    while (bytes >= 8) {                                     // slicing-by-8
+        uint32_t lo, hi;
+        memcpy(&lo, p, 4); memcpy(&hi, p + 4, 4);
+        lo ^= c;
+        c = table[7][lo & 0xff] ^ table[6][(lo >> 8) & 0xff] ^ table[5][(lo >> 16) & 0xff] ^ table[4][lo >> 24] ^
+            table[3][hi & 0xff] ^ table[2][(hi >> 8) & 0xff] ^ table[1][(hi >> 16) & 0xff] ^ table[0][hi >> 24];
+        p += 8; bytes -= 8;
+    }
+    while (bytes--) c = table[0][(c ^ *p++) & 0xff] ^ (c >> 8);
+    return c ^ 0xffffffffu;
+}
+
 int ssdb_profile_step(ssdb_net* n, const float* images_dev, const float* labels_dev, int B, char (*names_out)[32], float* ms_out,
                       int* launches_out, int cap) {
     SSDB_REQUIRE(n && images_dev && labels_dev && names_out && ms_out && launches_out && cap > 0, "bad arguments");

@@ -43,6 +43,7 @@ _ll = C.c_longlong
 
 # name -> (restype, argtypes); mirrors include/ssd_b200.h one to one
 SIGNATURES = {
+    'ssdb_crc32c': (C.c_uint32, [C.c_uint32, _p, C.c_size_t]),
     'ssdb_version': (_i, []),
     'ssdb_last_error': (C.c_char_p, []),
     'ssdb_device_ok': (_i, []),

@@ -22,6 +22,8 @@ import os
 import numpy as np
 
 import ssdb
+import tf_bundle
+import vgg_import
 from ssdutils import get_preset_by_name
 
 
@@ -109,17 +111,27 @@ class SSDVGG:
     def build_from_vgg(self, vgg_dir, num_classes, a_trous=True, progress_hook='tqdm'):
         """ssdvgg.py:96-118.  The reference downloads a pretrained VGG-16 saved-model
         (ssdvgg.py:153-187, network access) and decimates fc6/fc7 into conv6/conv7.
-        Here: if ``<vgg_dir>/vgg16_ssd_init.npz`` exists its tensors (reference variable
-        names) are loaded; otherwise the trunk gets a He-normal stand-in (no network in
-        this environment) and the new layers the reference's Xavier-uniform / zero-bias /
-        scale-20 initialisers (ssdvgg.py:46-47,59-60,336)."""
+        Here: if ``<vgg_dir>/vgg/variables/variables.index`` exists (the saved-model the reference
+        downloads), its variables are read straight from the TensorFlow tensor bundle and fc6 / fc7
+        are decimated like ssdvgg.py:245-280 (vgg_import.py, no TensorFlow needed); else if
+        ``<vgg_dir>/vgg16_ssd_init.npz`` exists its tensors (reference variable names) are loaded;
+        otherwise the trunk gets a He-normal stand-in (no network in this environment).  The new
+        layers always get the reference's Xavier-uniform / zero-bias / scale-20 initialisers
+        (ssdvgg.py:46-47,59-60,336)."""
         if not a_trous:
             raise NotImplementedError('only the a-trous variant (the reference default, used by both CLIs) is built')
         self.num_classes = num_classes + 1
         self.num_vars = num_classes + 5
         self._host_params = self._initial_params(num_classes, seed=7)
         path = os.path.join(vgg_dir or '', 'vgg16_ssd_init.npz')
-        if vgg_dir and os.path.exists(path):
+        if vgg_dir and vgg_import.find_bundle(vgg_dir):
+            for k, v in vgg_import.load_vgg_dir(vgg_dir).items():
+                if k in self._host_params and self._host_params[k].shape == v.shape:
+                    self._host_params[k] = v
+                else:
+                    raise ValueError('VGG variable %s has shape %s, the engine expects %s' %
+                                     (k, v.shape, self._host_params[k].shape if k in self._host_params else None))
+        elif vgg_dir and os.path.exists(path):
             with np.load(path) as z:
                 for k in z.files:
                     if k in self._host_params:
@@ -130,6 +142,15 @@ class SSDVGG:
         """ssdvgg.py:120-130: restore a trained model.  `checkpoint_file` is an .npz written
         by ``save`` (tensors under the reference's variable names); the metagraph argument is
         accepted for signature compatibility and ignored (there is no TF graph to import)."""
+        if os.path.exists(checkpoint_file + '.index'):            # a TensorFlow checkpoint-V2 bundle (ours or the reference's)
+            t = tf_bundle.read_bundle(checkpoint_file)
+            self._host_params = {k: v.astype(np.float32) for k, v in t.items() if k.endswith(('/filter', '/biases', '/scale'))
+                                 and '/Momentum' not in k}
+            row = int(self._host_params['classifiers/classifier0_0/biases'].shape[0])
+            self.num_vars = row
+            self.num_classes = row - 4
+            self._built = True
+            return
         with np.load(checkpoint_file if checkpoint_file.endswith('.npz') else checkpoint_file + '.npz') as z:
             self._host_params = {k: z[k].astype(np.float32) for k in z.files if not k.startswith('__')}
             row = int(z['__num_vars']) if '__num_vars' in z.files else 25
@@ -152,9 +173,14 @@ class SSDVGG:
         returned so callers that fetch it keep working (it evaluates to None)."""
         return Fetch('net_summaries/net_summaries:0')
 
-    def save(self, path):
-        """Write every trainable tensor under the reference's variable names (.npz)."""
+    def save(self, path, tf_checkpoint=False):
+        """Write every trainable tensor under the reference's variable names: an .npz (default), or with
+        ``tf_checkpoint=True`` a TensorFlow checkpoint-V2 bundle ``<path>.index`` / ``<path>.data-00000-of-00001`` like the
+        reference's ``saver.save(sess, 'e<N>.ckpt')`` (train.py:336-343), readable by TensorFlow tools."""
         arrays = self.get_params()
+        if tf_checkpoint:
+            tf_bundle.write_bundle(path, arrays)
+            return
         arrays['__num_vars'] = np.array(self.num_vars)
         np.savez(path if path.endswith('.npz') else path + '.npz', **arrays)
 
