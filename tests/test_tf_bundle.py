@@ -125,3 +125,19 @@ def test_vgg_saved_model_directory_to_engine_tensors(tmp_path):
     assert np.array_equal(P['mod_conv7/biases'], variables['fc7/biases'][::4])
     with pytest.raises(FileNotFoundError):
         vgg_import.load_vgg_dir(str(tmp_path / 'nowhere'))
+
+
+def test_ssdvgg_checkpoint_round_trip_as_tf_bundle(tmp_path):
+    """SSDVGG.save(tf_checkpoint=True) -> build_from_metagraph: every tensor back under the reference's variable names
+    (host side only: no engine is created, so this runs without a GPU)."""
+    from ssdvgg import SSDVGG, Session
+    a = SSDVGG(Session(), 'vgg300'); a.build_from_vgg(None, 20)
+    prefix = str(tmp_path / 'e5.ckpt')
+    a.save(prefix, tf_checkpoint=True)
+    names = tb.list_entries(prefix)
+    assert 'conv4_3/filter' in names and 'l2_norm_conv4_3/scale' in names and 'classifiers/classifier5_3/biases' in names
+    assert names['mod_conv6/filter']['shape'] == [3, 3, 512, 1024]
+    b = SSDVGG(Session(), 'vgg300'); b.build_from_metagraph(None, prefix)
+    pa, pb = a.get_params(), b.get_params()
+    assert sorted(pa) == sorted(pb) and b.num_vars == 25 and b.num_classes == 21
+    assert all(np.array_equal(pa[k], pb[k]) for k in pa)
