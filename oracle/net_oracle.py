@@ -121,19 +121,35 @@ def preprocess(x_nhwc):
     return torch.stack([b - VGG_MEAN_RGB[2], g - VGG_MEAN_RGB[1], r - VGG_MEAN_RGB[0]], dim=1)
 
 
-def forward(P, x_nhwc, preset_name, num_classes=20, taps=None):
+def round_tf32(t):
+    """Round to the tf32 grid (10 explicit mantissa bits), nearest with ties away from zero, like the engine's
+    `cvt.rna.tf32.f32` at every producer (csrc/common.cuh tf32_rn); returned in the input dtype."""
+    bits = t.to(torch.float32).contiguous().view(torch.int32)
+    bits = (bits + 0x1000) & ~0x1fff
+    return bits.view(torch.float32).to(t.dtype)
+
+
+def forward(P, x_nhwc, preset_name, num_classes=20, taps=None, producer_round=None):
     """Returns output [B, A, C+5] (logits | offsets), pre-softmax (ssdvgg.py:365-366).
-    `taps`, if a dict, receives the intermediate feature maps (NCHW) by name."""
+    `taps`, if a dict, receives the intermediate feature maps (NCHW) by name.
+    `producer_round` (e.g. round_tf32) is applied where the engine rounds: to the pre-processed image, to every filter,
+    to the output of every convolution that feeds another one (after bias + ReLU) and to the L2-norm output.  With exact
+    products and wide accumulation this is the arithmetic model of the engine's tensor-core path: its distance from the
+    plain float64 graph is the error floor of tf32 operands for this network, independent of any kernel, and the engine
+    itself should match the model far more tightly than it matches float64."""
     maps = PRESETS[preset_name]['maps']
     spec = {s['name']: s for s in conv_specs(preset_name, num_classes)}
+    rnd = producer_round if producer_round is not None else (lambda t: t)
     def conv(name, x):
         s = spec[name]
-        y = conv_tf(x, P[name + '/filter'], P[name + '/biases'], s['stride'], s['dilation'],
+        y = conv_tf(x, rnd(P[name + '/filter']), P[name + '/biases'], s['stride'], s['dilation'],
                     s['padding'], s['relu'])
+        if not name.startswith('classifiers/'):
+            y = rnd(y)
         if taps is not None:
             taps[name] = y
         return y
-    x = preprocess(x_nhwc.to(P['conv1_1/filter'].dtype))
+    x = rnd(preprocess(x_nhwc.to(P['conv1_1/filter'].dtype)))
     x = conv('conv1_2', conv('conv1_1', x)); x = max_pool_tf(x, 2, 2)
     x = conv('conv2_2', conv('conv2_1', x)); x = max_pool_tf(x, 2, 2)
     x = conv('conv3_3', conv('conv3_2', conv('conv3_1', x))); x = max_pool_tf(x, 2, 2)
@@ -147,7 +163,7 @@ def forward(P, x_nhwc, preset_name, num_classes=20, taps=None):
     c112 = conv('conv11_2', conv('conv11_1', c102))
     # l2_normalization (ssdvgg.py:80-84): scale * x * rsqrt(max(sum x^2, 1e-12))
     ss = (c43 * c43).sum(dim=1, keepdim=True).clamp_min(1e-12)
-    n43 = c43 * torch.rsqrt(ss) * P['l2_norm_conv4_3/scale'].view(1, -1, 1, 1)
+    n43 = rnd(c43 * torch.rsqrt(ss) * P['l2_norm_conv4_3/scale'].view(1, -1, 1, 1))
     if taps is not None:
         taps['l2_norm_conv4_3'] = n43
     fmaps = [n43, c7, c82, c92, c102, c112]

@@ -60,6 +60,17 @@ def test_forward_and_train_step(preset, B, mode):
         report['argmax_agree'] = float(agree)
         assert agree > 0.99, agree
         assert report['softmax_abs'] < 2e-2
+        # the same graph with tf32 rounding exactly where the engine rounds (filters, pre-processed image, conv outputs
+        # that feed convs, L2-norm output), exact products, float64 accumulation: the arithmetic MODEL of the tensor-core
+        # path.  Its distance from float64 is the tf32 floor (tools/tf32_floor.py, profiles/r1_tf32_floor_*.json: 1.0e-3
+        # RMS, 1.3-1.6e-3 max-norm); the engine must match the model itself far more tightly.
+        with torch.no_grad():
+            model = no.result_from_output(no.forward(P, torch.tensor(x), preset, producer_round=no.round_tf32)).numpy()
+        report['locator_rel_vs_tf32_model'] = _relmax(res[..., 21:], model[..., 21:])
+        report['locator_rel_rms_vs_tf32_model'] = float(np.sqrt(((res[..., 21:] - model[..., 21:]) ** 2).mean() / (model[..., 21:] ** 2).mean()))
+        report['argmax_agree_vs_tf32_model'] = float((res[..., :21].argmax(-1) == model[..., :21].argmax(-1)).mean())
+        print('PARITY-MODEL', report['locator_rel_vs_tf32_model'], report['locator_rel_rms_vs_tf32_model'], report['argmax_agree_vs_tf32_model'])
+        assert report['locator_rel_vs_tf32_model'] < 3e-4
     assert _relmax(res[..., 21:], ref[..., 21:]) < tol
     # one training step
     V = {k: torch.zeros_like(v) for k, v in P.items()}
