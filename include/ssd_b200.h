@@ -39,9 +39,12 @@ extern "C" {
 #define SSDB_ENOTFOUND  -5   /* unknown preset / tensor name                   */
 
 /* conv implementation selector for the ssdb_op_conv* test hooks */
-#define SSDB_CONV_AUTO   0   /* what the engine would pick for the shape       */
+#define SSDB_CONV_AUTO   0   /* what the engine would pick for the shape (split tensor-core kernels where they apply) */
 #define SSDB_CONV_SIMT   1   /* CUDA-core implicit GEMM (odd shapes, tails)    */
-#define SSDB_CONV_TC     2   /* tcgen05 / TMEM / TMA implicit GEMM (tf32)      */
+#define SSDB_CONV_TC     2   /* tcgen05 / TMEM / TMA implicit GEMM, tf32 operands (comparison mode)   */
+#define SSDB_CONV_TC_SPLIT 3 /* tcgen05 / TMEM / TMA implicit GEMM, split bf16 operands: every fp32
+                                operand is a (hi, lo) bf16 pair and every product three kind::f16 MMAs
+                                (hi*hi + lo*hi + hi*lo) -- the engine's default: fp32-grade results      */
 
 typedef struct ssdb_net ssdb_net;
 
@@ -181,6 +184,10 @@ int ssdb_set_preprocess(ssdb_net* net, int swap_rb, const float mean[3]);
  *   result  [B, A, C+5] softmax scores | offsets (may be NULL: keep on device) */
 int ssdb_forward(ssdb_net* net, const float* images_dev, int B, float* result_dev, void* stream);
 int ssdb_forward_host(ssdb_net* net, const float* images_host, int B, float* result_host);
+
+/* sess.run(net.logits, ...) (ssdvgg.py:365-366): the raw head output of the LAST forward / train / eval call,
+ * [B, A, C+5] = C+1 class logits (pre-softmax) | 4 box offsets, copied to host memory. */
+int ssdb_read_output_host(ssdb_net* net, int B, float* output_host);
 
 /* sess.run([net.result, net.losses, net.optimizer], {image_input, labels})
  * (train.py:262-266): forward + multibox loss + backward + Momentum update

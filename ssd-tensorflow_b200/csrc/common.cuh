@@ -69,74 +69,153 @@ struct ConvEpilogue {
     int round_tf32 = 0;
 };
 
+// Storage format of activation / activation-gradient tensors (and of the packed filter copies the tensor-core kernels read).
+//   ACT_F32  plain float32 NHWC (SIMT mode; tf32 mode stores tf32-rounded float32 values in it)
+//   ACT_S32  "split": every aligned group of 32 consecutive elements (32 channels of one pixel: channel counts are
+//            multiples of 32) occupies the same 128 bytes as in ACT_F32, but holds 32 bf16 HIGH parts followed by 32
+//            bf16 LOW parts:  hi = bf16_rn(v), lo = bf16_rn(v - hi), value = hi + lo (16 significand bits, exact in
+//            float32).  A 128-byte row is then at once a K-major SWIZZLE_128B operand row of 64 bf16 (tcgen05
+//            kind::f16: the products hi*hi + lo*hi + hi*lo are three K = 16 MMAs per 16 channels that differ only in
+//            the 32-byte K offsets of their descriptors) and, seen through a TMA map with a 64-byte inner box, two
+//            MN-major SWIZZLE_64B blocks (wgrad).  Same HBM footprint and traffic as float32, ~2^-17 operand error
+//            instead of tf32's 2^-11.
+enum ActFmt { ACT_F32 = 0, ACT_S32 = 1 };
+
 #ifdef __CUDACC__
 __device__ __forceinline__ float tf32_rn(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+
+// two floats -> packed bf16x2 (round to nearest even); `a` lands in the low half
+__device__ __forceinline__ uint32_t bf16x2_rn(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ float bf16_lo_f(uint32_t packed) { return __uint_as_float(packed << 16); }
+__device__ __forceinline__ float bf16_hi_f(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
+
+// split two values into their (hi, lo) bf16 pairs
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = bf16x2_rn(a, b);
+    lo = bf16x2_rn(a - bf16_lo_f(hi), b - bf16_hi_f(hi));
+}
+
+// byte address of element `e` (flat element index; 32-element groups are aligned because channel counts are
+// multiples of 32) of an ACT_S32 tensor: the HIGH part; the LOW part is 64 bytes further
+__device__ __forceinline__ const unsigned char* s32_addr(const float* t, long long e) {
+    return reinterpret_cast<const unsigned char*>(t) + (e >> 5) * 128 + (e & 31) * 2;
+}
+__device__ __forceinline__ unsigned char* s32_addr(float* t, long long e) {
+    return reinterpret_cast<unsigned char*>(t) + (e >> 5) * 128 + (e & 31) * 2;
+}
+
+// four consecutive elements starting at flat element index e (e % 4 == 0)
+template <int FMT>
+__device__ __forceinline__ float4 act_ld4(const float* t, long long e) {
+    if (FMT == ACT_F32) return *reinterpret_cast<const float4*>(t + e);
+    const unsigned char* p = s32_addr(t, e);
+    const uint2 h = *reinterpret_cast<const uint2*>(p);
+    const uint2 l = *reinterpret_cast<const uint2*>(p + 64);
+    return make_float4(bf16_lo_f(h.x) + bf16_lo_f(l.x), bf16_hi_f(h.x) + bf16_hi_f(l.x),
+                       bf16_lo_f(h.y) + bf16_lo_f(l.y), bf16_hi_f(h.y) + bf16_hi_f(l.y));
+}
+// only the sign / zero test of four elements (ReLU mask): the HIGH parts decide (hi == 0 <=> value == 0)
+template <int FMT>
+__device__ __forceinline__ float4 act_ld4_sign(const float* t, long long e) {
+    if (FMT == ACT_F32) return *reinterpret_cast<const float4*>(t + e);
+    const uint2 h = *reinterpret_cast<const uint2*>(s32_addr(t, e));
+    return make_float4(bf16_lo_f(h.x), bf16_hi_f(h.x), bf16_lo_f(h.y), bf16_hi_f(h.y));
+}
+template <int FMT>
+__device__ __forceinline__ void act_st4(float* t, long long e, float4 v) {
+    if (FMT == ACT_F32) { *reinterpret_cast<float4*>(t + e) = v; return; }
+    uint2 h, l;
+    split2(v.x, v.y, h.x, l.x);
+    split2(v.z, v.w, h.y, l.y);
+    unsigned char* p = s32_addr(t, e);
+    *reinterpret_cast<uint2*>(p) = h;
+    *reinterpret_cast<uint2*>(p + 64) = l;
+}
+template <int FMT>
+__device__ __forceinline__ float act_ld1(const float* t, long long e) {
+    if (FMT == ACT_F32) return t[e];
+    const unsigned char* p = s32_addr(t, e);
+    const uint32_t h = *reinterpret_cast<const unsigned short*>(p), l = *reinterpret_cast<const unsigned short*>(p + 64);
+    return __uint_as_float(h << 16) + __uint_as_float(l << 16);
+}
 #endif
 
 // ---- SIMT (CUDA-core) implicit GEMM: every shape, used for tails / stride 2 / Cin=3 ----
-int conv_simt_fprop(const ConvGeom& g, const float* x, const float* w, const ConvEpilogue& ep,
+// `fmt` (ActFmt) is the storage format of the activation-like tensors (x, y, dz, dx, mask); filters, biases, the head
+// output (scatter) and the raw image (Cin = 3) are always plain float32.
+int conv_simt_fprop(const ConvGeom& g, const float* x, const float* w, int fmt, const ConvEpilogue& ep,
                     float* y, cudaStream_t st);
-int conv_simt_dgrad(const ConvGeom& g, const float* dz, const float* w, const float* mask_x,
+int conv_simt_dgrad(const ConvGeom& g, const float* dz, const float* w, int fmt, const float* mask_x,
                     int beta, int round_out, float* dx, cudaStream_t st);
 // partial: workspace of at least conv_simt_wgrad_ws(g) floats
 size_t conv_simt_wgrad_ws(const ConvGeom& g);
-int conv_simt_wgrad(const ConvGeom& g, const float* x, const float* dz, const ConvEpilogue& ep,
+int conv_simt_wgrad(const ConvGeom& g, const float* x, const float* dz, int fmt, const ConvEpilogue& ep,
                     float* dw, float* partial, cudaStream_t st);
 // db[n] = sum over pixels of dz[p][n]  (deterministic two-stage), partial >= 1184*Cout floats
-int bias_grad(const float* dz, long long pixels, int Cout, float* db, float* partial, cudaStream_t st);
+int bias_grad(const float* dz, int fmt, long long pixels, int Cout, float* db, float* partial, cudaStream_t st);
 
-// ---- tcgen05 / TMEM / TMA implicit GEMM (tf32 operands, fp32 accumulate) ----
+// ---- tcgen05 / TMEM / TMA implicit GEMM ----
+// fmt = ACT_F32: tf32 operands (activations stored tf32-rounded), ACT_S32: split bf16 operands (3 MMAs per product);
+// fp32 accumulation in tensor memory either way
 bool conv_tc_supported_fprop(const ConvGeom& g);
 bool conv_tc_supported_dgrad(const ConvGeom& g);
-bool conv_tc_supported_wgrad(const ConvGeom& g);
-// w_t: per-tap transposed filter [k*k][CoutPad][Cin] (K-major B operand), see pack_filter_t
-int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_pad,
+bool conv_tc_supported_wgrad(const ConvGeom& g, int fmt);
+// w_t: per-tap transposed filter [k*k][CoutPad][Cin] (K-major B operand) in format fmt, see pack_filter_t
+int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_pad, int fmt,
                   const ConvEpilogue& ep, float* y, cudaStream_t st);
-int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, const float* mask_x,
+// w_hwio: the HWIO filter in format fmt (tf32-rounded floats, or split along Cout)
+int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, int fmt, const float* mask_x,
                   int beta, int round_out, float* dx, cudaStream_t st);
-size_t conv_tc_wgrad_ws(const ConvGeom& g);
-// db != null: the bias gradient is produced by the same kernel (all-ones slot)
-int conv_tc_wgrad(const ConvGeom& g, const float* x, const float* dz, float* dw, float* db, float* partial,
+size_t conv_tc_wgrad_ws(const ConvGeom& g, int fmt);
+// db != null: the bias gradient is produced by the same kernel (all-ones slot); dw / db are plain float32
+int conv_tc_wgrad(const ConvGeom& g, const float* x, const float* dz, int fmt, float* dw, float* db, float* partial,
                   cudaStream_t st);
-int pack_filter_t(const float* w_hwio, int taps, int Cin, int Cout, int cout_pad, float* w_t,
+int pack_filter_t(const float* w_hwio, int taps, int Cin, int Cout, int cout_pad, int fmt, float* w_t,
                   cudaStream_t st);
 
-// ---- pools, L2 norm ----
-int maxpool_fwd(const float* x, int B, int H, int W, int C, int k, int stride, int pad_t, int pad_l,
+// ---- pools, L2 norm (activation tensors in format fmt) ----
+int maxpool_fwd(const float* x, int fmt, int B, int H, int W, int C, int k, int stride, int pad_t, int pad_l,
                 int Ho, int Wo, float* y, cudaStream_t st);
 // dx = (beta*dx + routed dy) * (x > 0)
-int maxpool_bwd(const float* x, const float* dy, int B, int H, int W, int C, int k, int stride,
+int maxpool_bwd(const float* x, const float* dy, int fmt, int B, int H, int W, int C, int k, int stride,
                 int pad_t, int pad_l, int Ho, int Wo, int beta, int relu_mask, int round_out, float* dx, cudaStream_t st);
 // overlapping pools (3x3 stride 1): forward records the winning window cell (1 byte per element), backward routes by it
-int maxpool_fwd_arg(const float* x, int B, int H, int W, int C, int k, int stride, int pad_t, int pad_l, int Ho, int Wo,
+int maxpool_fwd_arg(const float* x, int fmt, int B, int H, int W, int C, int k, int stride, int pad_t, int pad_l, int Ho, int Wo,
                     float* y, unsigned char* arg, cudaStream_t st);
-int maxpool_bwd_arg(const float* x, const float* dy, const unsigned char* arg, int B, int H, int W, int C, int k, int stride, int pad_t,
+int maxpool_bwd_arg(const float* x, const float* dy, const unsigned char* arg, int fmt, int B, int H, int W, int C, int k, int stride, int pad_t,
                     int pad_l, int Ho, int Wo, int beta, int relu_mask, int round_out, float* dx, cudaStream_t st);
 // non-overlapping 2x2/s2 pools: one code byte per output element (winning cell + "winner > 0"), so the backward reads no activations
-int maxpool2x2_fwd_code(const float* x, int B, int H, int W, int C, int Ho, int Wo, float* y, unsigned char* code, cudaStream_t st);
-int maxpool2x2_bwd_code(const float* dy, const unsigned char* code, int B, int H, int W, int C, int Ho, int Wo, int relu_mask,
+int maxpool2x2_fwd_code(const float* x, int fmt, int B, int H, int W, int C, int Ho, int Wo, float* y, unsigned char* code, cudaStream_t st);
+int maxpool2x2_bwd_code(const float* dy, const unsigned char* code, int fmt, int B, int H, int W, int C, int Ho, int Wo, int relu_mask,
                         int round_out, float* dx, cudaStream_t st);
-int l2norm_fwd(const float* x, const float* scale, long long pixels, int C, int round_out, float* y, cudaStream_t st);
-int l2norm_bwd(const float* x, const float* scale, const float* dy, long long pixels, int C, int beta,
+int l2norm_fwd(const float* x, const float* scale, int fmt, long long pixels, int C, int round_out, float* y, cudaStream_t st);
+int l2norm_bwd(const float* x, const float* scale, const float* dy, int fmt, long long pixels, int C, int beta,
                int round_out, float* dx, float* dscale, float* partial, cudaStream_t st);
 
 // ---- conv1_1 (Cin = 3): explicit 3x3 patch matrix so that the layer runs as a 1x1 tensor-core conv ----
 // patches[B*S*S][32]: 27 pre-processed (mean-subtracted, optionally R/B-swapped) taps in (kh, kw, c) order + 5 zeros,
-// tf32-rounded; SAME padding (zeros outside the image, after pre-processing, as in the graph)
-int conv1_im2col(const float* images, int B, int S, int swap_rb, const float mean[3], float* patches, cudaStream_t st);
+// in format fmt (tf32-rounded floats / split); SAME padding (zeros outside the image, after pre-processing, as in the graph)
+int conv1_im2col(const float* images, int B, int S, int swap_rb, const float mean[3], int fmt, float* patches, cudaStream_t st);
 // w32[32][Cout] <- w[27][Cout] (rows 27..31 zero)
 int conv1_pad_filter(const float* w27, int Cout, float* w32, cudaStream_t st);
 
 // ---- head layout helpers ----
-// dz[B,H,W,Npad] (NHWC, zero padded channels) <- grad[B,A,V]
+// dz[B,H,W,Npad] (NHWC, zero padded channels, format fmt) <- grad[B,A,V]
 int head_grad_gather(const float* grad, int B, int A, int V, int anchor_base, int HW, int nbox,
-                     int Npad, int round_out, float* dz, cudaStream_t st);
+                     int Npad, int fmt, int round_out, float* dz, cudaStream_t st);
 // dst[i] = tf32_rn(src[i])
 int round_tf32_copy(const float* src, float* dst, long long n, cudaStream_t st);
+// plain float32 <-> ACT_S32 (n % 32 == 0)
+int split_copy(const float* src, float* dst_s32, long long n, cudaStream_t st);
+int unsplit_copy(const float* src_s32, float* dst, long long n, cudaStream_t st);
 int softmax_result(const float* output, long long rows, int C, float* result, cudaStream_t st);
 
 // ---- optimizer ----

@@ -37,7 +37,7 @@ __device__ __forceinline__ float prep(const SimtArgs& p, const float* px, int c)
 }
 
 // value(s) of the im2col matrix: input pixel for output position (b,oy,ox), tap, channel c..c+VEC-1
-template <int VEC>
+template <int VEC, int FMT>
 __device__ __forceinline__ void gather_x(const SimtArgs& p, int b, int oy, int ox, int tap, int c, float* v) {
     const ConvGeom& g = p.g;
     int kh = tap / g.k, kw = tap - kh * g.k;
@@ -46,16 +46,16 @@ __device__ __forceinline__ void gather_x(const SimtArgs& p, int b, int oy, int o
 #pragma unroll
     for (int i = 0; i < VEC; ++i) v[i] = 0.f;
     if (iy < 0 || iy >= g.H || ix < 0 || ix >= g.W) return;
-    const float* px = p.a + (((long long)b * g.H + iy) * g.W + ix) * g.Cin;
+    const long long e = (((long long)b * g.H + iy) * g.W + ix) * g.Cin;
     if (VEC == 4) {
-        float4 t = *reinterpret_cast<const float4*>(px + c);
+        float4 t = act_ld4<FMT>(p.a, e + c);
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     } else {
-        v[0] = p.preprocess ? prep(p, px, c) : px[c];
+        v[0] = p.preprocess ? prep(p, p.a + e, c) : act_ld1<FMT>(p.a, e + c);    // the raw image (preprocess) is plain float32
     }
 }
 
-template <int MODE, int VEC>
+template <int MODE, int VEC, int FMT>
 __global__ void __launch_bounds__(NT) conv_simt_kernel(SimtArgs p) {
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN + 4];
@@ -99,10 +99,10 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(SimtArgs p) {
             long long kk = k0 + a_k;
             if (a_row_ok) {
                 if (VEC == 4) {
-                    if (kk < p.K) { int tap = (int)(kk / g.Cin); int c = (int)(kk - (long long)tap * g.Cin); gather_x<4>(p, a_b, a_y, a_x, tap, c, v); }
+                    if (kk < p.K) { int tap = (int)(kk / g.Cin); int c = (int)(kk - (long long)tap * g.Cin); gather_x<4, FMT>(p, a_b, a_y, a_x, tap, c, v); }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) if (kk + i < p.K) { int tap = (int)((kk + i) / g.Cin); int c = (int)(kk + i - (long long)tap * g.Cin); gather_x<1>(p, a_b, a_y, a_x, tap, c, &v[i]); }
+                    for (int i = 0; i < 4; ++i) if (kk + i < p.K) { int tap = (int)((kk + i) / g.Cin); int c = (int)(kk + i - (long long)tap * g.Cin); gather_x<1, FMT>(p, a_b, a_y, a_x, tap, c, &v[i]); }
                 }
             }
 #pragma unroll
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(SimtArgs p) {
                 if (ny >= 0 && nx >= 0 && (ny % g.stride) == 0 && (nx % g.stride) == 0) {
                     int oy = ny / g.stride, ox = nx / g.stride;
                     if (oy < g.Ho && ox < g.Wo) {
-                        float4 tv = *reinterpret_cast<const float4*>(p.a + (((long long)a_b * g.Ho + oy) * g.Wo + ox) * g.Cout + n);
+                        float4 tv = act_ld4<FMT>(p.a, (((long long)a_b * g.Ho + oy) * g.Wo + ox) * g.Cout + n);
                         v[0] = tv.x; v[1] = tv.y; v[2] = tv.z; v[3] = tv.w;
                     }
                 }
@@ -135,10 +135,10 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(SimtArgs p) {
                 int oy = r / g.Wo, ox = r - oy * g.Wo;
                 long long mm = m0 + a_m;
                 if (VEC == 4) {
-                    if (mm < p.M) { int tap = (int)(mm / g.Cin); int c = (int)(mm - (long long)tap * g.Cin); gather_x<4>(p, b, oy, ox, tap, c, v); }
+                    if (mm < p.M) { int tap = (int)(mm / g.Cin); int c = (int)(mm - (long long)tap * g.Cin); gather_x<4, FMT>(p, b, oy, ox, tap, c, v); }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) if (mm + i < p.M) { int tap = (int)((mm + i) / g.Cin); int c = (int)(mm + i - (long long)tap * g.Cin); gather_x<1>(p, b, oy, ox, tap, c, &v[i]); }
+                    for (int i = 0; i < 4; ++i) if (mm + i < p.M) { int tap = (int)((mm + i) / g.Cin); int c = (int)(mm + i - (long long)tap * g.Cin); gather_x<1, FMT>(p, b, oy, ox, tap, c, &v[i]); }
                 }
             }
             *reinterpret_cast<float4*>(&As[a_p][a_m]) = make_float4(v[0], v[1], v[2], v[3]);
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(SimtArgs p) {
             int b_p = t >> 4, b_n = (t & 15) * 4;
             long long pix = k0 + b_p;
             float4 tv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (pix < red_end && n0 + b_n < p.N) tv = *reinterpret_cast<const float4*>(p.b + pix * g.Cout + n0 + b_n);
+            if (pix < red_end && n0 + b_n < p.N) tv = act_ld4<FMT>(p.b, pix * g.Cout + n0 + b_n);
             *reinterpret_cast<float4*>(&Bs[b_p][b_n]) = tv;
         }
         __syncthreads();
@@ -206,24 +206,24 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(SimtArgs p) {
                     for (int j = 0; j < 4; ++j) {
                         r[j] = acc[i][j] + (p.aux ? p.aux[n + j] : 0.f);
                         if (p.relu) r[j] = fmaxf(r[j], 0.f);
-                        if (p.round_out) r[j] = tf32_rn(r[j]);
+                        if (FMT == ACT_F32 && p.round_out) r[j] = tf32_rn(r[j]);
                     }
-                    *reinterpret_cast<float4*>(p.out + m * g.Cout + n) = make_float4(r[0], r[1], r[2], r[3]);
+                    act_st4<FMT>(p.out, m * g.Cout + n, make_float4(r[0], r[1], r[2], r[3]));
                 }
             }
         } else if (MODE == DGRAD) {
             int n = n0 + tx * 4;
             if (n < p.N) {
-                float* dst = p.out + m * g.Cin + n;
+                const long long e = m * g.Cin + n;
                 float r[4] = {acc[i][0], acc[i][1], acc[i][2], acc[i][3]};
-                if (p.beta) { float4 o = *reinterpret_cast<const float4*>(dst); r[0] += o.x; r[1] += o.y; r[2] += o.z; r[3] += o.w; }
+                if (p.beta) { float4 o = act_ld4<FMT>(p.out, e); r[0] += o.x; r[1] += o.y; r[2] += o.z; r[3] += o.w; }
                 if (p.aux) {
-                    float4 mk = *reinterpret_cast<const float4*>(p.aux + m * g.Cin + n);
+                    float4 mk = act_ld4_sign<FMT>(p.aux, e);
                     r[0] = mk.x > 0.f ? r[0] : 0.f; r[1] = mk.y > 0.f ? r[1] : 0.f;
                     r[2] = mk.z > 0.f ? r[2] : 0.f; r[3] = mk.w > 0.f ? r[3] : 0.f;
                 }
-                if (p.round_out) { r[0] = tf32_rn(r[0]); r[1] = tf32_rn(r[1]); r[2] = tf32_rn(r[2]); r[3] = tf32_rn(r[3]); }
-                *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
+                if (FMT == ACT_F32 && p.round_out) { r[0] = tf32_rn(r[0]); r[1] = tf32_rn(r[1]); r[2] = tf32_rn(r[2]); r[3] = tf32_rn(r[3]); }
+                act_st4<FMT>(p.out, e, make_float4(r[0], r[1], r[2], r[3]));
             }
         } else {
             int n = n0 + tx * 4;
@@ -247,6 +247,7 @@ __global__ void reduce_splits_kernel(const float* __restrict__ partial, long lon
 // stage 1 of the bias gradient (column sums of dz[pixels][C]): a block owns a contiguous slab of
 // pixel rows; threads are (C/4 float4 columns) x (256/(C/4) row lanes), 4 independent 16-byte loads
 // in flight per thread, shared-memory reduction over the row lanes, one partial row per block.
+template <int FMT>
 __global__ void __launch_bounds__(256) bias_grad_stage1(const float* __restrict__ dz, long long pixels, int C,
                                                          long long rows_per_block, float* __restrict__ partial) {
     __shared__ float4 red[256];
@@ -259,17 +260,16 @@ __global__ void __launch_bounds__(256) bias_grad_stage1(const float* __restrict_
     if (lane < lanes) {
         const long long r0 = (long long)blockIdx.x * rows_per_block;
         const long long r1 = min(pixels, r0 + rows_per_block);
-        const float4* base = reinterpret_cast<const float4*>(dz);
         long long r = r0 + lane;
         for (; r + 3LL * lanes < r1; r += 4LL * lanes) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                float4 v = __ldg(base + (r + (long long)u * lanes) * c4n + col);
+                float4 v = act_ld4<FMT>(dz, ((r + (long long)u * lanes) * c4n + col) * 4);
                 acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
             }
         }
         for (; r < r1; r += lanes) {
-            float4 v = __ldg(base + r * c4n + col);
+            float4 v = act_ld4<FMT>(dz, (r * c4n + col) * 4);
             acc[0].x += v.x; acc[0].y += v.y; acc[0].z += v.z; acc[0].w += v.w;
         }
     }
@@ -302,27 +302,34 @@ void fill_common(SimtArgs& p, const ConvGeom& g) {
 
 }  // namespace
 
-int conv_simt_fprop(const ConvGeom& g, const float* x, const float* w, const ConvEpilogue& ep, float* y, cudaStream_t st) {
+int conv_simt_fprop(const ConvGeom& g, const float* x, const float* w, int fmt, const ConvEpilogue& ep, float* y, cudaStream_t st) {
     SSDB_REQUIRE(g.Cout % 4 == 0, "Cout must be a multiple of 4");
+    SSDB_REQUIRE(fmt == ACT_F32 || ep.scatter || g.Cout % 32 == 0, "split activations need channel counts that are multiples of 32");
     SimtArgs p; fill_common(p, g);
     p.a = x; p.b = w; p.out = y; p.aux = ep.bias; p.relu = ep.relu; p.round_out = ep.round_tf32;
     p.scatter = ep.scatter; p.V = ep.V; p.n_valid = ep.n_valid; p.anchor_base = ep.anchor_base; p.A = ep.A;
     p.preprocess = ep.preprocess; p.swap_rb = ep.swap_rb; p.mean0 = ep.mean[0]; p.mean1 = ep.mean[1]; p.mean2 = ep.mean[2];
     p.M = (long long)g.B * g.Ho * g.Wo; p.K = (long long)g.k * g.k * g.Cin; p.N = g.Cout;
     dim3 grid((unsigned)((p.M + BM - 1) / BM), (unsigned)((p.N + BN - 1) / BN));
-    if (g.Cin % 4 == 0 && !ep.preprocess) conv_simt_kernel<FPROP, 4><<<grid, NT, 0, st>>>(p);
-    else conv_simt_kernel<FPROP, 1><<<grid, NT, 0, st>>>(p);
+    if (g.Cin % 4 == 0 && !ep.preprocess) {
+        if (fmt == ACT_S32) conv_simt_kernel<FPROP, 4, ACT_S32><<<grid, NT, 0, st>>>(p);
+        else conv_simt_kernel<FPROP, 4, ACT_F32><<<grid, NT, 0, st>>>(p);
+    } else {
+        if (fmt == ACT_S32) conv_simt_kernel<FPROP, 1, ACT_S32><<<grid, NT, 0, st>>>(p);
+        else conv_simt_kernel<FPROP, 1, ACT_F32><<<grid, NT, 0, st>>>(p);
+    }
     SSDB_LAUNCH_CHECK();
     return SSDB_OK;
 }
 
-int conv_simt_dgrad(const ConvGeom& g, const float* dz, const float* w, const float* mask_x, int beta, int round_out, float* dx, cudaStream_t st) {
+int conv_simt_dgrad(const ConvGeom& g, const float* dz, const float* w, int fmt, const float* mask_x, int beta, int round_out, float* dx, cudaStream_t st) {
     SSDB_REQUIRE(g.Cout % 4 == 0 && g.Cin % 4 == 0, "channels must be multiples of 4");
     SimtArgs p; fill_common(p, g);
     p.a = dz; p.b = w; p.out = dx; p.aux = mask_x; p.beta = beta; p.round_out = round_out;
     p.M = (long long)g.B * g.H * g.W; p.K = (long long)g.k * g.k * g.Cout; p.N = g.Cin;
     dim3 grid((unsigned)((p.M + BM - 1) / BM), (unsigned)((p.N + BN - 1) / BN));
-    conv_simt_kernel<DGRAD, 4><<<grid, NT, 0, st>>>(p);
+    if (fmt == ACT_S32) conv_simt_kernel<DGRAD, 4, ACT_S32><<<grid, NT, 0, st>>>(p);
+    else conv_simt_kernel<DGRAD, 4, ACT_F32><<<grid, NT, 0, st>>>(p);
     SSDB_LAUNCH_CHECK();
     return SSDB_OK;
 }
@@ -331,7 +338,7 @@ size_t conv_simt_wgrad_ws(const ConvGeom& g) {
     return (size_t)wgrad_splits(g) * g.k * g.k * g.Cin * g.Cout;
 }
 
-int conv_simt_wgrad(const ConvGeom& g, const float* x, const float* dz, const ConvEpilogue& ep, float* dw, float* partial, cudaStream_t st) {
+int conv_simt_wgrad(const ConvGeom& g, const float* x, const float* dz, int fmt, const ConvEpilogue& ep, float* dw, float* partial, cudaStream_t st) {
     SSDB_REQUIRE(g.Cout % 4 == 0, "Cout must be a multiple of 4");
     SimtArgs p; fill_common(p, g);
     p.a = x; p.b = dz; p.out = partial;
@@ -343,8 +350,13 @@ int conv_simt_wgrad(const ConvGeom& g, const float* x, const float* dz, const Co
     splits = (int)((p.K + per - 1) / per);
     p.red_per_split = per;
     dim3 grid((unsigned)((p.M + BM - 1) / BM), (unsigned)((p.N + BN - 1) / BN), (unsigned)splits);
-    if (g.Cin % 4 == 0 && !ep.preprocess) conv_simt_kernel<WGRAD, 4><<<grid, NT, 0, st>>>(p);
-    else conv_simt_kernel<WGRAD, 1><<<grid, NT, 0, st>>>(p);
+    if (g.Cin % 4 == 0 && !ep.preprocess) {
+        if (fmt == ACT_S32) conv_simt_kernel<WGRAD, 4, ACT_S32><<<grid, NT, 0, st>>>(p);
+        else conv_simt_kernel<WGRAD, 4, ACT_F32><<<grid, NT, 0, st>>>(p);
+    } else {
+        if (fmt == ACT_S32) conv_simt_kernel<WGRAD, 1, ACT_S32><<<grid, NT, 0, st>>>(p);
+        else conv_simt_kernel<WGRAD, 1, ACT_F32><<<grid, NT, 0, st>>>(p);
+    }
     SSDB_LAUNCH_CHECK();
     long long n = p.M * g.Cout;
     reduce_splits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, n, splits, dw);
@@ -352,14 +364,15 @@ int conv_simt_wgrad(const ConvGeom& g, const float* x, const float* dz, const Co
     return SSDB_OK;
 }
 
-int bias_grad(const float* dz, long long pixels, int Cout, float* db, float* partial, cudaStream_t st) {
+int bias_grad(const float* dz, int fmt, long long pixels, int Cout, float* db, float* partial, cudaStream_t st) {
     SSDB_REQUIRE(Cout % 4 == 0 && Cout <= 1024, "bias gradient needs Cout % 4 == 0 and Cout <= 1024");
     long long want = 148 * 8;
     long long rows_per_block = (pixels + want - 1) / want;
     if (rows_per_block < 32) rows_per_block = 32;
     int nb = (int)((pixels + rows_per_block - 1) / rows_per_block);
     if (nb < 1) nb = 1;
-    bias_grad_stage1<<<nb, 256, 0, st>>>(dz, pixels, Cout, rows_per_block, partial);
+    if (fmt == ACT_S32) bias_grad_stage1<ACT_S32><<<nb, 256, 0, st>>>(dz, pixels, Cout, rows_per_block, partial);
+    else bias_grad_stage1<ACT_F32><<<nb, 256, 0, st>>>(dz, pixels, Cout, rows_per_block, partial);
     SSDB_LAUNCH_CHECK();
     reduce_splits_kernel<<<(Cout + 255) / 256, 256, 0, st>>>(partial, Cout, nb, db);
     SSDB_LAUNCH_CHECK();

@@ -111,6 +111,14 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// kind::f16 with bf16 operands (K = 16 per instruction): the split-operand mode
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -175,6 +183,10 @@ struct TcArgs {
     const float* mask;              // dgrad: ReLU mask source (same shape as dst) or null
     int relu, beta, round_out;
     int scatter, V, n_valid, anchor_base, A;
+    // split-operand mode (ACT_S32 storage, common.cuh): source, filter, mask and destination hold bf16 (hi | lo) pairs per
+    // 32-channel group; every 32-channel slab is contracted by six kind::f16 MMAs (hi*hi, lo*hi, hi*lo; K = 16 each)
+    // instead of four kind::tf32 ones.  split_terms (bring-up): 1 = hi*hi only, 2 = + lo*hi, 3 = all.
+    int split, split_terms;
 };
 
 // epilogue of one 128-row tile: TMEM -> registers -> (per-warp shared-memory transpose) -> global.
@@ -183,6 +195,7 @@ struct TcArgs {
 // the bottleneck of the short-K layers).  Each warp therefore stages its 32 pixel x 32 channel chunk in 4 KB of shared
 // memory (16-byte slots XOR-swizzled by row) and writes it back with 8 lanes per pixel: every instruction moves four
 // complete 128-byte rows, and the bias / ReLU / tf32 rounding (fprop) or beta / ReLU-mask (dgrad) reads are coalesced too.
+template <int FMT>
 __device__ __forceinline__ void epilogue_tile(const TcArgs& p, int mt, int nt, uint32_t t_row, int row, int lane, float4* stage) {
     const int rows_valid = p.TW * p.TH * p.TN;
     const int tx = mt % p.tiles_x; const int r1 = mt / p.tiles_x;
@@ -237,8 +250,8 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& p, int mt, int nt, u
                 if (prs[it] < 0 || !chok) continue;
                 v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
                 if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                if (p.round_out) { v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w); }
-                *reinterpret_cast<float4*>(p.dst + prs[it] * p.Cd + ch) = v;
+                if (FMT == ACT_F32 && p.round_out) { v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w); }
+                act_st4<FMT>(p.dst, prs[it] * p.Cd + ch, v);
             }
         } else {
             // dgrad: issue every mask / old-value load of the chunk first (8 independent cache lines per lane in flight),
@@ -247,8 +260,8 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& p, int mt, int nt, u
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
                 const bool okr = prs[it] >= 0 && chok;
-                m4[it] = (p.mask && okr) ? __ldg(reinterpret_cast<const float4*>(p.mask + prs[it] * p.Cd + ch)) : make_float4(1.f, 1.f, 1.f, 1.f);
-                o4[it] = (p.beta && okr) ? *reinterpret_cast<const float4*>(p.dst + prs[it] * p.Cd + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+                m4[it] = (p.mask && okr) ? act_ld4_sign<FMT>(p.mask, prs[it] * p.Cd + ch) : make_float4(1.f, 1.f, 1.f, 1.f);
+                o4[it] = (p.beta && okr) ? act_ld4<FMT>(p.dst, prs[it] * p.Cd + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
@@ -257,8 +270,8 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& p, int mt, int nt, u
                 if (prs[it] < 0 || !chok) continue;
                 v.x += o4[it].x; v.y += o4[it].y; v.z += o4[it].z; v.w += o4[it].w;
                 v.x = m4[it].x > 0.f ? v.x : 0.f; v.y = m4[it].y > 0.f ? v.y : 0.f; v.z = m4[it].z > 0.f ? v.z : 0.f; v.w = m4[it].w > 0.f ? v.w : 0.f;
-                if (p.round_out) { v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w); }
-                *reinterpret_cast<float4*>(p.dst + prs[it] * p.Cd + ch) = v;
+                if (FMT == ACT_F32 && p.round_out) { v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w); }
+                act_st4<FMT>(p.dst, prs[it] * p.Cd + ch, v);
             }
         }
     }
@@ -338,7 +351,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (elect_one_sync()) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+            // instruction descriptor: fp32 accumulate, A / B format tf32 (2) or bf16 (1), both K-major, N, M
+            const uint32_t fmt = p.split ? 1u : 2u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
@@ -360,12 +375,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
                             const uint64_t a0 = make_kmajor_desc(sa + woff, (uint32_t)p.a_sbo, p.use_bo);
                             const uint64_t a1 = make_kmajor_desc(sa + (uint32_t)p.a_slot + woff, (uint32_t)p.a_sbo, p.use_bo);
                             const uint64_t bd = make_kmajor_desc(sa + b_off + (uint32_t)t * b_bytes);
+                            if (p.split) {
+                                // a 128-byte row = 16 hi | 16 hi | 16 lo | 16 lo (bf16) of 32 channels: K offsets 0, 1 = high parts,
+                                // 2, 3 = low parts (32 bytes = +2 in 16-byte units each).  x*w ~ xh*wh + xl*wh + xh*wl.
 #pragma unroll
-                            for (int k = 0; k < BLOCK_K / 8; ++k) {
-                                // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
-                                tc_mma_tf32(d0, a0 + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, started);
-                                if (two) tc_mma_tf32(d1, a1 + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, started);
-                                started = 1;
+                                for (int c = 0; c < 6; ++c) {
+                                    if (c >= 2 * p.split_terms) break;
+                                    const int ka = (c < 2) ? c : (c < 4 ? c : c - 4);       // 0 1 | 2 3 | 0 1
+                                    const int kb = (c < 2) ? c : (c < 4 ? c - 2 : c - 2);   // 0 1 | 0 1 | 2 3
+                                    tc_mma_bf16(d0, a0 + (uint64_t)(ka * 2), bd + (uint64_t)(kb * 2), idesc, started);
+                                    if (two) tc_mma_bf16(d1, a1 + (uint64_t)(ka * 2), bd + (uint64_t)(kb * 2), idesc, started);
+                                    started = 1;
+                                }
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < BLOCK_K / 8; ++k) {
+                                    // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
+                                    tc_mma_tf32(d0, a0 + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, started);
+                                    if (two) tc_mma_tf32(d1, a1 + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, started);
+                                    started = 1;
+                                }
                             }
                         }
                         tc_commit(empty0 + 8 * stage);              // frees the smem slot when these MMAs retire
@@ -388,8 +417,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
-            epilogue_tile(p, p.mtu * mp, nt, t_row, row, lane, stage);
-            if (two) epilogue_tile(p, 2 * mp + 1, nt, t_row + (uint32_t)noff, row, lane, stage);
+            if (p.split) {
+                epilogue_tile<ACT_S32>(p, p.mtu * mp, nt, t_row, row, lane, stage);
+                if (two) epilogue_tile<ACT_S32>(p, 2 * mp + 1, nt, t_row + (uint32_t)noff, row, lane, stage);
+            } else {
+                epilogue_tile<ACT_F32>(p, p.mtu * mp, nt, t_row, row, lane, stage);
+                if (two) epilogue_tile<ACT_F32>(p, 2 * mp + 1, nt, t_row + (uint32_t)noff, row, lane, stage);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
@@ -629,6 +663,7 @@ struct WgRwArgs {
     int splits, tiles_per_split;
     int want_bias;
     int stage_bytes, stages;
+    int terms;                      // split kernel bring-up: 1 = hi*hi only, 2 = + lo*hi, 3 = all products
     long long psize;
     float* partial;
 };
@@ -787,6 +822,360 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     }
 }
 
+// ------------------------------------------------------------------ split-operand (ACT_S32) wgrad kernels
+// Same decomposition as the two kernels above, but x and dz are ACT_S32 tensors (bf16 hi | lo pairs per 32-channel group)
+// and the MMAs are kind::f16.  A TMA map with a 64-byte inner box (32 bf16) and a 64-byte-strided outer dimension
+// q = 2 * channel block + part brings every 32-channel block as TWO [pixels][64 B] sub-blocks (high parts, then low
+// parts) in the SWIZZLE_64B layout -- the MN-major canonical layout for 16-bit operands: 32 channels contiguous, pixel rows
+// 64 bytes apart, groups of 8 pixel rows SBO apart, 32-channel blocks LBO apart.  The high (or low) parts of consecutive
+// channel blocks are every second sub-block, so "4 slots x 32 channels" is one descriptor with LBO = 2 sub-blocks, started
+// at the first high or the first low sub-block.  dW ~ xh'zh + xl'zh + xh'zl: three K = 16 (pixel) MMAs into the SAME
+// accumulator, which therefore has the layout of the tf32 kernels and the same epilogue.  16-bit MN-major operands run at
+// the full MMA rate (the 32-bit ones above at half), so three bf16 MMAs per 16 pixels replace two half-rate tf32 ones.
+__device__ __forceinline__ uint64_t make_mn64_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                      // SWIZZLE_64B
+    return d;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_wgrad_s_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz, const WgArgs p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t bars = base + RING_BYTES;
+    const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
+    const uint32_t tmem_slot = tempty0 + 16;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int STAGES = stages_for(p.mtu);
+    const int STAGE_BYTES = stage_bytes_for(p.mtu);
+    const int spu = 4 * p.mtu;                                  // slots per unit
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dz) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int units = p.m_tiles * p.n_tiles * p.splits;
+    const int pix_tiles = p.ptx * p.pty * p.ptn;
+    const uint32_t sub_bytes = (uint32_t)p.P * 64u;           // one part (hi or lo) of a 32-channel block
+    const uint32_t blk_bytes = 2u * sub_bytes;                // one 32-channel block: hi sub-block, lo sub-block
+    const int nblk_b = p.block_n / 32;
+    const uint32_t b_off = (uint32_t)spu * blk_bytes;          // B blocks follow the mtu x 4 A blocks
+
+    if (warp == 0) {
+        if (elect_one_sync()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int mt = u % p.m_tiles; const int r1 = u / p.m_tiles;
+                const int nt = r1 % p.n_tiles; const int sp = r1 / p.n_tiles;
+                const int q0 = sp * p.tiles_per_split;
+                const int q1 = min(pix_tiles, q0 + p.tiles_per_split);
+                int na = p.slots - mt * spu; na = na > spu ? spu : na;      // valid A blocks of this unit
+                for (int q = q0; q < q1; ++q) {
+                    const int qx = q % p.ptx; const int r2 = q / p.ptx;
+                    const int qy = r2 % p.pty; const int qn = r2 / p.pty;
+                    const int x0 = qx * p.PW, y0 = qy * p.PH, n0 = qn * p.PN;
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t fb = full0 + 8 * stage;
+                    mbar_expect_tx(fb, (uint32_t)(na + nblk_b) * blk_bytes);
+                    const uint32_t sa = base + stage * STAGE_BYTES;
+                    for (int j = 0; j < na; j += p.load_blocks) {
+                        const int slot = mt * spu + j;
+                        if (slot == p.bias_slot) {           // high parts = 1.0, low parts = 0
+                            bulk_load_1d(sa + (uint32_t)j * blk_bytes, p.ones, sub_bytes, fb);
+                            bulk_load_1d(sa + (uint32_t)j * blk_bytes + sub_bytes, p.ones + 2048, sub_bytes, fb);
+                            break;
+                        }
+                        const int tap = slot / p.cblocks, cb = slot - tap * p.cblocks;
+                        const int kh = tap / p.kdim, kw = tap - kh * p.kdim;
+                        tma_load_5d(sa + (uint32_t)j * blk_bytes, &map_x, fb, 0, x0 * p.sstride + p.off0 + kw * p.offstep,
+                                    y0 * p.sstride + p.off0 + kh * p.offstep, n0, 2 * cb);
+                    }
+                    tma_load_5d(sa + b_off, &map_dz, fb, 0, x0, y0, n0, 2 * nt * nblk_b);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one_sync()) {
+            // bf16 A / B, fp32 accumulate, both operands MN-major ("transposed")
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            const int terms = p.debug > 0 && p.debug <= 3 ? p.debug : 3;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int mt = u % p.m_tiles; const int sp = (u / p.m_tiles) / p.n_tiles;
+                const int q0 = sp * p.tiles_per_split;
+                const int q1 = min(pix_tiles, q0 + p.tiles_per_split);
+                const bool two = p.mtu == 2 && p.slots - mt * 8 > 4;
+                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d0 = tmem_base, d1 = tmem_base + (uint32_t)MAX_N;
+                for (int q = q0; q < q1; ++q) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * STAGE_BYTES;
+                    // [0] = high parts, [1] = low parts: the same blocks, one sub-block further
+                    uint64_t a0[2], a1[2], bd[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        a0[h] = make_mn64_desc(sa + (uint32_t)h * sub_bytes, blk_bytes, 512u);
+                        a1[h] = make_mn64_desc(sa + 4u * blk_bytes + (uint32_t)h * sub_bytes, blk_bytes, 512u);
+                        bd[h] = make_mn64_desc(sa + b_off + (uint32_t)h * sub_bytes, blk_bytes, 512u);
+                    }
+                    const int ksteps = p.P / 16;
+                    for (int k = 0; k < ksteps; ++k) {     // 16 pixel rows = 1024 bytes = +64 in 16-byte units
+                        const uint64_t ko = (uint64_t)(k * 64);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            if (c >= terms) break;
+                            const int ha = c == 1 ? 1 : 0, hb = c == 2 ? 1 : 0;      // hi*hi, lo*hi, hi*lo
+                            const uint32_t accum = (q > q0 || k > 0 || c > 0) ? 1u : 0u;
+                            tc_mma_bf16(d0, a0[ha] + ko, bd[hb] + ko, idesc, accum);
+                            if (two) tc_mma_bf16(d1, a1[ha] + ko, bd[hb] + ko, idesc, accum);
+                        }
+                    }
+                    tc_commit(empty0 + 8 * stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull0 + 8 * acc);
+                acc_phase ^= 1;
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        const long long wsize = (long long)p.taps * p.Cin * p.Cout;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int mt = u % p.m_tiles; const int r1 = u / p.m_tiles;
+            const int nt = r1 % p.n_tiles; const int sp = r1 / p.n_tiles;
+            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            tc_fence_after();
+            for (int half = 0; half < 2; ++half) {
+                const int slot = mt * spu + half * 4 + quarter;
+                if (half >= p.mtu || mt * spu + half * 4 >= p.slots) break;   // warp-uniform: no (valid) second tile
+                const bool is_bias = slot == p.bias_slot;
+                const bool ok = slot < p.slots && (!is_bias || lane == 0);
+                const int tap = (ok && !is_bias) ? slot / p.cblocks : 0, cb = (ok && !is_bias) ? slot - tap * p.cblocks : 0;
+                float* drow = p.partial + (long long)sp * p.psize +
+                              (is_bias ? wsize : ((long long)tap * p.Cin + cb * 32 + lane) * p.Cout);
+                const uint32_t t_row = tmem_base + (uint32_t)(half * MAX_N) + ((uint32_t)(quarter * 32) << 16);
+                for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+                    uint32_t r[32];
+                    __syncwarp();
+                    tc_ld32(t_row + (uint32_t)c0, r);
+                    tc_wait_ld();
+                    const int ch0 = nt * p.block_n + c0;
+                    if (ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            if (ch0 + j < p.Cout)
+                                *reinterpret_cast<float4*>(drow + ch0 + j) =
+                                    make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// window variant (see conv_tc_wgrad_rw_kernel): the x box of a channel block arrives as a high and a low sub-box of
+// [PH + 2 lines][11 pixels][64 B]; one K = 16 MMA consumes TWO 8-pixel lines (the second 8-row group is one line further:
+// SBO = 11 rows in the x box, 8 rows in the dz box), windows kw = 0..3 are one row (64 bytes) apart.
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_wgrad_rw_s_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz, const WgRwArgs p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t bars = base + RING_BYTES;
+    const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
+    const uint32_t tmem_slot = tempty0 + 16;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+    const uint32_t ones_addr = bars + 1024u;                                  // 2 KB of bf16 1.0 inside the epilogue staging area
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull0, 1); mbar_init(tempty0, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dz) : "memory");
+    }
+    {   // resident block of bf16 ones (16 pixel rows x 64 bytes are read, 2 KB are filled)
+        uint32_t* ones = reinterpret_cast<uint32_t*>(smem_raw + (ones_addr - raw));
+        for (int i = threadIdx.x; i < 512; i += NUM_THREADS) ones[i] = 0x3f803f80u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int utypes = p.cgroups * p.n_tiles;
+    const int units = utypes * p.splits;
+    const int pix_tiles = p.ptx * p.pty * p.ptn;
+    const int nblk_b = p.block_n / 32;
+    const uint32_t xsub = (uint32_t)(11 * (p.PH + 2)) * 64u;          // one part of one channel block of x
+    const uint32_t zsub = (uint32_t)(8 * p.PH) * 64u;                 // one part of one channel block of dz
+    const uint32_t z_off = ((uint32_t)(2 * p.cpu) * xsub + 1023u) & ~1023u;
+    const int STAGES = p.stages;
+    const int noff = (p.block_n + 31) & ~31;
+
+    if (warp == 0) {
+        if (elect_one_sync()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int ut = u % utypes, sp = u / utypes;
+                const int cg = ut % p.cgroups, nt = ut / p.cgroups;
+                const int q0 = sp * p.tiles_per_split;
+                const int q1 = min(pix_tiles, q0 + p.tiles_per_split);
+                for (int q = q0; q < q1; ++q) {
+                    const int qx = q % p.ptx; const int r2 = q / p.ptx;
+                    const int qy = r2 % p.pty; const int n0 = r2 / p.pty;
+                    const int x0 = qx * 8, y0 = qy * p.PH;
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t fb = full0 + 8 * stage;
+                    const uint32_t sa = base + stage * p.stage_bytes;
+                    mbar_expect_tx(fb, (uint32_t)(2 * p.cpu) * xsub + (uint32_t)(2 * nblk_b) * zsub);
+                    tma_load_5d(sa, &map_x, fb, 0, x0 - p.pad, y0 - p.pad, n0, 2 * cg * p.cpu);
+                    tma_load_5d(sa + z_off, &map_dz, fb, 0, x0, y0, n0, 2 * nt * nblk_b);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one_sync()) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+            int stage = 0; uint32_t phase = 0; uint32_t acc_phase = 0;
+            const uint64_t ones_desc = make_mn64_desc(ones_addr, 0u, 512u);
+            const int terms = p.terms;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int ut = u % utypes, sp = u / utypes;
+                const int cg = ut % p.cgroups;
+                const bool do_bias = p.want_bias && cg == 0;
+                const int q0 = sp * p.tiles_per_split;
+                const int q1 = min(pix_tiles, q0 + p.tiles_per_split);
+                mbar_wait(tempty0, acc_phase ^ 1);
+                tc_fence_after();
+                for (int q = q0; q < q1; ++q) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * p.stage_bytes;
+                    // dz: 32-channel blocks 2 sub-blocks apart, line pairs contiguous (8 rows per line: SBO = 512)
+                    const uint64_t bz[2] = {make_mn64_desc(sa + z_off, 2u * zsub, 512u), make_mn64_desc(sa + z_off + zsub, 2u * zsub, 512u)};
+                    for (int jp = 0; jp < p.PH / 2; ++jp) {                      // two 8-pixel lines = one K = 16 MMA per accumulator and term
+                        const uint32_t first = (q > q0 || jp > 0) ? 1u : 0u;
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh)
+                            for (int t = 0; t < p.cpu; ++t) {
+                                // x: windows one row (64 B) apart, lines 11 rows apart
+                                const uint32_t xa = sa + (uint32_t)(2 * t) * xsub + (uint32_t)((2 * jp + kh) * 11) * 64u;
+                                const uint64_t ax[2] = {make_mn64_desc(xa, 64u, 704u), make_mn64_desc(xa + xsub, 64u, 704u)};
+                                const uint32_t d = tmem_base + (uint32_t)((kh * p.cpu + t) * noff);
+                                const uint64_t zo = (uint64_t)(jp * 64);         // 16 rows x 64 B = 1024 B
+#pragma unroll
+                                for (int c = 0; c < 3; ++c) {
+                                    if (c >= terms) break;
+                                    const int ha = c == 1 ? 1 : 0, hb = c == 2 ? 1 : 0;
+                                    tc_mma_bf16(d, ax[ha], bz[hb] + zo, idesc, (first || c > 0) ? 1u : 0u);
+                                }
+                            }
+                        if (do_bias) {
+                            const uint32_t d = tmem_base + (uint32_t)(3 * p.cpu * noff);
+                            tc_mma_bf16(d, ones_desc, bz[0] + (uint64_t)(jp * 64), idesc, first);
+                            tc_mma_bf16(d, ones_desc, bz[1] + (uint64_t)(jp * 64), idesc, 1u);
+                        }
+                    }
+                    tc_commit(empty0 + 8 * stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull0);
+                acc_phase ^= 1;
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        uint32_t acc_phase = 0;
+        const long long wsize = 9LL * p.Cin * p.Cout;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int ut = u % utypes, sp = u / utypes;
+            const int cg = ut % p.cgroups, nt = ut / p.cgroups;
+            const bool do_bias = p.want_bias && cg == 0;
+            mbar_wait(tfull0, acc_phase);
+            tc_fence_after();
+            const int nacc = 3 * p.cpu + (do_bias ? 1 : 0);
+            for (int ai = 0; ai < nacc; ++ai) {
+                const bool is_bias = ai == 3 * p.cpu;
+                const int kh = ai / p.cpu, t = ai - kh * p.cpu;
+                const bool ok = is_bias ? (quarter == 0 && lane == 0) : (quarter < 3);
+                const int c = (cg * p.cpu + t) * 32 + lane;
+                float* drow = p.partial + (long long)sp * p.psize +
+                              (is_bias ? wsize : ((long long)(kh * 3 + quarter) * p.Cin + c) * p.Cout);
+                const uint32_t t_row = tmem_base + (uint32_t)(ai * noff) + ((uint32_t)(quarter * 32) << 16);
+                for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+                    uint32_t r[32];
+                    __syncwarp();
+                    tc_ld32(t_row + (uint32_t)c0, r);
+                    tc_wait_ld();
+                    const int ch0 = nt * p.block_n + c0;
+                    if (ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            if (ch0 + j < p.Cout)
+                                *reinterpret_cast<float4*>(drow + ch0 + j) =
+                                    make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0);
+            acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // out[i] = sum_z partial[z][i]; the first nw floats go to dw, the remaining (bias) ones to db
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, long long psize, long long nw, int splits,
                                        float* __restrict__ dw, float* __restrict__ db) {
@@ -803,18 +1192,30 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, long l
 }
 
 // per-tap transpose: w_t[tap][n][c] = w[tap][c][n] (n < Cout), zero rows for n >= Cout
-__global__ void pack_filter_t_kernel(const float* __restrict__ w, int taps, int Cin, int Cout, int cout_pad, float* __restrict__ wt) {
+// fmt = ACT_F32: tf32-rounded floats; ACT_S32: bf16 (hi | lo) pairs per 32 input channels (Cin % 32 == 0)
+__global__ void pack_filter_t_kernel(const float* __restrict__ w, int taps, int Cin, int Cout, int cout_pad, int fmt, float* __restrict__ wt) {
     __shared__ float tile[32][33];
     const int tap = blockIdx.z;
     const int c0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int c = c0 + i, n = n0 + threadIdx.x;
-        tile[i][threadIdx.x] = (c < Cin && n < Cout) ? tf32_rn(w[((long long)tap * Cin + c) * Cout + n]) : 0.f;
+        float v = (c < Cin && n < Cout) ? w[((long long)tap * Cin + c) * Cout + n] : 0.f;
+        tile[i][threadIdx.x] = fmt == ACT_F32 ? tf32_rn(v) : v;
     }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int n = n0 + i, c = c0 + threadIdx.x;
-        if (n < cout_pad && c < Cin) wt[((long long)tap * cout_pad + n) * Cin + c] = tile[threadIdx.x][i];
+        if (n < cout_pad && c < Cin) {
+            const long long e = ((long long)tap * cout_pad + n) * Cin + c;
+            const float v = tile[threadIdx.x][i];
+            if (fmt == ACT_F32) wt[e] = v;
+            else {
+                const float hi = bf16_lo_f(bf16x2_rn(v, 0.f));
+                unsigned char* q = s32_addr(wt, e);
+                *reinterpret_cast<unsigned short*>(q) = (unsigned short)(__float_as_uint(hi) >> 16);
+                *reinterpret_cast<unsigned short*>(q + 64) = (unsigned short)(bf16x2_rn(v - hi, 0.f) & 0xffffu);
+            }
+        }
     }
 }
 
@@ -1028,14 +1429,21 @@ bool conv_tc_supported_dgrad(const ConvGeom& g) {
     return t.eff >= 0.45;
 }
 
-int pack_filter_t(const float* w_hwio, int taps, int Cin, int Cout, int cout_pad, float* w_t, cudaStream_t st) {
+int pack_filter_t(const float* w_hwio, int taps, int Cin, int Cout, int cout_pad, int fmt, float* w_t, cudaStream_t st) {
+    SSDB_REQUIRE(fmt == ACT_F32 || Cin % 32 == 0, "split filter copies need Cin % 32 == 0");
     dim3 grid((Cin + 31) / 32, (cout_pad + 31) / 32, taps), block(32, 8);
-    pack_filter_t_kernel<<<grid, block, 0, st>>>(w_hwio, taps, Cin, Cout, cout_pad, w_t);
+    pack_filter_t_kernel<<<grid, block, 0, st>>>(w_hwio, taps, Cin, Cout, cout_pad, fmt, w_t);
     SSDB_LAUNCH_CHECK();
     return SSDB_OK;
 }
 
-int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_pad, const ConvEpilogue& ep, float* y, cudaStream_t st) {
+static int split_terms_env() {
+    const char* ov = getenv("SSDB_SPLIT_TERMS");       // bring-up switch, read per call
+    const int t = ov ? atoi(ov) : 3;
+    return (t < 1 || t > 3) ? 3 : t;
+}
+
+int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_pad, int fmt, const ConvEpilogue& ep, float* y, cudaStream_t st) {
     SSDB_REQUIRE(conv_tc_supported_fprop(g), "shape not supported by the tcgen05 fprop kernel");
     TileGeom t = pick_tile(g.B, g.Ho, g.Wo);
     TcArgs a{};
@@ -1060,6 +1468,7 @@ int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_
     fill_groups(a, g.k, tdy, tdx, rw);
     SSDB_REQUIRE(g.pad_t == g.pad_l, "tcgen05 path assumes equal top/left padding");
     a.dst = y; a.bias = ep.bias; a.mask = nullptr; a.relu = ep.relu; a.beta = 0; a.round_out = ep.round_tf32;
+    a.split = fmt == ACT_S32 ? 1 : 0; a.split_terms = split_terms_env();
     a.scatter = ep.scatter; a.V = ep.V; a.n_valid = ep.n_valid; a.anchor_base = ep.anchor_base; a.A = ep.A;
     CUtensorMap ms, mw;
     int rc = encode_act_map(&ms, x, g.B, g.H, g.W, g.Cin, rw ? a.a_sbo / 128 : t.TW, t.TH, t.TN, CU_TENSOR_MAP_SWIZZLE_128B, g.stride); if (rc) return rc;
@@ -1067,7 +1476,7 @@ int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_
     return launch_tc(ms, mw, a, st);
 }
 
-int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, const float* mask_x, int beta, int round_out, float* dx, cudaStream_t st) {
+int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, int fmt, const float* mask_x, int beta, int round_out, float* dx, cudaStream_t st) {
     SSDB_REQUIRE(conv_tc_supported_dgrad(g), "shape not supported by the tcgen05 dgrad kernel");
     // A conv with stride s scatters: destination pixel (y, x) only sees taps with (y + pad - kh*dil) % s == 0.  Launch one
     // unit-stride contraction per parity class (py, px) of the destination, each with its own tap subset.
@@ -1116,6 +1525,7 @@ int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, const
                 a.stages = RING_BYTES / a.stage_bytes; if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
             }
             a.dst = dx; a.bias = nullptr; a.mask = mask_x; a.relu = 0; a.beta = beta; a.round_out = round_out;
+            a.split = fmt == ACT_S32 ? 1 : 0; a.split_terms = split_terms_env();
             CUtensorMap ms, mw;
             int rc = encode_act_map(&ms, dz, g.B, g.Ho, g.Wo, g.Cout, rw ? a.a_sbo / 128 : t.TW, t.TH, t.TN); if (rc) return rc;
             rc = encode_w_map(&mw, w_hwio, (long long)g.k * g.k * g.Cin, g.Cout, a.block_n); if (rc) return rc;
@@ -1130,14 +1540,14 @@ namespace {
 struct PixGeom { int PW, PH, PN, P; double eff; };
 
 // pixel box for the wgrad contraction: P = PW*PH*PN a multiple of 8, at most p_max, least waste
-PixGeom pick_pix(int B, int H, int W, int p_max) {
+PixGeom pick_pix(int B, int H, int W, int p_max, int p_mult = 8) {
     PixGeom best{0, 0, 0, 0, 0.0};
     const double total = (double)B * H * W;
     for (int pw = 1; pw <= W && pw <= p_max; ++pw)
         for (int ph = 1; ph <= H && pw * ph <= p_max; ++ph)
             for (int pn = 1; pn <= B && pw * ph * pn <= p_max; ++pn) {
                 int P = pw * ph * pn;
-                if (P % 8) continue;
+                if (P % p_mult) continue;
                 long long tiles = (long long)((W + pw - 1) / pw) * ((H + ph - 1) / ph) * ((B + pn - 1) / pn);
                 double eff = total / ((double)tiles * P);
                 // a pipeline stage is one box: small boxes starve the tensor core (one MMA per 8 pixels and a
@@ -1170,6 +1580,33 @@ int encode_act_map5(CUtensorMap* m, const float* ptr, int B, int H, int W, int C
     return SSDB_OK;
 }
 
+// 5-D view of an ACT_S32 tensor for the MN-major (wgrad) operands: (32 bf16 of one part, x, y, image, q = 2 * channel block + part)
+int encode_act_map5s(CUtensorMap* m, const float* ptr, int B, int H, int W, int C, int bw, int bh, int bn, int nq, int estride) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return SSDB_ECUDA; }
+    cuuint64_t dims[5] = {32, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)(C / 32 * 2)};
+    cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4, 64};
+    cuuint32_t box[5] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn, (cuuint32_t)nq};
+    cuuint32_t es[5] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<float*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(split 5-D activation %dx%dx%dx%d box %d,%d,%d,%d) failed: %d", B, H, W, C, bw, bh, bn, nq, (int)r); return SSDB_ECUDA; }
+    return SSDB_OK;
+}
+
+// 8 KB of bf16 1.0 followed by 8 KB of zeros: the (hi, lo) sub-blocks of the split kernels' bias slot
+const float* ones_buffer_split() {
+    static float* d = nullptr;
+    if (!d) {
+        std::vector<uint32_t> h(4096, 0u);
+        for (int i = 0; i < 2048; ++i) h[i] = 0x3f803f80u;
+        if (cudaMalloc(reinterpret_cast<void**>(&d), h.size() * sizeof(uint32_t)) != cudaSuccess) return nullptr;
+        cudaMemcpy(d, h.data(), h.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    }
+    return d;
+}
+
 const float* ones_buffer() {
     static float* d = nullptr;
     if (!d) {
@@ -1183,7 +1620,7 @@ const float* ones_buffer() {
 struct WgRwPlan { WgRwArgs a; bool ok; };
 
 // window plan: 3x3, dilation 1, stride 1, SAME, few output channels
-WgRwPlan plan_wgrad_rw(const ConvGeom& g) {
+WgRwPlan plan_wgrad_rw(const ConvGeom& g, int fmt) {
     WgRwPlan pl{}; pl.ok = false;
     if (const char* ov = getenv("SSDB_WG_RW")) { if (atoi(ov) == 0) return pl; }
     if (g.k != 3 || g.dil != 1 || g.stride != 1 || g.pad_t != 1 || g.pad_l != 1 || g.Cin % 32 != 0 || g.Cout % 32 != 0) return pl;
@@ -1203,13 +1640,16 @@ WgRwPlan plan_wgrad_rw(const ConvGeom& g) {
     if ((3 * a.cpu + 1) * noff > TMEM_COLS) return pl;
     a.cgroups = a.cblocks / a.cpu;
     // output lines per stage: as many as fit (<= 8) with at least 3 stages in the ring
-    int PH = g.H < 8 ? g.H : 8;
-    for (;; --PH) {
+    // (split kernel: one K = 16 MMA consumes two lines, so PH is even)
+    const int ph_step = fmt == ACT_S32 ? 2 : 1;
+    int PH = g.H < 8 ? (g.H + ph_step - 1) / ph_step * ph_step : 8;
+    for (;; PH -= ph_step) {
         int sb = (a.cpu * 11 * (PH + 2) * 128 + 1023) / 1024 * 1024 + (a.block_n / 32) * 8 * PH * 128;
         sb = (sb + 1023) / 1024 * 1024;
-        if (RING_BYTES / sb >= 3 || PH == 1) { a.stage_bytes = sb; break; }
+        if (RING_BYTES / sb >= 3 || PH <= ph_step) { a.stage_bytes = sb; break; }
     }
-    if (PH < 2) return pl;
+    if (PH < 2 || RING_BYTES / a.stage_bytes < 2) return pl;
+    a.terms = split_terms_env();
     a.PH = PH;
     a.stages = RING_BYTES / a.stage_bytes; if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
     a.ptx = (g.W + 7) / 8; a.pty = (g.H + PH - 1) / PH; a.ptn = g.B;
@@ -1248,7 +1688,7 @@ int encode_rw_map(CUtensorMap* m, const float* ptr, int B, int H, int W, int C, 
 
 struct WgPlan { WgArgs a; bool ok; };
 
-WgPlan plan_wgrad(const ConvGeom& g) {
+WgPlan plan_wgrad(const ConvGeom& g, int fmt) {
     WgPlan pl{}; pl.ok = false;
     if ((g.stride != 1 && g.stride != 2) || g.Cin % 32 != 0 || g.Cout % 32 != 0 || g.pad_t != g.pad_l || g.k < 1 || g.k > 7) return pl;
     if (g.Cout > MAX_N && g.Cout % MAX_N != 0) return pl;
@@ -1259,12 +1699,13 @@ WgPlan plan_wgrad(const ConvGeom& g) {
     if (const char* ov = getenv("SSDB_WG_MTU")) { int v = atoi(ov); if (v == 1 || v == 2) a.mtu = v; }
     int blocks = 4 * a.mtu + a.block_n / 32;
     int p_max = stage_bytes_for(a.mtu) / (blocks * 128);
-    p_max = p_max / 8 * 8; if (p_max > 64) p_max = 64;
+    const int p_mult = fmt == ACT_S32 ? 16 : 8;             // pixels per MMA (K of one instruction)
+    p_max = p_max / p_mult * p_mult; if (p_max > 64) p_max = 64;
     if (g.stride == 2 && p_max > 32) p_max = 32;            // strided boxes: keep every box dimension <= 256 / stride
-    PixGeom pg = pick_pix(g.B, g.Ho, g.Wo, p_max);
+    PixGeom pg = pick_pix(g.B, g.Ho, g.Wo, p_max, p_mult);
     if (const char* ov = getenv("SSDB_WG_BOX")) {          // bring-up override: "PW,PH,PN"
         int a1 = 0, a2 = 0, a3 = 0;
-        if (sscanf(ov, "%d,%d,%d", &a1, &a2, &a3) == 3 && a1 * a2 * a3 % 8 == 0 && a1 * a2 * a3 <= p_max) {
+        if (sscanf(ov, "%d,%d,%d", &a1, &a2, &a3) == 3 && a1 * a2 * a3 % p_mult == 0 && a1 * a2 * a3 <= p_max) {
             pg.PW = a1; pg.PH = a2; pg.PN = a3; pg.P = a1 * a2 * a3; pg.eff = 1.0;
         }
     }
@@ -1296,53 +1737,77 @@ WgPlan plan_wgrad(const ConvGeom& g) {
 
 }  // namespace
 
-bool conv_tc_supported_wgrad(const ConvGeom& g) { return plan_wgrad_rw(g).ok || plan_wgrad(g).ok; }
+bool conv_tc_supported_wgrad(const ConvGeom& g, int fmt) { return plan_wgrad_rw(g, fmt).ok || plan_wgrad(g, fmt).ok; }
 
-size_t conv_tc_wgrad_ws(const ConvGeom& g) {
+size_t conv_tc_wgrad_ws(const ConvGeom& g, int fmt) {
     size_t need = 0;
-    WgRwPlan rw = plan_wgrad_rw(g);
+    WgRwPlan rw = plan_wgrad_rw(g, fmt);
     if (rw.ok) need = (size_t)rw.a.splits * (size_t)rw.a.psize;
-    WgPlan pl = plan_wgrad(g);
+    WgPlan pl = plan_wgrad(g, fmt);
     if (pl.ok) { size_t n2 = (size_t)pl.a.splits * (size_t)pl.a.psize; if (n2 > need) need = n2; }
     return need;
 }
 
-int conv_tc_wgrad(const ConvGeom& g, const float* x, const float* dz, float* dw, float* db, float* partial, cudaStream_t st) {
-    WgRwPlan rw = plan_wgrad_rw(g);
+int conv_tc_wgrad(const ConvGeom& g, const float* x, const float* dz, int fmt, float* dw, float* db, float* partial, cudaStream_t st) {
+    const bool split = fmt == ACT_S32;
+    WgRwPlan rw = plan_wgrad_rw(g, fmt);
     if (rw.ok) {
         WgRwArgs a = rw.a;
         a.partial = partial;
         a.want_bias = db ? 1 : 0;
         CUtensorMap mx, mz;
-        int rc = encode_rw_map(&mx, x, g.B, g.H, g.W, g.Cin, 11, a.PH + 2, 1, a.cpu); if (rc) return rc;
-        rc = encode_rw_map(&mz, dz, g.B, g.Ho, g.Wo, g.Cout, 8, a.PH, 1, a.block_n / 32); if (rc) return rc;
+        int rc;
+        if (split) {
+            rc = encode_act_map5s(&mx, x, g.B, g.H, g.W, g.Cin, 11, a.PH + 2, 1, 2 * a.cpu, 1); if (rc) return rc;
+            rc = encode_act_map5s(&mz, dz, g.B, g.Ho, g.Wo, g.Cout, 8, a.PH, 1, 2 * (a.block_n / 32), 1); if (rc) return rc;
+        } else {
+            rc = encode_rw_map(&mx, x, g.B, g.H, g.W, g.Cin, 11, a.PH + 2, 1, a.cpu); if (rc) return rc;
+            rc = encode_rw_map(&mz, dz, g.B, g.Ho, g.Wo, g.Cout, 8, a.PH, 1, a.block_n / 32); if (rc) return rc;
+        }
         static bool attr_rw = false;
-        if (!attr_rw) { SSDB_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_rw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_rw = true; }
+        if (!attr_rw) {
+            SSDB_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_rw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            SSDB_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_rw_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            attr_rw = true;
+        }
         long long units = (long long)a.cgroups * a.n_tiles * a.splits;
         int grid = (int)(units < num_sms() ? units : num_sms());
-        conv_tc_wgrad_rw_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mx, mz, a);
+        if (split) conv_tc_wgrad_rw_s_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mx, mz, a);
+        else conv_tc_wgrad_rw_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mx, mz, a);
         SSDB_LAUNCH_CHECK();
         long long nw = 9LL * g.Cin * g.Cout;
         reduce_partials_kernel<<<(unsigned)((a.psize / 4 + 255) / 256), 256, 0, st>>>(partial, a.psize, nw, a.splits, dw, db);
         SSDB_LAUNCH_CHECK();
         return SSDB_OK;
     }
-    WgPlan pl = plan_wgrad(g);
+    WgPlan pl = plan_wgrad(g, fmt);
     SSDB_REQUIRE(pl.ok, "shape not supported by the tcgen05 wgrad kernel");
     WgArgs a = pl.a;
     a.partial = partial;
-    a.ones = ones_buffer();
+    a.ones = split ? ones_buffer_split() : ones_buffer();
     { const char* dbg = getenv("SSDB_WG_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
+    if (split) a.debug = split_terms_env() < 3 ? split_terms_env() : 0;
     SSDB_REQUIRE(a.ones != nullptr, "could not allocate the ones buffer");
     if (!db) { a.bias_slot = -1; a.slots = a.taps * a.cblocks; a.m_tiles = (a.slots + 4 * a.mtu - 1) / (4 * a.mtu); }
     CUtensorMap mx, mz;
-    int rc = encode_act_map5(&mx, x, g.B, g.H, g.W, g.Cin, a.PW, a.PH, a.PN, a.load_blocks, g.stride); if (rc) return rc;
-    rc = encode_act_map5(&mz, dz, g.B, g.Ho, g.Wo, g.Cout, a.PW, a.PH, a.PN, a.block_n / 32, 1); if (rc) return rc;
+    int rc;
+    if (split) {
+        rc = encode_act_map5s(&mx, x, g.B, g.H, g.W, g.Cin, a.PW * g.stride, a.PH * g.stride, a.PN, 2 * a.load_blocks, g.stride); if (rc) return rc;
+        rc = encode_act_map5s(&mz, dz, g.B, g.Ho, g.Wo, g.Cout, a.PW, a.PH, a.PN, 2 * (a.block_n / 32), 1); if (rc) return rc;
+    } else {
+        rc = encode_act_map5(&mx, x, g.B, g.H, g.W, g.Cin, a.PW, a.PH, a.PN, a.load_blocks, g.stride); if (rc) return rc;
+        rc = encode_act_map5(&mz, dz, g.B, g.Ho, g.Wo, g.Cout, a.PW, a.PH, a.PN, a.block_n / 32, 1); if (rc) return rc;
+    }
     static bool attr = false;
-    if (!attr) { SSDB_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr = true; }
+    if (!attr) {
+        SSDB_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        SSDB_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr = true;
+    }
     long long units = (long long)a.m_tiles * a.n_tiles * a.splits;
     int grid = (int)(units < num_sms() ? units : num_sms());
-    conv_tc_wgrad_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mx, mz, a);
+    if (split) conv_tc_wgrad_s_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mx, mz, a);
+    else conv_tc_wgrad_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mx, mz, a);
     SSDB_LAUNCH_CHECK();
     long long nw = (long long)a.taps * g.Cin * g.Cout;
     reduce_partials_kernel<<<(unsigned)((a.psize / 4 + 255) / 256), 256, 0, st>>>(partial, a.psize, nw, a.splits, dw, db);

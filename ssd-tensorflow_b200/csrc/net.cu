@@ -95,7 +95,9 @@ struct ssdb_net {
     float *patches = nullptr, *c1_w32 = nullptr, *c1_wt = nullptr, *c1_dw32 = nullptr;
     unsigned char* pool5_arg = nullptr;   // winning window cell of mod_pool5 (3x3 stride 1), one byte per output element
     std::vector<unsigned char*> pool_code; // per op: code bytes of the 2x2/s2 pools (null for every other op)
-    bool round = true;                 // activations / gradients are stored tf32-rounded (off in pure-SIMT mode)
+    bool round = false;                // tf32 mode: activations / gradients are stored tf32-rounded
+    int fmt = ACT_S32;                 // storage format of activations / gradients / packed filters (common.cuh): split bf16
+                                       // pairs (default), plain float32 in the tf32 and SIMT modes
     float *acts = nullptr, *gacts = nullptr;
     float *out = nullptr, *out_grad = nullptr, *result = nullptr, *dz_head = nullptr;
     float *images_stage = nullptr, *labels_stage = nullptr;
@@ -287,14 +289,16 @@ bool use_tc(const ssdb_net* n, bool supported) {
 int repack_filters(ssdb_net* n, cudaStream_t st) {
     for (const Op& op : n->ops) {
         if (!op.has_wt) continue;
-        int rc = pack_filter_t(n->params + n->masters[op.w].off, op.k * op.k, op.cin, op.cout, op.cout_pad, n->wt + op.wt_off, st);
+        int rc = pack_filter_t(n->params + n->masters[op.w].off, op.k * op.k, op.cin, op.cout, op.cout_pad, n->fmt, n->wt + op.wt_off, st);
         if (rc) return rc;
     }
+    // dgrad B operand: the HWIO filters themselves, tf32-rounded or split along Cout (every tensor starts on a 1024-element boundary)
     if (n->round) { int rc = round_tf32_copy(n->params, n->wr, (long long)n->n_flat, st); if (rc) return rc; }
+    else if (n->fmt == ACT_S32) { int rc = split_copy(n->params, n->wr, (long long)n->n_flat, st); if (rc) return rc; }
     if (n->patches) {
         const Op& c1 = n->ops[0];
         int rc = conv1_pad_filter(n->params + n->masters[c1.w].off, c1.cout, n->c1_w32, st); if (rc) return rc;
-        rc = pack_filter_t(n->c1_w32, 1, 32, c1.cout, c1.cout, n->c1_wt, st); if (rc) return rc;
+        rc = pack_filter_t(n->c1_w32, 1, 32, c1.cout, c1.cout, n->fmt, n->c1_wt, st); if (rc) return rc;
     }
     n->wt_dirty = false;
     return SSDB_OK;
@@ -328,9 +332,9 @@ int run_first_conv_chunk(ssdb_net* n, const float* images, int b0, int Bc, cudaS
     ep.bias = n->params + n->masters[op.b].off; ep.relu = op.relu ? 1 : 0; ep.round_tf32 = n->round ? 1 : 0;
     const size_t px = (size_t)b0 * n->S * n->S;
     float* patches = n->patches + px * 32;
-    int rc = conv1_im2col(images + px * 3, Bc, n->S, n->swap_rb, n->mean, patches, st); if (rc) return rc;
+    int rc = conv1_im2col(images + px * 3, Bc, n->S, n->swap_rb, n->mean, n->fmt, patches, st); if (rc) return rc;
     ConvGeom g1 = g; g1.Cin = 32; g1.k = 1; g1.pad_t = g1.pad_l = 0; g1.dil = 1;
-    return conv_tc_fprop(g1, patches, n->c1_wt, op.cout, ep, n->act(op.out, n->max_batch) + px * op.cout, st);
+    return conv_tc_fprop(g1, patches, n->c1_wt, op.cout, n->fmt, ep, n->act(op.out, n->max_batch) + px * op.cout, st);
 }
 
 int run_forward(ssdb_net* n, const float* images, int B, cudaStream_t st, bool skip_first = false) {
@@ -350,25 +354,25 @@ int run_forward(ssdb_net* n, const float* images, int B, cudaStream_t st, bool s
             if (op.head) { ep.scatter = 1; ep.V = n->V; ep.n_valid = op.nbox * n->V; ep.anchor_base = op.anchor_base; ep.A = n->A; }
             if (op.in < 0) { ep.preprocess = 1; ep.swap_rb = n->swap_rb; ep.mean[0] = n->mean[0]; ep.mean[1] = n->mean[1]; ep.mean[2] = n->mean[2]; }
             if (op.in < 0 && n->patches) {
-                rc = conv1_im2col(images, B, n->S, n->swap_rb, n->mean, n->patches, st); if (rc) return rc;
+                rc = conv1_im2col(images, B, n->S, n->swap_rb, n->mean, n->fmt, n->patches, st); if (rc) return rc;
                 ConvGeom g1 = g; g1.Cin = 32; g1.k = 1; g1.pad_t = g1.pad_l = 0; g1.dil = 1;
                 ConvEpilogue e1 = ep; e1.preprocess = 0;
-                rc = conv_tc_fprop(g1, n->patches, n->c1_wt, op.cout, e1, y, st);
+                rc = conv_tc_fprop(g1, n->patches, n->c1_wt, op.cout, n->fmt, e1, y, st);
             } else if (op.has_wt && use_tc(n, conv_tc_supported_fprop(g)))
-                rc = conv_tc_fprop(g, x, n->wt + op.wt_off, op.cout_pad, ep, y, st);
+                rc = conv_tc_fprop(g, x, n->wt + op.wt_off, op.cout_pad, n->fmt, ep, y, st);
             else
-                rc = conv_simt_fprop(g, x, n->params + n->masters[op.w].off, ep, y, st);
+                rc = conv_simt_fprop(g, x, n->params + n->masters[op.w].off, n->fmt, ep, y, st);
         } else if (op.type == OP_POOL) {
             const Buf& bi = n->bufs[op.in]; const Buf& bo = n->bufs[op.out];
             if (op.stride == 1 && n->pool5_arg)
-                rc = maxpool_fwd_arg(n->act(op.in, B), B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W, n->act(op.out, B), n->pool5_arg, st);
+                rc = maxpool_fwd_arg(n->act(op.in, B), n->fmt, B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W, n->act(op.out, B), n->pool5_arg, st);
             else if (n->pool_code[&op - n->ops.data()])
-                rc = maxpool2x2_fwd_code(n->act(op.in, B), B, bi.H, bi.W, bi.C, bo.H, bo.W, n->act(op.out, B), n->pool_code[&op - n->ops.data()], st);
+                rc = maxpool2x2_fwd_code(n->act(op.in, B), n->fmt, B, bi.H, bi.W, bi.C, bo.H, bo.W, n->act(op.out, B), n->pool_code[&op - n->ops.data()], st);
             else
-                rc = maxpool_fwd(n->act(op.in, B), B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W, n->act(op.out, B), st);
+                rc = maxpool_fwd(n->act(op.in, B), n->fmt, B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W, n->act(op.out, B), st);
         } else {
             const Buf& bi = n->bufs[op.in];
-            rc = l2norm_fwd(n->act(op.in, B), n->params + n->masters[op.w].off, (long long)B * bi.H * bi.W, bi.C, n->round ? 1 : 0, n->act(op.out, B), st);
+            rc = l2norm_fwd(n->act(op.in, B), n->params + n->masters[op.w].off, n->fmt, (long long)B * bi.H * bi.W, bi.C, n->round ? 1 : 0, n->act(op.out, B), st);
         }
         if (rc) return rc;
     }
@@ -387,7 +391,7 @@ int run_backward(ssdb_net* n, int B, cudaStream_t st) {
             const float* dz;
             if (op.head) {
                 const Buf& fb = n->bufs[op.in];
-                rc = head_grad_gather(n->out_grad, B, n->A, n->V, op.anchor_base, fb.H * fb.W, op.nbox, op.cout, n->round ? 1 : 0, n->dz_head, st);
+                rc = head_grad_gather(n->out_grad, B, n->A, n->V, op.anchor_base, fb.H * fb.W, op.nbox, op.cout, n->fmt, n->round ? 1 : 0, n->dz_head, st);
                 if (rc) return rc;
                 dz = n->dz_head;
             } else {
@@ -401,20 +405,20 @@ int run_backward(ssdb_net* n, int B, cudaStream_t st) {
             if (op.in < 0 && n->patches) {
                 ProfScope ps(n, st, std::string("bwd_w:") + op.name, conv_flops(g));
                 ConvGeom g1 = g; g1.Cin = 32; g1.k = 1; g1.pad_t = g1.pad_l = 0; g1.dil = 1;
-                rc = conv_tc_wgrad(g1, n->patches, dz, n->c1_dw32, db, n->partial, st); if (rc) return rc;
+                rc = conv_tc_wgrad(g1, n->patches, dz, n->fmt, n->c1_dw32, db, n->partial, st); if (rc) return rc;
                 SSDB_CUDA(cudaMemcpyAsync(dw, n->c1_dw32, (size_t)27 * op.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
                 continue;
             }
-            const bool tcw = op.in >= 0 && use_tc(n, conv_tc_supported_wgrad(g));
-            if (!tcw) { ProfScope ps(n, st, std::string("bwd_b:") + op.name); rc = bias_grad(dz, pixels, op.cout, db, n->partial, st); }
+            const bool tcw = op.in >= 0 && use_tc(n, conv_tc_supported_wgrad(g, n->fmt));
+            if (!tcw) { ProfScope ps(n, st, std::string("bwd_b:") + op.name); rc = bias_grad(dz, n->fmt, pixels, op.cout, db, n->partial, st); }
             if (rc) return rc;
             ProfScope* psw = new ProfScope(n, st, std::string("bwd_w:") + op.name, conv_flops(g));
             ConvEpilogue ep;
             if (op.in < 0) { ep.preprocess = 1; ep.swap_rb = n->swap_rb; ep.mean[0] = n->mean[0]; ep.mean[1] = n->mean[1]; ep.mean[2] = n->mean[2]; }
             if (tcw)
-                rc = conv_tc_wgrad(g, x, dz, dw, db, n->partial, st);
+                rc = conv_tc_wgrad(g, x, dz, n->fmt, dw, db, n->partial, st);
             else
-                rc = conv_simt_wgrad(g, op.in < 0 ? n->images_stage : x, dz, ep, dw, n->partial, st);
+                rc = conv_simt_wgrad(g, op.in < 0 ? n->images_stage : x, dz, n->fmt, ep, dw, n->partial, st);
             delete psw;
             if (rc) return rc;
             if (op.in >= 0) {
@@ -422,9 +426,9 @@ int run_backward(ssdb_net* n, int B, cudaStream_t st) {
                 const float* mask = n->bufs[op.in].relu_out ? x : nullptr;
                 int beta = written[op.in] ? 1 : 0;
                 if (use_tc(n, conv_tc_supported_dgrad(g)))
-                    rc = conv_tc_dgrad(g, dz, n->wr + n->masters[op.w].off, mask, beta, 1, n->gact(op.in, B), st);
+                    rc = conv_tc_dgrad(g, dz, n->wr + n->masters[op.w].off, n->fmt, mask, beta, n->round ? 1 : 0, n->gact(op.in, B), st);
                 else
-                    rc = conv_simt_dgrad(g, dz, n->params + n->masters[op.w].off, mask, beta, n->round ? 1 : 0, n->gact(op.in, B), st);
+                    rc = conv_simt_dgrad(g, dz, n->params + n->masters[op.w].off, n->fmt, mask, beta, n->round ? 1 : 0, n->gact(op.in, B), st);
                 written[op.in] = 1;
             }
         } else if (op.type == OP_POOL) {
@@ -432,20 +436,20 @@ int run_backward(ssdb_net* n, int B, cudaStream_t st) {
             SSDB_REQUIRE(written[op.out], "internal: gradient of a pool output was never produced");
             const Buf& bi = n->bufs[op.in]; const Buf& bo = n->bufs[op.out];
             if (op.stride == 1 && n->pool5_arg)
-                rc = maxpool_bwd_arg(n->act(op.in, B), n->gact(op.out, B), n->pool5_arg, B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W,
+                rc = maxpool_bwd_arg(n->act(op.in, B), n->gact(op.out, B), n->pool5_arg, n->fmt, B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W,
                                      written[op.in] ? 1 : 0, bi.relu_out ? 1 : 0, n->round ? 1 : 0, n->gact(op.in, B), st);
             else if (n->pool_code[&op - n->ops.data()] && !written[op.in])
-                rc = maxpool2x2_bwd_code(n->gact(op.out, B), n->pool_code[&op - n->ops.data()], B, bi.H, bi.W, bi.C, bo.H, bo.W, bi.relu_out ? 1 : 0,
+                rc = maxpool2x2_bwd_code(n->gact(op.out, B), n->pool_code[&op - n->ops.data()], n->fmt, B, bi.H, bi.W, bi.C, bo.H, bo.W, bi.relu_out ? 1 : 0,
                                          n->round ? 1 : 0, n->gact(op.in, B), st);
             else
-            rc = maxpool_bwd(n->act(op.in, B), n->gact(op.out, B), B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W,
+            rc = maxpool_bwd(n->act(op.in, B), n->gact(op.out, B), n->fmt, B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W,
                              written[op.in] ? 1 : 0, bi.relu_out ? 1 : 0, n->round ? 1 : 0, n->gact(op.in, B), st);
             written[op.in] = 1;
         } else {
             ProfScope ps(n, st, std::string("bwd:") + op.name);
             SSDB_REQUIRE(written[op.out], "internal: gradient of the L2-norm output was never produced");
             const Buf& bi = n->bufs[op.in];
-            rc = l2norm_bwd(n->act(op.in, B), n->params + n->masters[op.w].off, n->gact(op.out, B), (long long)B * bi.H * bi.W, bi.C,
+            rc = l2norm_bwd(n->act(op.in, B), n->params + n->masters[op.w].off, n->gact(op.out, B), n->fmt, (long long)B * bi.H * bi.W, bi.C,
                             written[op.in] ? 1 : 0, n->round ? 1 : 0, n->gact(op.in, B), n->grads + n->masters[op.w].off, n->partial, st);
             written[op.in] = 1;
         }
@@ -508,8 +512,13 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
     if (!P) { set_error("No such preset: %s", preset); return SSDB_ENOTFOUND; }
     ssdb_net* n = new ssdb_net();
     n->preset = P; n->C = num_classes; n->V = num_classes + 5; n->S = P->image; n->max_batch = max_batch;
+    // SSDB_CONV: (unset) / "split" = tensor cores with split bf16 operands (fp32-grade products, the product mode);
+    // "tf32" = tensor cores with tf32 operands (10-bit significands: outside the 1e-3 parity bar, kept for comparison);
+    // "simt" = fp32 CUDA-core kernels only
     const char* mode = getenv("SSDB_CONV");
-    if (mode && !strcmp(mode, "simt")) { n->conv_mode = SSDB_CONV_SIMT; n->round = false; }
+    if (mode && !strcmp(mode, "simt")) { n->conv_mode = SSDB_CONV_SIMT; n->round = false; n->fmt = ACT_F32; }
+    else if (mode && !strcmp(mode, "tf32")) { n->round = true; n->fmt = ACT_F32; }
+    else if (mode && strcmp(mode, "split") && strcmp(mode, "auto") && mode[0]) { set_error("SSDB_CONV=%s: expected split, tf32 or simt", mode); delete n; return SSDB_EINVAL; }
     build_plan(n);
     if (n->A != P->num_anchors) { set_error("internal: anchor count %d != %d", n->A, P->num_anchors); delete n; return SSDB_EINVAL; }
     // workspace sizes
@@ -519,7 +528,7 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
         if (op.type != OP_CONV) continue;
         ConvGeom g = geom_of(n, op, max_batch);
         size_t w = conv_simt_wgrad_ws(g); if (w > partial) partial = w;
-        w = conv_tc_wgrad_ws(g); if (w > partial) partial = w;
+        w = conv_tc_wgrad_ws(g, n->fmt); if (w > partial) partial = w;
         if (op.head) { size_t d = (size_t)max_batch * g.H * g.W * op.cout; if (d > dzh) dzh = d; }
     }
     n->partial_floats = partial;
@@ -546,13 +555,13 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
             const Buf& bo = n->bufs[op.out];
             ALLOC(n->pool_code[i], (size_t)max_batch * bo.H * bo.W * bo.C, unsigned char);
         }
-    if (n->round) {
+    if (n->conv_mode != SSDB_CONV_SIMT) {
         const Op& c1 = n->ops[0];
         ConvGeom g1 = geom_of(n, c1, max_batch); g1.Cin = 32; g1.k = 1; g1.pad_t = g1.pad_l = 0;
-        if (conv_tc_supported_fprop(g1) && conv_tc_supported_wgrad(g1)) {
+        if (conv_tc_supported_fprop(g1) && conv_tc_supported_wgrad(g1, n->fmt)) {
             ALLOC(n->patches, (size_t)max_batch * n->S * n->S * 32, float);
             ALLOC(n->c1_w32, 32 * c1.cout, float); ALLOC(n->c1_wt, 32 * c1.cout, float); ALLOC(n->c1_dw32, 32 * c1.cout, float);
-            size_t w = conv_tc_wgrad_ws(g1);
+            size_t w = conv_tc_wgrad_ws(g1, n->fmt);
             if (w > n->partial_floats) { cudaFree(n->partial); n->partial_floats = w; ALLOC(n->partial, w, float); }
         }
     }
@@ -699,6 +708,14 @@ int ssdb_forward_host(ssdb_net* n, const float* images_host, int B, float* resul
     rc = softmax_result(n->out, (long long)B * n->A, n->C, n->result, st); if (rc) return rc;
     SSDB_CUDA(cudaMemcpyAsync(result_host, n->result, (size_t)B * n->A * n->V * sizeof(float), cudaMemcpyDeviceToHost, st));
     SSDB_CUDA(cudaStreamSynchronize(st));
+    return SSDB_OK;
+}
+
+int ssdb_read_output_host(ssdb_net* n, int B, float* output_host) {
+    SSDB_REQUIRE(n && output_host && B >= 1 && B <= n->max_batch, "bad arguments");
+    SSDB_REQUIRE(n->last_B >= B, "no forward pass has produced that many rows yet");
+    SSDB_CUDA(cudaDeviceSynchronize());
+    SSDB_CUDA(cudaMemcpy(output_host, n->out, (size_t)B * n->A * n->V * sizeof(float), cudaMemcpyDeviceToHost));
     return SSDB_OK;
 }
 
@@ -896,25 +913,52 @@ static ConvGeom make_geom(int B, int H, int W, int Cin, int Cout, int k, int str
     return g;
 }
 
+// temporary device buffers of the layer test hooks, released (stream-ordered) when the hook returns
+struct TmpBufs {
+    cudaStream_t st; std::vector<void*> ptrs;
+    explicit TmpBufs(cudaStream_t s) : st(s) {}
+    float* get(size_t floats) {
+        void* p = nullptr;
+        if (cudaMallocAsync(&p, (floats ? floats : 1) * sizeof(float), st) != cudaSuccess) return nullptr;
+        ptrs.push_back(p);
+        return static_cast<float*>(p);
+    }
+    ~TmpBufs() { for (void* p : ptrs) cudaFreeAsync(p, st); }
+};
+
+// which kernel family and operand format a test-hook `impl` selects
+static bool hook_mode(int impl, bool tc_supported, bool* tc, int* fmt) {
+    *tc = impl == SSDB_CONV_TC || impl == SSDB_CONV_TC_SPLIT || (impl == SSDB_CONV_AUTO && tc_supported);
+    *fmt = (*tc && impl != SSDB_CONV_TC) ? ACT_S32 : ACT_F32;
+    return !*tc || tc_supported;
+}
+
+// the engine's operand preparation: tf32 rounding (ACT_F32) or the bf16 split (ACT_S32; n must be a multiple of 32)
+static int hook_prepare(const float* src, float* dst, long long n, int fmt, cudaStream_t st) {
+    return fmt == ACT_S32 ? split_copy(src, dst, n, st) : round_tf32_copy(src, dst, n, st);
+}
+
 int ssdb_op_conv_fprop(int impl, const float* x, const float* w_hwio, const float* bias, int B, int H, int W, int Cin, int Cout, int k,
                        int stride, int dil, int pad_t, int pad_l, int Ho, int Wo, int relu, float* y, void* stream) {
     SSDB_REQUIRE(x && w_hwio && y, "bad arguments");
     ConvGeom g = make_geom(B, H, W, Cin, Cout, k, stride, dil, pad_t, pad_l, Ho, Wo);
     ConvEpilogue ep; ep.bias = bias; ep.relu = relu;
     cudaStream_t st = (cudaStream_t)stream;
-    bool tc = impl == SSDB_CONV_TC || (impl == SSDB_CONV_AUTO && conv_tc_supported_fprop(g));
-    if (!tc) return conv_simt_fprop(g, x, w_hwio, ep, y, st);
-    SSDB_REQUIRE(conv_tc_supported_fprop(g), "shape not supported by the tcgen05 kernel");
+    bool tc; int fmt;
+    SSDB_REQUIRE(hook_mode(impl, conv_tc_supported_fprop(g), &tc, &fmt), "shape not supported by the tcgen05 kernel");
+    if (!tc) return conv_simt_fprop(g, x, w_hwio, ACT_F32, ep, y, st);
+    SSDB_REQUIRE(fmt == ACT_F32 || Cout % 32 == 0, "split mode needs Cout % 32 == 0");
     int bn = Cout > 256 ? 256 : (Cout + 15) / 16 * 16;
     int cout_pad = (Cout + bn - 1) / bn * bn;
-    float *wt = nullptr, *xr = nullptr;
-    long long nx = (long long)B * H * W * Cin;
-    SSDB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&wt), (size_t)k * k * cout_pad * Cin * sizeof(float), st));
-    SSDB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&xr), (size_t)nx * sizeof(float), st));
-    int rc = pack_filter_t(w_hwio, k * k, Cin, Cout, cout_pad, wt, st);
-    if (!rc) rc = round_tf32_copy(x, xr, nx, st);          // the engine stores activations tf32-rounded
-    if (!rc) rc = conv_tc_fprop(g, xr, wt, cout_pad, ep, y, st);
-    cudaFreeAsync(wt, st); cudaFreeAsync(xr, st);
+    long long nx = (long long)B * H * W * Cin, ny = (long long)B * Ho * Wo * Cout;
+    TmpBufs tmp(st);
+    float* wt = tmp.get((size_t)k * k * cout_pad * Cin); float* xr = tmp.get((size_t)nx);
+    float* ys = fmt == ACT_S32 ? tmp.get((size_t)ny) : y;
+    SSDB_REQUIRE(wt && xr && ys, "out of device memory");
+    int rc = pack_filter_t(w_hwio, k * k, Cin, Cout, cout_pad, fmt, wt, st);
+    if (!rc) rc = hook_prepare(x, xr, nx, fmt, st);
+    if (!rc) rc = conv_tc_fprop(g, xr, wt, cout_pad, fmt, ep, ys, st);
+    if (!rc && fmt == ACT_S32) rc = unsplit_copy(ys, y, ny, st);
     return rc;
 }
 
@@ -922,17 +966,24 @@ int ssdb_op_conv_dgrad(int impl, const float* dz, const float* w_hwio, const flo
                        int stride, int dil, int pad_t, int pad_l, int Ho, int Wo, int beta, float* dx, void* stream) {
     SSDB_REQUIRE(dz && w_hwio && dx, "bad arguments");
     ConvGeom g = make_geom(B, H, W, Cin, Cout, k, stride, dil, pad_t, pad_l, Ho, Wo);
-    bool tc = impl == SSDB_CONV_TC || (impl == SSDB_CONV_AUTO && conv_tc_supported_dgrad(g));
     cudaStream_t st = (cudaStream_t)stream;
-    if (!tc) return conv_simt_dgrad(g, dz, w_hwio, mask_x, beta, 0, dx, st);
-    float *zr = nullptr, *wr = nullptr;
-    long long nz = (long long)B * Ho * Wo * Cout, nw = (long long)k * k * Cin * Cout;
-    SSDB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&zr), (size_t)nz * sizeof(float), st));
-    SSDB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&wr), (size_t)nw * sizeof(float), st));
-    int rc = round_tf32_copy(dz, zr, nz, st);
-    if (!rc) rc = round_tf32_copy(w_hwio, wr, nw, st);
-    if (!rc) rc = conv_tc_dgrad(g, zr, wr, mask_x, beta, 0, dx, st);
-    cudaFreeAsync(zr, st); cudaFreeAsync(wr, st);
+    bool tc; int fmt;
+    SSDB_REQUIRE(hook_mode(impl, conv_tc_supported_dgrad(g), &tc, &fmt), "shape not supported by the tcgen05 kernel");
+    if (!tc) return conv_simt_dgrad(g, dz, w_hwio, ACT_F32, mask_x, beta, 0, dx, st);
+    long long nz = (long long)B * Ho * Wo * Cout, nw = (long long)k * k * Cin * Cout, nx = (long long)B * H * W * Cin;
+    TmpBufs tmp(st);
+    float* zr = tmp.get((size_t)nz); float* wr = tmp.get((size_t)nw);
+    SSDB_REQUIRE(zr && wr, "out of device memory");
+    int rc = hook_prepare(dz, zr, nz, fmt, st);
+    if (!rc) rc = hook_prepare(w_hwio, wr, nw, fmt, st);
+    if (rc) return rc;
+    if (fmt == ACT_F32) return conv_tc_dgrad(g, zr, wr, fmt, mask_x, beta, 0, dx, st);
+    float* ms = mask_x ? tmp.get((size_t)nx) : nullptr; float* ds = tmp.get((size_t)nx);
+    SSDB_REQUIRE(ds && (ms || !mask_x), "out of device memory");
+    if (mask_x) { rc = split_copy(mask_x, ms, nx, st); if (rc) return rc; }
+    if (beta) { rc = split_copy(dx, ds, nx, st); if (rc) return rc; }
+    rc = conv_tc_dgrad(g, zr, wr, fmt, ms, beta, 0, ds, st);
+    if (!rc) rc = unsplit_copy(ds, dx, nx, st);
     return rc;
 }
 
@@ -941,28 +992,29 @@ int ssdb_op_conv_wgrad(int impl, const float* x, const float* dz, int B, int H, 
     SSDB_REQUIRE(x && dz && dw, "bad arguments");
     ConvGeom g = make_geom(B, H, W, Cin, Cout, k, stride, dil, pad_t, pad_l, Ho, Wo);
     cudaStream_t st = (cudaStream_t)stream;
-    bool tc = impl == SSDB_CONV_TC || (impl == SSDB_CONV_AUTO && conv_tc_supported_wgrad(g));
-    size_t ws = tc ? conv_tc_wgrad_ws(g) : conv_simt_wgrad_ws(g);
+    bool tc = impl == SSDB_CONV_TC || impl == SSDB_CONV_TC_SPLIT;
+    int fmt = impl == SSDB_CONV_TC ? ACT_F32 : ACT_S32;
+    if (impl == SSDB_CONV_AUTO) { tc = conv_tc_supported_wgrad(g, ACT_S32); fmt = tc ? ACT_S32 : ACT_F32; }
+    if (!tc) fmt = ACT_F32;
+    size_t ws = tc ? conv_tc_wgrad_ws(g, fmt) : conv_simt_wgrad_ws(g);
     if (ws < (size_t)1184 * Cout) ws = (size_t)1184 * Cout;
-    float* partial = nullptr;
-    SSDB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&partial), ws * sizeof(float), st));
+    TmpBufs tmp(st);
+    float* partial = tmp.get(ws);
+    SSDB_REQUIRE(partial, "out of device memory");
     ConvEpilogue ep;
     int rc = SSDB_OK;
     if (tc) {
-        SSDB_REQUIRE(conv_tc_supported_wgrad(g), "shape not supported by the tcgen05 wgrad kernel");
-        float *xr = nullptr, *zr = nullptr;
+        SSDB_REQUIRE(conv_tc_supported_wgrad(g, fmt), "shape not supported by the tcgen05 wgrad kernel");
         long long nx = (long long)B * H * W * Cin, nz = (long long)B * Ho * Wo * Cout;
-        SSDB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&xr), (size_t)nx * sizeof(float), st));
-        SSDB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&zr), (size_t)nz * sizeof(float), st));
-        rc = round_tf32_copy(x, xr, nx, st);
-        if (!rc) rc = round_tf32_copy(dz, zr, nz, st);
-        if (!rc) rc = conv_tc_wgrad(g, xr, zr, dw, db, partial, st);      // db from the all-ones slot (of the ROUNDED dz)
-        cudaFreeAsync(xr, st); cudaFreeAsync(zr, st);
+        float* xr = tmp.get((size_t)nx); float* zr = tmp.get((size_t)nz);
+        SSDB_REQUIRE(xr && zr, "out of device memory");
+        rc = hook_prepare(x, xr, nx, fmt, st);
+        if (!rc) rc = hook_prepare(dz, zr, nz, fmt, st);
+        if (!rc) rc = conv_tc_wgrad(g, xr, zr, fmt, dw, db, partial, st);      // db from the all-ones slot (of the prepared dz)
     } else {
-        rc = conv_simt_wgrad(g, x, dz, ep, dw, partial, st);
-        if (!rc && db) rc = bias_grad(dz, (long long)B * Ho * Wo, Cout, db, partial, st);
+        rc = conv_simt_wgrad(g, x, dz, ACT_F32, ep, dw, partial, st);
+        if (!rc && db) rc = bias_grad(dz, ACT_F32, (long long)B * Ho * Wo, Cout, db, partial, st);
     }
-    cudaFreeAsync(partial, st);
     return rc;
 }
 

@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libssd_b200.so')
 
-CONV_AUTO, CONV_SIMT, CONV_TC = 0, 1, 2
+CONV_AUTO, CONV_SIMT, CONV_TC, CONV_TC_SPLIT = 0, 1, 2, 3
 PARAM, GRAD, MOMENTUM = 0, 1, 2
 
 
@@ -69,6 +69,7 @@ SIGNATURES = {
     'ssdb_set_preprocess': (_i, [_p, _i, C.POINTER(_f)]),
     'ssdb_forward': (_i, [_p, _p, _i, _p, _p]),
     'ssdb_forward_host': (_i, [_p, _p, _i, _p]),
+    'ssdb_read_output_host': (_i, [_p, _i, _p]),
     'ssdb_train_step': (_i, [_p, _p, _p, _p, _p, _i, _i, _f, _f, _f, _f, _i, _p, _p, _p]),
     'ssdb_train_step_host': (_i, [_p, _p, _p, _i, _f, _f, _f, _p, _p]),
     'ssdb_train_step_host_noupdate': (_i, [_p, _p, _p, _i, _f, _p, _p]),
@@ -232,6 +233,12 @@ class Net:
         res = self.result_buffer(B)
         check(lib().ssdb_forward_host(self._h, px, B, res.ctypes.data_as(_p)))
         return res
+
+    def read_output(self, B):
+        """Raw head output [B, A, C+5] (logits | offsets, pre-softmax) of the last forward / train / eval call."""
+        out = np.empty((B, self.num_anchors, self.row), np.float32)
+        check(lib().ssdb_read_output_host(self._h, B, out.ctypes.data_as(_p)))
+        return out
 
     def train_step_host(self, images, labels, lr, momentum, weight_decay, want_result=True, result_out=None):
         x, px = _np(images, np.float32)

@@ -13,6 +13,9 @@ pytestmark = pytest.mark.gpu
 
 FP32_TOL = 2e-5     # fp32 accumulate, different summation order
 TF32_TOL = 2e-3     # tf32 operands (10-bit mantissa), fp32 accumulate; relative to max |ref|
+SPLIT_TOL = 5e-5    # split bf16 operands (hi + lo = 16 significand bits, three MMAs per product), fp32 accumulate
+TC_IMPLS = [(ssdb.CONV_TC_SPLIT, SPLIT_TOL), (ssdb.CONV_TC, TF32_TOL)]     # the engine's default first
+TC_IDS = ['split', 'tf32']
 
 # (B, H, Cin, Cout, k, stride, dil, padding)
 SIMT_CASES = [
@@ -47,9 +50,9 @@ def _check_all(impl, case, tol):
     rng = np.random.default_rng(1)
     dz = rng.standard_normal((B, Ho, Ho, Cout), dtype=np.float32)
     z.backward(torch.tensor(dz).permute(0, 3, 1, 2).to(z.dtype))
-    dw, db = run_wgrad(impl if impl == ssdb.CONV_SIMT else ssdb.CONV_AUTO, x, dz, k, stride, dil, pad)
+    dw, db = run_wgrad(impl, x, dz, k, stride, dil, pad)
     assert rel_err(dw, wt.grad.numpy()) < tol, ('wgrad', case, rel_err(dw, wt.grad.numpy()))
-    assert rel_err(db, bt.grad.numpy()) < (FP32_TOL * 10 if impl == ssdb.CONV_SIMT else TF32_TOL), ('bgrad', case, rel_err(db, bt.grad.numpy()))
+    assert rel_err(db, bt.grad.numpy()) < max(tol, FP32_TOL * 10), ('bgrad', case, rel_err(db, bt.grad.numpy()))
     if Cin % 4 == 0:
         dx_ref = xt.grad.permute(0, 2, 3, 1).numpy()
         mask = x
@@ -66,9 +69,24 @@ def test_simt_conv_matches_oracle(case):
     _check_all(ssdb.CONV_SIMT, case, FP32_TOL)
 
 
+@pytest.mark.parametrize('impl,tol', TC_IMPLS, ids=TC_IDS)
 @pytest.mark.parametrize('case', TC_CASES)
-def test_tcgen05_conv_matches_oracle(case):
-    _check_all(ssdb.CONV_TC, case, TF32_TOL)
+def test_tcgen05_conv_matches_oracle(case, impl, tol):
+    _check_all(impl, case, tol)
+
+
+# real layer shapes of vgg300 (reduced batch) straight against the float64 oracle, split mode:
+# conv1_2, conv4_3, mod_conv6 (dilation 6), conv7 (1x1), head of map 1 (6 boxes, N = 160), conv8_2 (stride 2), conv11_2 (VALID)
+ORACLE_NET_CASES = [
+    (1, 300, 64, 64, 3, 1, 1, 'SAME'), (2, 38, 512, 512, 3, 1, 1, 'SAME'), (2, 19, 512, 1024, 3, 1, 6, 'SAME'),
+    (4, 19, 1024, 1024, 1, 1, 1, 'SAME'), (4, 19, 1024, 160, 3, 1, 1, 'SAME'), (4, 19, 256, 512, 3, 2, 1, 'SAME'),
+    (16, 3, 128, 256, 3, 1, 1, 'VALID'),
+]
+
+
+@pytest.mark.parametrize('case', ORACLE_NET_CASES)
+def test_split_conv_matches_oracle_on_network_shapes(case):
+    _check_all(ssdb.CONV_TC_SPLIT, case, SPLIT_TOL)
 
 
 # every distinct stride-1 conv shape of vgg300 / vgg512 (H, Cin, Cout, k, dil, padding) at a small batch:
@@ -83,48 +101,51 @@ NET_SHAPES = [
 ]
 
 
+@pytest.mark.parametrize('impl,tol', TC_IMPLS, ids=TC_IDS)
 @pytest.mark.parametrize('shape', NET_SHAPES)
-def test_tcgen05_matches_simt_on_network_shapes(shape):
+def test_tcgen05_matches_simt_on_network_shapes(shape, impl, tol):
     H, Cin, Cout, k, dil, padding = shape
     B = 2 if H >= 64 else (4 if H >= 19 else 16)
     x, w, b, pad, Ho = conv_case(B, H, Cin, Cout, k, 1, dil, padding, seed=H * 7 + Cin)
     rng = np.random.default_rng(3)
     dz = rng.standard_normal((B, Ho, Ho, Cout), dtype=np.float32)
     y_s = run_fprop(ssdb.CONV_SIMT, x, w, b, k, 1, dil, pad, Ho)
-    y_t = run_fprop(ssdb.CONV_TC, x, w, b, k, 1, dil, pad, Ho)
-    assert rel_err(y_t, y_s) < TF32_TOL, ('fprop', shape, rel_err(y_t, y_s))
+    y_t = run_fprop(impl, x, w, b, k, 1, dil, pad, Ho)
+    assert rel_err(y_t, y_s) < tol, ('fprop', shape, rel_err(y_t, y_s))
     d_s = run_dgrad(ssdb.CONV_SIMT, dz, w, x, x.shape, k, 1, dil, pad)
-    d_t = run_dgrad(ssdb.CONV_TC, dz, w, x, x.shape, k, 1, dil, pad)
-    assert rel_err(d_t, d_s) < TF32_TOL, ('dgrad', shape, rel_err(d_t, d_s))
+    d_t = run_dgrad(impl, dz, w, x, x.shape, k, 1, dil, pad)
+    assert rel_err(d_t, d_s) < tol, ('dgrad', shape, rel_err(d_t, d_s))
     w_s, _ = run_wgrad(ssdb.CONV_SIMT, x, dz, k, 1, dil, pad)
-    w_t, _ = run_wgrad(ssdb.CONV_TC, x, dz, k, 1, dil, pad)
-    assert rel_err(w_t, w_s) < TF32_TOL, ('wgrad', shape, rel_err(w_t, w_s))
+    w_t, _ = run_wgrad(impl, x, dz, k, 1, dil, pad)
+    assert rel_err(w_t, w_s) < tol, ('wgrad', shape, rel_err(w_t, w_s))
 
 
+@pytest.mark.parametrize('impl,tol', TC_IMPLS, ids=TC_IDS)
 @pytest.mark.parametrize('case', [(4, 19, 256, 512, 3, 2, 1, 'SAME'), (4, 10, 128, 256, 3, 2, 1, 'SAME'), (2, 32, 64, 64, 3, 2, 1, 'SAME')])
-def test_tcgen05_stride2_matches_simt(case):
+def test_tcgen05_stride2_matches_simt(case, impl, tol):
     B, H, Cin, Cout, k, stride, dil, padding = case
     x, w, b, pad, Ho = conv_case(B, H, Cin, Cout, k, stride, dil, padding, seed=11)
     rng = np.random.default_rng(5)
     dz = rng.standard_normal((B, Ho, Ho, Cout), dtype=np.float32)
     w_s, b_s = run_wgrad(ssdb.CONV_SIMT, x, dz, k, stride, dil, pad)
-    w_t, b_t = run_wgrad(ssdb.CONV_TC, x, dz, k, stride, dil, pad)
-    assert rel_err(w_t, w_s) < TF32_TOL, ('wgrad s2', case, rel_err(w_t, w_s))
-    assert rel_err(b_t, b_s) < TF32_TOL, ('bias s2', case, rel_err(b_t, b_s))
+    w_t, b_t = run_wgrad(impl, x, dz, k, stride, dil, pad)
+    assert rel_err(w_t, w_s) < tol, ('wgrad s2', case, rel_err(w_t, w_s))
+    assert rel_err(b_t, b_s) < tol, ('bias s2', case, rel_err(b_t, b_s))
     y_s = run_fprop(ssdb.CONV_SIMT, x, w, b, k, stride, dil, pad, Ho)
-    y_t = run_fprop(ssdb.CONV_TC, x, w, b, k, stride, dil, pad, Ho)
-    assert rel_err(y_t, y_s) < TF32_TOL, ('fprop s2', case, rel_err(y_t, y_s))
+    y_t = run_fprop(impl, x, w, b, k, stride, dil, pad, Ho)
+    assert rel_err(y_t, y_s) < tol, ('fprop s2', case, rel_err(y_t, y_s))
     d_s = run_dgrad(ssdb.CONV_SIMT, dz, w, x, x.shape, k, stride, dil, pad)
-    d_t = run_dgrad(ssdb.CONV_TC, dz, w, x, x.shape, k, stride, dil, pad)
-    assert rel_err(d_t, d_s) < TF32_TOL, ('dgrad s2', case, rel_err(d_t, d_s))
+    d_t = run_dgrad(impl, dz, w, x, x.shape, k, stride, dil, pad)
+    assert rel_err(d_t, d_s) < tol, ('dgrad s2', case, rel_err(d_t, d_s))
     old = rng.standard_normal(x.shape, dtype=np.float32)
     d_s = run_dgrad(ssdb.CONV_SIMT, dz, w, None, x.shape, k, stride, dil, pad, beta=1, dx0=old)
-    d_t = run_dgrad(ssdb.CONV_TC, dz, w, None, x.shape, k, stride, dil, pad, beta=1, dx0=old)
-    assert rel_err(d_t, d_s) < TF32_TOL, ('dgrad s2 beta', case, rel_err(d_t, d_s))
+    d_t = run_dgrad(impl, dz, w, None, x.shape, k, stride, dil, pad, beta=1, dx0=old)
+    assert rel_err(d_t, d_s) < tol, ('dgrad s2 beta', case, rel_err(d_t, d_s))
 
 
+@pytest.mark.parametrize('impl,tol', TC_IMPLS, ids=TC_IDS)
 @pytest.mark.parametrize('case', [(2, 64, 64, 64), (3, 40, 128, 128), (2, 38, 512, 128), (4, 19, 64, 96), (2, 150, 64, 128), (2, 38, 256, 512), (4, 19, 512, 1024), (2, 75, 128, 256)])
-def test_tcgen05_row_window_wgrad_matches_simt(case):
+def test_tcgen05_row_window_wgrad_matches_simt(case, impl, tol):
     """3x3 SAME layers with <= 128 output channels take the row-window wgrad kernel (one x box per filter row)."""
     B, H, Cin, Cout = case
     x, w, b, pad, Ho = conv_case(B, H, Cin, Cout, 3, 1, 1, 'SAME', seed=H + Cout)
@@ -133,8 +154,8 @@ def test_tcgen05_row_window_wgrad_matches_simt(case):
     w_s, b_s = run_wgrad(ssdb.CONV_SIMT, x, dz, 3, 1, 1, pad)
     os.environ['SSDB_WG_RW_MAXN'] = '1024'          # exercise the window kernel on the wide layers too (N tiles of 128)
     try:
-        w_t, b_t = run_wgrad(ssdb.CONV_TC, x, dz, 3, 1, 1, pad)
+        w_t, b_t = run_wgrad(impl, x, dz, 3, 1, 1, pad)
     finally:
         os.environ.pop('SSDB_WG_RW_MAXN', None)
-    assert rel_err(w_t, w_s) < TF32_TOL, ('wgrad rw', case, rel_err(w_t, w_s))
-    assert rel_err(b_t, b_s) < TF32_TOL, ('bias rw', case, rel_err(b_t, b_s))
+    assert rel_err(w_t, w_s) < tol, ('wgrad rw', case, rel_err(w_t, w_s))
+    assert rel_err(b_t, b_s) < tol, ('bias rw', case, rel_err(b_t, b_s))

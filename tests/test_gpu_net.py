@@ -1,5 +1,10 @@
 """GPU parity of the whole engine against the torch restatement of the reference graph:
-forward result, losses, every parameter gradient and one Momentum step."""
+raw logits, offsets, softmax result, losses, every parameter gradient and one Momentum step.
+
+north_star's bar: class logits / box offsets within 1e-3 (relative, fp32).  The engine's DEFAULT mode
+('split': tensor cores with split bf16 operands) must meet it with a wide margin on both presets; the
+fp32 CUDA-core mode ('simt') is the exact cross-check; 'tf32' is the comparison mode that does NOT meet the
+bar (10-bit significands: ~1.5e-3) and is only checked against its own known floor."""
 import json
 import os
 
@@ -14,6 +19,10 @@ import synth
 
 pytestmark = pytest.mark.gpu
 
+NORTH_STAR_TOL = 1e-3
+# measured headroom of the product mode (B200: 1.3e-4 / 1.4e-4); a regression to tf32-grade arithmetic would trip this long before 1e-3
+SPLIT_EXPECT = 3e-4
+
 
 def _load(net, P):
     names = dict(net.tensors())
@@ -27,69 +36,61 @@ def _relmax(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
-@pytest.mark.parametrize('mode', ['simt', 'auto'])
-@pytest.mark.parametrize('preset,B', [('vgg300', 2), ('vgg512', 1)])
-def test_forward_and_train_step(preset, B, mode):
-    os.environ['SSDB_CONV'] = mode
+def _make(preset, B, mode):
+    if mode == 'default':
+        os.environ.pop('SSDB_CONV', None)           # the product path: whatever the library picks with no override
+    else:
+        os.environ['SSDB_CONV'] = mode
     try:
-        net = ssdb.Net(preset, 20, max_batch=B)
+        return ssdb.Net(preset, 20, max_batch=B)
     finally:
         os.environ.pop('SSDB_CONV', None)
-    tol = 1e-3 if mode == 'simt' else 4e-3     # gradients: tol*10 (ReLU / max-pool / mining decisions can flip)
+
+
+@pytest.mark.parametrize('mode', ['default', 'simt', 'tf32'])
+@pytest.mark.parametrize('preset,B', [('vgg300', 2), ('vgg512', 1)])
+def test_forward_and_train_step(preset, B, mode):
+    net = _make(preset, B, mode)
     side = bo.PRESETS[preset]['image']
     P = no.init_params(preset, dtype=torch.float64)
     _load(net, P)
     anc = bo.anchors(preset); aabs = bo.anchors_abs(anc)
     x = synth.images(0, B, side)
     labels = np.stack([bo.make_labels(synth.gt_boxes(i), anc, aabs, 20)[0] for i in range(B)])
-    # forward only
-    res = net.forward_host(x)
-    out = no.forward(P, torch.tensor(x), preset)
-    ref = no.result_from_output(out).numpy()
+    # ---------------- forward: raw logits, offsets, softmax
+    res = net.forward_host(x).copy()
+    raw = net.read_output(B)
+    out = no.forward(P, torch.tensor(x), preset).numpy()
+    ref = no.result_from_output(torch.tensor(out)).numpy()
     report = {'preset': preset, 'mode': mode, 'B': B}
+    report['logits_rel'] = _relmax(raw[..., :21], out[..., :21])          # relative to max |logit|
+    report['locator_rel'] = _relmax(raw[..., 21:], out[..., 21:])
+    report['locator_rel_rms'] = float(np.sqrt(((raw[..., 21:] - out[..., 21:]) ** 2).mean() / (out[..., 21:] ** 2).mean()))
     report['softmax_abs'] = float(np.abs(res[..., :21] - ref[..., :21]).max())
-    report['locator_rel'] = _relmax(res[..., 21:], ref[..., 21:])
-    report['locator_rel_rms'] = float(np.sqrt(((res[..., 21:] - ref[..., 21:]) ** 2).mean() / (ref[..., 21:] ** 2).mean()))
-    if mode == 'simt':
-        # fp32 accumulate in another order than the float64 oracle; |logit| ~ 1e3 on this input, so 1e-6
-        # relative on a logit is ~1e-3 absolute before the softmax
-        assert report['softmax_abs'] < 3e-3
+    report['argmax_agree'] = float((res[..., :21].argmax(-1) == ref[..., :21].argmax(-1)).mean())
+    assert np.array_equal(res[..., 21:], raw[..., 21:]), 'result offsets are not the raw head offsets'
+    print('PARITY-FWD', json.dumps(report))
+    if mode == 'tf32':
+        # comparison mode: sits on the error floor of tf32 operands (profiles/r1_tf32_floor_*.json: 1.3e-3 / 1.6e-3 max-norm)
+        assert report['logits_rel'] < 4e-3 and report['locator_rel'] < 4e-3, report
+        assert report['argmax_agree'] > 0.99
     else:
-        # tf32 operands: with |logit| ~ 1e3 on this synthetic input an error of 1e-3 relative moves softmax
-        # scores of near-tied classes; the linear outputs (offsets, same kernels) carry the tolerance check
-        agree = (res[..., :21].argmax(-1) == ref[..., :21].argmax(-1)).mean()
-        report['argmax_agree'] = float(agree)
-        assert agree > 0.99, agree
-        assert report['softmax_abs'] < 2e-2
-        # The same graph with tf32 rounding exactly where the engine rounds (filters, pre-processed image, conv outputs that
-        # feed convs, L2-norm output), exact products, float64 accumulation: the error FLOOR of tf32 operands for this
-        # network (tools/tf32_floor.py, profiles/r1_tf32_floor_*.json: 1.0e-3 RMS, 1.3-1.6e-3 max-norm vs float64).  The
-        # engine must not be worse than that floor by more than rounding luck.  (It cannot match the model element by
-        # element: fp32 accumulation noise flips the tf32 rounding of activations near a grid midpoint; measured on B200,
-        # vgg300: engine vs model 1.31e-3 max-norm / 0.91e-3 RMS, i.e. the two errors are ~60 % correlated.)
-        with torch.no_grad():
-            model = no.result_from_output(no.forward(P, torch.tensor(x), preset, producer_round=no.round_tf32)).numpy()
-        rms = lambda a, b: float(np.sqrt(((a - b) ** 2).mean() / (b ** 2).mean()))
-        report['floor_locator_rel'] = _relmax(model[..., 21:], ref[..., 21:])
-        report['floor_locator_rel_rms'] = rms(model[..., 21:], ref[..., 21:])
-        report['locator_rel_vs_tf32_model'] = _relmax(res[..., 21:], model[..., 21:])
-        report['locator_rel_rms_vs_tf32_model'] = rms(res[..., 21:], model[..., 21:])
-        print('PARITY-FLOOR', json.dumps({k: report[k] for k in report if 'floor' in k or 'model' in k}))
-        assert report['locator_rel_rms'] <= 1.25 * report['floor_locator_rel_rms'], report
-        assert report['locator_rel'] <= 1.5 * report['floor_locator_rel'], report
-        assert report['locator_rel_vs_tf32_model'] < 4e-3
-    assert _relmax(res[..., 21:], ref[..., 21:]) < tol
-    # one training step
+        assert report['logits_rel'] < NORTH_STAR_TOL, report
+        assert report['locator_rel'] < NORTH_STAR_TOL, report
+        assert report['logits_rel'] < SPLIT_EXPECT and report['locator_rel'] < SPLIT_EXPECT, report
+        # |logit| ~ 1e3 on this synthetic input: 2e-5 relative on a logit is 2e-2 absolute before the softmax
+        assert report['argmax_agree'] > 0.9995, report
+        assert report['softmax_abs'] < (3e-3 if mode == 'simt' else 5e-2), report
+    # ---------------- one training step
+    tol = 4e-3 if mode == 'tf32' else NORTH_STAR_TOL
     V = {k: torch.zeros_like(v) for k, v in P.items()}
     L, out0, grads = no.train_step(P, V, torch.tensor(x), torch.tensor(labels), preset, lr=0.00075, momentum=0.9, weight_decay=0.0005)
     res2, losses = net.train_step_host(x, labels, 0.00075, 0.9, 0.0005)
     for key, i in (('total', 0), ('localization', 1), ('confidence', 2), ('l2', 3)):
-        assert abs(losses[i] - L[key]) <= tol * 5 * abs(L[key]) + 1e-6, (key, losses[i], L[key])
-    # Gradients go through ReLU masks, max-pool arg-maxes and the hard-negative selection: forward noise flips
-    # some of those decisions, so the gradient error is NOT proportional to the forward error.  Pure fp32 vs the
-    # float64 oracle already differs by ~3e-3 (max-norm); tf32 forward noise is ~1e3 x larger, hence ~sqrt(1e3) x
-    # more flip noise.  Each tensor-core kernel is checked tightly on every network shape in test_gpu_conv.py.
-    gtol = 1e-2 if mode == 'simt' else 0.2
+        assert abs(losses[i] - L[key]) <= tol * abs(L[key]) + 1e-6, (key, losses[i], L[key])
+    # Gradients go through ReLU masks, max-pool arg-maxes and the hard-negative selection, so forward noise can flip
+    # decisions; tests/test_gpu_grad.py removes the flips (margins) and checks 2e-3.  Here: the plain synthetic input.
+    gtol = {'simt': 1e-2, 'default': 2e-2, 'tf32': 0.2}[mode]
     bad = []
     worst = (None, 0.0, 0.0)
     for k, shape in net.tensors():
@@ -106,8 +107,9 @@ def test_forward_and_train_step(preset, B, mode):
     report['losses'] = [float(v) for v in losses]
     report['losses_ref'] = [L['total'], L['localization'], L['confidence'], L['l2']]
     report['worst_grad'] = [worst[0], worst[1], worst[2]]
-    os.makedirs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out'), exist_ok=True)
-    with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out', 'net_parity_%s_%s.json' % (preset, mode)), 'w') as f:
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, 'gpurun_out'), exist_ok=True)
+    with open(os.path.join(root, 'gpurun_out', 'net_parity_%s_%s.json' % (preset, mode)), 'w') as f:
         json.dump(report, f)
     print('PARITY', json.dumps(report))
     assert not bad, bad[:10]
