@@ -149,6 +149,13 @@ int ssdb_op_conv_wgrad(int impl, const float* x, const float* dz,
                        int B, int H, int W, int Cin, int Cout, int k, int stride, int dil,
                        int pad_t, int pad_l, int Ho, int Wo, float* dw, float* db, void* stream);
 
+/* Layer micro-benchmark hook: device time (ms, CUDA events, 2 warm-up launches, mean of `iters`) of ONE convolution kernel
+ * of the engine on synthetic data already in the engine's operand format (activations half zeros like a ReLU output,
+ * gradients dense), i.e. the bare kernel as a training step launches it.  kind: 0 fprop (+bias+ReLU), 1 dgrad
+ * (with_mask: ReLU mask of x; beta: accumulate), 2 wgrad (+bias gradient).  impl as above (AUTO = split tensor-core). */
+int ssdb_op_conv_bench(int kind, int impl, int B, int H, int W, int Cin, int Cout, int k, int stride, int dil,
+                       int pad_t, int pad_l, int Ho, int Wo, int with_mask, int beta, int iters, float* ms_out);
+
 /* ------------------------------------------------------------------------
  * Network engine.  Replaces SSDVGG (ssdvgg.py:87-649) + the tf.Session that
  * runs it (train.py:166,262-266; infer.py:211,225-227).
@@ -208,6 +215,27 @@ int ssdb_train_step_host(ssdb_net* net, const float* images_host, const float* l
  * update -- the caller all-reduces ssdb_flat_buffer(net, 1) across ranks and then calls ssdb_apply_update(1/world). */
 int ssdb_train_step_host_noupdate(ssdb_net* net, const float* images_host, const float* labels_host, int B,
                                   float weight_decay, float* losses_out_host, float* result_host);
+/* The same training step fed with RAW ground truth instead of the dense label tensor: anchor matching
+ * (LabelCreatorTransform, transforms.py:72-114, which the reference runs in its data-loader workers and ships to the
+ * device as 873 KB of labels per image, train.py:257-266) happens inside the fused match + loss kernels, in exact
+ * integer arithmetic; the host -> device traffic per image drops from 1.95 MB to 1.08 MB.
+ *   gt        [B, G, 5] float64 rows (labelid, cx, cy, w, h), proportional coordinates like utils.Box; G <= 128
+ *   gt_count  [B] int32 valid rows per image (0 allowed: an all-background image contributes zero loss, ssdvgg.py:417-419)
+ *   apply_update 1: full step; 0: stop after the backward, gradients in the flat buffer (data-parallel callers
+ *             all-reduce, then ssdb_apply_update); -1: forward + loss only (the validation pass, train.py:291-294)
+ *   match_out [B, A] int32 owner GT row per anchor, -1 = background (may be NULL)
+ * Label ids outside [0, C) are rejected with SSDB_EINVAL (the reference would raise an IndexError). */
+int ssdb_train_step_host_gt(ssdb_net* net, const float* images_host, const double* gt_host, const int* gt_count_host,
+                            int G, int B, float lr, float momentum, float weight_decay, int apply_update,
+                            float* losses_out_host, float* result_host, int* match_out_host);
+
+/* infer.py:225-235 / detect.py:103-112 as ONE call: sess.run(net.result) followed per image by decode_boxes +
+ * suppress_overlaps.  The result tensor stays in device memory, the fused decode + top-k + class-wise NMS kernels
+ * (ssdb_decode_nms) read it there, and only the detections come back: [B, cap_eff, 8] int32 rows + [B, 2] counts in
+ * the layout of ssdb_decode_nms (cap <= 0: no cap).  result_host (may be NULL) additionally receives net.result. */
+int ssdb_forward_detect_host(ssdb_net* net, const float* images_host, int B, float conf_thr, int cap, double iou_thr,
+                             int* dets_out_host, int* counts_out_host, float* result_host);
+
 /* validation pass (train.py:291-294): forward + loss, no backward */
 int ssdb_eval_step(ssdb_net* net, const float* images_dev, const float* labels_dev, int B,
                    float weight_decay, float* losses_out_dev, float* result_dev, void* stream);
@@ -224,6 +252,13 @@ int ssdb_pinned_free(void* host_ptr);
  * (tf.train.Saver, train.py:208,336-343; the VGG saved-model, ssdvgg.py:190-207), used by tf_bundle.py to read / write
  * those files without TensorFlow when payloads are hundreds of megabytes. */
 unsigned int ssdb_crc32c(unsigned int crc, const void* data_host, size_t bytes);
+
+/* Test / diagnosis hooks: an intermediate tensor of the last step as plain float32 NHWC on the host.
+ * name = an op of the plan ("conv1_1" .. "conv11_2", "pool1" .. "pool4", "mod_pool5", "l2_norm_conv4_3") for the activation it
+ * wrote, "grad:<op>" for the gradient with respect to it, "output" / "output_grad" for the raw head output [B, A, C+5] and
+ * its gradient.  ssdb_debug_shape: (H, W, C) of an op's activation. */
+int ssdb_debug_read(ssdb_net* net, const char* name, int B, float* host_out, long long count);
+int ssdb_debug_shape(const ssdb_net* net, const char* name, int shape_out[3]);
 
 /* number of kernels this library launched since load (bench.py's gpu_launches) */
 long long ssdb_launch_count(void);

@@ -94,8 +94,9 @@ def _same_pad(n, k_eff, stride):
     return total // 2, total - total // 2
 
 
-def conv_tf(x, w_hwio, b, stride=1, dilation=1, padding='SAME', relu=True):
-    """tf.nn.conv2d / atrous_conv2d + bias_add (+ relu) on NCHW x with TF padding."""
+def conv_tf(x, w_hwio, b, stride=1, dilation=1, padding='SAME', relu=True, relu_mask=None):
+    """tf.nn.conv2d / atrous_conv2d + bias_add (+ relu) on NCHW x with TF padding.
+    relu_mask (0/1 tensor): use these ReLU decisions instead of the sign of this pass's own pre-activations."""
     k = w_hwio.shape[0]
     if padding == 'SAME':
         ke = (k - 1) * dilation + 1
@@ -103,15 +104,22 @@ def conv_tf(x, w_hwio, b, stride=1, dilation=1, padding='SAME', relu=True):
         pl, pr = _same_pad(x.shape[3], ke, stride)
         x = F.pad(x, (pl, pr, pt, pb))
     y = F.conv2d(x, w_hwio.permute(3, 2, 0, 1), b, stride=stride, dilation=dilation)
+    if relu and relu_mask is not None:
+        return y * relu_mask
     return F.relu(y) if relu else y
 
 
-def max_pool_tf(x, k, stride):
-    """tf.nn.max_pool padding='SAME' (pad value -inf)."""
+def max_pool_tf(x, k, stride, route_like=None):
+    """tf.nn.max_pool padding='SAME' (pad value -inf).
+    route_like: a tensor of x's shape whose window arg-maxes are used instead of x's own (x is gathered at them)."""
     pt, pb = _same_pad(x.shape[2], k, stride)
     pl, pr = _same_pad(x.shape[3], k, stride)
     x = F.pad(x, (pl, pr, pt, pb), value=float('-inf'))
-    return F.max_pool2d(x, k, stride)
+    if route_like is None:
+        return F.max_pool2d(x, k, stride)
+    r = F.pad(route_like.to(x.dtype), (pl, pr, pt, pb), value=float('-inf'))
+    _, idx = F.max_pool2d(r, k, stride, return_indices=True)
+    return x.flatten(2).gather(2, idx.flatten(2)).view_as(idx)
 
 
 def preprocess(x_nhwc):
@@ -129,33 +137,39 @@ def round_tf32(t):
     return bits.view(torch.float32).to(t.dtype)
 
 
-def forward(P, x_nhwc, preset_name, num_classes=20, taps=None, producer_round=None):
+def forward(P, x_nhwc, preset_name, num_classes=20, taps=None, producer_round=None, decisions=None):
     """Returns output [B, A, C+5] (logits | offsets), pre-softmax (ssdvgg.py:365-366).
     `taps`, if a dict, receives the intermediate feature maps (NCHW) by name.
     `producer_round` (e.g. round_tf32) is applied where the engine rounds: to the pre-processed image, to every filter,
     to the output of every convolution that feeds another one (after bias + ReLU) and to the L2-norm output.  With exact
     products and wide accumulation this is the arithmetic model of the engine's tensor-core path: its distance from the
     plain float64 graph is the error floor of tf32 operands for this network, independent of any kernel, and the engine
-    itself should match the model far more tightly than it matches float64."""
+    itself should match the model far more tightly than it matches float64.
+    `decisions` (dict name -> NCHW activation tensor of ANOTHER forward pass of the same network, e.g. the engine's): every
+    non-linear decision is taken from it -- the ReLU of conv <name> passes where decisions[<name>] > 0, the max-pool <name>
+    routes to the window arg-max of its input there (decisions[<producer of its input>]).  The graph then is the same
+    piecewise-linear function as the other pass, so gradients can be compared without decision flips."""
     maps = PRESETS[preset_name]['maps']
     spec = {s['name']: s for s in conv_specs(preset_name, num_classes)}
     rnd = producer_round if producer_round is not None else (lambda t: t)
+    dec = decisions or {}
     def conv(name, x):
         s = spec[name]
+        mask = (dec[name] > 0).to(x.dtype) if (name in dec and s['relu']) else None
         y = conv_tf(x, rnd(P[name + '/filter']), P[name + '/biases'], s['stride'], s['dilation'],
-                    s['padding'], s['relu'])
+                    s['padding'], s['relu'], relu_mask=mask)
         if not name.startswith('classifiers/'):
             y = rnd(y)
         if taps is not None:
             taps[name] = y
         return y
     x = rnd(preprocess(x_nhwc.to(P['conv1_1/filter'].dtype)))
-    x = conv('conv1_2', conv('conv1_1', x)); x = max_pool_tf(x, 2, 2)
-    x = conv('conv2_2', conv('conv2_1', x)); x = max_pool_tf(x, 2, 2)
-    x = conv('conv3_3', conv('conv3_2', conv('conv3_1', x))); x = max_pool_tf(x, 2, 2)
-    c43 = conv('conv4_3', conv('conv4_2', conv('conv4_1', x))); x = max_pool_tf(c43, 2, 2)
+    x = conv('conv1_2', conv('conv1_1', x)); x = max_pool_tf(x, 2, 2, dec.get('conv1_2'))
+    x = conv('conv2_2', conv('conv2_1', x)); x = max_pool_tf(x, 2, 2, dec.get('conv2_2'))
+    x = conv('conv3_3', conv('conv3_2', conv('conv3_1', x))); x = max_pool_tf(x, 2, 2, dec.get('conv3_3'))
+    c43 = conv('conv4_3', conv('conv4_2', conv('conv4_1', x))); x = max_pool_tf(c43, 2, 2, dec.get('conv4_3'))
     x = conv('conv5_3', conv('conv5_2', conv('conv5_1', x)))
-    x = max_pool_tf(x, 3, 1)                                       # mod_pool5
+    x = max_pool_tf(x, 3, 1, dec.get('conv5_3'))                   # mod_pool5
     c7 = conv('mod_conv7', conv('mod_conv6', x))
     c82 = conv('conv8_2', conv('conv8_1', c7))
     c92 = conv('conv9_2', conv('conv9_1', c82))
@@ -187,8 +201,9 @@ def result_from_output(out, num_classes=20):
     return torch.cat([torch.softmax(out[..., :nc], dim=-1), out[..., nc:]], dim=-1)
 
 
-def multibox_loss(out, labels, num_classes=20):
-    """(confidence_loss, localization_loss) restating ssdvgg.py:380-560."""
+def multibox_loss(out, labels, num_classes=20, selected=None):
+    """(confidence_loss, localization_loss) restating ssdvgg.py:380-560.
+    selected ([B, A] bool): use this set of hard negatives instead of this pass's own top_k (see forward(decisions=...))."""
     nc = num_classes + 1
     logits, loc = out[..., :nc], out[..., nc:]
     gt_cl, gt_loc = labels[..., :nc], labels[..., nc:]
@@ -205,6 +220,8 @@ def multibox_loss(out, labels, num_classes=20):
     kmax = torch.minimum(neg_num, 3 * pos_num).unsqueeze(1)
     keep = torch.arange(A).unsqueeze(0) < kmax
     neg_sum = torch.where(keep, top, torch.zeros_like(top)).sum(dim=-1)
+    if selected is not None:
+        neg_sum = torch.where(selected & ~pos_mask, ce, zeros).sum(dim=-1)
     safe = torch.where(pos_num == 0, torch.full_like(ce[:, 0], 10e-15), pos_num.to(ce.dtype))
     conf = torch.where(pos_num == 0, torch.zeros_like(pos_sum), (pos_sum + neg_sum) / safe)
     d = loc - gt_loc
@@ -220,21 +237,21 @@ def l2_term(P):
     return sum((v * v).sum() / 2 for k, v in P.items() if k.endswith('/filter'))
 
 
-def losses(P, x_nhwc, labels, preset_name, num_classes=20, weight_decay=0.0005):
-    out = forward(P, x_nhwc, preset_name, num_classes)
-    conf, loc = multibox_loss(out, labels.to(out.dtype), num_classes)
+def losses(P, x_nhwc, labels, preset_name, num_classes=20, weight_decay=0.0005, decisions=None, selected=None):
+    out = forward(P, x_nhwc, preset_name, num_classes, decisions=decisions)
+    conf, loc = multibox_loss(out, labels.to(out.dtype), num_classes, selected=selected)
     l2 = weight_decay * l2_term(P)
     return dict(total=conf + loc + l2, confidence=conf, localization=loc, l2=l2), out
 
 
 def train_step(P, V, x_nhwc, labels, preset_name, num_classes=20, lr=0.00075,
-               momentum=0.9, weight_decay=0.0005):
+               momentum=0.9, weight_decay=0.0005, decisions=None, selected=None):
     """One MomentumOptimizer.minimize step (accum = mu*accum + g; var -= lr*accum).
     Mutates P and V in place; returns (losses, pre-update output, grads)."""
     for v in P.values():
         v.requires_grad_(True)
         v.grad = None
-    L, out = losses(P, x_nhwc, labels, preset_name, num_classes, weight_decay)
+    L, out = losses(P, x_nhwc, labels, preset_name, num_classes, weight_decay, decisions, selected)
     L['total'].backward()
     grads = {k: v.grad.detach().clone() for k, v in P.items()}
     with torch.no_grad():

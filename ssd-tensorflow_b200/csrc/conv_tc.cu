@@ -195,7 +195,7 @@ struct TcArgs {
 // the bottleneck of the short-K layers).  Each warp therefore stages its 32 pixel x 32 channel chunk in 4 KB of shared
 // memory (16-byte slots XOR-swizzled by row) and writes it back with 8 lanes per pixel: every instruction moves four
 // complete 128-byte rows, and the bias / ReLU / tf32 rounding (fprop) or beta / ReLU-mask (dgrad) reads are coalesced too.
-template <int FMT>
+template <int FMT, bool SCATTER>
 __device__ __forceinline__ void epilogue_tile(const TcArgs& p, int mt, int nt, uint32_t t_row, int row, int lane, float4* stage) {
     const int rows_valid = p.TW * p.TH * p.TN;
     const int tx = mt % p.tiles_x; const int r1 = mt / p.tiles_x;
@@ -212,7 +212,7 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& p, int mt, int nt, u
         tc_ld32(t_row + (uint32_t)c0, r);
         tc_wait_ld();
         const int ch0 = nt * p.block_n + c0;
-        if (p.mode == 0 && p.scatter) {
+        if (SCATTER) {
             if (ok) {
                 const int hw = p.Hd * p.Wd;
                 const int pimg = y * p.Wd + x;
@@ -234,6 +234,77 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& p, int mt, int nt, u
             stage[lane * 8 + (j4 ^ (lane & 7))] = make_float4(__uint_as_float(r[j4 * 4]), __uint_as_float(r[j4 * 4 + 1]),
                                                               __uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3]));
         __syncwarp();
+        if (FMT == ACT_S32) {
+            // split storage: 4 lanes per pixel, 8 channels each = one 16-byte piece of the pixel's 64 high-part bytes and
+            // one of its 64 low-part bytes; an instruction moves 8 rows x 64 contiguous bytes.  Every mask / old-value load
+            // of the chunk is issued as RAW bits before anything consumes them (a load -> convert chain per row would
+            // expose the memory latency once per row: measured 4.6 us per chunk).
+            const int q = lane & 3, sub8 = lane >> 2;
+            const int chs = ch0 + q * 8;
+            const bool chok8 = chs < p.cd_valid;
+            long long pr8[4];
+#pragma unroll
+            for (int it = 0; it < 4; ++it) pr8[it] = __shfl_sync(0xffffffffu, pix, it * 8 + sub8);
+            float bv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bv[j] = 0.f;
+            if (p.mode == 0 && p.bias && chok8) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + chs)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + chs + 4));
+                bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+            }
+            uint4 mraw[4], ohi[4], olo[4];
+            const bool want_mask = p.mode == 1 && p.mask != nullptr, want_old = p.mode == 1 && p.beta;
+            if (want_mask) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {      // rows that are not stored read row 0 (a valid address) instead of branching
+                    const long long e = (pr8[it] >= 0 && chok8) ? pr8[it] * p.Cd + chs : 0;
+                    mraw[it] = __ldg(reinterpret_cast<const uint4*>(s32_addr(p.mask, e)));
+                }
+            }
+            if (want_old) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const long long e = (pr8[it] >= 0 && chok8) ? pr8[it] * p.Cd + chs : 0;
+                    const unsigned char* a = s32_addr(p.dst, e);
+                    ohi[it] = *reinterpret_cast<const uint4*>(a);
+                    olo[it] = *reinterpret_cast<const uint4*>(a + 64);
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int rr = it * 8 + sub8;
+                const float4 v0 = stage[rr * 8 + ((2 * q) ^ (rr & 7))], v1 = stage[rr * 8 + ((2 * q + 1) ^ (rr & 7))];
+                float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                if (p.mode == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { v[j] += bv[j]; if (p.relu) v[j] = fmaxf(v[j], 0.f); }
+                } else {
+                    if (want_old) {
+                        const uint32_t oh[4] = {ohi[it].x, ohi[it].y, ohi[it].z, ohi[it].w}, ol[4] = {olo[it].x, olo[it].y, olo[it].z, olo[it].w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            v[2 * j] += bf16_lo_f(oh[j]) + bf16_lo_f(ol[j]);
+                            v[2 * j + 1] += bf16_hi_f(oh[j]) + bf16_hi_f(ol[j]);
+                        }
+                    }
+                    if (want_mask) {
+                        const uint32_t mh[4] = {mraw[it].x, mraw[it].y, mraw[it].z, mraw[it].w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {        // x > 0  <=>  its high part is a positive bf16 (sign clear, not zero)
+                            if (!((mh[j] & 0x8000u) == 0u && (mh[j] & 0x7fffu) != 0u)) v[2 * j] = 0.f;
+                            if (!((mh[j] & 0x80000000u) == 0u && (mh[j] & 0x7fff0000u) != 0u)) v[2 * j + 1] = 0.f;
+                        }
+                    }
+                }
+                if (pr8[it] < 0 || !chok8) continue;
+                uint4 h, l;
+                split2(v[0], v[1], h.x, l.x); split2(v[2], v[3], h.y, l.y); split2(v[4], v[5], h.z, l.z); split2(v[6], v[7], h.w, l.w);
+                unsigned char* a = s32_addr(p.dst, pr8[it] * p.Cd + chs);
+                *reinterpret_cast<uint4*>(a) = h;
+                *reinterpret_cast<uint4*>(a + 64) = l;
+            }
+            continue;
+        }
         const int c4 = lane & 7, sub = lane >> 3;
         const int ch = ch0 + c4 * 4;
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -277,6 +348,8 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& p, int mt, int nt, u
     }
 }
 
+// FMT: operand / storage format (ACT_F32 = tf32 MMAs, ACT_S32 = split bf16 MMAs); SCATTER: the head epilogue (fprop only)
+template <int FMT, bool SCATTER>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w, const TcArgs p) {
     extern __shared__ unsigned char smem_raw[];
@@ -352,7 +425,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
         // ===================== MMA issuer =====================
         if (elect_one_sync()) {
             // instruction descriptor: fp32 accumulate, A / B format tf32 (2) or bf16 (1), both K-major, N, M
-            const uint32_t fmt = p.split ? 1u : 2u;
+            const uint32_t fmt = FMT == ACT_S32 ? 1u : 2u;
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -375,7 +448,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
                             const uint64_t a0 = make_kmajor_desc(sa + woff, (uint32_t)p.a_sbo, p.use_bo);
                             const uint64_t a1 = make_kmajor_desc(sa + (uint32_t)p.a_slot + woff, (uint32_t)p.a_sbo, p.use_bo);
                             const uint64_t bd = make_kmajor_desc(sa + b_off + (uint32_t)t * b_bytes);
-                            if (p.split) {
+                            if (FMT == ACT_S32) {
                                 // a 128-byte row = 16 hi | 16 hi | 16 lo | 16 lo (bf16) of 32 channels: K offsets 0, 1 = high parts,
                                 // 2, 3 = low parts (32 bytes = +2 in 16-byte units each).  x*w ~ xh*wh + xl*wh + xh*wl.
 #pragma unroll
@@ -417,13 +490,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
-            if (p.split) {
-                epilogue_tile<ACT_S32>(p, p.mtu * mp, nt, t_row, row, lane, stage);
-                if (two) epilogue_tile<ACT_S32>(p, 2 * mp + 1, nt, t_row + (uint32_t)noff, row, lane, stage);
-            } else {
-                epilogue_tile<ACT_F32>(p, p.mtu * mp, nt, t_row, row, lane, stage);
-                if (two) epilogue_tile<ACT_F32>(p, 2 * mp + 1, nt, t_row + (uint32_t)noff, row, lane, stage);
-            }
+            for (int j = 0; j < (two ? 2 : 1); ++j)      // one copy of the epilogue code for both tiles of a unit
+                epilogue_tile<FMT, SCATTER>(p, p.mtu * mp + j, nt, t_row + (uint32_t)(j * noff), row, lane, stage);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
@@ -1176,6 +1244,190 @@ conv_tc_wgrad_rw_s_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
     }
 }
 
+// ------------------------------------------------------------------ window wgrad, roles swapped ("rw2"): 3x3, stride 1, SAME, Cout % 128 == 0
+// The plain split kernel moves 16 operand blocks per 16 pixels for two 128 x 256 accumulators and is bound by the L2 -> SM
+// rate (measured: tensor pipe 62 %); the window kernel above pays 25 % dummy MMA rows and stops at N = 128.  Here dz is the
+// M operand (128 output channels = 4 blocks) and x the N operand: the three kw taps of a filter row are three 32-channel
+// blocks ONE PIXEL apart in the same x box (LBO = dil * 64 bytes), so N = 96 with no dummy window, and the three kh taps are
+// three accumulators fed from lines j + kh * dil of that box.  Per 64 output pixels a unit loads one (8 + 2 dil) x (PH + 2 dil)
+// x box of ONE channel block (hi + lo) and the dz blocks of its 128 output channels: 45 KB per 1728 MMA cycles = 26 B / cycle,
+// well under the L2 rate, with every MMA row and column useful.  The bias gradient is one more N = 16 accumulator whose B
+// operand is a resident block of ones.  Accumulator lanes are OUTPUT channels, so the epilogue stores are coalesced along Cout.
+struct WgR2Args {
+    int PH, dil;                    // output lines per stage (even); dilation = padding
+    int ptx, pty, ptn;              // pixel tiling of the dz map (x in steps of 8, one image per box)
+    int cblocks, mblocks;           // Cin / 32, Cout / 128
+    int Cin, Cout;
+    int splits, tiles_per_split;
+    int want_bias, terms;
+    int stage_bytes, stages;
+    long long psize;
+    float* partial;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_wgrad_r2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz, const WgR2Args p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t bars = base + RING_BYTES;
+    const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
+    const uint32_t tmem_slot = tempty0 + 16;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+    const uint32_t ones_addr = bars + 1024u;                                  // 2 KB of bf16 1.0 inside the epilogue staging area
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull0, 1); mbar_init(tempty0, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dz) : "memory");
+    }
+    {
+        uint32_t* ones = reinterpret_cast<uint32_t*>(smem_raw + (ones_addr - raw));
+        for (int i = threadIdx.x; i < 512; i += NUM_THREADS) ones[i] = 0x3f803f80u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int utypes = p.cblocks * p.mblocks;                     // (channel block of x, 128 output channels) pairs of one pixel range run side by side
+    const int units = utypes * p.splits;
+    const int pix_tiles = p.ptx * p.pty * p.ptn;
+    const int bw = 8 + 2 * p.dil, bh = p.PH + 2 * p.dil;          // x box in pixels
+    const uint32_t xsub = (uint32_t)(bw * bh) * 64u;              // one part (hi or lo) of the x box
+    const uint32_t zsub = (uint32_t)(8 * p.PH) * 64u;             // one part of one 32-channel block of dz
+    const uint32_t z_off = (2u * xsub + 1023u) & ~1023u;
+    const int STAGES = p.stages;
+    constexpr uint32_t ACC_N = 96;                                // 3 kw windows x 32 input channels
+
+    if (warp == 0) {
+        if (elect_one_sync()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int ut = u % utypes, sp = u / utypes;
+                const int cb = ut % p.cblocks, mt = ut / p.cblocks;
+                const int q0 = sp * p.tiles_per_split;
+                const int q1 = min(pix_tiles, q0 + p.tiles_per_split);
+                for (int q = q0; q < q1; ++q) {
+                    const int qx = q % p.ptx; const int r2 = q / p.ptx;
+                    const int qy = r2 % p.pty; const int n0 = r2 / p.pty;
+                    const int x0 = qx * 8, y0 = qy * p.PH;
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t fb = full0 + 8 * stage;
+                    const uint32_t sa = base + stage * p.stage_bytes;
+                    mbar_expect_tx(fb, 2u * xsub + 8u * zsub);
+                    tma_load_5d(sa, &map_x, fb, 0, x0 - p.dil, y0 - p.dil, n0, 2 * cb);
+                    tma_load_5d(sa + z_off, &map_dz, fb, 0, x0, y0, n0, 8 * mt);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one_sync()) {
+            // bf16 A / B, fp32 accumulate, both MN-major; M = 128 output channels, N = 96 (taps) or 16 (bias)
+            const uint32_t idesc_common = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BLOCK_M >> 4) << 24);
+            const uint32_t idesc = idesc_common | ((ACC_N >> 3) << 17);
+            const uint32_t idesc_bias = idesc_common | ((16u >> 3) << 17);
+            int stage = 0; uint32_t phase = 0; uint32_t acc_phase = 0;
+            const uint64_t ones_desc = make_mn64_desc(ones_addr, 0u, 512u);
+            const int terms = p.terms;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int ut = u % utypes, sp = u / utypes;
+                const int cb = ut % p.cblocks;
+                const bool do_bias = p.want_bias && cb == 0;
+                const int q0 = sp * p.tiles_per_split;
+                const int q1 = min(pix_tiles, q0 + p.tiles_per_split);
+                mbar_wait(tempty0, acc_phase ^ 1);
+                tc_fence_after();
+                for (int q = q0; q < q1; ++q) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * p.stage_bytes;
+                    // dz (M operand): 32-channel blocks two sub-blocks apart, a line pair = 16 contiguous rows (SBO = 512)
+                    const uint64_t az[2] = {make_mn64_desc(sa + z_off, 2u * zsub, 512u), make_mn64_desc(sa + z_off + zsub, 2u * zsub, 512u)};
+                    for (int jp = 0; jp < p.PH / 2; ++jp) {
+                        const uint32_t first = (q > q0 || jp > 0) ? 1u : 0u;
+                        const uint64_t zo = (uint64_t)(jp * 64);             // 16 rows x 64 B = 1024 B
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh) {
+                            // x (N operand): windows kw = 0, 1, 2 are dil pixels (dil * 64 B) apart, the second 8-row group is the next line
+                            const uint32_t xa = sa + (uint32_t)((2 * jp + kh * p.dil) * bw) * 64u;
+                            const uint64_t bx[2] = {make_mn64_desc(xa, (uint32_t)p.dil * 64u, (uint32_t)bw * 64u),
+                                                    make_mn64_desc(xa + xsub, (uint32_t)p.dil * 64u, (uint32_t)bw * 64u)};
+                            const uint32_t d = tmem_base + (uint32_t)kh * ACC_N;
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                if (c >= terms) break;
+                                const int ha = c == 1 ? 1 : 0, hb = c == 2 ? 1 : 0;      // (dz, x): hi*hi, lo*hi, hi*lo
+                                tc_mma_bf16(d, az[ha] + zo, bx[hb], idesc, (first || c > 0) ? 1u : 0u);
+                            }
+                        }
+                        if (do_bias) {
+                            const uint32_t d = tmem_base + 3u * ACC_N;
+                            tc_mma_bf16(d, az[0] + zo, ones_desc, idesc_bias, first);
+                            tc_mma_bf16(d, az[1] + zo, ones_desc, idesc_bias, 1u);
+                        }
+                    }
+                    tc_commit(empty0 + 8 * stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull0);
+                acc_phase ^= 1;
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        uint32_t acc_phase = 0;
+        const long long wsize = 9LL * p.Cin * p.Cout;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int ut = u % utypes, sp = u / utypes;
+            const int cb = ut % p.cblocks, mt = ut / p.cblocks;
+            const bool do_bias = p.want_bias && cb == 0;
+            mbar_wait(tfull0, acc_phase);
+            tc_fence_after();
+            const int m = mt * 128 + quarter * 32 + lane;                   // this thread's output channel
+            float* pbase = p.partial + (long long)sp * p.psize;
+            const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+            for (int kh = 0; kh < 3; ++kh)
+                for (int w = 0; w < 3; ++w) {
+                    uint32_t r[32];
+                    __syncwarp();
+                    tc_ld32(t_lane + (uint32_t)(kh * ACC_N + w * 32), r);
+                    tc_wait_ld();
+                    float* dst = pbase + ((long long)(kh * 3 + w) * p.Cin + cb * 32) * p.Cout + m;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) dst[(long long)j * p.Cout] = __uint_as_float(r[j]);   // 32 lanes = 32 consecutive output channels
+                }
+            if (do_bias) {
+                uint32_t r[32];
+                __syncwarp();
+                tc_ld32(t_lane + 3u * ACC_N, r);                            // 16 identical columns (+ 16 unused ones)
+                tc_wait_ld();
+                pbase[wsize + m] = __uint_as_float(r[0]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0);
+            acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // out[i] = sum_z partial[z][i]; the first nw floats go to dw, the remaining (bias) ones to db
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, long long psize, long long nw, int splits,
                                        float* __restrict__ dw, float* __restrict__ db) {
@@ -1301,7 +1553,13 @@ constexpr int DUAL_SMEM_BYTES = DUAL_RING_BYTES + 1024 + 256 + EPI_STAGE_BYTES; 
 
 int launch_tc(const CUtensorMap& ms, const CUtensorMap& mw, const TcArgs& a_in, cudaStream_t st) {
     static bool attr = false;
-    if (!attr) { SSDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr = true; }
+    if (!attr) {
+        SSDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<ACT_F32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        SSDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<ACT_F32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        SSDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<ACT_S32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        SSDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<ACT_S32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr = true;
+    }
     TcArgs a = a_in;
     a.ring_bytes = RING_BYTES; a.tmem_cols = TMEM_COLS; a.acc_stride = ACC_STRIDE;
     long long m_tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_n;
@@ -1327,7 +1585,14 @@ int launch_tc(const CUtensorMap& ms, const CUtensorMap& mw, const TcArgs& a_in, 
     long long total = ((m_tiles + a.mtu - 1) / a.mtu) * a.n_tiles;
     const long long slots = (long long)num_sms() * ctas_per_sm;
     int grid = (int)(total < slots ? total : slots);
-    conv_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(ms, mw, a);
+    const bool scatter = a.mode == 0 && a.scatter;
+    if (a.split) {
+        if (scatter) conv_tc_kernel<ACT_S32, true><<<grid, NUM_THREADS, smem, st>>>(ms, mw, a);
+        else conv_tc_kernel<ACT_S32, false><<<grid, NUM_THREADS, smem, st>>>(ms, mw, a);
+    } else {
+        if (scatter) conv_tc_kernel<ACT_F32, true><<<grid, NUM_THREADS, smem, st>>>(ms, mw, a);
+        else conv_tc_kernel<ACT_F32, false><<<grid, NUM_THREADS, smem, st>>>(ms, mw, a);
+    }
     SSDB_LAUNCH_CHECK();
     return SSDB_OK;
 }
@@ -1437,6 +1702,18 @@ int pack_filter_t(const float* w_hwio, int taps, int Cin, int Cout, int cout_pad
     return SSDB_OK;
 }
 
+// row-window mode with 64 < N <= 128: one M tile per unit keeps three 68 KB stages but re-reads the whole filter for
+// every 128 pixels (the L2 -> SM traffic of conv2_x and the 4-box heads is then 70% filter bytes, and the kernel sits at
+// the L2 -> SM rate); two M tiles share the filter tile at the price of a two-stage ring of 88 KB stages.  Measured on
+// B200 (split mode, batch 64): conv2_1 fprop 0.605 -> 0.442 ms, conv2_2 fprop 1.140 -> 0.824, dgrad 1.169 -> 0.896,
+// head0 fprop 0.358 -> 0.237.  SSDB_RW_MTU2=0 restores one tile per unit.
+static int rw_wide_mtu(int mtu_from_cost_model) {
+    const char* ov = getenv("SSDB_RW_MTU2");
+    if (ov && !atoi(ov)) return 1;
+    (void)mtu_from_cost_model;
+    return 2;
+}
+
 static int split_terms_env() {
     const char* ov = getenv("SSDB_SPLIT_TERMS");       // bring-up switch, read per call
     const int t = ov ? atoi(ov) : 3;
@@ -1463,7 +1740,7 @@ int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_
     if (rw) {
         t.TW = 8; t.TH = wth; t.TN = wtn; a.TW = 8; a.TH = wth; a.TN = wtn;
         a.tiles_x = (g.Wo + 7) / 8; a.tiles_y = (g.Ho + wth - 1) / wth; a.tiles_n = (g.B + wtn - 1) / wtn;
-        if (a.block_n > 64) a.mtu = 1;                        // 2 x 20 KB + 3 x 16 KB would leave only two stages
+        if (a.block_n > 64) a.mtu = rw_wide_mtu(a.mtu);        // 2 x 20 KB + 3 x 16 KB would leave only two stages
     }
     fill_groups(a, g.k, tdy, tdx, rw);
     SSDB_REQUIRE(g.pad_t == g.pad_l, "tcgen05 path assumes equal top/left padding");
@@ -1500,7 +1777,7 @@ int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, int f
             if (rw) {
                 t.TW = 8; t.TH = wth; t.TN = wtn; a.TW = 8; a.TH = wth; a.TN = wtn;
                 a.tiles_x = (Wc + 7) / 8; a.tiles_y = (Hc + wth - 1) / wth; a.tiles_n = (g.B + wtn - 1) / wtn;
-                if (a.block_n > 64) a.mtu = 1;
+                if (a.block_n > 64) a.mtu = rw_wide_mtu(a.mtu);
                 int tdy[9], tdx[9];
                 for (int tt = 0; tt < g.k * g.k; ++tt) { tdy[tt] = g.pad_t - (tt / g.k) * g.dil; tdx[tt] = g.pad_l - (tt % g.k) * g.dil; }
                 fill_groups(a, g.k, tdy, tdx, true);
@@ -1686,6 +1963,64 @@ int encode_rw_map(CUtensorMap* m, const float* ptr, int B, int H, int W, int C, 
     return SSDB_OK;
 }
 
+struct WgR2Plan { WgR2Args a; bool ok; };
+
+// rw2 plan: 3x3, stride 1, SAME (pad = dilation), split operands, Cout a multiple of 128, a pixel tiling that wastes little
+WgR2Plan plan_wgrad_r2(const ConvGeom& g, int fmt) {
+    WgR2Plan pl{}; pl.ok = false;
+    if (fmt != ACT_S32) return pl;
+    if (const char* ov = getenv("SSDB_WG_R2")) { if (atoi(ov) == 0) return pl; }
+    if (g.k != 3 || g.stride != 1 || g.pad_t != g.dil || g.pad_l != g.dil || g.Cin % 32 != 0 || g.Cout % 128 != 0) return pl;
+    if (g.Ho != g.H || g.Wo != g.W || g.dil < 1 || g.dil > 2) return pl;
+    WgR2Args& a = pl.a;
+    a.dil = g.dil; a.Cin = g.Cin; a.Cout = g.Cout; a.cblocks = g.Cin / 32; a.mblocks = g.Cout / 128;
+    a.ptx = (g.W + 7) / 8; a.ptn = g.B;
+    // even PH <= 8: the tallest box within 8 % of the best pixel efficiency (a stage of a 2-line box is only 16 pixels of MMA work)
+    double eff_of[5] = {0, 0, 0, 0, 0}, best = 0.0;
+    for (int ph = 2; ph <= 8; ph += 2) {
+        const int pty = (g.H + ph - 1) / ph;
+        eff_of[ph / 2] = (double)g.H * g.W / ((double)a.ptx * 8 * pty * ph);
+        if (eff_of[ph / 2] > best) best = eff_of[ph / 2];
+    }
+    int PH = 0;
+    for (int ph = 8; ph >= 2; ph -= 2) if (eff_of[ph / 2] >= 0.92 * best) { PH = ph; break; }
+    double min_eff = 0.8;
+    if (const char* ov = getenv("SSDB_WG_R2_EFF")) min_eff = atof(ov);
+    if (PH == 0 || eff_of[PH / 2] < min_eff) return pl;
+    a.PH = PH; a.pty = (g.H + PH - 1) / PH;
+    const int bw = 8 + 2 * g.dil, bh = PH + 2 * g.dil;
+    int sb = (2 * bw * bh * 64 + 1023) / 1024 * 1024 + 8 * 8 * PH * 64;
+    sb = (sb + 1023) / 1024 * 1024;
+    a.stage_bytes = sb;
+    a.stages = RING_BYTES / sb; if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
+    if (a.stages < 2) return pl;
+    a.psize = 9LL * g.Cin * g.Cout + g.Cout;
+    a.want_bias = 1; a.terms = split_terms_env();
+    const long long pix_tiles = (long long)a.ptx * a.pty * a.ptn;
+    const long long ut = (long long)a.cblocks * a.mblocks;
+    // split the pixel range so that the units fill whole waves of the persistent grid: between 2 and 8 units per SM, the
+    // count whose last wave is fullest (every split adds one partial filter to write and reduce, so fewer wins ties)
+    const long long sms = num_sms();
+    const long long max_splits = (pix_tiles + 7) / 8;
+    long long lo = (2 * sms + ut - 1) / ut, hi = (8 * sms + ut - 1) / ut;
+    if (lo < 1) lo = 1;
+    if (hi > max_splits) hi = max_splits;
+    if (hi > 512) hi = 512;
+    if (lo > hi) lo = hi;
+    long long pick = lo; double pick_eff = 0.0;
+    for (long long sp = lo; sp <= hi; ++sp) {
+        const long long tps = (pix_tiles + sp - 1) / sp, real = (pix_tiles + tps - 1) / tps;
+        const long long units = real * ut, waves = (units + sms - 1) / sms;
+        const double eff = (double)units / (double)(waves * sms);
+        if (eff > pick_eff + 0.02) { pick_eff = eff; pick = sp; }
+    }
+    a.tiles_per_split = (int)((pix_tiles + pick - 1) / pick);
+    a.splits = (int)((pix_tiles + a.tiles_per_split - 1) / a.tiles_per_split);
+    a.partial = nullptr;
+    pl.ok = true;
+    return pl;
+}
+
 struct WgPlan { WgArgs a; bool ok; };
 
 WgPlan plan_wgrad(const ConvGeom& g, int fmt) {
@@ -1737,12 +2072,14 @@ WgPlan plan_wgrad(const ConvGeom& g, int fmt) {
 
 }  // namespace
 
-bool conv_tc_supported_wgrad(const ConvGeom& g, int fmt) { return plan_wgrad_rw(g, fmt).ok || plan_wgrad(g, fmt).ok; }
+bool conv_tc_supported_wgrad(const ConvGeom& g, int fmt) { return plan_wgrad_r2(g, fmt).ok || plan_wgrad_rw(g, fmt).ok || plan_wgrad(g, fmt).ok; }
 
 size_t conv_tc_wgrad_ws(const ConvGeom& g, int fmt) {
     size_t need = 0;
+    WgR2Plan r2 = plan_wgrad_r2(g, fmt);
+    if (r2.ok) need = (size_t)r2.a.splits * (size_t)r2.a.psize;
     WgRwPlan rw = plan_wgrad_rw(g, fmt);
-    if (rw.ok) need = (size_t)rw.a.splits * (size_t)rw.a.psize;
+    if (rw.ok) { size_t n1 = (size_t)rw.a.splits * (size_t)rw.a.psize; if (n1 > need) need = n1; }
     WgPlan pl = plan_wgrad(g, fmt);
     if (pl.ok) { size_t n2 = (size_t)pl.a.splits * (size_t)pl.a.psize; if (n2 > need) need = n2; }
     return need;
@@ -1750,6 +2087,25 @@ size_t conv_tc_wgrad_ws(const ConvGeom& g, int fmt) {
 
 int conv_tc_wgrad(const ConvGeom& g, const float* x, const float* dz, int fmt, float* dw, float* db, float* partial, cudaStream_t st) {
     const bool split = fmt == ACT_S32;
+    WgR2Plan r2 = plan_wgrad_r2(g, fmt);
+    if (r2.ok) {
+        WgR2Args a = r2.a;
+        a.partial = partial;
+        a.want_bias = db ? 1 : 0;
+        CUtensorMap mx, mz;
+        int rc = encode_act_map5s(&mx, x, g.B, g.H, g.W, g.Cin, 8 + 2 * a.dil, a.PH + 2 * a.dil, 1, 2, 1); if (rc) return rc;
+        rc = encode_act_map5s(&mz, dz, g.B, g.Ho, g.Wo, g.Cout, 8, a.PH, 1, 8, 1); if (rc) return rc;
+        static bool attr_r2 = false;
+        if (!attr_r2) { SSDB_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_r2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_r2 = true; }
+        long long units = (long long)a.cblocks * a.mblocks * a.splits;
+        int grid = (int)(units < num_sms() ? units : num_sms());
+        conv_tc_wgrad_r2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mx, mz, a);
+        SSDB_LAUNCH_CHECK();
+        long long nw = 9LL * g.Cin * g.Cout;
+        reduce_partials_kernel<<<(unsigned)((a.psize / 4 + 255) / 256), 256, 0, st>>>(partial, a.psize, nw, a.splits, dw, db);
+        SSDB_LAUNCH_CHECK();
+        return SSDB_OK;
+    }
     WgRwPlan rw = plan_wgrad_rw(g, fmt);
     if (rw.ok) {
         WgRwArgs a = rw.a;

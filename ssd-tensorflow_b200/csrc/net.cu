@@ -101,6 +101,9 @@ struct ssdb_net {
     float *acts = nullptr, *gacts = nullptr;
     float *out = nullptr, *out_grad = nullptr, *result = nullptr, *dz_head = nullptr;
     float *images_stage = nullptr, *labels_stage = nullptr;
+    double* gt_stage = nullptr; int* gt_count_stage = nullptr;    // raw ground truth of the host entry points ([max_batch, 128, 5] + counts)
+    int* match_stage = nullptr;                                   // [max_batch, A] owner GT per anchor (fused match), on request
+    int *det_rows = nullptr, *det_counts = nullptr;               // ssdb_forward_detect_host: [max_batch, A, 8] / [max_batch, 2]
     float *partial = nullptr; size_t partial_floats = 0;
     float *small_ws = nullptr;         // [0..3] losses, [4..5] conf/loc, [6] l2 sum, then per-image + partials
     unsigned int* counter = nullptr;
@@ -543,6 +546,8 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
     ALLOC(n->partial, partial, float); ALLOC(n->small_ws, 4096 + 2 * (size_t)max_batch, float);
     ALLOC(n->counter, 1, unsigned int); ALLOC(n->decay_mask, n->n_flat / OPT_BLOCK, unsigned char);
     ALLOC(n->anchors, (size_t)n->A * 4, double);
+    ALLOC(n->gt_stage, (size_t)max_batch * 128 * 5, double); ALLOC(n->gt_count_stage, max_batch, int);
+    ALLOC(n->match_stage, (size_t)max_batch * n->A, int);
     ALLOC(n->loss_ws, multibox_loss_ws_bytes(max_batch, n->A), unsigned char);
     SSDB_CUDA(cudaMemset(n->loss_ws, 0, multibox_loss_ws_bytes(max_batch, n->A)));
     for (const Op& op : n->ops)
@@ -593,7 +598,8 @@ int ssdb_destroy(ssdb_net* n) {
     if (!n) return SSDB_OK;
     cudaDeviceSynchronize();
     void* ptrs[] = {n->pool5_arg, n->patches, n->c1_w32, n->c1_wt, n->c1_dw32, n->wr, n->params, n->grads, n->moms, n->wt, n->acts, n->gacts, n->out, n->out_grad, n->result, n->labels_stage,
-                    n->dz_head, n->images_stage, n->partial, n->small_ws, n->counter, n->decay_mask, n->anchors, n->loss_ws, n->det_ws};
+                    n->dz_head, n->images_stage, n->partial, n->small_ws, n->counter, n->decay_mask, n->anchors, n->loss_ws, n->det_ws,
+                    n->gt_stage, n->gt_count_stage, n->match_stage, n->det_rows, n->det_counts};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (unsigned char* p : n->pool_code) if (p) cudaFree(p);
     if (n->host_small) cudaFreeHost(n->host_small);
@@ -719,13 +725,62 @@ int ssdb_read_output_host(ssdb_net* n, int B, float* output_host) {
     return SSDB_OK;
 }
 
+// Test / diagnosis hook: any intermediate tensor of the last step as plain float32 on the host.
+//   "<op name>"        activation written by that op (conv1_1 ... conv11_2, pool1..4, mod_pool5, l2_norm_conv4_3), NHWC
+//   "grad:<op name>"   gradient with respect to that activation (after a backward)
+//   "output" / "output_grad"   the raw head output [B, A, C+5] / its gradient
+int ssdb_debug_read(ssdb_net* n, const char* name, int B, float* host_out, long long count) {
+    SSDB_REQUIRE(n && name && host_out && B >= 1 && B <= n->max_batch, "bad arguments");
+    SSDB_CUDA(cudaDeviceSynchronize());
+    std::string nm(name);
+    if (nm == "output" || nm == "output_grad") {
+        SSDB_REQUIRE(count == (long long)B * n->A * n->V, "element count does not match [B, A, C+5]");
+        SSDB_CUDA(cudaMemcpy(host_out, nm == "output" ? n->out : n->out_grad, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost));
+        return SSDB_OK;
+    }
+    const bool grad = nm.rfind("grad:", 0) == 0;
+    if (grad) nm = nm.substr(5);
+    for (const Op& op : n->ops) {
+        if (op.name != nm || op.out < 0) continue;
+        const Buf& b = n->bufs[op.out];
+        const long long want = (long long)B * b.H * b.W * b.C;
+        SSDB_REQUIRE(count == want, "element count does not match the activation shape");
+        const float* src = grad ? n->gact(op.out, B) : n->act(op.out, B);
+        if (n->fmt == ACT_S32) {
+            float* tmp = nullptr;
+            SSDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&tmp), (size_t)want * sizeof(float)));
+            int rc = unsplit_copy(src, tmp, want, nullptr);
+            if (!rc && cudaMemcpy(host_out, tmp, (size_t)want * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("copy failed"); rc = SSDB_ECUDA; }
+            cudaFree(tmp);
+            return rc;
+        }
+        SSDB_CUDA(cudaMemcpy(host_out, src, (size_t)want * sizeof(float), cudaMemcpyDeviceToHost));
+        return SSDB_OK;
+    }
+    set_error("no such activation: %s", name);
+    return SSDB_ENOTFOUND;
+}
+
+int ssdb_debug_shape(const ssdb_net* n, const char* name, int shape_out[3]) {
+    SSDB_REQUIRE(n && name && shape_out, "bad arguments");
+    for (const Op& op : n->ops)
+        if (op.name == name && op.out >= 0) {
+            const Buf& b = n->bufs[op.out];
+            shape_out[0] = b.H; shape_out[1] = b.W; shape_out[2] = b.C;
+            return SSDB_OK;
+        }
+    set_error("no such activation: %s", name);
+    return SSDB_ENOTFOUND;
+}
+
 static int loss_and_finalize(ssdb_net* n, const float* labels_dev, const double* gt_dev, const int* gt_count_dev, int G, int B,
-                             float weight_decay, float grad_scale, bool want_grad, float* losses_out_dev, float* result_dev, cudaStream_t st) {
+                             float weight_decay, float grad_scale, bool want_grad, float* losses_out_dev, float* result_dev, cudaStream_t st,
+                             int* match_out_dev = nullptr) {
     float* conf_loc = n->small_ws + 4;
     float* l2s = n->small_ws + 6;
     ProfScope ps(n, st, "loss");
     int rc = multibox_loss_launch(n->out, labels_dev, gt_dev, gt_count_dev, G, n->anchors, B, n->A, n->C, grad_scale, conf_loc,
-                                  want_grad ? n->out_grad : nullptr, result_dev ? result_dev : n->result, nullptr, n->loss_ws, st);
+                                  want_grad ? n->out_grad : nullptr, result_dev ? result_dev : n->result, match_out_dev, n->loss_ws, st);
     if (rc) return rc;
     rc = l2_sum(n->params, (long long)n->n_flat, n->decay_mask, n->small_ws + 8, l2s, st); if (rc) return rc;
     finalize_losses_kernel<<<1, 32, 0, st>>>(conf_loc, l2s, weight_decay, losses_out_dev ? losses_out_dev : n->small_ws);
@@ -755,29 +810,57 @@ int ssdb_train_step(ssdb_net* n, const float* images_dev, const float* labels_de
     return rc;
 }
 
-static int train_step_host_impl(ssdb_net* n, const float* images_host, const float* labels_host, int B, float lr, float momentum,
-                                float weight_decay, int apply_update, float* losses_out_host, float* result_host) {
-    SSDB_REQUIRE(n && images_host && labels_host && B >= 1 && B <= n->max_batch, "bad arguments");
+// ground truth of the host entry points: every label id must be a class index (the reference would raise an IndexError on
+// transforms.py:107; unchecked it would index out of bounds in the kernels) and every count within [0, G]
+static int check_gt_host(const double* gt, const int* gt_count, int B, int G, int C) {
+    SSDB_REQUIRE(G >= 1 && G <= 128, "G (ground-truth slots per image) must be in [1,128]");
+    for (int b = 0; b < B; ++b) {
+        SSDB_REQUIRE(gt_count[b] >= 0 && gt_count[b] <= G, "ground-truth count outside [0, G]");
+        for (int k = 0; k < gt_count[b]; ++k) {
+            const double id = gt[((size_t)b * G + k) * 5];
+            if (!(id >= 0.0 && id < (double)C && id == (double)(int)id)) {
+                set_error("ground-truth box %d of image %d has label id %g: expected an integer in [0, %d)", k, b, id, C);
+                return SSDB_EINVAL;
+            }
+        }
+    }
+    return SSDB_OK;
+}
+
+static int train_step_host_impl(ssdb_net* n, const float* images_host, const float* labels_host, const double* gt_host, const int* gt_count_host,
+                                int G, int B, float lr, float momentum, float weight_decay, int apply_update, float* losses_out_host,
+                                float* result_host, int* match_out_host) {
+    SSDB_REQUIRE(n && images_host && (labels_host || (gt_host && gt_count_host)) && B >= 1 && B <= n->max_batch, "bad arguments");
+    if (!labels_host) { int rc = check_gt_host(gt_host, gt_count_host, B, G, n->C); if (rc) return rc; }
     // copies ride a second stream: the labels arrive while the forward runs (they are first needed by the loss) and the
     // result leaves while the backward runs; only the image upload is on the critical path
     cudaStream_t st = n->own_stream, cs = n->copy_stream;
     const size_t bav = (size_t)B * n->A * n->V * sizeof(float);
     // both uploads share one DMA direction: images first (critical path, chunked so that conv1_1 starts after the first
-    // quarter), labels behind them
+    // quarter), labels (873 KB per image) or raw ground truth (40 bytes per box) behind them
     bool first_done = false;
     int rc = upload_images_chunked(n, images_host, B, st, cs, &first_done); if (rc) return rc;
-    SSDB_CUDA(cudaMemcpyAsync(n->labels_stage, labels_host, bav, cudaMemcpyHostToDevice, cs));
+    if (labels_host) SSDB_CUDA(cudaMemcpyAsync(n->labels_stage, labels_host, bav, cudaMemcpyHostToDevice, cs));
+    else {
+        SSDB_CUDA(cudaMemcpyAsync(n->gt_stage, gt_host, (size_t)B * G * 5 * sizeof(double), cudaMemcpyHostToDevice, cs));
+        SSDB_CUDA(cudaMemcpyAsync(n->gt_count_stage, gt_count_host, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, cs));
+    }
     SSDB_CUDA(cudaEventRecord(n->ev_labels, cs));
     rc = run_forward(n, n->images_stage, B, st, first_done); if (rc) return rc;
     SSDB_CUDA(cudaStreamWaitEvent(st, n->ev_labels, 0));
-    rc = loss_and_finalize(n, n->labels_stage, nullptr, nullptr, 0, B, weight_decay, 1.0f, true, n->small_ws, n->result, st); if (rc) return rc;
-    if (result_host) {
+    const bool want_grad = apply_update >= 0;
+    if (labels_host) rc = loss_and_finalize(n, n->labels_stage, nullptr, nullptr, 0, B, weight_decay, 1.0f, want_grad, n->small_ws, n->result, st);
+    else rc = loss_and_finalize(n, nullptr, n->gt_stage, n->gt_count_stage, G, B, weight_decay, 1.0f, want_grad, n->small_ws, n->result, st,
+                                match_out_host ? n->match_stage : nullptr);
+    if (rc) return rc;
+    if (result_host || match_out_host) {
         SSDB_CUDA(cudaEventRecord(n->ev_result, st));
         SSDB_CUDA(cudaStreamWaitEvent(cs, n->ev_result, 0));
-        SSDB_CUDA(cudaMemcpyAsync(result_host, n->result, bav, cudaMemcpyDeviceToHost, cs));
+        if (result_host) SSDB_CUDA(cudaMemcpyAsync(result_host, n->result, bav, cudaMemcpyDeviceToHost, cs));
+        if (match_out_host) SSDB_CUDA(cudaMemcpyAsync(match_out_host, n->match_stage, (size_t)B * n->A * sizeof(int), cudaMemcpyDeviceToHost, cs));
     }
-    rc = run_backward(n, B, st); if (rc) return rc;
-    if (apply_update) { rc = ssdb_apply_update(n, lr, momentum, weight_decay, 1.0f, st); if (rc) return rc; }
+    if (apply_update >= 0) { rc = run_backward(n, B, st); if (rc) return rc; }
+    if (apply_update > 0) { rc = ssdb_apply_update(n, lr, momentum, weight_decay, 1.0f, st); if (rc) return rc; }
     SSDB_CUDA(cudaMemcpyAsync(n->host_small, n->small_ws, 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
     SSDB_CUDA(cudaStreamSynchronize(st));
     SSDB_CUDA(cudaStreamSynchronize(cs));
@@ -787,12 +870,54 @@ static int train_step_host_impl(ssdb_net* n, const float* images_host, const flo
 
 int ssdb_train_step_host(ssdb_net* n, const float* images_host, const float* labels_host, int B, float lr, float momentum,
                          float weight_decay, float* losses_out_host, float* result_host) {
-    return train_step_host_impl(n, images_host, labels_host, B, lr, momentum, weight_decay, 1, losses_out_host, result_host);
+    SSDB_REQUIRE(labels_host, "labels are required (ssdb_train_step_host_gt takes raw ground truth)");
+    return train_step_host_impl(n, images_host, labels_host, nullptr, nullptr, 0, B, lr, momentum, weight_decay, 1, losses_out_host, result_host, nullptr);
 }
 
 int ssdb_train_step_host_noupdate(ssdb_net* n, const float* images_host, const float* labels_host, int B, float weight_decay,
                                   float* losses_out_host, float* result_host) {
-    return train_step_host_impl(n, images_host, labels_host, B, 0.f, 0.f, weight_decay, 0, losses_out_host, result_host);
+    SSDB_REQUIRE(labels_host, "labels are required (ssdb_train_step_host_gt takes raw ground truth)");
+    return train_step_host_impl(n, images_host, labels_host, nullptr, nullptr, 0, B, 0.f, 0.f, weight_decay, 0, losses_out_host, result_host, nullptr);
+}
+
+int ssdb_train_step_host_gt(ssdb_net* n, const float* images_host, const double* gt_host, const int* gt_count_host, int G, int B,
+                            float lr, float momentum, float weight_decay, int apply_update, float* losses_out_host, float* result_host,
+                            int* match_out_host) {
+    SSDB_REQUIRE(gt_host && gt_count_host, "ground truth is required");
+    return train_step_host_impl(n, images_host, nullptr, gt_host, gt_count_host, G, B, lr, momentum, weight_decay,
+                                apply_update > 0 ? 1 : (apply_update < 0 ? -1 : 0), losses_out_host, result_host, match_out_host);
+}
+
+// forward, then decode + top-k + class-wise NMS straight on the device-resident result: only the detections go back
+int ssdb_forward_detect_host(ssdb_net* n, const float* images_host, int B, float conf_thr, int cap, double iou_thr, int* dets_out_host,
+                             int* counts_out_host, float* result_host) {
+    SSDB_REQUIRE(n && images_host && dets_out_host && counts_out_host && B >= 1 && B <= n->max_batch, "bad arguments");
+    cudaStream_t st = n->own_stream;
+    const int cap_eff = (cap > 0 && cap < n->A) ? cap : n->A;
+    if (!n->det_rows) {
+        SSDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&n->det_rows), (size_t)n->max_batch * n->A * 8 * sizeof(int)));
+        SSDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&n->det_counts), (size_t)n->max_batch * 2 * sizeof(int)));
+    }
+    if (!n->det_ws) SSDB_CUDA(cudaMalloc(&n->det_ws, decode_nms_scratch_bytes(n->max_batch, n->A, 0)));
+    bool first_done = false;
+    int rc = upload_images_chunked(n, images_host, B, st, n->copy_stream, &first_done); if (rc) return rc;
+    rc = run_forward(n, n->images_stage, B, st, first_done); if (rc) return rc;
+    rc = softmax_result(n->out, (long long)B * n->A, n->C, n->result, st); if (rc) return rc;
+    if (result_host) {       // optional: the caller also wants net.result (it leaves on the copy stream, behind the kernels below)
+        SSDB_CUDA(cudaEventRecord(n->ev_result, st));
+        SSDB_CUDA(cudaStreamWaitEvent(n->copy_stream, n->ev_result, 0));
+        SSDB_CUDA(cudaMemcpyAsync(result_host, n->result, (size_t)B * n->A * n->V * sizeof(float), cudaMemcpyDeviceToHost, n->copy_stream));
+    }
+    SSDB_CUDA(cudaMemsetAsync(n->det_rows, 0, (size_t)B * cap_eff * 8 * sizeof(int), st));
+    rc = decode_nms_launch(n->result, B, n->A, n->C, n->anchors, conf_thr, cap, iou_thr, n->det_rows, n->det_counts, n->det_ws,
+                           decode_nms_scratch_bytes(n->max_batch, n->A, 0), st);
+    if (rc) return rc;
+    SSDB_CUDA(cudaMemcpyAsync(counts_out_host, n->det_counts, (size_t)B * 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    SSDB_CUDA(cudaMemcpy2DAsync(dets_out_host, (size_t)cap_eff * 8 * sizeof(int), n->det_rows, (size_t)cap_eff * 8 * sizeof(int),
+                                (size_t)cap_eff * 8 * sizeof(int), (size_t)B, cudaMemcpyDeviceToHost, st));
+    SSDB_CUDA(cudaStreamSynchronize(st));
+    SSDB_CUDA(cudaStreamSynchronize(n->copy_stream));
+    return SSDB_OK;
 }
 
 int ssdb_eval_step(ssdb_net* n, const float* images_dev, const float* labels_dev, int B, float weight_decay, float* losses_out_dev,
@@ -810,24 +935,50 @@ int ssdb_match_anchors(const double* gt_dev, const int* gt_count_dev, int B, int
     return match_anchors_launch(gt_dev, gt_count_dev, B, G, anchors_prop_dev, A, C, match_out_dev, labels_out_dev, (cudaStream_t)stream);
 }
 
+// Device scratch of the stateless *_host entry points: one grow-only arena per device (a process may drive several
+// GPUs), carved per call; calls are serialised by the arena mutex (the reference is single-threaded per session anyway).
+// Nothing is allocated or freed per call once the arena has grown to the largest request, and an error return leaks nothing.
+namespace {
+struct HostArena { unsigned char* p = nullptr; size_t cap = 0; };
+std::mutex g_arena_mu;
+std::map<int, HostArena> g_arenas;
+int arena_get(size_t bytes, unsigned char** out) {
+    int dev = 0;
+    SSDB_CUDA(cudaGetDevice(&dev));
+    HostArena& a = g_arenas[dev];
+    if (bytes > a.cap) {
+        if (a.p) { SSDB_CUDA(cudaDeviceSynchronize()); cudaFree(a.p); a.p = nullptr; a.cap = 0; }
+        SSDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&a.p), bytes));
+        a.cap = bytes;
+    }
+    *out = a.p;
+    return SSDB_OK;
+}
+size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+}  // namespace
+
 int ssdb_match_anchors_host(const double* gt, const int* gt_count, int B, int G, const double* anchors, int A, int C, int* match_out,
                             float* labels_out) {
     SSDB_REQUIRE(gt && gt_count && anchors && B >= 1 && G >= 1, "bad arguments");
     int rc = ssdb_device_ok(); if (rc) return rc;
-    double *d_gt = nullptr, *d_anc = nullptr; int *d_cnt = nullptr, *d_match = nullptr; float* d_lab = nullptr;
-    SSDB_CUDA(cudaMalloc(&d_gt, (size_t)B * G * 5 * 8)); SSDB_CUDA(cudaMalloc(&d_anc, (size_t)A * 4 * 8));
-    SSDB_CUDA(cudaMalloc(&d_cnt, (size_t)B * 4));
-    if (match_out) SSDB_CUDA(cudaMalloc(&d_match, (size_t)B * A * 4));
-    if (labels_out) SSDB_CUDA(cudaMalloc(&d_lab, (size_t)B * A * (C + 5) * 4));
-    SSDB_CUDA(cudaMemcpy(d_gt, gt, (size_t)B * G * 5 * 8, cudaMemcpyHostToDevice));
-    SSDB_CUDA(cudaMemcpy(d_anc, anchors, (size_t)A * 4 * 8, cudaMemcpyHostToDevice));
-    SSDB_CUDA(cudaMemcpy(d_cnt, gt_count, (size_t)B * 4, cudaMemcpyHostToDevice));
-    rc = match_anchors_launch(d_gt, d_cnt, B, G, d_anc, A, C, d_match, d_lab, nullptr);
-    if (!rc && match_out) SSDB_CUDA(cudaMemcpy(match_out, d_match, (size_t)B * A * 4, cudaMemcpyDeviceToHost));
-    if (!rc && labels_out) SSDB_CUDA(cudaMemcpy(labels_out, d_lab, (size_t)B * A * (C + 5) * 4, cudaMemcpyDeviceToHost));
-    SSDB_CUDA(cudaDeviceSynchronize());
-    cudaFree(d_gt); cudaFree(d_anc); cudaFree(d_cnt); if (d_match) cudaFree(d_match); if (d_lab) cudaFree(d_lab);
-    return rc;
+    rc = check_gt_host(gt, gt_count, B, G, C); if (rc) return rc;
+    std::lock_guard<std::mutex> lock(g_arena_mu);
+    const size_t s_gt = up256((size_t)B * G * 5 * 8), s_anc = up256((size_t)A * 4 * 8), s_cnt = up256((size_t)B * 4);
+    const size_t s_match = match_out ? up256((size_t)B * A * 4) : 0, s_lab = labels_out ? up256((size_t)B * A * (C + 5) * 4) : 0;
+    unsigned char* base = nullptr;
+    rc = arena_get(s_gt + s_anc + s_cnt + s_match + s_lab, &base); if (rc) return rc;
+    double* d_gt = reinterpret_cast<double*>(base); double* d_anc = reinterpret_cast<double*>(base + s_gt);
+    int* d_cnt = reinterpret_cast<int*>(base + s_gt + s_anc);
+    int* d_match = match_out ? reinterpret_cast<int*>(base + s_gt + s_anc + s_cnt) : nullptr;
+    float* d_lab = labels_out ? reinterpret_cast<float*>(base + s_gt + s_anc + s_cnt + s_match) : nullptr;
+    SSDB_CUDA(cudaMemcpyAsync(d_gt, gt, (size_t)B * G * 5 * 8, cudaMemcpyHostToDevice, nullptr));
+    SSDB_CUDA(cudaMemcpyAsync(d_anc, anchors, (size_t)A * 4 * 8, cudaMemcpyHostToDevice, nullptr));
+    SSDB_CUDA(cudaMemcpyAsync(d_cnt, gt_count, (size_t)B * 4, cudaMemcpyHostToDevice, nullptr));
+    rc = match_anchors_launch(d_gt, d_cnt, B, G, d_anc, A, C, d_match, d_lab, nullptr); if (rc) return rc;
+    if (match_out) SSDB_CUDA(cudaMemcpyAsync(match_out, d_match, (size_t)B * A * 4, cudaMemcpyDeviceToHost, nullptr));
+    if (labels_out) SSDB_CUDA(cudaMemcpyAsync(labels_out, d_lab, (size_t)B * A * (C + 5) * 4, cudaMemcpyDeviceToHost, nullptr));
+    SSDB_CUDA(cudaStreamSynchronize(nullptr));
+    return SSDB_OK;
 }
 
 // grow-only scratch per stream: calls on one stream are ordered, calls on different streams never share a buffer
@@ -858,18 +1009,24 @@ int ssdb_decode_nms_host(const float* pred, int B, int A, int C, const double* a
                          int* dets_out, int* counts_out) {
     SSDB_REQUIRE(pred && anchors && dets_out && counts_out && B >= 1, "bad arguments");
     int rc = ssdb_device_ok(); if (rc) return rc;
-    int cap_eff = (cap > 0 && cap < A) ? cap : A;
-    float* d_pred = nullptr; double* d_anc = nullptr; int *d_dets = nullptr, *d_cnt = nullptr;
-    size_t pb = (size_t)B * A * (C + 5) * 4, db = (size_t)B * cap_eff * 8 * 4;
-    SSDB_CUDA(cudaMalloc(&d_pred, pb)); SSDB_CUDA(cudaMalloc(&d_anc, (size_t)A * 4 * 8));
-    SSDB_CUDA(cudaMalloc(&d_dets, db)); SSDB_CUDA(cudaMalloc(&d_cnt, (size_t)B * 2 * 4));
-    SSDB_CUDA(cudaMemcpy(d_pred, pred, pb, cudaMemcpyHostToDevice));
-    SSDB_CUDA(cudaMemcpy(d_anc, anchors, (size_t)A * 4 * 8, cudaMemcpyHostToDevice));
-    SSDB_CUDA(cudaMemset(d_dets, 0, db));
-    rc = ssdb_decode_nms(d_pred, B, A, C, d_anc, conf_thr, cap, iou_thr, d_dets, d_cnt, nullptr);
-    if (!rc) { SSDB_CUDA(cudaMemcpy(dets_out, d_dets, db, cudaMemcpyDeviceToHost)); SSDB_CUDA(cudaMemcpy(counts_out, d_cnt, (size_t)B * 2 * 4, cudaMemcpyDeviceToHost)); }
-    cudaFree(d_pred); cudaFree(d_anc); cudaFree(d_dets); cudaFree(d_cnt);
-    return rc;
+    std::lock_guard<std::mutex> lock(g_arena_mu);
+    const int cap_eff = (cap > 0 && cap < A) ? cap : A;
+    const size_t pb = (size_t)B * A * (C + 5) * 4, db = (size_t)B * cap_eff * 8 * 4, sb = decode_nms_scratch_bytes(B, A, cap);
+    const size_t s_pred = up256(pb), s_anc = up256((size_t)A * 4 * 8), s_dets = up256(db), s_cnt = up256((size_t)B * 2 * 4);
+    unsigned char* base = nullptr;
+    rc = arena_get(s_pred + s_anc + s_dets + s_cnt + up256(sb), &base); if (rc) return rc;
+    float* d_pred = reinterpret_cast<float*>(base); double* d_anc = reinterpret_cast<double*>(base + s_pred);
+    int* d_dets = reinterpret_cast<int*>(base + s_pred + s_anc); int* d_cnt = reinterpret_cast<int*>(base + s_pred + s_anc + s_dets);
+    void* scratch = base + s_pred + s_anc + s_dets + s_cnt;
+    // page-locked host buffers (ssdb_pinned_alloc, torch pin_memory) make these DMA transfers at the full PCIe rate
+    SSDB_CUDA(cudaMemcpyAsync(d_pred, pred, pb, cudaMemcpyHostToDevice, nullptr));
+    SSDB_CUDA(cudaMemcpyAsync(d_anc, anchors, (size_t)A * 4 * 8, cudaMemcpyHostToDevice, nullptr));
+    SSDB_CUDA(cudaMemsetAsync(d_dets, 0, db, nullptr));                  // rows beyond an image's count read as zeros
+    rc = decode_nms_launch(d_pred, B, A, C, d_anc, conf_thr, cap, iou_thr, d_dets, d_cnt, scratch, sb, nullptr); if (rc) return rc;
+    SSDB_CUDA(cudaMemcpyAsync(dets_out, d_dets, db, cudaMemcpyDeviceToHost, nullptr));
+    SSDB_CUDA(cudaMemcpyAsync(counts_out, d_cnt, (size_t)B * 2 * 4, cudaMemcpyDeviceToHost, nullptr));
+    SSDB_CUDA(cudaStreamSynchronize(nullptr));
+    return SSDB_OK;
 }
 
 int ssdb_nms_host(const int* boxes, const int* labelid, const float* conf, int n, int nclass, double iou_thr, int* keep_out, int* count_out) {
@@ -1015,6 +1172,79 @@ int ssdb_op_conv_wgrad(int impl, const float* x, const float* dz, int B, int H, 
         rc = conv_simt_wgrad(g, x, dz, ACT_F32, ep, dw, partial, st);
         if (!rc && db) rc = bias_grad(dz, ACT_F32, (long long)B * Ho * Wo, Cout, db, partial, st);
     }
+    return rc;
+}
+
+// deterministic pseudo-random fill: value in [-1, 1), a fraction `zero_frac` of the elements exactly 0 (ReLU-like sparsity)
+__global__ void bench_fill_kernel(float* p, long long n, unsigned seed, float zero_frac, float scale) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned h = (unsigned)i * 2654435761u ^ seed;
+    h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+    float u = (float)(h >> 8) * (1.0f / 16777216.0f);
+    unsigned h2 = h * 0x9e3779b9u; h2 ^= h2 >> 15;
+    float z = (float)(h2 >> 8) * (1.0f / 16777216.0f);
+    p[i] = z < zero_frac ? 0.f : (2.f * u - 1.f) * scale;
+}
+
+int ssdb_op_conv_bench(int kind, int impl, int B, int H, int W, int Cin, int Cout, int k, int stride, int dil, int pad_t, int pad_l,
+                       int Ho, int Wo, int with_mask, int beta, int iters, float* ms_out) {
+    SSDB_REQUIRE(kind >= 0 && kind <= 2 && iters >= 1 && ms_out, "bad arguments");
+    int rc = ssdb_device_ok(); if (rc) return rc;
+    ConvGeom g = make_geom(B, H, W, Cin, Cout, k, stride, dil, pad_t, pad_l, Ho, Wo);
+    const bool tc = impl != SSDB_CONV_SIMT;
+    const int fmt = impl == SSDB_CONV_TC ? ACT_F32 : (impl == SSDB_CONV_SIMT ? ACT_F32 : ACT_S32);
+    cudaStream_t st = nullptr;
+    SSDB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    const long long nx = (long long)B * H * W * Cin, ny = (long long)B * Ho * Wo * Cout, nw = (long long)k * k * Cin * Cout;
+    const int bn = Cout > 256 ? 256 : (Cout + 15) / 16 * 16;
+    const int cout_pad = (Cout + bn - 1) / bn * bn;
+    size_t ws = tc ? conv_tc_wgrad_ws(g, fmt) : conv_simt_wgrad_ws(g);
+    if (ws < (size_t)1184 * Cout) ws = (size_t)1184 * Cout;
+    float *x = nullptr, *y = nullptr, *w = nullptr, *tmp = nullptr, *wt = nullptr, *wr = nullptr, *dw = nullptr, *db = nullptr, *partial = nullptr, *bias = nullptr, *dx = nullptr;
+    const long long nmax = nx > ny ? nx : ny;
+#define BALLOC(ptr, count) SSDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&(ptr)), (size_t)(count) * sizeof(float)))
+    BALLOC(x, nx); BALLOC(y, ny); BALLOC(w, nw); BALLOC(tmp, nmax > nw ? nmax : nw); BALLOC(wt, (size_t)k * k * cout_pad * Cin); BALLOC(wr, nw);
+    BALLOC(dw, nw); BALLOC(db, Cout); BALLOC(partial, ws); BALLOC(bias, Cout); BALLOC(dx, nx);
+#undef BALLOC
+    auto fill = [&](float* p, long long n, unsigned seed, float zf, float sc) {
+        bench_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, seed, zf, sc);
+    };
+    auto prep = [&](float* dst, long long n, unsigned seed, float zf, float sc) -> int {   // random data in the engine's operand format
+        fill(tmp, n, seed, zf, sc);
+        if (!tc) { SSDB_CUDA(cudaMemcpyAsync(dst, tmp, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st)); return SSDB_OK; }
+        return hook_prepare(tmp, dst, n, fmt, st);
+    };
+    rc = prep(x, nx, 1u, 0.5f, 1.f);                                  // activations: half zeros (post-ReLU)
+    if (!rc) rc = prep(y, ny, 2u, 0.f, 1.f);                          // dz: dense
+    if (!rc) rc = prep(dx, nx, 5u, 0.f, 1.f);
+    fill(w, nw, 3u, 0.f, 0.05f); fill(bias, Cout, 4u, 0.f, 0.1f);
+    if (!rc && tc) rc = pack_filter_t(w, k * k, Cin, Cout, cout_pad, fmt, wt, st);
+    if (!rc && tc) rc = hook_prepare(w, wr, nw, fmt, st);
+    ConvEpilogue ep; ep.bias = bias; ep.relu = 1; ep.round_tf32 = (tc && fmt == ACT_F32) ? 1 : 0;
+    auto once = [&]() -> int {
+        if (kind == 0) return tc ? conv_tc_fprop(g, x, wt, cout_pad, fmt, ep, y, st) : conv_simt_fprop(g, x, w, ACT_F32, ep, y, st);
+        if (kind == 1) return tc ? conv_tc_dgrad(g, y, wr, fmt, with_mask ? x : nullptr, beta, fmt == ACT_F32 ? 1 : 0, dx, st)
+                                 : conv_simt_dgrad(g, y, w, ACT_F32, with_mask ? x : nullptr, beta, 0, dx, st);
+        if (tc) return conv_tc_wgrad(g, x, y, fmt, dw, db, partial, st);
+        ConvEpilogue e2;
+        return conv_simt_wgrad(g, x, y, ACT_F32, e2, dw, partial, st);
+    };
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 2 && !rc; ++i) rc = once();
+    if (!rc) {
+        cudaEventRecord(e0, st);
+        for (int i = 0; i < iters && !rc; ++i) rc = once();
+        cudaEventRecord(e1, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error("conv bench failed: %s", cudaGetErrorString(e)); rc = SSDB_ECUDA; }
+        else { float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); *ms_out = ms / iters; }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaStreamSynchronize(st);
+    for (float* p : {x, y, w, tmp, wt, wr, dw, db, partial, bias, dx}) cudaFree(p);
+    cudaStreamDestroy(st);
     return rc;
 }
 

@@ -50,9 +50,15 @@ def main():
         for b in range(args.batches):
             first = b * args.batch_size
             x = synth.images(first, args.batch_size, side)
-            result = sess.run(net.result, feed_dict={net.image_input: x, net.keep_prob: 1})
-            # infer.py:233-235: decode with no cap, suppress, keep the first 200 of the class-grouped list
-            dets = [d[:200] for d in ssdutils.detect_batch(result, anchors, args.threshold, lid2name, None)]
+            # infer.py:225-235 as one flow on the device: forward, then decode (no cap) + suppress on the resident result
+            # tensor; only the detections cross PCIe (the 873 KB/image result comes back only for --dump-predictions).
+            # Then, like the reference, keep the first 200 of the class-grouped list.
+            if args.dump_predictions:
+                result = sess.run(net.result, feed_dict={net.image_input: x, net.keep_prob: 1})
+                dets = ssdutils.detect_batch(result, anchors, args.threshold, lid2name, None)
+            else:
+                dets = net.detect(x, args.threshold, lid2name, None)
+            dets = [d[:200] for d in dets]
             print('[i] batch %d: %s detections per image' % (b, [len(d) for d in dets][:8]))
             for i, boxes in enumerate(dets):
                 gt = synth.gt_boxes(first + i)

@@ -64,6 +64,16 @@ class DataParallelTrainer:
         torch.cuda.current_stream().synchronize()
         return res, losses
 
+    def step_host_gt(self, images, gt, gt_count, lr, momentum, weight_decay):
+        """step_host with raw ground truth [B,G,5] + counts instead of dense labels (fused anchor matching)."""
+        import torch
+        res, losses, _ = self.net.train_step_host_gt(images, gt, gt_count, weight_decay=weight_decay, apply_update=0)
+        scale = average_gradients(self.grads, self.world, self.group)
+        st = torch.cuda.current_stream().cuda_stream
+        self.net.apply_update(lr, momentum, weight_decay, grad_post_scale=scale, stream=st)
+        torch.cuda.current_stream().synchronize()
+        return res, losses
+
     def step(self, images_ptr, labels_ptr, local_batch, lr, momentum, weight_decay, losses_ptr=None, result_ptr=None,
              gt_ptr=None, gt_count_ptr=None, G=0):
         import torch

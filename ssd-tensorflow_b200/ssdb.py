@@ -57,6 +57,7 @@ SIGNATURES = {
     'ssdb_op_conv_fprop': (_i, [_i, _p, _p, _p] + [_i] * 13 + [_p, _p]),
     'ssdb_op_conv_dgrad': (_i, [_i, _p, _p, _p] + [_i] * 13 + [_p, _p]),
     'ssdb_op_conv_wgrad': (_i, [_i, _p, _p] + [_i] * 12 + [_p, _p, _p]),
+    'ssdb_op_conv_bench': (_i, [_i] * 17 + [C.POINTER(_f)]),
     'ssdb_create': (_i, [C.c_char_p, _i, _i, C.c_uint, C.POINTER(_p)]),
     'ssdb_destroy': (_i, [_p]),
     'ssdb_num_anchors': (_i, [_p]),
@@ -73,10 +74,14 @@ SIGNATURES = {
     'ssdb_train_step': (_i, [_p, _p, _p, _p, _p, _i, _i, _f, _f, _f, _f, _i, _p, _p, _p]),
     'ssdb_train_step_host': (_i, [_p, _p, _p, _i, _f, _f, _f, _p, _p]),
     'ssdb_train_step_host_noupdate': (_i, [_p, _p, _p, _i, _f, _p, _p]),
+    'ssdb_train_step_host_gt': (_i, [_p, _p, _p, _p, _i, _i, _f, _f, _f, _i, _p, _p, _p]),
+    'ssdb_forward_detect_host': (_i, [_p, _p, _i, _f, _i, _d, _p, _p, _p]),
     'ssdb_eval_step': (_i, [_p, _p, _p, _i, _f, _p, _p, _p]),
     'ssdb_apply_update': (_i, [_p, _f, _f, _f, _f, _p]),
     'ssdb_pinned_alloc': (_i, [_ll, C.POINTER(_p)]),
     'ssdb_pinned_free': (_i, [_p]),
+    'ssdb_debug_read': (_i, [_p, C.c_char_p, _i, _p, _ll]),
+    'ssdb_debug_shape': (_i, [_p, C.c_char_p, C.POINTER(_i)]),
     'ssdb_launch_count': (_ll, []),
     'ssdb_profile_step': (_i, [_p, _p, _p, _i, _p, _p, _p, _i]),
 }
@@ -146,7 +151,7 @@ def nms_host(boxes_abs, labelid, conf, iou_thr):
 
 
 class PinnedArray:
-    """float32 NumPy view of page-locked host memory owned by the library."""
+    """float32 NumPy view of page-locked host memory owned by the library (explicit free)."""
     def __init__(self, shape):
         self.ptr = _p()
         n = int(np.prod(shape))
@@ -159,6 +164,50 @@ class PinnedArray:
             self.array = None
             lib().ssdb_pinned_free(self.ptr)
             self.ptr = _p()
+
+
+class _PinnedBlock:
+    """Page-locked host block that lives as long as any NumPy array made from it: arrays created with ``np.asarray(block)``
+    keep the block as their base, and the memory is released only when the last of them (and the pool entry) is gone."""
+    def __init__(self, count):
+        self.count = int(count)
+        self.ptr = _p()
+        check(lib().ssdb_pinned_alloc(self.count * 4, C.byref(self.ptr)))
+        self.__array_interface__ = {'shape': (self.count,), 'typestr': '<f4', 'data': (self.ptr.value, False), 'version': 3}
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().ssdb_pinned_free(self.ptr)
+                self.ptr = _p()
+        except Exception:
+            pass
+
+
+class PinnedPool:
+    """Result buffers of the host entry points.  ``tf.Session.run`` hands out fresh arrays, so a result must neither be
+    overwritten by the next run nor die with the engine: a block is reused only when no array refers to it any more
+    (the usual training loop drops the previous result every step, so the steady state is one or two blocks and no
+    allocation or copy per step)."""
+    MAX_BLOCKS = 8
+
+    def __init__(self, count):
+        self.count = int(count)
+        self.blocks = []
+
+    def take(self):
+        import sys
+        for b in self.blocks:
+            if sys.getrefcount(b) <= 3:          # the list, the loop variable, the call argument: no array holds it
+                return np.asarray(b)
+        if len(self.blocks) < self.MAX_BLOCKS:
+            b = _PinnedBlock(self.count)
+            self.blocks.append(b)
+            return np.asarray(b)
+        return np.empty(self.count, np.float32)   # every block is still referenced by the caller: plain (pageable) memory
+
+    def clear(self):
+        self.blocks = []                           # blocks that are still referenced stay alive through their arrays
 
 
 # ---------------------------------------------------------------- engine handle
@@ -178,14 +227,15 @@ class Net:
         self._pinned_result = None
 
     def result_buffer(self, B):
-        """Pinned [B, A, C+5] view reused by the host entry points (valid until the next call)."""
+        """A page-locked [B, A, C+5] array for one result.  The array owns a reference to its memory block: it stays
+        valid after later calls and after close(); the block returns to the pool when the caller drops the array."""
         if self._pinned_result is None:
-            self._pinned_result = PinnedArray((self.max_batch, self.num_anchors, self.row))
-        return self._pinned_result.array[:B]
+            self._pinned_result = PinnedPool(self.max_batch * self.num_anchors * self.row)
+        return self._pinned_result.take()[:B * self.num_anchors * self.row].reshape(B, self.num_anchors, self.row)
 
     def close(self):
         if self._pinned_result is not None:
-            self._pinned_result.free()
+            self._pinned_result.clear()
             self._pinned_result = None
         if self._h:
             lib().ssdb_destroy(self._h)
@@ -240,6 +290,19 @@ class Net:
         check(lib().ssdb_read_output_host(self._h, B, out.ctypes.data_as(_p)))
         return out
 
+    def debug_read(self, name, B):
+        """An intermediate tensor of the last step as float32: '<op>' -> [B,H,W,C] activation, 'grad:<op>' its gradient,
+        'output' / 'output_grad' -> [B,A,C+5]."""
+        if name in ('output', 'output_grad'):
+            shape = (B, self.num_anchors, self.row)
+        else:
+            hwc = (_i * 3)()
+            check(lib().ssdb_debug_shape(self._h, name.split(':')[-1].encode(), hwc))
+            shape = (B, hwc[0], hwc[1], hwc[2])
+        out = np.empty(shape, np.float32)
+        check(lib().ssdb_debug_read(self._h, name.encode(), B, out.ctypes.data_as(_p), out.size))
+        return out
+
     def train_step_host(self, images, labels, lr, momentum, weight_decay, want_result=True, result_out=None):
         x, px = _np(images, np.float32)
         y, py = _np(labels, np.float32)
@@ -259,6 +322,41 @@ class Net:
         losses = np.empty(4, np.float32)
         check(lib().ssdb_train_step_host_noupdate(self._h, px, py, B, weight_decay, losses.ctypes.data_as(_p), res.ctypes.data_as(_p)))
         return res, losses
+
+    def train_step_host_gt(self, images, gt, gt_count, lr=0.0, momentum=0.0, weight_decay=0.0005, apply_update=True,
+                           want_result=True, result_out=None, want_match=False):
+        """The training step fed with raw ground truth [B,G,5] float64 + counts [B] (fused anchor matching):
+        returns (result or None, losses[4], match [B,A] or None).  apply_update: True / 1 full step, False / 0 backward
+        only (gradients stay in the flat buffer), -1 forward + loss only."""
+        x, px = _np(images, np.float32)
+        g, pg = _np(gt, np.float64)
+        c, pc = _np(gt_count, np.int32)
+        B = x.shape[0]
+        if g.ndim != 3 or g.shape[0] != B or g.shape[2] != 5 or c.shape != (B,):
+            raise ValueError('gt must be [B, G, 5] and gt_count [B]')
+        res = result_out if result_out is not None else (self.result_buffer(B) if want_result else None)
+        match = np.empty((B, self.num_anchors), np.int32) if want_match else None
+        losses = np.empty(4, np.float32)
+        mode = apply_update if isinstance(apply_update, int) and not isinstance(apply_update, bool) else (1 if apply_update else 0)
+        check(lib().ssdb_train_step_host_gt(self._h, px, pg, pc, g.shape[1], B, lr, momentum, weight_decay, mode,
+                                            losses.ctypes.data_as(_p), res.ctypes.data_as(_p) if res is not None else None,
+                                            match.ctypes.data_as(_p) if want_match else None))
+        return res, losses, match
+
+    def forward_detect_host(self, images, conf_thr=0.01, cap=200, iou_thr=0.45, want_result=False):
+        """forward + decode + class-wise NMS with the result tensor kept on the device:
+        (dets [B,cap_eff,8] int32, counts [B,2] int32[, result])."""
+        x, px = _np(images, np.float32)
+        B = x.shape[0]
+        cap_i = int(cap) if cap is not None else 0
+        cap_eff = cap_i if 0 < cap_i < self.num_anchors else self.num_anchors
+        dets = np.zeros((B, cap_eff, 8), np.int32)
+        counts = np.zeros((B, 2), np.int32)
+        res = self.result_buffer(B) if want_result else None
+        check(lib().ssdb_forward_detect_host(self._h, px, B, float(np.float32(conf_thr)), cap_i, float(iou_thr),
+                                             dets.ctypes.data_as(_p), counts.ctypes.data_as(_p),
+                                             res.ctypes.data_as(_p) if want_result else None))
+        return (dets, counts, res) if want_result else (dets, counts)
 
     # device-pointer calls
     def forward(self, images_ptr, B, result_ptr=None, stream=None):

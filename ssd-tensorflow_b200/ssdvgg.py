@@ -81,6 +81,51 @@ def _trunk_scope(name):
     return name.startswith(('conv1_', 'conv2_', 'conv3_', 'conv4_', 'conv5_', 'mod_conv'))
 
 
+def _flatten(f, out):
+    """fetch structure (handles nested in lists / tuples / dicts, like tf.Session.run accepts) -> flat list of handles"""
+    if isinstance(f, (list, tuple)):
+        for v in f:
+            _flatten(v, out)
+    elif isinstance(f, dict):
+        for v in f.values():
+            _flatten(v, out)
+    else:
+        out.append(f)
+
+
+def _assemble(f, values):
+    """the fetch structure with every handle replaced by its value"""
+    if isinstance(f, (list, tuple)):
+        return [_assemble(v, values) for v in f]
+    if isinstance(f, dict):
+        return {k: _assemble(v, values) for k, v in f.items()}
+    return values.get(f)
+
+
+def _pack_gt(gt, counts, B):
+    """net.gt_boxes feed -> ([B, G, 5] float64, [B] int32).  Accepts the packed array (+ counts; all rows valid if omitted)
+    or per-image sequences of utils.Box / (labelid, cx, cy, w, h) rows."""
+    if isinstance(gt, np.ndarray) and gt.ndim == 3:
+        arr = np.ascontiguousarray(gt, np.float64)
+        cnt = np.full(B, arr.shape[1], np.int32) if counts is None else np.ascontiguousarray(counts, np.int32)
+        if arr.shape[0] != B or arr.shape[2] != 5 or cnt.shape != (B,):
+            raise ValueError('gt_boxes must be [B, G, 5] with gt_counts [B]')
+        return arr, cnt
+    if len(gt) != B:
+        raise ValueError('gt_boxes must hold one box list per image')
+    G = max(1, max(len(g) for g in gt))
+    arr = np.zeros((B, G, 5), np.float64)
+    cnt = np.zeros(B, np.int32)
+    for b, boxes in enumerate(gt):
+        cnt[b] = len(boxes)
+        for k, bx in enumerate(boxes):
+            if hasattr(bx, 'center'):
+                arr[b, k] = (bx.labelid, bx.center.x, bx.center.y, bx.size.w, bx.size.h)
+            else:
+                arr[b, k] = bx
+    return arr, cnt
+
+
 class SSDVGG:
     def __init__(self, session, preset):
         self.preset = preset if not isinstance(preset, str) else get_preset_by_name(preset)
@@ -90,11 +135,20 @@ class SSDVGG:
         self._engine = None
         self._host_params = None     # name -> ndarray, until an engine exists (and to survive re-creation)
         self._opt = None
+        self._host_momentum = None   # name -> ndarray restored from a checkpoint, loaded into the engine when it is created
+        self._restored_step = 0
+        self.epoch = 0               # epochs completed (kept in checkpoints so that --continue-training resumes the loop)
         self._build_names()
         # fetch / feed handles (same attribute names as the reference)
         self.image_input = Fetch('image_input:0')
         self.keep_prob = Fetch('keep_prob:0')
         self.labels = Fetch('labels:0')
+        # raw ground truth instead of the dense label tensor (fused anchor matching on the GPU): feed either
+        # net.gt_boxes = [B, G, 5] float64 rows (labelid, cx, cy, w, h) with net.gt_counts = [B] int32, or net.gt_boxes = the
+        # reference's own per-image lists of utils.Box (what train_generator yields as `gt`, train.py:257)
+        self.gt_boxes = Fetch('gt_boxes')
+        self.gt_counts = Fetch('gt_counts')
+        self.match = Fetch('match')          # fetchable with net.gt_boxes: [B, A] owner GT per anchor, -1 = background
         self.result = Fetch('result/result:0')
         self.logits = Fetch('output/logits')
         self.classifier = Fetch('result/classifier')
@@ -144,16 +198,19 @@ class SSDVGG:
         accepted for signature compatibility and ignored (there is no TF graph to import)."""
         if os.path.exists(checkpoint_file + '.index'):            # a TensorFlow checkpoint-V2 bundle (ours or the reference's)
             t = tf_bundle.read_bundle(checkpoint_file)
-            self._host_params = {k: v.astype(np.float32) for k, v in t.items() if k.endswith(('/filter', '/biases', '/scale'))
-                                 and '/Momentum' not in k}
-            row = int(self._host_params['classifiers/classifier0_0/biases'].shape[0])
-            self.num_vars = row
-            self.num_classes = row - 4
-            self._built = True
-            return
-        with np.load(checkpoint_file if checkpoint_file.endswith('.npz') else checkpoint_file + '.npz') as z:
-            self._host_params = {k: z[k].astype(np.float32) for k in z.files if not k.startswith('__')}
-            row = int(z['__num_vars']) if '__num_vars' in z.files else 25
+            epoch = 0
+        else:
+            with np.load(checkpoint_file if checkpoint_file.endswith('.npz') else checkpoint_file + '.npz') as z:
+                t = {k: z[k] for k in z.files if not k.startswith('__')}
+                epoch = int(z['__epoch']) if '__epoch' in z.files else 0
+        ok = ('/filter', '/biases', '/scale')
+        self._host_params = {k: np.asarray(v, np.float32) for k, v in t.items() if k.endswith(ok)}
+        # optimizer state, restored like the reference's Saver does (train.py:101-134,191-193): Momentum slots + global_step
+        self._host_momentum = {k[:-len('/Momentum')]: np.asarray(v, np.float32) for k, v in t.items()
+                               if k.endswith('/Momentum') and k[:-len('/Momentum')].endswith(ok)}
+        self._restored_step = int(np.asarray(t['global_step']).reshape(-1)[0]) if 'global_step' in t else 0
+        self.epoch = epoch
+        row = int(self._host_params['classifiers/classifier0_0/biases'].shape[0])
         self.num_vars = row
         self.num_classes = row - 4
         self._built = True
@@ -162,11 +219,14 @@ class SSDVGG:
         """ssdvgg.py:375-599.  `learning_rate` is a float or a zero-argument callable
         (see piecewise_constant)."""
         self._opt = dict(lr=learning_rate, wd=float(weight_decay), mu=float(momentum), step=global_step)
+        if global_step is not None and self._restored_step and global_step.value == 0:
+            global_step.value = self._restored_step        # a restored model continues its learning-rate schedule
 
-    def build_optimizer_from_metagraph(self):
-        """ssdvgg.py:133-150: re-attach the optimizer of a restored model (defaults of train.py)."""
-        if self._opt is None:
-            self._opt = dict(lr=0.00075, wd=0.0005, mu=0.9, step=None)
+    def build_optimizer_from_metagraph(self, learning_rate=0.00075, weight_decay=0.0005, momentum=0.9, global_step=None):
+        """ssdvgg.py:133-150: re-attach the optimizer of a restored model.  The reference finds its hyper-parameters in the
+        imported metagraph; there is no graph here, so they are arguments (defaults of train.py:69-76).  The Momentum
+        accumulators and global_step come from the checkpoint (build_from_metagraph)."""
+        self.build_optimizer(learning_rate, weight_decay, momentum, global_step)
 
     def build_summaries(self, restore):
         """ssdvgg.py:625-649: TensorBoard histograms are observability, out of scope; a handle is
@@ -178,15 +238,22 @@ class SSDVGG:
         ``tf_checkpoint=True`` a TensorFlow checkpoint-V2 bundle ``<path>.index`` / ``<path>.data-00000-of-00001`` like the
         reference's ``saver.save(sess, 'e<N>.ckpt')`` (train.py:336-343), readable by TensorFlow tools."""
         arrays = self.get_params()
+        # the optimizer state the reference's Saver keeps (train.py:208): Momentum slots '<var>/Momentum' and global_step
+        for k, v in self.get_params(ssdb.MOMENTUM).items():
+            arrays[k + '/Momentum'] = v
+        step = self._opt['step'].value if self._opt is not None and self._opt.get('step') is not None else self._restored_step
+        arrays['global_step'] = np.array(step, np.int64)
         if tf_checkpoint:
             tf_bundle.write_bundle(path, arrays)
             return
         arrays['__num_vars'] = np.array(self.num_vars)
+        arrays['__epoch'] = np.array(self.epoch, np.int64)
         np.savez(path if path.endswith('.npz') else path + '.npz', **arrays)
 
     def close(self):
         if self._engine is not None:
             self._host_params = self.get_params()
+            self._host_momentum = self.get_params(ssdb.MOMENTUM)
             self._engine.close()
             self._engine = None
 
@@ -256,21 +323,18 @@ class SSDVGG:
             eng.set_tensor(k, src[k])
             if state:
                 eng.set_tensor(k, state[1][k], ssdb.MOMENTUM)
+            elif self._host_momentum and k in self._host_momentum:
+                eng.set_tensor(k, self._host_momentum[k], ssdb.MOMENTUM)
         self._engine = eng
         return eng
 
     # ------------------------------------------------------------------ execution
     def _run(self, fetches, feed):
+        # (no recursive closures here: a function that refers to itself forms a reference cycle with everything it captured,
+        # and the result arrays -- page-locked pool blocks -- would then wait for the cyclic collector instead of being
+        # released when the caller drops them)
         flat = []
-
-        def walk(f):
-            if isinstance(f, (list, tuple)):
-                for v in f: walk(v)
-            elif isinstance(f, dict):
-                for v in f.values(): walk(v)
-            else:
-                flat.append(f)
-        walk(fetches)
+        _flatten(fetches, flat)
         if self.image_input not in feed:
             raise ValueError('feed_dict must provide net.image_input')
         x = np.ascontiguousarray(feed[self.image_input], np.float32)
@@ -279,40 +343,58 @@ class SSDVGG:
         loss_handles = set(self.losses.values())
         want_train = any(f is self.optimizer for f in flat)
         want_loss = any(f in loss_handles for f in flat)
+        want_match = any(f is self.match for f in flat)
         eng = self._ensure_engine(x.shape[0])
+        B = x.shape[0]
         values = {}
         if want_train or want_loss:
-            if self.labels not in feed:
-                raise ValueError('feed_dict must provide net.labels for loss / optimizer fetches')
+            if self.labels not in feed and self.gt_boxes not in feed:
+                raise ValueError('feed_dict must provide net.labels (or net.gt_boxes) for loss / optimizer fetches')
             if self._opt is None:
                 raise RuntimeError('call build_optimizer first')
-            y = np.ascontiguousarray(feed[self.labels], np.float32)
             lr = self._opt['lr']() if callable(self._opt['lr']) else float(self._opt['lr'])
-            if want_train:
-                res, ls = eng.train_step_host(x, y, lr, self._opt['mu'], self._opt['wd'])
-                if self._opt['step'] is not None:
-                    self._opt['step'].value += 1
+            if self.gt_boxes in feed:
+                gt, cnt = _pack_gt(feed[self.gt_boxes], feed.get(self.gt_counts), B)
+                res, ls, match = eng.train_step_host_gt(x, gt, cnt, lr, self._opt['mu'], self._opt['wd'],
+                                                        apply_update=1 if want_train else -1, want_match=want_match)
+                values[self.match] = match
             else:
-                res, ls = self._eval_host(eng, x, y)
+                if want_match:
+                    raise ValueError('net.match is produced by the fused matcher: feed net.gt_boxes')
+                y = np.ascontiguousarray(feed[self.labels], np.float32)
+                if want_train:
+                    res, ls = eng.train_step_host(x, y, lr, self._opt['mu'], self._opt['wd'])
+                else:
+                    res, ls = self._eval_host(eng, x, y)
+            if want_train and self._opt['step'] is not None:
+                self._opt['step'].value += 1
             values[self.loss], values[self.localization_loss] = ls[0], ls[1]
             values[self.confidence_loss], values[self.l2_loss] = ls[2], ls[3]
         else:
             res = eng.forward_host(x)
         nc = self.num_vars - 4
+        # like tf.Session.run, every fetch is an array of its own: `res` owns its (pooled, page-locked) memory block,
+        # so it survives later runs and close()
         values[self.result] = res
         values[self.classifier] = res[..., :nc]
         values[self.locator] = res[..., nc:]
         values[self.optimizer] = None
+        if any(f is self.logits for f in flat):
+            values[self.logits] = eng.read_output(B)[..., :nc]      # ssdvgg.py:366: the pre-softmax class scores
 
-        def build(f):
-            if isinstance(f, (list, tuple)):
-                return [build(v) for v in f]
-            if isinstance(f, dict):
-                return {k: build(v) for k, v in f.items()}
-            if f is self.logits:
-                raise NotImplementedError('raw logits are not exported; fetch net.result / net.classifier')
-            return values.get(f)
-        return build(fetches)
+        return _assemble(fetches, values)
+
+    def detect(self, images, confidence_threshold=0.01, lid2name={}, detections_cap=200, overlap_threshold=0.45, rows=False):
+        """infer.py:225-235 in one call: forward, then decode_boxes + suppress_overlaps on the device-resident result
+        (ssdb_forward_detect_host); only the detections cross PCIe.  Returns per image the reference's
+        ``[(confidence, Box), ...]`` list (or, with rows=True, the kernels' integer rows + counts)."""
+        from ssdutils import _boxes_from_rows
+        x = np.ascontiguousarray(images, np.float32)
+        eng = self._ensure_engine(x.shape[0])
+        dets, counts = eng.forward_detect_host(x, confidence_threshold, detections_cap, overlap_threshold)
+        if rows:
+            return dets, counts
+        return [_boxes_from_rows(dets[i, :counts[i, 0]], lid2name) for i in range(x.shape[0])]
 
     def _eval_host(self, eng, x, y):
         import torch                      # device-memory plumbing only

@@ -38,9 +38,14 @@ def main():
     ap.add_argument('--preset', default='vgg300')
     ap.add_argument('--synthetic', type=str2bool, default='True')
     ap.add_argument('--batches-per-epoch', type=int, default=4)
+    ap.add_argument('--valid-batches', type=int, default=1, help='validation batches per epoch (train.py:287-303)')
+    ap.add_argument('--feed', default='gt', choices=['gt', 'labels'],
+                    help="'gt': raw ground-truth boxes, anchors matched inside the fused loss kernels; "
+                         "'labels': the reference's dense label tensor (create_labels = LabelCreatorTransform on the GPU)")
     args = ap.parse_args()
     if not args.synthetic:
-        print('[!] only --synthetic input is built here (the VOC loader is outside the hot path)')
+        print('[!] only --synthetic input is built here: the VOC loader / augmentation pipeline (training_data.py, transforms.py) '
+              'is outside the hot path; feed your own batches through Session.run like the loop below does')
         return 1
     preset = ssdutils.get_preset_by_name(args.preset)
     anchors = ssdutils.get_anchors_for_preset(preset)
@@ -49,44 +54,82 @@ def main():
     with Session() as sess:
         net = SSDVGG(sess, preset)
         ckpt = os.path.join(args.name, 'final.npz')
-        if args.continue_training and os.path.exists(ckpt):
-            net.build_from_metagraph(None, ckpt)
+        step = GlobalStep(0)
+        lr = piecewise_constant(step, lr_boundaries, lr_values)
+        start_epoch = 0
+        if args.continue_training:
+            # train.py:101-134: resume from the newest e<N> checkpoint (weights, Momentum slots, global_step, epoch)
+            last = _latest_checkpoint(args.name)
+            if last is None:
+                print('[!] No checkpoints found in ' + args.name)
+                return 1
+            net.build_from_metagraph(None, last)
+            net.build_optimizer_from_metagraph(lr, args.weight_decay, args.momentum, step)
+            start_epoch = net.epoch
+            print('[i] resuming from %s: epoch %d, global step %d' % (last, start_epoch, step.value))
         else:
             net.build_from_vgg(args.vgg_dir, 20)
-        step = GlobalStep(0)
-        net.build_optimizer(learning_rate=piecewise_constant(step, lr_boundaries, lr_values),
-                            weight_decay=args.weight_decay, momentum=args.momentum, global_step=step)
+            net.build_optimizer(learning_rate=lr, weight_decay=args.weight_decay, momentum=args.momentum, global_step=step)
         side = preset.image_size.w
         lid2name = {i: 'class%d' % i for i in range(20)}
-        ap_calc = APCalculator()
-        for e in range(args.epochs):
+        train_ap, valid_ap = APCalculator(), APCalculator()
+
+        def batch(first):
+            x = synth.images(first, args.batch_size, side)
+            gts = [synth.gt_boxes(first + i) for i in range(args.batch_size)]
+            if args.feed == 'gt':
+                gt, cnt = synth.pack_gt(gts, 8)
+                return x, gts, {net.image_input: x, net.gt_boxes: gt, net.gt_counts: cnt}
+            boxes = [[ssdutils.Box(None, int(g[0]), ssdutils.Point(g[1], g[2]), ssdutils.Size(g[3], g[4])) for g in gt] for gt in gts]
+            y, _ = ssdutils.create_labels(boxes, anchors, 20)
+            return x, gts, {net.image_input: x, net.labels: y}
+
+        valid_first = 10 ** 6           # a disjoint range of synthetic sample indices plays the validation split
+        losses = vlosses = None
+        for e in range(start_epoch, args.epochs):
             t0 = time.time()
-            ap_calc.clear()
-            for b in range(args.batches_per_epoch):
-                first = (e * args.batches_per_epoch + b) * args.batch_size
-                x = synth.images(first, args.batch_size, side)
-                gts = [synth.gt_boxes(first + i) for i in range(args.batch_size)]
-                boxes = [[ssdutils.Box(None, int(g[0]), ssdutils.Point(g[1], g[2]), ssdutils.Size(g[3], g[4])) for g in gt] for gt in gts]
-                y, _ = ssdutils.create_labels(boxes, anchors, 20)
-                result, losses, _ = sess.run([net.result, net.losses, net.optimizer],
-                                             feed_dict={net.image_input: x, net.labels: y})
+            train_ap.clear(); valid_ap.clear()
+            for b in range(args.batches_per_epoch):          # train.py:254-281
+                x, gts, feed = batch((e * args.batches_per_epoch + b) * args.batch_size)
+                result, losses, _ = sess.run([net.result, net.losses, net.optimizer], feed_dict=feed)
                 if np.isnan(losses['confidence']):
                     print('[!] Confidence loss is NaN.')
                 if e == 0:
                     continue
                 # train.py:275-278: decode + NMS of every sample, fed to the AP calculator -- one batched launch here
                 dets, counts = ssdutils.detect_batch_rows(result, anchors, 0.5, 200)
-                ap_calc.add_detections_batch(gts, dets, counts, lid2name)
-            aps = ap_calc.compute_aps() if e > 0 else {}
-            print('[i] epoch %d: total %.4f loc %.4f conf %.4f l2 %.4f | mAP %.4f over %d classes | %.2fs' %
-                  (e, losses['total'], losses['localization'], losses['confidence'], losses['l2'],
-                   APs2mAP(aps), len(aps), time.time() - t0))
+                train_ap.add_detections_batch(gts, dets, counts, lid2name)
+            for b in range(args.valid_batches):              # train.py:287-303: forward + loss only, then decode + NMS + AP
+                x, gts, feed = batch(valid_first + b * args.batch_size)
+                result, vlosses = sess.run([net.result, net.losses], feed_dict=feed)
+                dets, counts = ssdutils.detect_batch_rows(result, anchors, 0.5, 200)
+                valid_ap.add_detections_batch(gts, dets, counts, lid2name)
+            aps = train_ap.compute_aps() if e > 0 else {}
+            vaps = valid_ap.compute_aps() if args.valid_batches else {}
+            print('[i] epoch %d: train total %.4f loc %.4f conf %.4f l2 %.4f mAP %.4f | valid total %.4f mAP %.4f | %.2fs' %
+                  (e, losses['total'], losses['localization'], losses['confidence'], losses['l2'], APs2mAP(aps),
+                   vlosses['total'] if vlosses else float('nan'), APs2mAP(vaps), time.time() - t0))
+            net.epoch = e + 1
             if (e + 1) % args.checkpoint_interval == 0:
                 os.makedirs(args.name, exist_ok=True)
                 net.save(os.path.join(args.name, 'e%d' % (e + 1)))
         os.makedirs(args.name, exist_ok=True)
         net.save(ckpt)
     return 0
+
+
+def _latest_checkpoint(directory):
+    """Highest-numbered e<N>.npz of a run directory (train.py:104-118), or final.npz, or None."""
+    import re
+    best, path = -1, None
+    if os.path.isdir(directory):
+        for f in os.listdir(directory):
+            m = re.match(r'^e(\d+)\.npz$', f)
+            if m and int(m.group(1)) > best:
+                best, path = int(m.group(1)), os.path.join(directory, f)
+        if path is None and os.path.exists(os.path.join(directory, 'final.npz')):
+            path = os.path.join(directory, 'final.npz')
+    return path
 
 
 if __name__ == '__main__':

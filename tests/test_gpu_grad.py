@@ -1,0 +1,84 @@
+"""GPU: whole-network gradients of the product mode WITHOUT decision flips.
+
+Gradients pass through ReLU masks, max-pool arg-maxes and the hard-negative selection; two forward passes that differ by
+1e-4 take a handful of those decisions differently, and each flip changes gradient entries by O(1) of their size -- that
+is what the 1-9 % max-norm gradient differences of tests/test_gpu_net.py are made of.  Here the oracle takes every decision
+from the ENGINE's own forward pass (its stored activations and its selected-negative set, read back through
+ssdb_debug_read), so both sides differentiate the same piecewise-linear function and the remaining difference is
+arithmetic only.  Bar: 2e-3 max-norm on every tensor (measured: ~1e-4)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import box_oracle as bo
+import net_oracle as no
+import ssdb
+import synth
+
+pytestmark = pytest.mark.gpu
+
+RELU_LAYERS = ['conv1_1', 'conv1_2', 'conv2_1', 'conv2_2', 'conv3_1', 'conv3_2', 'conv3_3', 'conv4_1', 'conv4_2', 'conv4_3',
+               'conv5_1', 'conv5_2', 'conv5_3', 'mod_conv6', 'mod_conv7', 'conv8_1', 'conv8_2', 'conv9_1', 'conv9_2',
+               'conv10_1', 'conv10_2', 'conv11_1', 'conv11_2']
+
+
+@pytest.mark.parametrize('preset,B,mode', [('vgg300', 2, 'default'), ('vgg512', 1, 'default'), ('vgg300', 1, 'tf32')])
+def test_gradients_with_the_engines_own_decisions(preset, B, mode):
+    if mode != 'default':
+        os.environ['SSDB_CONV'] = mode
+    try:
+        net = ssdb.Net(preset, 20, max_batch=B)
+    finally:
+        os.environ.pop('SSDB_CONV', None)
+    side = bo.PRESETS[preset]['image']
+    P = no.init_params(preset, dtype=torch.float64)
+    for k, shape in net.tensors():
+        net.set_tensor(k, P[k].numpy().astype(np.float32))
+    anc = bo.anchors(preset); aabs = bo.anchors_abs(anc)
+    x = synth.images(0, B, side)
+    labels = np.stack([bo.make_labels(synth.gt_boxes(i), anc, aabs, 20)[0] for i in range(B)])
+    net.train_step_host(x, labels, 0.0, 0.0, 0.0005)                      # lr = 0: parameters stay, gradients are left in the flat buffer
+    layers = RELU_LAYERS + (['conv12_1', 'conv12_2'] if preset == 'vgg512' else [])
+    dec = {name: torch.tensor(net.debug_read(name, B)).permute(0, 3, 1, 2) for name in layers}
+    og = net.debug_read('output_grad', B)
+    selected = torch.tensor(np.abs(og).sum(-1) > 0)
+    # how many decisions does the oracle's own pass take differently?
+    taps = {}
+    with torch.no_grad():
+        no.forward(P, torch.tensor(x), preset, taps=taps)
+    flips = {n: int(((taps[n] > 0) != (dec[n] > 0)).sum()) for n in layers}
+    total = sum(int(dec[n].numel()) for n in layers)
+    V = {k: torch.zeros_like(v) for k, v in P.items()}
+    Pd = {k: v.clone() for k, v in P.items()}
+    L, _, grads = no.train_step(Pd, V, torch.tensor(x), torch.tensor(labels), preset, lr=0.0, momentum=0.0, weight_decay=0.0005,
+                                decisions=dec, selected=selected)
+    V2 = {k: torch.zeros_like(v) for k, v in P.items()}
+    P2 = {k: v.clone() for k, v in P.items()}
+    _, _, grads_own = no.train_step(P2, V2, torch.tensor(x), torch.tensor(labels), preset, lr=0.0, momentum=0.0, weight_decay=0.0005)
+    worst, worst_own = (None, 0.0), (None, 0.0)
+    tol = 2e-3 if mode == 'default' else 2e-2
+    bad = []
+    for k, shape in net.tensors():
+        g = net.get_tensor(k, shape, ssdb.GRAD).astype(np.float64)
+        l2term = 0.0005 * P[k].numpy() if k.endswith('/filter') else 0.0      # the engine adds the L2 term inside the update kernel
+        want = grads[k].numpy() - l2term
+        own = grads_own[k].numpy() - l2term
+        e = float(np.abs(g - want).max() / max(np.abs(want).max(), 1e-30))
+        eo = float(np.abs(g - own).max() / max(np.abs(own).max(), 1e-30))
+        if e > worst[1]:
+            worst = (k, e)
+        if eo > worst_own[1]:
+            worst_own = (k, eo)
+        if e > tol:
+            bad.append((k, e))
+    report = {'preset': preset, 'B': B, 'mode': mode, 'worst_grad_same_decisions': list(worst), 'worst_grad_own_decisions': list(worst_own),
+              'relu_flips': sum(flips.values()), 'relu_decisions': total}
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, 'gpurun_out'), exist_ok=True)
+    json.dump(report, open(os.path.join(root, 'gpurun_out', 'grad_parity_%s_%s.json' % (preset, mode)), 'w'))
+    print('GRAD', json.dumps(report))
+    assert not bad, bad[:10]
+    net.close()

@@ -126,3 +126,131 @@ def test_ap_from_gpu_detections_equals_reference_fixture(golden_dir):
         ids = [int(k) for k in g['aps_%s_ids' % tag]]
         assert np.array_equal(np.array([aps[lid2name[k]] for k in ids]), g['aps_' + tag])
         assert ap.APs2mAP(aps) == g['map_' + tag][0]
+
+
+def _model(sess, lr=1e-5):
+    preset = ssdutils.get_preset_by_name('vgg300')
+    net = SSDVGG(sess, preset)
+    net.build_from_vgg(None, 20)
+    step = GlobalStep(0)
+    net.build_optimizer(learning_rate=lr, weight_decay=0.0005, momentum=0.9, global_step=step)
+    return net, step, ssdutils.get_anchors_for_preset(preset)
+
+
+def test_gt_feed_is_the_dense_label_step_with_the_match_inside():
+    """net.gt_boxes (raw ground truth, fused match + loss on the product path: ssdb_train_step_host_gt) against net.labels
+    (dense labels built by LabelCreatorTransform's GPU port) and against the oracle's matching: same match indices,
+    same losses, same result, same parameters after the step (transforms.py:72-114 -> train.py:262-266)."""
+    x = synth.images(0, 3, 300)
+    gts = [synth.gt_boxes(i) for i in range(2)] + [np.zeros((0, 5))]          # the third image has no box at all
+    boxes = [[utils.Box(None, int(r[0]), utils.Point(r[1], r[2]), utils.Size(r[3], r[4])) for r in gt] for gt in gts]
+    anc_arr = bo.anchors('vgg300'); aabs = bo.anchors_abs(anc_arr)
+    p0 = _model(Session())[0].get_params()
+    with Session() as s1:
+        n1, _, anc = _model(s1)
+        y, _ = ssdutils.create_labels(boxes, anc, 20)
+        r1, l1, _ = s1.run([n1.result, n1.losses, n1.optimizer], feed_dict={n1.image_input: x, n1.labels: y})
+        p1 = n1.get_params()
+    with Session() as s2:
+        n2, step, _ = _model(s2)
+        # validation fetch with raw GT: forward + loss only, nothing moves
+        rv, lv, mv = s2.run([n2.result, n2.losses, n2.match], feed_dict={n2.image_input: x, n2.gt_boxes: boxes})
+        assert step.value == 0 and all(np.array_equal(v, p0[k]) for k, v in n2.get_params().items())
+        r2, l2, _, m2 = s2.run([n2.result, n2.losses, n2.optimizer, n2.match], feed_dict={n2.image_input: x, n2.gt_boxes: boxes})
+        p2 = n2.get_params()
+        assert step.value == 1
+    for b in range(3):
+        want = bo.make_labels(gts[b], anc_arr, aabs, 20)[1] if len(gts[b]) else np.full(8732, -1)
+        assert np.array_equal(m2[b], want), 'match indices of image %d differ from the oracle' % b
+        assert np.array_equal(mv[b], want)
+    assert np.array_equal(np.array(r1), np.array(r2)) and np.array_equal(np.array(rv), np.array(r2))
+    for k in ('total', 'localization', 'confidence', 'l2'):
+        assert abs(l1[k] - l2[k]) <= 2e-6 * abs(l1[k]), (k, l1[k], l2[k])
+        assert abs(lv[k] - l2[k]) <= 2e-6 * abs(l1[k])
+    # the two loss paths differ only in how the log() of the encoded offsets is rounded (<= 1 float32 ulp, tests/test_gpu_box.py)
+    for k in p1:
+        upd = np.abs(p1[k] - p0[k]).max()                      # size of the update both runs applied
+        d = np.abs(p1[k] - p2[k]).max()
+        assert d <= 1e-3 * upd + 2.4e-7 * max(np.abs(p1[k]).max(), 1e-30), (k, d, upd)
+    # packed-array form of the same feed, and a bad label id
+    gt, cnt = synth.pack_gt(gts, 8)
+    with Session() as s3:
+        n3, _, _ = _model(s3)
+        _, l3 = s3.run([n3.result, n3.losses], feed_dict={n3.image_input: x, n3.gt_boxes: gt, n3.gt_counts: cnt})
+        assert abs(l3['total'] - l2['total']) <= 2e-6 * abs(l2['total'])
+        gt[0, 0, 0] = 20
+        import ssdb
+        with pytest.raises(ssdb.SSDBError):
+            s3.run([n3.losses], feed_dict={n3.image_input: x, n3.gt_boxes: gt, n3.gt_counts: cnt})
+
+
+def test_detect_on_the_device_resident_result_equals_the_two_step_flow():
+    """SSDVGG.detect (ssdb_forward_detect_host: forward, then decode + NMS on the resident result; infer.py:225-235 as one
+    flow) == sess.run(net.result) followed by detect_batch on the host copy, for a cap of 200 and for no cap."""
+    x = synth.images(40, 3, 300)
+    with Session() as sess:
+        net, _, anc = _model(sess)
+        res = sess.run(net.result, feed_dict={net.image_input: x, net.keep_prob: 1})
+        for cap, thr in ((200, 0.01), (None, 0.02), (7, 0.01)):
+            want = ssdutils.detect_batch(res, anc, thr, {}, cap)
+            got = net.detect(x, thr, {}, cap)
+            assert len(want) == len(got) == 3
+            assert sum(len(w) for w in want) > 0
+            for w, g in zip(want, got):
+                assert [(float(c), b) for c, b in w] == [(float(c), b) for c, b in g]
+            dets, counts = net.detect(x, thr, {}, cap, rows=True)
+            d2, c2 = ssdutils.detect_batch_rows(res, anc, thr, cap)
+            assert np.array_equal(counts, c2)
+            for i in range(3):
+                assert np.array_equal(dets[i, :counts[i, 0]], d2[i, :c2[i, 0]])
+
+
+def test_fetched_arrays_are_the_callers_own():
+    """tf.Session.run returns fresh arrays: a result must survive later runs, a larger batch (engine re-creation) and close()."""
+    x1, x2 = synth.images(0, 2, 300), synth.images(7, 2, 300)
+    sess = Session()
+    net, _, _ = _model(sess)
+    r1 = sess.run(net.result, feed_dict={net.image_input: x1})
+    keep = np.array(r1)
+    c1 = sess.run(net.classifier, feed_dict={net.image_input: x1})
+    r2 = sess.run(net.result, feed_dict={net.image_input: x2})
+    assert np.array_equal(r1, keep) and not np.array_equal(r2, keep)
+    assert np.array_equal(c1, keep[..., :21])
+    r3 = sess.run(net.result, feed_dict={net.image_input: synth.images(0, 3, 300)})      # larger batch: new engine
+    assert np.allclose(r3[:2], keep, rtol=0, atol=1e-4)       # another batch size tiles the GEMMs differently: same values up to summation order
+    lg = sess.run(net.logits, feed_dict={net.image_input: x1})                              # ssdvgg.py:366
+    assert lg.shape == (2, 8732, 21)
+    e = np.exp(lg - lg.max(-1, keepdims=True)); sm = e / e.sum(-1, keepdims=True)
+    assert np.abs(sm - keep[..., :21]).max() < 1e-5
+    sess.close()
+    assert np.array_equal(r1, keep) and np.allclose(r3[:2], keep, rtol=0, atol=1e-4) and np.isfinite(r2).all()
+
+
+def test_continue_training_restores_momentum_step_and_epoch(tmp_path):
+    """train.py:101-134,191-193: the Saver restores the variables, the Momentum slots and global_step; a resumed run must
+    take exactly the step the uninterrupted run takes."""
+    x = synth.images(0, 2, 300)
+    gt, cnt = synth.pack_gt([synth.gt_boxes(i) for i in range(2)], 8)
+    for tf_ckpt in (False, True):
+        with Session() as sess:
+            net, step, _ = _model(sess, lr=piecewise_constant(GlobalStep(0), [1], [1e-5, 1e-6]))
+            net._opt['lr'] = piecewise_constant(step, [1], [1e-5, 1e-6])
+            feed = {net.image_input: x, net.gt_boxes: gt, net.gt_counts: cnt}
+            sess.run([net.losses, net.optimizer], feed_dict=feed)
+            sess.run([net.losses, net.optimizer], feed_dict=feed)
+            net.epoch = 3
+            path = str(tmp_path / ('e3_%d' % tf_ckpt))
+            net.save(path, tf_checkpoint=tf_ckpt)
+            sess.run([net.losses, net.optimizer], feed_dict=feed)
+            want = net.get_params(); want_m = net.get_params(2)
+        with Session() as s2:
+            n2 = SSDVGG(s2, ssdutils.get_preset_by_name('vgg300'))
+            n2.build_from_metagraph(None, path if tf_ckpt else path + '.npz')
+            step2 = GlobalStep(0)
+            n2.build_optimizer_from_metagraph(piecewise_constant(step2, [1], [1e-5, 1e-6]), 0.0005, 0.9, step2)
+            assert step2.value == 2 and (tf_ckpt or n2.epoch == 3)
+            s2.run([n2.losses, n2.optimizer], feed_dict={n2.image_input: x, n2.gt_boxes: gt, n2.gt_counts: cnt})
+            got = n2.get_params(); got_m = n2.get_params(2)
+        for k in want:
+            assert np.array_equal(want[k], got[k]), k
+            assert np.array_equal(want_m[k], got_m[k]), k
