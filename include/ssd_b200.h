@@ -182,6 +182,15 @@ int ssdb_get_tensor(ssdb_net* net, const char* name, int which, float* host_out,
 int ssdb_set_tensor(ssdb_net* net, const char* name, int which, const float* host_in, long long count);
 /* The flat device buffers (for the data-parallel all-reduce on gradients only). */
 int ssdb_flat_buffer(ssdb_net* net, int which, void** dev_ptr_out, long long* count_out);
+/* Gradient buckets for a data-parallel all-reduce that overlaps the backward.  The flat gradient buffer is cut into
+ * contiguous ranges that become final in the order the backward writes them -- [mod_conv6 .. end) (conv6 / conv7, extra
+ * layers, scale, classifiers) first, then [conv4_1 .. mod_conv6), then [conv1_1 .. conv4_1) -- and the engine records a
+ * CUDA event on the step's stream when a range is complete.  ssdb_grad_buckets fills up to `cap` (begin, end) float
+ * offsets and returns the number of buckets; ssdb_wait_grad_bucket makes `stream` wait for bucket `bucket` of the LAST
+ * ssdb_train_step (cudaStreamWaitEvent), so the caller can start that range's ncclAllReduce on a side stream while the
+ * remaining dgrad / wgrad kernels run. */
+int ssdb_grad_buckets(const ssdb_net* net, int cap, long long* begin_out, long long* end_out);
+int ssdb_wait_grad_bucket(ssdb_net* net, int bucket, void* stream);
 /* Input pre-processing that the reference leaves to the third-party VGG graph
  * (ssdvgg.py:190-207): y[c] = x[swap_rb ? 2-c : c] - mean[c].  Default: swap, ImageNet means. */
 int ssdb_set_preprocess(ssdb_net* net, int swap_rb, const float mean[3]);

@@ -44,13 +44,17 @@ constexpr int B_BYTES = MAX_N * BLOCK_K * 4;     // 32 KB
 // epilogue overlaps the next tile).  mtu = 2: 3 stages x 64 KB, 8 MMAs per stage, 1.5x less L2 -> smem traffic per FLOP,
 // but with N = 256 both accumulators fill TMEM and the epilogue is exposed.  Measured on B200: mtu = 2 pays off in the
 // wgrad kernel for N >= 128 (long units), not in fprop / dgrad, whose mid layers already run at ~88% of the tf32 peak.
-constexpr int RING_BYTES = 204 * 1024;           // 4 x 48 KB, 3 x 64 KB, or 3 x 68 KB (row-window mode, N = 128)
+constexpr int RING_BYTES = 192 * 1024;           // 4 x 48 KB, 3 x 64 KB, or 2 x 88 KB (row-window mode, N = 128, two M tiles)
 constexpr int ACC_STRIDE = 256;                  // TMEM columns per accumulator buffer
-constexpr int EPI_STAGE_BYTES = 4 * 32 * 128;         // per-warp 32 x 32 fp32 transpose buffers of the epilogue
+constexpr int EPI_WARPS_MAX = 8;
+constexpr int EPI_STAGE_BYTES = EPI_WARPS_MAX * 32 * 128;   // per-warp 32 x 32 fp32 transpose buffers of the epilogue
 constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 __host__ __device__ constexpr int stage_bytes_for(int mtu) { return mtu * A_BYTES + B_BYTES; }
 __host__ __device__ constexpr int stages_for(int mtu) { return mtu == 1 ? 4 : 3; }
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 192;                 // TMA warp + MMA warp + 4 epilogue warps (wgrad kernels, two-CTA fprop / dgrad)
+constexpr int TC_THREADS = 320;                  // fprop / dgrad: 8 epilogue warps, two per TMEM lane quarter, alternating 32-column chunks.
+                                                 // With N = 256 and two M tiles both accumulators fill TMEM and the epilogue is exposed
+                                                 // (dgrad: + mask reads): twice the warps drain it in half the time.
 constexpr int TMEM_COLS = 512;
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -196,7 +200,8 @@ struct TcArgs {
 // memory (16-byte slots XOR-swizzled by row) and writes it back with 8 lanes per pixel: every instruction moves four
 // complete 128-byte rows, and the bias / ReLU / tf32 rounding (fprop) or beta / ReLU-mask (dgrad) reads are coalesced too.
 template <int FMT, bool SCATTER>
-__device__ __forceinline__ void epilogue_tile(const TcArgs& p, int mt, int nt, uint32_t t_row, int row, int lane, float4* stage) {
+__device__ __forceinline__ void epilogue_tile(const TcArgs& p, int mt, int nt, uint32_t t_row, int row, int lane, float4* stage,
+                                              int chunk0, int chunk_step) {
     const int rows_valid = p.TW * p.TH * p.TN;
     const int tx = mt % p.tiles_x; const int r1 = mt / p.tiles_x;
     const int ty = r1 % p.tiles_y; const int tn = r1 / p.tiles_y;
@@ -206,7 +211,7 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& p, int mt, int nt, u
     const int x = xi * p.dscale + p.dpx, y = yi * p.dscale + p.dpy;              // destination pixel
     const bool ok = row < rows_valid && x < p.Wd && y < p.Hd && n < p.Bn;
     const long long pix = ok ? ((long long)n * p.Hd + y) * p.Wd + x : -1;
-    for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+    for (int c0 = chunk0 * 32; c0 < p.block_n; c0 += 32 * chunk_step) {      // this warp's share of the 32-column chunks
         uint32_t r[32];
         __syncwarp();
         tc_ld32(t_row + (uint32_t)c0, r);
@@ -350,7 +355,7 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& p, int mt, int nt, u
 
 // FMT: operand / storage format (ACT_F32 = tf32 MMAs, ACT_S32 = split bf16 MMAs); SCATTER: the head epilogue (fprop only)
 template <int FMT, bool SCATTER>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w, const TcArgs p) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -365,10 +370,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
     const uint32_t b_off = (uint32_t)(p.mtu * p.a_slot);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nepi = (int)(blockDim.x >> 5) - 2;                  // epilogue warps: 4 (two CTAs per SM) or 8
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, (uint32_t)nepi); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_src) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
@@ -479,10 +485,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
             }
         }
     } else {
-        // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+        // ===================== epilogue (4 or 8 warps: a warp may only read the TMEM lane quarter warp % 4) =====================
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
-        float4* stage = reinterpret_cast<float4*>(smem_raw + (bars + 256 - raw)) + quarter * 256;
+        const int ew = warp - 2;                                      // 0 .. nepi - 1
+        const int chunk0 = ew >> 2, chunk_step = nepi >> 2;           // with 8 warps the two warps of a quarter alternate chunks
+        float4* stage = reinterpret_cast<float4*>(smem_raw + (bars + 256 - raw)) + ew * 256;
         int acc = 0; uint32_t acc_phase = 0;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
             const int mp = u / p.n_tiles, nt = u - mp * p.n_tiles;
@@ -491,7 +499,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
             for (int j = 0; j < (two ? 2 : 1); ++j)      // one copy of the epilogue code for both tiles of a unit
-                epilogue_tile<FMT, SCATTER>(p, p.mtu * mp + j, nt, t_row + (uint32_t)(j * noff), row, lane, stage);
+                epilogue_tile<FMT, SCATTER>(p, p.mtu * mp + j, nt, t_row + (uint32_t)(j * noff), row, lane, stage, chunk0, chunk_step);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
@@ -1549,7 +1557,7 @@ int num_sms() {
 // bytes in flight; a second resident CTA doubles the epilogue / TMA parallelism.  Each CTA then gets half the ring (2-3
 // stages), a 256-column TMEM allocation (two 128-column accumulator buffers) and one M tile per unit.
 constexpr int DUAL_RING_BYTES = 92 * 1024;
-constexpr int DUAL_SMEM_BYTES = DUAL_RING_BYTES + 1024 + 256 + EPI_STAGE_BYTES;      // 109.25 KB: two fit in 227 KB
+constexpr int DUAL_SMEM_BYTES = DUAL_RING_BYTES + 1024 + 256 + 4 * 32 * 128;         // 109.25 KB (4 epilogue warps): two fit in 227 KB
 
 int launch_tc(const CUtensorMap& ms, const CUtensorMap& mw, const TcArgs& a_in, cudaStream_t st) {
     static bool attr = false;
@@ -1586,12 +1594,15 @@ int launch_tc(const CUtensorMap& ms, const CUtensorMap& mw, const TcArgs& a_in, 
     const long long slots = (long long)num_sms() * ctas_per_sm;
     int grid = (int)(total < slots ? total : slots);
     const bool scatter = a.mode == 0 && a.scatter;
+    static int wide = -1;
+    if (wide < 0) { const char* ov = getenv("SSDB_TC_EPI8"); wide = ov ? (atoi(ov) ? 1 : 0) : 1; }
+    const int threads = (ctas_per_sm == 2 || !wide) ? NUM_THREADS : TC_THREADS;
     if (a.split) {
-        if (scatter) conv_tc_kernel<ACT_S32, true><<<grid, NUM_THREADS, smem, st>>>(ms, mw, a);
-        else conv_tc_kernel<ACT_S32, false><<<grid, NUM_THREADS, smem, st>>>(ms, mw, a);
+        if (scatter) conv_tc_kernel<ACT_S32, true><<<grid, threads, smem, st>>>(ms, mw, a);
+        else conv_tc_kernel<ACT_S32, false><<<grid, threads, smem, st>>>(ms, mw, a);
     } else {
-        if (scatter) conv_tc_kernel<ACT_F32, true><<<grid, NUM_THREADS, smem, st>>>(ms, mw, a);
-        else conv_tc_kernel<ACT_F32, false><<<grid, NUM_THREADS, smem, st>>>(ms, mw, a);
+        if (scatter) conv_tc_kernel<ACT_F32, true><<<grid, threads, smem, st>>>(ms, mw, a);
+        else conv_tc_kernel<ACT_F32, false><<<grid, threads, smem, st>>>(ms, mw, a);
     }
     SSDB_LAUNCH_CHECK();
     return SSDB_OK;
@@ -1600,14 +1611,18 @@ int launch_tc(const CUtensorMap& ms, const CUtensorMap& mw, const TcArgs& a_in, 
 // One or two M tiles per unit?  Two tiles share one B tile (1.5x less L2 -> smem traffic per FLOP, measured 15-20% on
 // long-K layers), but halve the number of units (wave quantisation on the small maps) and, when both accumulators fill
 // TMEM (N = 256), expose the epilogue -- heavier in dgrad (mask / old-value reads).  Cost model fitted to B200 timings.
-int tc_mtu(int block_n, long long m_tiles, int n_tiles, int kblocks, bool dgrad) {
+// Split mode (refit on B200, 8 epilogue warps, tools/layer_bench.py with SSDB_TC_MTU=1 / 2): a one-tile unit moves 48 KB
+// per 32-channel slab and sits at the L2 -> SM rate (~1130 cycles), a two-tile unit moves 64 KB and is MMA-bound (12 MMAs,
+// 1536 cycles): a two-tile unit costs 1.36x a one-tile unit, plus an exposed-epilogue term that the batched-load epilogue
+// made small.  Two tiles then win everywhere except where halving the unit count costs a wave (conv8_x at batch 64).
+int tc_mtu(int block_n, long long m_tiles, int n_tiles, int kblocks, bool dgrad, bool split) {
     if (const char* ov = getenv("SSDB_TC_MTU")) { int v = atoi(ov); if (v == 1 || v == 2) return v; }
     const int sms = num_sms();
     const long long w1 = (m_tiles * n_tiles + sms - 1) / sms;
     const long long w2 = (((m_tiles + 1) / 2) * n_tiles + sms - 1) / sms;
     const int noff = (block_n + 31) & ~31;
-    const double e = (2 * noff <= ACC_STRIDE) ? 0.0 : (dgrad ? 15.0 : 4.0);
-    const double c2 = 2.0 * (0.85 + e / (double)(kblocks > 0 ? kblocks : 1));
+    const double e = (2 * noff <= ACC_STRIDE) ? 0.0 : (split ? (dgrad ? 3.0 : 1.0) : (dgrad ? 15.0 : 4.0));
+    const double c2 = 2.0 * ((split ? 0.70 : 0.85) + e / (double)(kblocks > 0 ? kblocks : 1));
     return (double)w2 * c2 < (double)w1 ? 2 : 1;
 }
 
@@ -1734,7 +1749,7 @@ int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_
     int tdy[9], tdx[9];
     for (int t = 0; t < g.k * g.k; ++t) { tdy[t] = (t / g.k) * g.dil - g.pad_t; tdx[t] = (t % g.k) * g.dil - g.pad_l; }
     a.sstride = g.stride; a.dscale = 1; a.dpy = a.dpx = 0; a.mode = 0;
-    a.mtu = tc_mtu(a.block_n, (long long)a.tiles_x * a.tiles_y * a.tiles_n, a.n_tiles, g.k * g.k * a.cblocks, false);
+    a.mtu = tc_mtu(a.block_n, (long long)a.tiles_x * a.tiles_y * a.tiles_n, a.n_tiles, g.k * g.k * a.cblocks, false, fmt == ACT_S32);
     int wth = 0, wtn = 0;
     const bool rw = want_row_window(g, a.block_n, g.B, g.Ho, g.Wo, t.eff, &wth, &wtn);
     if (rw) {
@@ -1770,7 +1785,7 @@ int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, int f
             a.Hd = g.H; a.Wd = g.W; a.Bn = g.B; a.Cd = g.Cin; a.cd_valid = g.Cin;
             a.cblocks = g.Cout / BLOCK_K; a.rows_per_tap = g.Cin;
             a.sstride = 1; a.dscale = s; a.dpy = py; a.dpx = px; a.mode = 1;
-            a.mtu = tc_mtu(a.block_n, (long long)a.tiles_x * a.tiles_y * a.tiles_n, a.n_tiles, g.k * g.k * a.cblocks / (s * s), true);
+            a.mtu = tc_mtu(a.block_n, (long long)a.tiles_x * a.tiles_y * a.tiles_n, a.n_tiles, g.k * g.k * a.cblocks / (s * s), true, fmt == ACT_S32);
             SSDB_REQUIRE(g.k <= 3, "tcgen05 path supports 1x1 and 3x3 filters");
             int wth = 0, wtn = 0;
             const bool rw = s == 1 && want_row_window(g, a.block_n, g.B, Hc, Wc, t.eff, &wth, &wtn);

@@ -118,6 +118,13 @@ struct ssdb_net {
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_labels = nullptr, ev_result = nullptr, ev_images = nullptr;
     cudaEvent_t ev_chunk[8] = {};      // image chunks of the host entry points
+    // gradient buckets for an all-reduce that overlaps the rest of the backward (ssdb_grad_buckets): contiguous ranges of
+    // the flat gradient buffer, final in the order the backward produces them (heads and deep layers first)
+    static constexpr int MAX_BUCKETS = 4;
+    int n_buckets = 0;
+    long long bucket_begin[MAX_BUCKETS] = {}, bucket_end[MAX_BUCKETS] = {};
+    int bucket_last_op[MAX_BUCKETS] = {};          // the backward has finished a bucket once this op's gradients are written
+    cudaEvent_t ev_bucket[MAX_BUCKETS] = {};
     int last_B = 0;
     // per-op device timing (ssdb_profile_step)
     bool prof = false;
@@ -410,6 +417,8 @@ int run_backward(ssdb_net* n, int B, cudaStream_t st) {
                 ConvGeom g1 = g; g1.Cin = 32; g1.k = 1; g1.pad_t = g1.pad_l = 0; g1.dil = 1;
                 rc = conv_tc_wgrad(g1, n->patches, dz, n->fmt, n->c1_dw32, db, n->partial, st); if (rc) return rc;
                 SSDB_CUDA(cudaMemcpyAsync(dw, n->c1_dw32, (size_t)27 * op.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                for (int b = 0; b < n->n_buckets; ++b)
+                    if (n->bucket_last_op[b] == oi) SSDB_CUDA(cudaEventRecord(n->ev_bucket[b], st));
                 continue;
             }
             const bool tcw = op.in >= 0 && use_tc(n, conv_tc_supported_wgrad(g, n->fmt));
@@ -457,6 +466,8 @@ int run_backward(ssdb_net* n, int B, cudaStream_t st) {
             written[op.in] = 1;
         }
         if (rc) return rc;
+        for (int b = 0; b < n->n_buckets; ++b)
+            if (n->bucket_last_op[b] == oi) SSDB_CUDA(cudaEventRecord(n->ev_bucket[b], st));
     }
     return SSDB_OK;
 }
@@ -590,6 +601,19 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
     SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_result, cudaEventDisableTiming));
     SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_images, cudaEventDisableTiming));
     for (int c = 0; c < 8; ++c) SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_chunk[c], cudaEventDisableTiming));
+    {   // buckets: [mod_conv6 .. end) (conv6/7, extras, scale, heads: final first), [conv4_1 .. mod_conv6), [start .. conv4_1)
+        const char* cuts[] = {"mod_conv6", "conv4_1"};
+        long long end = (long long)n->n_flat;
+        for (const char* cname : cuts)
+            for (size_t oi = 0; oi < n->ops.size(); ++oi)
+                if (n->ops[oi].name == cname && n->ops[oi].w >= 0) {
+                    const long long begin = (long long)n->masters[n->ops[oi].w].off;
+                    n->bucket_begin[n->n_buckets] = begin; n->bucket_end[n->n_buckets] = end; n->bucket_last_op[n->n_buckets] = (int)oi;
+                    end = begin; ++n->n_buckets;
+                }
+        n->bucket_begin[n->n_buckets] = 0; n->bucket_end[n->n_buckets] = end; n->bucket_last_op[n->n_buckets] = 0; ++n->n_buckets;
+        for (int b = 0; b < n->n_buckets; ++b) SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_bucket[b], cudaEventDisableTiming));
+    }
     *out = n;
     return SSDB_OK;
 }
@@ -609,6 +633,7 @@ int ssdb_destroy(ssdb_net* n) {
     if (n->ev_result) cudaEventDestroy(n->ev_result);
     if (n->ev_images) cudaEventDestroy(n->ev_images);
     for (int c = 0; c < 8; ++c) if (n->ev_chunk[c]) cudaEventDestroy(n->ev_chunk[c]);
+    for (int b = 0; b < ssdb_net::MAX_BUCKETS; ++b) if (n->ev_bucket[b]) cudaEventDestroy(n->ev_bucket[b]);
     delete n;
     return SSDB_OK;
 }
@@ -658,6 +683,19 @@ int ssdb_flat_buffer(ssdb_net* n, int which, void** dev_ptr_out, long long* coun
     SSDB_REQUIRE(n && which >= 0 && which <= 2 && dev_ptr_out && count_out, "bad arguments");
     *dev_ptr_out = which == 0 ? n->params : which == 1 ? n->grads : n->moms;
     *count_out = (long long)n->n_flat;
+    return SSDB_OK;
+}
+
+int ssdb_grad_buckets(const ssdb_net* n, int cap, long long* begin_out, long long* end_out) {
+    SSDB_REQUIRE(n && begin_out && end_out && cap >= 1, "bad arguments");
+    const int k = n->n_buckets < cap ? n->n_buckets : cap;
+    for (int b = 0; b < k; ++b) { begin_out[b] = n->bucket_begin[b]; end_out[b] = n->bucket_end[b]; }
+    return n->n_buckets;
+}
+
+int ssdb_wait_grad_bucket(ssdb_net* n, int bucket, void* stream) {
+    SSDB_REQUIRE(n && bucket >= 0 && bucket < n->n_buckets, "bad bucket index");
+    SSDB_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, n->ev_bucket[bucket], 0));
     return SSDB_OK;
 }
 

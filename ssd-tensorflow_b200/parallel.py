@@ -24,6 +24,19 @@ class _DeviceArray:
         self.__cuda_array_interface__ = {'shape': (int(count),), 'typestr': '<f4', 'data': (int(ptr), False), 'version': 3}
 
 
+def allreduce_buckets(tensor, buckets, world, group=None, before=None):
+    """Sum all-reduce of `tensor` bucket by bucket, in the given order (the order in which the backward finishes them).
+    `before(k)` is called right before bucket k is issued (the CUDA path makes the side stream wait for that bucket's
+    gradient-ready event there).  Returns the scale the caller folds into the update (1 / world)."""
+    import torch.distributed as dist
+    if world > 1:
+        for k, (lo, hi) in enumerate(buckets):
+            if before is not None:
+                before(k)
+            dist.all_reduce(tensor[lo:hi], op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / float(world)
+
+
 def average_gradients(tensor, world, group=None):
     """all-reduce(sum) in place; the caller folds 1/world into the update (returns that scale)."""
     import torch.distributed as dist
@@ -47,6 +60,8 @@ class DataParallelTrainer:
         self.grads = torch.as_tensor(_DeviceArray(ptr, count), device='cuda')
         pptr, _ = net.flat_buffer(ssdb.PARAM)
         self.params = torch.as_tensor(_DeviceArray(pptr, count), device='cuda')
+        self.buckets = net.grad_buckets()
+        self.side = torch.cuda.Stream() if self.world > 1 else None
 
     def broadcast_parameters(self, src=0):
         import torch.distributed as dist
@@ -81,5 +96,14 @@ class DataParallelTrainer:
         self.net.train_step(images_ptr, local_batch, labels_ptr=labels_ptr, gt_ptr=gt_ptr, gt_count_ptr=gt_count_ptr, G=G,
                             lr=lr, momentum=momentum, weight_decay=weight_decay, grad_scale=1.0, apply_update=False,
                             losses_ptr=losses_ptr, result_ptr=result_ptr, stream=st)
-        scale = average_gradients(self.grads, self.world, self.group)
+        if self.world > 1:
+            # the whole step is enqueued; the all-reduce of each gradient bucket starts on a side stream as soon as the
+            # backward has finished that range (heads / deep layers first) and overlaps the remaining dgrad / wgrad kernels;
+            # only the last, small bucket (conv1_1 .. conv3_3, 7 MB) is reduced after the backward
+            with torch.cuda.stream(self.side):
+                scale = allreduce_buckets(self.grads, self.buckets, self.world, self.group,
+                                          before=lambda k: self.net.wait_grad_bucket(k, self.side.cuda_stream))
+            torch.cuda.current_stream().wait_stream(self.side)
+        else:
+            scale = 1.0
         self.net.apply_update(lr, momentum, weight_decay, grad_post_scale=scale, stream=st)

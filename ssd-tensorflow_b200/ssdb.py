@@ -68,6 +68,8 @@ SIGNATURES = {
     'ssdb_set_tensor': (_i, [_p, C.c_char_p, _i, _p, _ll]),
     'ssdb_flat_buffer': (_i, [_p, _i, C.POINTER(_p), C.POINTER(_ll)]),
     'ssdb_set_preprocess': (_i, [_p, _i, C.POINTER(_f)]),
+    'ssdb_grad_buckets': (_i, [_p, _i, C.POINTER(_ll), C.POINTER(_ll)]),
+    'ssdb_wait_grad_bucket': (_i, [_p, _i, _p]),
     'ssdb_forward': (_i, [_p, _p, _i, _p, _p]),
     'ssdb_forward_host': (_i, [_p, _p, _i, _p]),
     'ssdb_read_output_host': (_i, [_p, _i, _p]),
@@ -271,6 +273,18 @@ class Net:
         cnt = _ll()
         check(lib().ssdb_flat_buffer(self._h, which, C.byref(ptr), C.byref(cnt)))
         return ptr.value, cnt.value
+
+    def grad_buckets(self):
+        """[(begin, end), ...] float offsets into the flat gradient buffer, in the order the backward completes them."""
+        b = (_ll * 8)(); e = (_ll * 8)()
+        n = lib().ssdb_grad_buckets(self._h, 8, b, e)
+        if n < 0:
+            check(n)
+        return [(int(b[k]), int(e[k])) for k in range(n)]
+
+    def wait_grad_bucket(self, bucket, stream):
+        """Make `stream` (a raw cudaStream_t) wait until bucket `bucket` of the last train_step is complete."""
+        check(lib().ssdb_wait_grad_bucket(self._h, int(bucket), stream))
 
     def set_preprocess(self, swap_rb, mean):
         m = (_f * 3)(*[float(v) for v in mean])

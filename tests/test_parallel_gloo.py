@@ -52,7 +52,16 @@ def _worker(rank, world, port, tmp):
     lo, hi = par.shard_range(B, rank, world)
     (gl,) = torch.autograd.grad(loss_of(lo, hi), w)
     gl = gl.clone()
+    # once in one piece, once bucket by bucket in the order the engine's backward completes them (tail of the flat buffer
+    # first): both must give the same averaged gradient
+    flat = gl.reshape(-1).clone()
+    n = flat.numel()
+    buckets = [(2 * n // 3, n), (n // 3, 2 * n // 3), (0, n // 3)]
+    seen = []
+    scale_b = par.allreduce_buckets(flat, buckets, world, before=seen.append)
+    assert seen == [0, 1, 2] and scale_b == 1.0 / world
     scale = par.average_gradients(gl, world)
+    assert torch.equal(flat.reshape(gl.shape), gl)
     gl *= scale
     (gfull,) = torch.autograd.grad(loss_of(0, B), w)
     err = float((gl - gfull).abs().max() / gfull.abs().max())

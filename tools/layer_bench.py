@@ -45,7 +45,8 @@ if __name__ == '__main__':
     preset = sys.argv[1] if len(sys.argv) > 1 else 'vgg300'
     B = int(sys.argv[2]) if len(sys.argv) > 2 else (64 if preset == 'vgg300' else 32)
     impl = {'split': ssdb.CONV_TC_SPLIT, 'tf32': ssdb.CONV_TC, 'simt': ssdb.CONV_SIMT}[sys.argv[3] if len(sys.argv) > 3 else 'split']
-    filt = sys.argv[4:]
+    filt = [a for a in sys.argv[4:] if not a.startswith('--')]
+    iters = 1 if '--once' in sys.argv else 5            # --once: 2 warm-up launches + 1 (short runs under ncu)
     ssdb.require_device()
     out = []
     tot = [0.0, 0.0, 0.0]
@@ -61,7 +62,7 @@ if __name__ == '__main__':
             ms = ctypes.c_float(0)
             mask = 0 if l['name'] in ('conv1_1',) else 1
             rc = ssdb.lib().ssdb_op_conv_bench(kind, impl, B, l['H'], l['H'], l['cin'], l['cout'], l['k'], l['stride'], l['dil'], l['pad'], l['pad'],
-                                               l['Ho'], l['Ho'], mask, 0, 5, ctypes.byref(ms))
+                                               l['Ho'], l['Ho'], mask, 0, iters, ctypes.byref(ms))
             if rc:
                 line += ' %s ERR(%s)' % (kn, ssdb.lib().ssdb_last_error().decode()[:60]); continue
             row[kn] = ms.value; tot[kind] += ms.value

@@ -39,16 +39,24 @@ def full_metrics(rep):
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
     out = ['# ncu --set full --clock-control none (%s)' % rep]
-    for r in data:
-        out.append('--- ' + r[idx['Kernel Name']].split('(')[0])
-        for w in WANT:
-            if w in idx:
+    extra = ['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed', 'sm__cycles_elapsed.avg.per_second', 'lts__t_bytes.sum',
+             'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'smsp__inst_executed.sum']
+    want = WANT + [w for w in extra if w not in WANT] + sorted(h for h in hdr if 'utchmma' in h and 'pct_of_peak_sustained_elapsed' in h and h not in WANT)
+    labels = LABELS or []
+    for k, r in enumerate(data):
+        out.append('--- ' + r[idx['Kernel Name']].split('(')[0] + ('   [%s]' % labels[k] if k < len(labels) else ''))
+        for w in want:
+            if w in idx and r[idx[w]] not in ('', 'n/a'):
                 out.append('  %-92s %16s %s' % (w, r[idx[w]], units[idx[w]]))
     return '\n'.join(out)
 
 
+LABELS = None
+
 if __name__ == '__main__':
     kind, src, dst = sys.argv[1:4]
+    if len(sys.argv) > 4:
+        LABELS = sys.argv[4].split(',')          # one label per captured launch, in launch order
     text = launch_shares(src) if kind == 'launches' else full_metrics(src)
     open(dst, 'w').write(text + '\n')
     print(text[:3000])
