@@ -165,7 +165,11 @@ int ssdb_op_conv_bench(int kind, int impl, int B, int H, int W, int Cin, int Cou
  * builds the layer plan for `preset` ("vgg300" | "vgg512", ssdutils.py:36-62),
  * allocates parameters / gradients / momentum (flat float32 buffers) and the
  * activation workspace for up to `max_batch` images.  Parameters start at zero:
- * load them with ssdb_set_tensor.  flags: reserved, pass 0. */
+ * load them with ssdb_set_tensor.  flags: 0, or SSDB_FLAG_INFERENCE. */
+#define SSDB_FLAG_INFERENCE 1u   /* frozen model (export_model.py:62-72 / detect.py:90-112): forward + detection only.  No
+                                    gradient, momentum, label or loss buffers (about half the memory), training entry points
+                                    return SSDB_EINVAL, and ssdb_forward_detect_host replays the whole device side -- ~60 forward
+                                    launches, softmax, decode + NMS -- as ONE CUDA graph per (batch, threshold, cap, IoU) */
 int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned flags, ssdb_net** out);
 int ssdb_destroy(ssdb_net* net);
 

@@ -113,6 +113,11 @@ struct ssdb_net {
     double* anchors = nullptr;
     float* host_small = nullptr;       // pinned
     bool wt_dirty = true, have_forward = false;
+    bool inference = false;            // SSDB_FLAG_INFERENCE: forward / detection only, no training state
+    // CUDA graphs of the frozen forward + detection (ssdb_forward_detect_host on an inference handle), one per
+    // (batch, threshold, cap, IoU); dropped when a parameter changes
+    struct DetGraph { int B; float thr; int cap; double iou; bool warmed; cudaGraphExec_t exec; };
+    std::vector<DetGraph> det_graphs;
     int conv_mode = SSDB_CONV_AUTO;
     int swap_rb = 1; float mean[3] = {103.939f, 116.779f, 123.68f};
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
@@ -134,6 +139,11 @@ struct ssdb_net {
     float* act(int id, int /*B*/) { return acts + bufs[id].off * (size_t)max_batch; }
     float* gact(int id, int /*B*/) { return gacts + bufs[id].off * (size_t)max_batch; }
 };
+
+static void drop_det_graphs(ssdb_net* n) {
+    for (auto& g : n->det_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    n->det_graphs.clear();
+}
 
 namespace ssdb {
 namespace {
@@ -304,7 +314,7 @@ int repack_filters(ssdb_net* n, cudaStream_t st) {
     }
     // dgrad B operand: the HWIO filters themselves, tf32-rounded or split along Cout (every tensor starts on a 1024-element boundary)
     if (n->round) { int rc = round_tf32_copy(n->params, n->wr, (long long)n->n_flat, st); if (rc) return rc; }
-    else if (n->fmt == ACT_S32) { int rc = split_copy(n->params, n->wr, (long long)n->n_flat, st); if (rc) return rc; }
+    else if (n->fmt == ACT_S32 && n->wr) { int rc = split_copy(n->params, n->wr, (long long)n->n_flat, st); if (rc) return rc; }
     if (n->patches) {
         const Op& c1 = n->ops[0];
         int rc = conv1_pad_filter(n->params + n->masters[c1.w].off, c1.cout, n->c1_w32, st); if (rc) return rc;
@@ -519,13 +529,15 @@ int ssdb_device_ok(void) {
 }
 
 int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned flags, ssdb_net** out) {
-    (void)flags;
     SSDB_REQUIRE(preset && out && max_batch >= 1 && num_classes >= 1 && num_classes + 5 <= 32, "bad arguments");
+    SSDB_REQUIRE((flags & ~(unsigned)SSDB_FLAG_INFERENCE) == 0, "unknown flags");
     int rc = ssdb_device_ok(); if (rc) return rc;
     const Preset* P = find_preset(preset);
     if (!P) { set_error("No such preset: %s", preset); return SSDB_ENOTFOUND; }
     ssdb_net* n = new ssdb_net();
     n->preset = P; n->C = num_classes; n->V = num_classes + 5; n->S = P->image; n->max_batch = max_batch;
+    n->inference = (flags & SSDB_FLAG_INFERENCE) != 0;
+    const bool train = !n->inference;
     // SSDB_CONV: (unset) / "split" = tensor cores with split bf16 operands (fp32-grade products, the product mode);
     // "tf32" = tensor cores with tf32 operands (10-bit significands: outside the 1e-3 parity bar, kept for comparison);
     // "simt" = fp32 CUDA-core kernels only
@@ -549,22 +561,31 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
     size_t bav = (size_t)max_batch * n->A * n->V;
     size_t img = (size_t)max_batch * n->S * n->S * 3;
 #define ALLOC(ptr, count, type) SSDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&(ptr)), (size_t)(count) * sizeof(type)))
-    ALLOC(n->params, n->n_flat, float); ALLOC(n->grads, n->n_flat, float); ALLOC(n->moms, n->n_flat, float);
-    ALLOC(n->wt, n->wt_floats ? n->wt_floats : 1, float); ALLOC(n->wr, n->n_flat, float);
-    ALLOC(n->acts, n->act_floats_per_image * max_batch, float); ALLOC(n->gacts, n->act_floats_per_image * max_batch, float);
-    ALLOC(n->out, bav, float); ALLOC(n->out_grad, bav, float); ALLOC(n->result, bav, float); ALLOC(n->labels_stage, bav, float);
-    ALLOC(n->dz_head, dzh ? dzh : 1, float); ALLOC(n->images_stage, img, float);
-    ALLOC(n->partial, partial, float); ALLOC(n->small_ws, 4096 + 2 * (size_t)max_batch, float);
+    // an inference handle (SSDB_FLAG_INFERENCE: the frozen model of export_model.py / detect.py) keeps only what the forward
+    // and the detection kernels touch: no gradients, momentum, gradient activations, label / loss buffers or pool codes
+    ALLOC(n->params, n->n_flat, float);
+    ALLOC(n->wt, n->wt_floats ? n->wt_floats : 1, float);
+    ALLOC(n->acts, n->act_floats_per_image * max_batch, float);
+    ALLOC(n->out, bav, float); ALLOC(n->result, bav, float);
+    ALLOC(n->images_stage, img, float);
+    ALLOC(n->small_ws, 4096 + 2 * (size_t)max_batch, float);
     ALLOC(n->counter, 1, unsigned int); ALLOC(n->decay_mask, n->n_flat / OPT_BLOCK, unsigned char);
     ALLOC(n->anchors, (size_t)n->A * 4, double);
-    ALLOC(n->gt_stage, (size_t)max_batch * 128 * 5, double); ALLOC(n->gt_count_stage, max_batch, int);
-    ALLOC(n->match_stage, (size_t)max_batch * n->A, int);
-    ALLOC(n->loss_ws, multibox_loss_ws_bytes(max_batch, n->A), unsigned char);
-    SSDB_CUDA(cudaMemset(n->loss_ws, 0, multibox_loss_ws_bytes(max_batch, n->A)));
-    for (const Op& op : n->ops)
-        if (op.type == OP_POOL && op.stride == 1) { const Buf& bo = n->bufs[op.out]; ALLOC(n->pool5_arg, (size_t)max_batch * bo.H * bo.W * bo.C, unsigned char); }
+    if (train) {
+        ALLOC(n->grads, n->n_flat, float); ALLOC(n->moms, n->n_flat, float); ALLOC(n->wr, n->n_flat, float);
+        ALLOC(n->gacts, n->act_floats_per_image * max_batch, float);
+        ALLOC(n->out_grad, bav, float); ALLOC(n->labels_stage, bav, float);
+        ALLOC(n->dz_head, dzh ? dzh : 1, float);
+        ALLOC(n->partial, partial, float);
+        ALLOC(n->gt_stage, (size_t)max_batch * 128 * 5, double); ALLOC(n->gt_count_stage, max_batch, int);
+        ALLOC(n->match_stage, (size_t)max_batch * n->A, int);
+        ALLOC(n->loss_ws, multibox_loss_ws_bytes(max_batch, n->A), unsigned char);
+        SSDB_CUDA(cudaMemset(n->loss_ws, 0, multibox_loss_ws_bytes(max_batch, n->A)));
+        for (const Op& op : n->ops)
+            if (op.type == OP_POOL && op.stride == 1) { const Buf& bo = n->bufs[op.out]; ALLOC(n->pool5_arg, (size_t)max_batch * bo.H * bo.W * bo.C, unsigned char); }
+    }
     n->pool_code.assign(n->ops.size(), nullptr);
-    if (!getenv("SSDB_POOL_CODE") || atoi(getenv("SSDB_POOL_CODE")))
+    if (train && (!getenv("SSDB_POOL_CODE") || atoi(getenv("SSDB_POOL_CODE"))))
         for (size_t i = 0; i < n->ops.size(); ++i) {
             const Op& op = n->ops[i];
             if (op.type != OP_POOL || op.k != 2 || op.stride != 2 || op.pad != 0) continue;
@@ -574,20 +595,22 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
     if (n->conv_mode != SSDB_CONV_SIMT) {
         const Op& c1 = n->ops[0];
         ConvGeom g1 = geom_of(n, c1, max_batch); g1.Cin = 32; g1.k = 1; g1.pad_t = g1.pad_l = 0;
-        if (conv_tc_supported_fprop(g1) && conv_tc_supported_wgrad(g1, n->fmt)) {
+        if (conv_tc_supported_fprop(g1) && (!train || conv_tc_supported_wgrad(g1, n->fmt))) {
             ALLOC(n->patches, (size_t)max_batch * n->S * n->S * 32, float);
             ALLOC(n->c1_w32, 32 * c1.cout, float); ALLOC(n->c1_wt, 32 * c1.cout, float); ALLOC(n->c1_dw32, 32 * c1.cout, float);
-            size_t w = conv_tc_wgrad_ws(g1, n->fmt);
+            size_t w = train ? conv_tc_wgrad_ws(g1, n->fmt) : 0;
             if (w > n->partial_floats) { cudaFree(n->partial); n->partial_floats = w; ALLOC(n->partial, w, float); }
         }
     }
 #undef ALLOC
     SSDB_CUDA(cudaMemset(n->params, 0, n->n_flat * sizeof(float)));
-    SSDB_CUDA(cudaMemset(n->grads, 0, n->n_flat * sizeof(float)));
-    SSDB_CUDA(cudaMemset(n->moms, 0, n->n_flat * sizeof(float)));
     SSDB_CUDA(cudaMemset(n->wt, 0, (n->wt_floats ? n->wt_floats : 1) * sizeof(float)));
     SSDB_CUDA(cudaMemset(n->counter, 0, sizeof(unsigned int)));
-    SSDB_CUDA(cudaMemset(n->gacts, 0, n->act_floats_per_image * max_batch * sizeof(float)));
+    if (train) {
+        SSDB_CUDA(cudaMemset(n->grads, 0, n->n_flat * sizeof(float)));
+        SSDB_CUDA(cudaMemset(n->moms, 0, n->n_flat * sizeof(float)));
+        SSDB_CUDA(cudaMemset(n->gacts, 0, n->act_floats_per_image * max_batch * sizeof(float)));
+    }
     std::vector<unsigned char> mask(n->n_flat / OPT_BLOCK, 0);
     for (const Master& m : n->masters)
         if (m.decay) for (size_t b = m.off / OPT_BLOCK; b < (m.off + m.count + OPT_BLOCK - 1) / OPT_BLOCK; ++b) mask[b] = 1;
@@ -621,6 +644,7 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
 int ssdb_destroy(ssdb_net* n) {
     if (!n) return SSDB_OK;
     cudaDeviceSynchronize();
+    drop_det_graphs(n);
     void* ptrs[] = {n->pool5_arg, n->patches, n->c1_w32, n->c1_wt, n->c1_dw32, n->wr, n->params, n->grads, n->moms, n->wt, n->acts, n->gacts, n->out, n->out_grad, n->result, n->labels_stage,
                     n->dz_head, n->images_stage, n->partial, n->small_ws, n->counter, n->decay_mask, n->anchors, n->loss_ws, n->det_ws,
                     n->gt_stage, n->gt_count_stage, n->match_stage, n->det_rows, n->det_counts};
@@ -659,8 +683,10 @@ static int tensor_io(ssdb_net* n, const char* name, int which, float* host, long
     const Master& m = n->masters[r.master];
     long long want = 1; for (int i = 0; i < r.rank; ++i) want *= r.shape[i];
     SSDB_REQUIRE(count == want, "element count does not match the tensor shape");
+    SSDB_REQUIRE(which == 0 || !n->inference, "an inference handle has no gradients or momentum");
     float* base = (which == 0 ? n->params : which == 1 ? n->grads : n->moms) + m.off;
     SSDB_CUDA(cudaDeviceSynchronize());
+    if (write && which == 0) drop_det_graphs(n);
     int last = m.shape[m.rank - 1];
     if (r.cols == last && r.col0 == 0) {
         if (write) SSDB_CUDA(cudaMemcpy(base, host, count * sizeof(float), cudaMemcpyHostToDevice));
@@ -681,6 +707,7 @@ int ssdb_set_tensor(ssdb_net* n, const char* name, int which, const float* host_
 
 int ssdb_flat_buffer(ssdb_net* n, int which, void** dev_ptr_out, long long* count_out) {
     SSDB_REQUIRE(n && which >= 0 && which <= 2 && dev_ptr_out && count_out, "bad arguments");
+    SSDB_REQUIRE(which == 0 || !n->inference, "an inference handle has no gradients or momentum");
     *dev_ptr_out = which == 0 ? n->params : which == 1 ? n->grads : n->moms;
     *count_out = (long long)n->n_flat;
     return SSDB_OK;
@@ -771,12 +798,14 @@ int ssdb_debug_read(ssdb_net* n, const char* name, int B, float* host_out, long 
     SSDB_REQUIRE(n && name && host_out && B >= 1 && B <= n->max_batch, "bad arguments");
     SSDB_CUDA(cudaDeviceSynchronize());
     std::string nm(name);
+    SSDB_REQUIRE(!(n->inference && nm == "output_grad"), "an inference handle has no gradients");
     if (nm == "output" || nm == "output_grad") {
         SSDB_REQUIRE(count == (long long)B * n->A * n->V, "element count does not match [B, A, C+5]");
         SSDB_CUDA(cudaMemcpy(host_out, nm == "output" ? n->out : n->out_grad, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost));
         return SSDB_OK;
     }
     const bool grad = nm.rfind("grad:", 0) == 0;
+    SSDB_REQUIRE(!n->inference || (!grad && nm != "output_grad"), "an inference handle has no gradients");
     if (grad) nm = nm.substr(5);
     for (const Op& op : n->ops) {
         if (op.name != nm || op.out < 0) continue;
@@ -827,7 +856,8 @@ static int loss_and_finalize(ssdb_net* n, const float* labels_dev, const double*
 }
 
 int ssdb_apply_update(ssdb_net* n, float lr, float momentum, float weight_decay, float grad_post_scale, void* stream) {
-    SSDB_REQUIRE(n, "bad arguments");
+    SSDB_REQUIRE(n && !n->inference, "bad arguments (or an inference handle)");
+    drop_det_graphs(n);
     ProfScope ps(n, (cudaStream_t)stream, "update");
     int rc = sgd_momentum(n->params, n->grads, n->moms, (long long)n->n_flat, n->decay_mask, lr, momentum, weight_decay, grad_post_scale,
                           (cudaStream_t)stream);
@@ -839,6 +869,7 @@ int ssdb_train_step(ssdb_net* n, const float* images_dev, const float* labels_de
                     int B, float lr, float momentum, float weight_decay, float grad_scale, int apply_update, float* losses_out_dev,
                     float* result_dev, void* stream) {
     SSDB_REQUIRE(n && images_dev && (labels_dev || (gt_dev && gt_count_dev)), "bad arguments");
+    SSDB_REQUIRE(!n->inference, "training entry point called on an inference handle");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = remember_images(n, images_dev, B, st); if (rc) return rc;
     rc = run_forward(n, images_dev, B, st); if (rc) return rc;
@@ -869,6 +900,7 @@ static int train_step_host_impl(ssdb_net* n, const float* images_host, const flo
                                 int G, int B, float lr, float momentum, float weight_decay, int apply_update, float* losses_out_host,
                                 float* result_host, int* match_out_host) {
     SSDB_REQUIRE(n && images_host && (labels_host || (gt_host && gt_count_host)) && B >= 1 && B <= n->max_batch, "bad arguments");
+    SSDB_REQUIRE(!n->inference, "training entry point called on an inference handle");
     if (!labels_host) { int rc = check_gt_host(gt_host, gt_count_host, B, G, n->C); if (rc) return rc; }
     // copies ride a second stream: the labels arrive while the forward runs (they are first needed by the loss) and the
     // result leaves while the backward runs; only the image upload is on the critical path
@@ -937,8 +969,51 @@ int ssdb_forward_detect_host(ssdb_net* n, const float* images_host, int B, float
         SSDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&n->det_counts), (size_t)n->max_batch * 2 * sizeof(int)));
     }
     if (!n->det_ws) SSDB_CUDA(cudaMalloc(&n->det_ws, decode_nms_scratch_bytes(n->max_batch, n->A, 0)));
+    int rc = SSDB_OK;
+    // Frozen model: the whole device side (im2col, ~60 forward launches, softmax, decode + NMS) is one CUDA graph per
+    // (batch, threshold, cap, IoU), captured on the second call with that key (the first runs eagerly: it sets the kernels'
+    // shared-memory attributes and allocates the lazily created tables, which must not happen inside a capture).
+    static int graphs_on = -1;
+    if (graphs_on < 0) { const char* ov = getenv("SSDB_GRAPH"); graphs_on = ov ? (atoi(ov) ? 1 : 0) : 1; }
+    if (n->inference && graphs_on && !result_host) {
+        if (n->wt_dirty) { rc = repack_filters(n, st); if (rc) return rc; drop_det_graphs(n); }
+        ssdb_net::DetGraph* dg = nullptr;
+        for (auto& g : n->det_graphs) if (g.B == B && g.thr == conf_thr && g.cap == cap && g.iou == iou_thr) dg = &g;
+        if (!dg) { n->det_graphs.push_back(ssdb_net::DetGraph{B, conf_thr, cap, iou_thr, false, nullptr}); dg = &n->det_graphs.back(); }
+        SSDB_CUDA(cudaMemcpyAsync(n->images_stage, images_host, (size_t)B * n->S * n->S * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+        auto device_side = [&]() -> int {
+            int r = run_forward(n, n->images_stage, B, st); if (r) return r;
+            r = softmax_result(n->out, (long long)B * n->A, n->C, n->result, st); if (r) return r;
+            SSDB_CUDA(cudaMemsetAsync(n->det_rows, 0, (size_t)B * cap_eff * 8 * sizeof(int), st));
+            return decode_nms_launch(n->result, B, n->A, n->C, n->anchors, conf_thr, cap, iou_thr, n->det_rows, n->det_counts, n->det_ws,
+                                     decode_nms_scratch_bytes(n->max_batch, n->A, 0), st);
+        };
+        if (!dg->warmed) { rc = device_side(); if (rc) return rc; dg->warmed = true; }
+        else {
+            if (!dg->exec) {
+                cudaGraph_t graph = nullptr;
+                SSDB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                rc = device_side();
+                cudaError_t ce = cudaStreamEndCapture(st, &graph);
+                if (rc || ce != cudaSuccess || !graph) {
+                    if (graph) cudaGraphDestroy(graph);
+                    if (!rc) { set_error("stream capture of the frozen forward failed: %s", cudaGetErrorString(ce)); rc = SSDB_ECUDA; }
+                    return rc;
+                }
+                ce = cudaGraphInstantiate(&dg->exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) { dg->exec = nullptr; set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); return SSDB_ECUDA; }
+            }
+            SSDB_CUDA(cudaGraphLaunch(dg->exec, st));
+            ++g_launches;
+        }
+        SSDB_CUDA(cudaMemcpyAsync(counts_out_host, n->det_counts, (size_t)B * 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        SSDB_CUDA(cudaMemcpyAsync(dets_out_host, n->det_rows, (size_t)B * cap_eff * 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        SSDB_CUDA(cudaStreamSynchronize(st));
+        return SSDB_OK;
+    }
     bool first_done = false;
-    int rc = upload_images_chunked(n, images_host, B, st, n->copy_stream, &first_done); if (rc) return rc;
+    rc = upload_images_chunked(n, images_host, B, st, n->copy_stream, &first_done); if (rc) return rc;
     rc = run_forward(n, n->images_stage, B, st, first_done); if (rc) return rc;
     rc = softmax_result(n->out, (long long)B * n->A, n->C, n->result, st); if (rc) return rc;
     if (result_host) {       // optional: the caller also wants net.result (it leaves on the copy stream, behind the kernels below)
@@ -961,6 +1036,7 @@ int ssdb_forward_detect_host(ssdb_net* n, const float* images_host, int B, float
 int ssdb_eval_step(ssdb_net* n, const float* images_dev, const float* labels_dev, int B, float weight_decay, float* losses_out_dev,
                    float* result_dev, void* stream) {
     SSDB_REQUIRE(n && images_dev && labels_dev, "bad arguments");
+    SSDB_REQUIRE(!n->inference, "loss entry point called on an inference handle");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = run_forward(n, images_dev, B, st); if (rc) return rc;
     return loss_and_finalize(n, labels_dev, nullptr, nullptr, 0, B, weight_decay, 1.0f, false, losses_out_dev, result_dev, st);
@@ -1327,6 +1403,7 @@ unsigned int ssdb_crc32c(unsigned int crc, const void* data_host, size_t bytes) 
 int ssdb_profile_step(ssdb_net* n, const float* images_dev, const float* labels_dev, int B, char (*names_out)[32], float* ms_out,
                       int* launches_out, int cap) {
     SSDB_REQUIRE(n && images_dev && labels_dev && names_out && ms_out && launches_out && cap > 0, "bad arguments");
+    SSDB_REQUIRE(!n->inference, "training entry point called on an inference handle");
     cudaStream_t st = n->own_stream;
     SSDB_CUDA(cudaStreamSynchronize(st));
     n->prof = true; n->prof_entries.clear();

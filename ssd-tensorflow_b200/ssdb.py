@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'libssd_b200.so')
 
 CONV_AUTO, CONV_SIMT, CONV_TC, CONV_TC_SPLIT = 0, 1, 2, 3
 PARAM, GRAD, MOMENTUM = 0, 1, 2
+FLAG_INFERENCE = 1
 
 
 class SSDBError(RuntimeError):
@@ -216,10 +217,13 @@ class PinnedPool:
 class Net:
     """Owner of one ssdb_net handle (one per GPU, not thread-safe)."""
 
-    def __init__(self, preset, num_classes=20, max_batch=8):
+    def __init__(self, preset, num_classes=20, max_batch=8, inference=False):
+        """inference=True: a frozen-model handle (SSDB_FLAG_INFERENCE): forward / detection only, half the memory, the
+        device side of forward_detect_host replayed as one CUDA graph."""
         require_device()
         self._h = _p()
-        check(lib().ssdb_create(preset.encode(), int(num_classes), int(max_batch), 0, C.byref(self._h)))
+        self.inference = bool(inference)
+        check(lib().ssdb_create(preset.encode(), int(num_classes), int(max_batch), FLAG_INFERENCE if inference else 0, C.byref(self._h)))
         self.preset = preset
         self.num_classes = int(num_classes)
         self.max_batch = int(max_batch)

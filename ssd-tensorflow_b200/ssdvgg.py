@@ -135,6 +135,7 @@ class SSDVGG:
         self._engine = None
         self._host_params = None     # name -> ndarray, until an engine exists (and to survive re-creation)
         self._opt = None
+        self._frozen = False         # build_from_frozen: inference-only engine (no training state, CUDA-graph forward)
         self._host_momentum = None   # name -> ndarray restored from a checkpoint, loaded into the engine when it is created
         self._restored_step = 0
         self.epoch = 0               # epochs completed (kept in checkpoints so that --continue-training resumes the loop)
@@ -215,7 +216,34 @@ class SSDVGG:
         self.num_classes = row - 4
         self._built = True
 
+    def export_frozen(self, path):
+        """export_model.py:62-72: freeze the model for deployment.  The reference folds the variables of a checkpoint into a
+        GraphDef (.pb); here the frozen model is the weights alone (reference variable names, no optimizer state) plus the
+        preset and class count -- everything ``build_from_frozen`` / detect.py need."""
+        arrays = self.get_params()
+        arrays['__num_vars'] = np.array(self.num_vars)
+        arrays['__preset'] = np.array(self.preset.name)
+        arrays['__frozen'] = np.array(1)
+        np.savez(path, **arrays)
+
+    def build_from_frozen(self, path):
+        """detect.py:62-92: load a frozen model.  The engine behind it is an inference handle: no gradient / momentum /
+        label buffers, and ``detect`` replays the forward + decode + NMS of a batch as one CUDA graph."""
+        with np.load(path) as z:
+            if '__frozen' not in z.files:
+                raise ValueError('%s is not a frozen model (use export_model.py)' % path)
+            if str(z['__preset']) != self.preset.name:
+                raise ValueError('frozen model is for preset %s, this SSDVGG is %s' % (z['__preset'], self.preset.name))
+            self._host_params = {k: z[k].astype(np.float32) for k in z.files if not k.startswith('__')}
+            row = int(z['__num_vars'])
+        self.num_vars = row
+        self.num_classes = row - 4
+        self._frozen = True
+        self._built = True
+
     def build_optimizer(self, learning_rate=0.001, weight_decay=0.0005, momentum=0.9, global_step=None):
+        if self._frozen:
+            raise RuntimeError('a frozen model cannot be trained')
         """ssdvgg.py:375-599.  `learning_rate` is a float or a zero-argument callable
         (see piecewise_constant)."""
         self._opt = dict(lr=learning_rate, wd=float(weight_decay), mu=float(momentum), step=global_step)
@@ -239,8 +267,10 @@ class SSDVGG:
         reference's ``saver.save(sess, 'e<N>.ckpt')`` (train.py:336-343), readable by TensorFlow tools."""
         arrays = self.get_params()
         # the optimizer state the reference's Saver keeps (train.py:208): Momentum slots '<var>/Momentum' and global_step
-        for k, v in self.get_params(ssdb.MOMENTUM).items():
-            arrays[k + '/Momentum'] = v
+        if not self._frozen:
+            mom = self.get_params(ssdb.MOMENTUM) if self._engine is not None else (self._host_momentum or {})
+            for k, v in mom.items():
+                arrays[k + '/Momentum'] = v
         step = self._opt['step'].value if self._opt is not None and self._opt.get('step') is not None else self._restored_step
         arrays['global_step'] = np.array(step, np.int64)
         if tf_checkpoint:
@@ -253,7 +283,7 @@ class SSDVGG:
     def close(self):
         if self._engine is not None:
             self._host_params = self.get_params()
-            self._host_momentum = self.get_params(ssdb.MOMENTUM)
+            self._host_momentum = None if self._frozen else self.get_params(ssdb.MOMENTUM)
             self._engine.close()
             self._engine = None
 
@@ -313,14 +343,16 @@ class SSDVGG:
             return self._engine
         state = None
         if self._engine is not None:
-            state = [self.get_params(w) for w in (ssdb.PARAM, ssdb.MOMENTUM)]
+            state = [self.get_params(ssdb.PARAM), None if self._frozen else self.get_params(ssdb.MOMENTUM)]
             self._engine.close()
-        eng = ssdb.Net(self.preset.name, self.num_vars - 5, max_batch=batch)
+        eng = ssdb.Net(self.preset.name, self.num_vars - 5, max_batch=batch, inference=self._frozen)
         src = state[0] if state else self._host_params
         for k, shape in eng.tensors():
             if tuple(src[k].shape) != tuple(shape):
                 raise ValueError('tensor %s has shape %s, expected %s' % (k, src[k].shape, shape))
             eng.set_tensor(k, src[k])
+            if self._frozen:
+                continue
             if state:
                 eng.set_tensor(k, state[1][k], ssdb.MOMENTUM)
             elif self._host_momentum and k in self._host_momentum:

@@ -254,3 +254,63 @@ def test_continue_training_restores_momentum_step_and_epoch(tmp_path):
         for k in want:
             assert np.array_equal(want[k], got[k]), k
             assert np.array_equal(want_m[k], got_m[k]), k
+
+
+def test_frozen_model_export_detect_and_cuda_graph(tmp_path):
+    """export_model.py -> detect.py (reference export_model.py:62-72, detect.py:90-112): the frozen, inference-only engine gives
+    the same detections as the training engine; the CUDA-graph replay (third call) the same as the eager first call; training
+    entry points refuse an inference handle; the CLI writes the reference's per-image text format."""
+    import subprocess, sys
+    import ssdb
+    x = synth.images(11, 4, 300)
+    with Session() as sess:
+        net, _, anc = _model(sess)
+        want = net.detect(x, 0.01, {}, 200, rows=True)
+        d = str(tmp_path / 'final')
+        net.save(d)
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'ssd-tensorflow_b200')
+    frozen = str(tmp_path / 'model.frozen.npz')
+    r = subprocess.run([sys.executable, os.path.join(pkg, 'export_model.py'), '--checkpoint-file', d + '.npz', '--output-file', frozen,
+                        '--output-tensors', 'result/result:0'], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    with Session() as s2:
+        n2 = SSDVGG(s2, ssdutils.get_preset_by_name('vgg300'))
+        n2.build_from_frozen(frozen)
+        with pytest.raises(RuntimeError):
+            n2.build_optimizer()
+        launches = []
+        for it in range(4):                       # eager, capture + launch, replay, replay
+            l0 = ssdb.launch_count()
+            got = n2.detect(x, 0.01, {}, 200, rows=True)
+            launches.append(ssdb.launch_count() - l0)
+            assert np.array_equal(got[1], want[1])
+            for i in range(4):
+                assert np.array_equal(got[0][i, :got[1][i, 0]], want[0][i, :want[1][i, 0]]), (it, i)
+        assert launches[0] > 50 and launches[2] == 1 and launches[3] == 1, launches       # one graph launch replaces the kernel list
+        eng = n2._engine
+        assert eng.inference
+        with pytest.raises(ssdb.SSDBError):
+            eng.train_step_host(x, np.zeros((4, 8732, 25), np.float32), 1e-5, 0.9, 0.0005)
+        with pytest.raises(ssdb.SSDBError):
+            eng.get_tensor('conv1_1/filter', (3, 3, 3, 64), ssdb.GRAD)
+        # another batch size and another threshold get their own graphs; plain forward still works on the handle
+        got1 = n2.detect(x[:1], 0.01, {}, 200, rows=True)
+        assert np.array_equal(got1[0][0, :got1[1][0, 0]], want[0][0, :want[1][0, 0]])
+        res = s2.run(n2.result, feed_dict={n2.image_input: x})
+        assert res.shape == (4, 8732, 25)
+    # the CLI on real image files
+    import cv2
+    files = []
+    for i in range(2):
+        f = str(tmp_path / ('img%d.png' % i))
+        cv2.imwrite(f, np.clip(synth.images(20 + i, 1, 320)[0], 0, 255).astype(np.uint8))
+        files.append(f)
+    out = str(tmp_path / 'out')
+    r = subprocess.run([sys.executable, os.path.join(pkg, 'detect.py'), '--model', frozen, '--output-dir', out, '--threshold', '0.01'] + files,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for f in files:
+        base = os.path.basename(f)
+        assert os.path.exists(os.path.join(out, base))
+        lines = open(os.path.join(out, base + '.txt')).read().splitlines()
+        assert 0 < len(lines) <= 200 and all(len(l.split()) == 6 for l in lines)
