@@ -200,7 +200,7 @@ def run_reference(args):
                          'sample': '%d timed steps of batch %d after %d warm-up, median' % (steps, sample, warm)},
         'e2e': {'value': rate, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 class TrainBench:
@@ -507,8 +507,31 @@ def forward_family(tb, with_cpu):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything that libraries print to fd 1 (NCCL's version banner, for one) goes to stderr; the JSON line is written to
+    the real stdout by emit(): stdout carries exactly one line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     args = parse()
+    quiet_stdout()
     if args.impl == 'reference':
         return run_reference(args)
     import torch
@@ -590,7 +613,7 @@ def main():
         if fwd:
             line['forward_only'] = fwd
         line.update(extras)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -1,9 +1,16 @@
 #!/bin/bash
-# 2-GPU data-parallel bench (run with: gpurun --gpus 2)
+# N-GPU data-parallel bench + DP parity + the reference arm under torchrun (run with: gpurun --gpus N)
 mkdir -p gpurun_out
-R=${1:-r1}
+R=${1:-r2}
 N=${2:-2}
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_${R}_n$N.json 2> gpurun_out/bench_${R}_n$N.err
-cat gpurun_out/bench_${R}_n$N.json | cut -c1-900; tail -5 gpurun_out/bench_${R}_n$N.err
+python - <<PY
+import json
+d=json.load(open('gpurun_out/bench_${R}_n$N.json'))
+print({k:d[k] for k in ('value','ms_per_step','n_gpus','clocks','gpu_launches')}); print('e2e', d['e2e']['value'], d['e2e']['ms_per_step'], 'gt', d['e2e_gt_feed']['value'])
+PY
+tail -3 gpurun_out/bench_${R}_n$N.err
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 tools/dp_parity.py > gpurun_out/dp_parity_${R}_n$N.log 2>&1
-tail -5 gpurun_out/dp_parity_${R}_n$N.log
+tail -3 gpurun_out/dp_parity_${R}_n$N.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 bench.py --impl reference --gpus $N --steps 3 --warmup 1 > gpurun_out/bench_ref_${R}_n$N.json 2> gpurun_out/bench_ref_${R}_n$N.err
+cut -c1-700 gpurun_out/bench_ref_${R}_n$N.json
