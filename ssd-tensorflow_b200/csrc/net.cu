@@ -100,6 +100,8 @@ struct ssdb_net {
                                        // pairs (default), plain float32 in the tf32 and SIMT modes
     float *acts = nullptr, *gacts = nullptr;
     float *out = nullptr, *out_grad = nullptr, *result = nullptr, *dz_head = nullptr;
+    std::vector<size_t> dz_head_off;   // per head (in backward order): offset of its dz buffer inside dz_head
+    float* l2n_partial = nullptr;      // workspace of l2norm_bwd (the wgrad kernels' `partial` may be in use on the side stream)
     float *images_stage = nullptr, *labels_stage = nullptr;
     double* gt_stage = nullptr; int* gt_count_stage = nullptr;    // raw ground truth of the host entry points ([max_batch, 128, 5] + counts)
     int* match_stage = nullptr;                                   // [max_batch, A] owner GT per anchor (fused match), on request
@@ -120,7 +122,8 @@ struct ssdb_net {
     std::vector<DetGraph> det_graphs;
     int conv_mode = SSDB_CONV_AUTO;
     int swap_rb = 1; float mean[3] = {103.939f, 116.779f, 123.68f};
-    cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+    cudaStream_t own_stream = nullptr, copy_stream = nullptr, side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_labels = nullptr, ev_result = nullptr, ev_images = nullptr;
     cudaEvent_t ev_chunk[8] = {};      // image chunks of the host entry points
     // gradient buckets for an all-reduce that overlaps the rest of the backward (ssdb_grad_buckets): contiguous ranges of
@@ -357,44 +360,76 @@ int run_first_conv_chunk(ssdb_net* n, const float* images, int b0, int Bc, cudaS
     return conv_tc_fprop(g1, patches, n->c1_wt, op.cout, n->fmt, ep, n->act(op.out, n->max_batch) + px * op.cout, st);
 }
 
+// Two streams per step.  The classifier convolutions (forward) and EVERY weight-gradient kernel (backward) go to a side
+// stream, ordered by events: a head starts when its feature map is written and runs beside the rest of the trunk; the
+// wgrad of a layer starts when its dz is final and runs beside the dgrad chain.  The kernels are persistent and take a whole
+// SM each, so two big layers simply queue; the gain is in the tails -- the last, partly filled wave of one kernel is topped
+// up by the other stream's CTAs -- and in the small layers (extras, heads of the small maps: 12-85 us each on a handful of
+// SMs), which now overlap each other.  Off while profiling per op (ssdb_profile_step) and with SSDB_DUAL_STREAM=0.
+bool dual_stream(const ssdb_net* n) {
+    static int on = -1;
+    if (on < 0) { const char* ov = getenv("SSDB_DUAL_STREAM"); on = ov ? (atoi(ov) ? 1 : 0) : 1; }
+    return on && !n->prof && n->side_stream != nullptr;
+}
+
+int run_one_forward_op(ssdb_net* n, const Op& op, const float* images, int B, cudaStream_t st) {
+    int rc = SSDB_OK;
+    ProfScope ps(n, st, std::string("fwd:") + op.name, op.type == OP_CONV ? conv_flops(geom_of(n, op, B)) : 0.0);
+    if (op.type == OP_CONV) {
+        ConvGeom g = geom_of(n, op, B);
+        ConvEpilogue ep;
+        ep.bias = n->params + n->masters[op.b].off; ep.relu = op.relu ? 1 : 0;
+        ep.round_tf32 = (n->round && !op.head) ? 1 : 0;
+        const float* x = op.in < 0 ? images : n->act(op.in, B);
+        float* y = op.out >= 0 ? n->act(op.out, B) : n->out;
+        if (op.head) { ep.scatter = 1; ep.V = n->V; ep.n_valid = op.nbox * n->V; ep.anchor_base = op.anchor_base; ep.A = n->A; }
+        if (op.in < 0) { ep.preprocess = 1; ep.swap_rb = n->swap_rb; ep.mean[0] = n->mean[0]; ep.mean[1] = n->mean[1]; ep.mean[2] = n->mean[2]; }
+        if (op.in < 0 && n->patches) {
+            rc = conv1_im2col(images, B, n->S, n->swap_rb, n->mean, n->fmt, n->patches, st); if (rc) return rc;
+            ConvGeom g1 = g; g1.Cin = 32; g1.k = 1; g1.pad_t = g1.pad_l = 0; g1.dil = 1;
+            ConvEpilogue e1 = ep; e1.preprocess = 0;
+            rc = conv_tc_fprop(g1, n->patches, n->c1_wt, op.cout, n->fmt, e1, y, st);
+        } else if (op.has_wt && use_tc(n, conv_tc_supported_fprop(g)))
+            rc = conv_tc_fprop(g, x, n->wt + op.wt_off, op.cout_pad, n->fmt, ep, y, st);
+        else
+            rc = conv_simt_fprop(g, x, n->params + n->masters[op.w].off, n->fmt, ep, y, st);
+    } else if (op.type == OP_POOL) {
+        const Buf& bi = n->bufs[op.in]; const Buf& bo = n->bufs[op.out];
+        if (op.stride == 1 && n->pool5_arg)
+            rc = maxpool_fwd_arg(n->act(op.in, B), n->fmt, B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W, n->act(op.out, B), n->pool5_arg, st);
+        else if (n->pool_code[&op - n->ops.data()])
+            rc = maxpool2x2_fwd_code(n->act(op.in, B), n->fmt, B, bi.H, bi.W, bi.C, bo.H, bo.W, n->act(op.out, B), n->pool_code[&op - n->ops.data()], st);
+        else
+            rc = maxpool_fwd(n->act(op.in, B), n->fmt, B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W, n->act(op.out, B), st);
+    } else {
+        const Buf& bi = n->bufs[op.in];
+        rc = l2norm_fwd(n->act(op.in, B), n->params + n->masters[op.w].off, n->fmt, (long long)B * bi.H * bi.W, bi.C, n->round ? 1 : 0, n->act(op.out, B), st);
+    }
+    return rc;
+}
+
 int run_forward(ssdb_net* n, const float* images, int B, cudaStream_t st, bool skip_first = false) {
     SSDB_REQUIRE(B >= 1 && B <= n->max_batch, "batch size out of range");
     if (n->wt_dirty) { ProfScope ps(n, st, "repack"); int rc = repack_filters(n, st); if (rc) return rc; }
+    const bool two = dual_stream(n);
+    cudaStream_t s2 = n->side_stream;
+    bool forked = false;
     for (const Op& op : n->ops) {
-        int rc = SSDB_OK;
         if (skip_first && &op == &n->ops[0]) continue;
-        ProfScope ps(n, st, std::string("fwd:") + op.name, op.type == OP_CONV ? conv_flops(geom_of(n, op, B)) : 0.0);
-        if (op.type == OP_CONV) {
-            ConvGeom g = geom_of(n, op, B);
-            ConvEpilogue ep;
-            ep.bias = n->params + n->masters[op.b].off; ep.relu = op.relu ? 1 : 0;
-            ep.round_tf32 = (n->round && !op.head) ? 1 : 0;
-            const float* x = op.in < 0 ? images : n->act(op.in, B);
-            float* y = op.out >= 0 ? n->act(op.out, B) : n->out;
-            if (op.head) { ep.scatter = 1; ep.V = n->V; ep.n_valid = op.nbox * n->V; ep.anchor_base = op.anchor_base; ep.A = n->A; }
-            if (op.in < 0) { ep.preprocess = 1; ep.swap_rb = n->swap_rb; ep.mean[0] = n->mean[0]; ep.mean[1] = n->mean[1]; ep.mean[2] = n->mean[2]; }
-            if (op.in < 0 && n->patches) {
-                rc = conv1_im2col(images, B, n->S, n->swap_rb, n->mean, n->fmt, n->patches, st); if (rc) return rc;
-                ConvGeom g1 = g; g1.Cin = 32; g1.k = 1; g1.pad_t = g1.pad_l = 0; g1.dil = 1;
-                ConvEpilogue e1 = ep; e1.preprocess = 0;
-                rc = conv_tc_fprop(g1, n->patches, n->c1_wt, op.cout, n->fmt, e1, y, st);
-            } else if (op.has_wt && use_tc(n, conv_tc_supported_fprop(g)))
-                rc = conv_tc_fprop(g, x, n->wt + op.wt_off, op.cout_pad, n->fmt, ep, y, st);
-            else
-                rc = conv_simt_fprop(g, x, n->params + n->masters[op.w].off, n->fmt, ep, y, st);
-        } else if (op.type == OP_POOL) {
-            const Buf& bi = n->bufs[op.in]; const Buf& bo = n->bufs[op.out];
-            if (op.stride == 1 && n->pool5_arg)
-                rc = maxpool_fwd_arg(n->act(op.in, B), n->fmt, B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W, n->act(op.out, B), n->pool5_arg, st);
-            else if (n->pool_code[&op - n->ops.data()])
-                rc = maxpool2x2_fwd_code(n->act(op.in, B), n->fmt, B, bi.H, bi.W, bi.C, bo.H, bo.W, n->act(op.out, B), n->pool_code[&op - n->ops.data()], st);
-            else
-                rc = maxpool_fwd(n->act(op.in, B), n->fmt, B, bi.H, bi.W, bi.C, op.k, op.stride, op.pad, op.pad, bo.H, bo.W, n->act(op.out, B), st);
-        } else {
-            const Buf& bi = n->bufs[op.in];
-            rc = l2norm_fwd(n->act(op.in, B), n->params + n->masters[op.w].off, n->fmt, (long long)B * bi.H * bi.W, bi.C, n->round ? 1 : 0, n->act(op.out, B), st);
+        if (op.head && two) continue;                      // launched right after the op that writes its feature map (below)
+        int rc = run_one_forward_op(n, op, images, B, st); if (rc) return rc;
+        if (!two) continue;
+        for (const Op& h : n->ops) {
+            if (!h.head || h.in != op.out) continue;
+            SSDB_CUDA(cudaEventRecord(n->ev_fork, st));
+            SSDB_CUDA(cudaStreamWaitEvent(s2, n->ev_fork, 0));
+            rc = run_one_forward_op(n, h, images, B, s2); if (rc) return rc;
+            forked = true;
         }
-        if (rc) return rc;
+    }
+    if (forked) {
+        SSDB_CUDA(cudaEventRecord(n->ev_join, s2));
+        SSDB_CUDA(cudaStreamWaitEvent(st, n->ev_join, 0));
     }
     n->have_forward = true; n->last_B = B;
     return SSDB_OK;
@@ -402,7 +437,10 @@ int run_forward(ssdb_net* n, const float* images, int B, cudaStream_t st, bool s
 
 int run_backward(ssdb_net* n, int B, cudaStream_t st) {
     SSDB_REQUIRE(n->have_forward && n->last_B == B, "backward without a matching forward");
+    const bool two = dual_stream(n);
+    cudaStream_t sw = two ? n->side_stream : st;            // the stream of the weight-gradient kernels
     std::vector<char> written(n->bufs.size(), 0);
+    int head_k = 0;
     for (int oi = (int)n->ops.size() - 1; oi >= 0; --oi) {
         const Op& op = n->ops[oi];
         int rc = SSDB_OK;
@@ -410,10 +448,13 @@ int run_backward(ssdb_net* n, int B, cudaStream_t st) {
             ConvGeom g = geom_of(n, op, B);
             const float* dz;
             if (op.head) {
+                // every head has its own dz buffer: its wgrad (side stream) and dgrad (main stream) read it while the next
+                // head's gather already runs
                 const Buf& fb = n->bufs[op.in];
-                rc = head_grad_gather(n->out_grad, B, n->A, n->V, op.anchor_base, fb.H * fb.W, op.nbox, op.cout, n->fmt, n->round ? 1 : 0, n->dz_head, st);
+                float* dzh = n->dz_head + n->dz_head_off[head_k++];
+                rc = head_grad_gather(n->out_grad, B, n->A, n->V, op.anchor_base, fb.H * fb.W, op.nbox, op.cout, n->fmt, n->round ? 1 : 0, dzh, st);
                 if (rc) return rc;
-                dz = n->dz_head;
+                dz = dzh;
             } else {
                 SSDB_REQUIRE(written[op.out], "internal: gradient of a conv output was never produced");
                 dz = n->gact(op.out, B);
@@ -422,27 +463,29 @@ int run_backward(ssdb_net* n, int B, cudaStream_t st) {
             float* dw = n->grads + n->masters[op.w].off;
             float* db = n->grads + n->masters[op.b].off;
             long long pixels = (long long)B * g.Ho * g.Wo;
-            if (op.in < 0 && n->patches) {
-                ProfScope ps(n, st, std::string("bwd_w:") + op.name, conv_flops(g));
-                ConvGeom g1 = g; g1.Cin = 32; g1.k = 1; g1.pad_t = g1.pad_l = 0; g1.dil = 1;
-                rc = conv_tc_wgrad(g1, n->patches, dz, n->fmt, n->c1_dw32, db, n->partial, st); if (rc) return rc;
-                SSDB_CUDA(cudaMemcpyAsync(dw, n->c1_dw32, (size_t)27 * op.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
-                for (int b = 0; b < n->n_buckets; ++b)
-                    if (n->bucket_last_op[b] == oi) SSDB_CUDA(cudaEventRecord(n->ev_bucket[b], st));
-                continue;
+            if (two) {                                       // dz of this layer is final here: the wgrad may start
+                SSDB_CUDA(cudaEventRecord(n->ev_fork, st));
+                SSDB_CUDA(cudaStreamWaitEvent(sw, n->ev_fork, 0));
             }
-            const bool tcw = op.in >= 0 && use_tc(n, conv_tc_supported_wgrad(g, n->fmt));
-            if (!tcw) { ProfScope ps(n, st, std::string("bwd_b:") + op.name); rc = bias_grad(dz, n->fmt, pixels, op.cout, db, n->partial, st); }
-            if (rc) return rc;
-            ProfScope* psw = new ProfScope(n, st, std::string("bwd_w:") + op.name, conv_flops(g));
-            ConvEpilogue ep;
-            if (op.in < 0) { ep.preprocess = 1; ep.swap_rb = n->swap_rb; ep.mean[0] = n->mean[0]; ep.mean[1] = n->mean[1]; ep.mean[2] = n->mean[2]; }
-            if (tcw)
-                rc = conv_tc_wgrad(g, x, dz, n->fmt, dw, db, n->partial, st);
-            else
-                rc = conv_simt_wgrad(g, op.in < 0 ? n->images_stage : x, dz, n->fmt, ep, dw, n->partial, st);
-            delete psw;
-            if (rc) return rc;
+            if (op.in < 0 && n->patches) {
+                ProfScope ps(n, sw, std::string("bwd_w:") + op.name, conv_flops(g));
+                ConvGeom g1 = g; g1.Cin = 32; g1.k = 1; g1.pad_t = g1.pad_l = 0; g1.dil = 1;
+                rc = conv_tc_wgrad(g1, n->patches, dz, n->fmt, n->c1_dw32, db, n->partial, sw); if (rc) return rc;
+                SSDB_CUDA(cudaMemcpyAsync(dw, n->c1_dw32, (size_t)27 * op.cout * sizeof(float), cudaMemcpyDeviceToDevice, sw));
+            } else {
+                const bool tcw = op.in >= 0 && use_tc(n, conv_tc_supported_wgrad(g, n->fmt));
+                if (!tcw) { ProfScope ps(n, sw, std::string("bwd_b:") + op.name); rc = bias_grad(dz, n->fmt, pixels, op.cout, db, n->partial, sw); }
+                if (rc) return rc;
+                ProfScope* psw = new ProfScope(n, sw, std::string("bwd_w:") + op.name, conv_flops(g));
+                ConvEpilogue ep;
+                if (op.in < 0) { ep.preprocess = 1; ep.swap_rb = n->swap_rb; ep.mean[0] = n->mean[0]; ep.mean[1] = n->mean[1]; ep.mean[2] = n->mean[2]; }
+                if (tcw)
+                    rc = conv_tc_wgrad(g, x, dz, n->fmt, dw, db, n->partial, sw);
+                else
+                    rc = conv_simt_wgrad(g, op.in < 0 ? n->images_stage : x, dz, n->fmt, ep, dw, n->partial, sw);
+                delete psw;
+                if (rc) return rc;
+            }
             if (op.in >= 0) {
                 ProfScope psd(n, st, std::string("bwd_d:") + op.name, conv_flops(g));
                 const float* mask = n->bufs[op.in].relu_out ? x : nullptr;
@@ -468,16 +511,22 @@ int run_backward(ssdb_net* n, int B, cudaStream_t st) {
                              written[op.in] ? 1 : 0, bi.relu_out ? 1 : 0, n->round ? 1 : 0, n->gact(op.in, B), st);
             written[op.in] = 1;
         } else {
+            // the scale gradient of the L2 normalisation is written on the main stream (its own small workspace); it belongs to
+            // the first gradient bucket, whose event is recorded on the wgrad stream AFTER a wait on a later main-stream event
             ProfScope ps(n, st, std::string("bwd:") + op.name);
             SSDB_REQUIRE(written[op.out], "internal: gradient of the L2-norm output was never produced");
             const Buf& bi = n->bufs[op.in];
             rc = l2norm_bwd(n->act(op.in, B), n->params + n->masters[op.w].off, n->gact(op.out, B), n->fmt, (long long)B * bi.H * bi.W, bi.C,
-                            written[op.in] ? 1 : 0, n->round ? 1 : 0, n->gact(op.in, B), n->grads + n->masters[op.w].off, n->partial, st);
+                            written[op.in] ? 1 : 0, n->round ? 1 : 0, n->gact(op.in, B), n->grads + n->masters[op.w].off, n->l2n_partial, st);
             written[op.in] = 1;
         }
         if (rc) return rc;
         for (int b = 0; b < n->n_buckets; ++b)
-            if (n->bucket_last_op[b] == oi) SSDB_CUDA(cudaEventRecord(n->ev_bucket[b], st));
+            if (n->bucket_last_op[b] == oi) SSDB_CUDA(cudaEventRecord(n->ev_bucket[b], sw));
+    }
+    if (two) {                                               // the update (or the caller's all-reduce) needs every weight gradient
+        SSDB_CUDA(cudaEventRecord(n->ev_join, sw));
+        SSDB_CUDA(cudaStreamWaitEvent(st, n->ev_join, 0));
     }
     return SSDB_OK;
 }
@@ -555,7 +604,13 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
         ConvGeom g = geom_of(n, op, max_batch);
         size_t w = conv_simt_wgrad_ws(g); if (w > partial) partial = w;
         w = conv_tc_wgrad_ws(g, n->fmt); if (w > partial) partial = w;
-        if (op.head) { size_t d = (size_t)max_batch * g.H * g.W * op.cout; if (d > dzh) dzh = d; }
+    }
+    for (int oi = (int)n->ops.size() - 1; oi >= 0; --oi) {       // one dz buffer per head, in the order the backward visits them
+        const Op& op = n->ops[oi];
+        if (op.type != OP_CONV || !op.head) continue;
+        ConvGeom g = geom_of(n, op, max_batch);
+        n->dz_head_off.push_back(dzh);
+        dzh += ((size_t)max_batch * g.H * g.W * op.cout + 255) / 256 * 256;
     }
     n->partial_floats = partial;
     size_t bav = (size_t)max_batch * n->A * n->V;
@@ -576,7 +631,7 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
         ALLOC(n->gacts, n->act_floats_per_image * max_batch, float);
         ALLOC(n->out_grad, bav, float); ALLOC(n->labels_stage, bav, float);
         ALLOC(n->dz_head, dzh ? dzh : 1, float);
-        ALLOC(n->partial, partial, float);
+        ALLOC(n->partial, partial, float); ALLOC(n->l2n_partial, (size_t)296 * 1024, float);
         ALLOC(n->gt_stage, (size_t)max_batch * 128 * 5, double); ALLOC(n->gt_count_stage, max_batch, int);
         ALLOC(n->match_stage, (size_t)max_batch * n->A, int);
         ALLOC(n->loss_ws, multibox_loss_ws_bytes(max_batch, n->A), unsigned char);
@@ -620,6 +675,9 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
     SSDB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&n->host_small), 64 * sizeof(float)));
     SSDB_CUDA(cudaStreamCreateWithFlags(&n->own_stream, cudaStreamNonBlocking));
     SSDB_CUDA(cudaStreamCreateWithFlags(&n->copy_stream, cudaStreamNonBlocking));
+    SSDB_CUDA(cudaStreamCreateWithFlags(&n->side_stream, cudaStreamNonBlocking));
+    SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming));
+    SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming));
     SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_labels, cudaEventDisableTiming));
     SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_result, cudaEventDisableTiming));
     SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_images, cudaEventDisableTiming));
@@ -647,12 +705,15 @@ int ssdb_destroy(ssdb_net* n) {
     drop_det_graphs(n);
     void* ptrs[] = {n->pool5_arg, n->patches, n->c1_w32, n->c1_wt, n->c1_dw32, n->wr, n->params, n->grads, n->moms, n->wt, n->acts, n->gacts, n->out, n->out_grad, n->result, n->labels_stage,
                     n->dz_head, n->images_stage, n->partial, n->small_ws, n->counter, n->decay_mask, n->anchors, n->loss_ws, n->det_ws,
-                    n->gt_stage, n->gt_count_stage, n->match_stage, n->det_rows, n->det_counts};
+                    n->gt_stage, n->gt_count_stage, n->match_stage, n->det_rows, n->det_counts, n->l2n_partial};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (unsigned char* p : n->pool_code) if (p) cudaFree(p);
     if (n->host_small) cudaFreeHost(n->host_small);
     if (n->own_stream) cudaStreamDestroy(n->own_stream);
     if (n->copy_stream) cudaStreamDestroy(n->copy_stream);
+    if (n->side_stream) cudaStreamDestroy(n->side_stream);
+    if (n->ev_fork) cudaEventDestroy(n->ev_fork);
+    if (n->ev_join) cudaEventDestroy(n->ev_join);
     if (n->ev_labels) cudaEventDestroy(n->ev_labels);
     if (n->ev_result) cudaEventDestroy(n->ev_result);
     if (n->ev_images) cudaEventDestroy(n->ev_images);
