@@ -41,6 +41,16 @@ extern long long g_launches;          // kernels launched by this library
         }                                                                            \
     } while (0)
 
+// Lazily created per-DEVICE state (shared-memory attributes, lookup tables, scratch): a process may drive several GPUs, and
+// a pointer or a function attribute set up on one device means nothing on another.  `static PerDevice<T> x;` + `x.get()`.
+constexpr int MAX_DEVICES = 64;
+inline int cur_device() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < MAX_DEVICES) ? d : 0; }
+template <class T>
+struct PerDevice {
+    T v[MAX_DEVICES] = {};
+    T& get() { return v[cur_device()]; }
+};
+
 // Geometry of one convolution (TF semantics; NHWC activations, HWIO filter).
 struct ConvGeom {
     int B, H, W, Cin;        // input

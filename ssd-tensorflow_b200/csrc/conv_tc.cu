@@ -1547,7 +1547,8 @@ TileGeom pick_tile(int B, int H, int W) {
 }
 
 int num_sms() {
-    static int n = 0;
+    static PerDevice<int> n_pd;
+    int& n = n_pd.get();
     if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
     return n;
 }
@@ -1560,7 +1561,8 @@ constexpr int DUAL_RING_BYTES = 92 * 1024;
 constexpr int DUAL_SMEM_BYTES = DUAL_RING_BYTES + 1024 + 256 + 4 * 32 * 128;         // 109.25 KB (4 epilogue warps): two fit in 227 KB
 
 int launch_tc(const CUtensorMap& ms, const CUtensorMap& mw, const TcArgs& a_in, cudaStream_t st) {
-    static bool attr = false;
+    static PerDevice<bool> attr_pd;
+    bool& attr = attr_pd.get();
     if (!attr) {
         SSDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<ACT_F32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         SSDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<ACT_F32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -1889,7 +1891,8 @@ int encode_act_map5s(CUtensorMap* m, const float* ptr, int B, int H, int W, int 
 
 // 8 KB of bf16 1.0 followed by 8 KB of zeros: the (hi, lo) sub-blocks of the split kernels' bias slot
 const float* ones_buffer_split() {
-    static float* d = nullptr;
+    static PerDevice<float*> d_pd;
+    float*& d = d_pd.get();
     if (!d) {
         std::vector<uint32_t> h(4096, 0u);
         for (int i = 0; i < 2048; ++i) h[i] = 0x3f803f80u;
@@ -1900,7 +1903,8 @@ const float* ones_buffer_split() {
 }
 
 const float* ones_buffer() {
-    static float* d = nullptr;
+    static PerDevice<float*> d_pd;
+    float*& d = d_pd.get();
     if (!d) {
         std::vector<float> h(64 * 32, 1.0f);
         if (cudaMalloc(reinterpret_cast<void**>(&d), h.size() * sizeof(float)) != cudaSuccess) return nullptr;
@@ -2110,7 +2114,8 @@ int conv_tc_wgrad(const ConvGeom& g, const float* x, const float* dz, int fmt, f
         CUtensorMap mx, mz;
         int rc = encode_act_map5s(&mx, x, g.B, g.H, g.W, g.Cin, 8 + 2 * a.dil, a.PH + 2 * a.dil, 1, 2, 1); if (rc) return rc;
         rc = encode_act_map5s(&mz, dz, g.B, g.Ho, g.Wo, g.Cout, 8, a.PH, 1, 8, 1); if (rc) return rc;
-        static bool attr_r2 = false;
+        static PerDevice<bool> attr_r2_pd;
+        bool& attr_r2 = attr_r2_pd.get();
         if (!attr_r2) { SSDB_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_r2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_r2 = true; }
         long long units = (long long)a.cblocks * a.mblocks * a.splits;
         int grid = (int)(units < num_sms() ? units : num_sms());
@@ -2135,7 +2140,8 @@ int conv_tc_wgrad(const ConvGeom& g, const float* x, const float* dz, int fmt, f
             rc = encode_rw_map(&mx, x, g.B, g.H, g.W, g.Cin, 11, a.PH + 2, 1, a.cpu); if (rc) return rc;
             rc = encode_rw_map(&mz, dz, g.B, g.Ho, g.Wo, g.Cout, 8, a.PH, 1, a.block_n / 32); if (rc) return rc;
         }
-        static bool attr_rw = false;
+        static PerDevice<bool> attr_rw_pd;
+        bool& attr_rw = attr_rw_pd.get();
         if (!attr_rw) {
             SSDB_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_rw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             SSDB_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_rw_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -2169,7 +2175,8 @@ int conv_tc_wgrad(const ConvGeom& g, const float* x, const float* dz, int fmt, f
         rc = encode_act_map5(&mx, x, g.B, g.H, g.W, g.Cin, a.PW, a.PH, a.PN, a.load_blocks, g.stride); if (rc) return rc;
         rc = encode_act_map5(&mz, dz, g.B, g.Ho, g.Wo, g.Cout, a.PW, a.PH, a.PN, a.block_n / 32, 1); if (rc) return rc;
     }
-    static bool attr = false;
+    static PerDevice<bool> attr_pd;
+    bool& attr = attr_pd.get();
     if (!attr) {
         SSDB_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         SSDB_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

@@ -546,7 +546,8 @@ int decode_nms_launch(const float* pred, int B, int A, int C, const double* anch
     p.P = next_pow2(p.cap_eff);
     size_t sh = ((size_t)A * 4 + 15) / 16 * 16;
     p.g_keys = nullptr; p.g_cand = nullptr; p.ckey_in = nullptr; p.cls_in = nullptr; p.fast = nms_v1() ? 0 : 1;
-    static double* table_dev = nullptr;
+    static PerDevice<double*> table_pd;
+    double*& table_dev = table_pd.get();
     if (!table_dev) {
         std::vector<double> t(2000);
         for (int k = 0; k < 2000; ++k) { volatile double half = (double)k / 2.0; t[k] = half / 1000.0; }
@@ -563,7 +564,8 @@ int decode_nms_launch(const float* pred, int B, int A, int C, const double* anch
         p.g_keys = reinterpret_cast<unsigned long long*>(sc + keys_bytes);
         p.g_cand = reinterpret_cast<int*>(sc + keys_bytes + (size_t)B * p.P * 8);
     }
-    static size_t dyn_max = 0;          // 227 KB per CTA minus the kernel's static shared memory
+    static PerDevice<size_t> dyn_pd;      // 227 KB per CTA minus the kernel's static shared memory
+    size_t& dyn_max = dyn_pd.get();
     if (!dyn_max) {
         cudaFuncAttributes fa;
         SSDB_CUDA(cudaFuncGetAttributes(&fa, decode_nms_kernel));
@@ -583,7 +585,8 @@ int decode_nms_launch(const float* pred, int B, int A, int C, const double* anch
         SSDB_LAUNCH_CHECK();
         p.ckey_in = ckey; p.cls_in = ccls;
     }
-    static long long* trace_dev = nullptr;
+    static PerDevice<long long*> trace_pd;
+    long long*& trace_dev = trace_pd.get();
     const bool tracing = getenv("SSDB_TRACE") != nullptr;
     p.trace = nullptr; p.trace_block = getenv("SSDB_TRACE_BLOCK") ? atoi(getenv("SSDB_TRACE_BLOCK")) : 0;
     if (tracing) {

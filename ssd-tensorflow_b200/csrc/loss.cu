@@ -35,6 +35,14 @@ constexpr int MAX_G = 128;        // ground-truth boxes per image
 
 struct IBox { int x0, x1, y0, y1; };
 
+// label id of a ground-truth row as an index: ids outside [0, C) (or NaN) are treated as background -- the host entry points
+// reject them (SSDB_EINVAL, like the reference's IndexError at transforms.py:107); for device-pointer callers this keeps
+// every access in bounds
+__device__ __forceinline__ int gt_class(const double* row, int C) {
+    const double id = row[0];
+    return (id >= 0.0 && id < (double)C) ? (int)id : C;
+}
+
 // utils.prop2abs on the 1000x1000 grid, float64, int() truncation
 __device__ __forceinline__ IBox prop2abs_1000(double cx, double cy, double w, double h) {
     double hw = __dmul_rn(__dmul_rn(w, 1000.0), 0.5);          // x * 0.5 == x / 2 exactly; float64 division is slow
@@ -144,7 +152,7 @@ __global__ void __launch_bounds__(LT) match_kernel(const double* __restrict__ gt
             for (int c = 0; c < V; ++c) row[c] = 0.f;
             if (owner < 0) row[C] = 1.f;
             else {
-                row[(int)gtb[owner * 5]] = 1.f;
+                row[gt_class(gtb + owner * 5, C)] = 1.f;
                 encode_loc(gtb + owner * 5, anchors + a * 4, row + C + 1);
             }
         }
@@ -239,7 +247,7 @@ __global__ void __launch_bounds__(LT) multibox_loss_kernel(
             own[a] = (signed char)owner;
             if (match_out) match_out[(long long)b * A + a] = owner;
             pos = owner >= 0;
-            int cls = pos ? (int)gtb[owner * 5] : C;
+            int cls = pos ? gt_class(gtb + owner * 5, C) : C;
             cev = lse - z[cls];
             if (pos) {
                 float t[4]; encode_loc(gtb + owner * 5, anchors + a * 4, t);
@@ -350,7 +358,7 @@ __global__ void __launch_bounds__(LT) multibox_loss_kernel(
                 if (kd == 1) { for (int c = 0; c < V; ++c) gr[c] = 0.f; continue; }
                 if (GT_MODE) {
                     int owner = own[a];
-                    int cls = owner >= 0 ? (int)gtb[owner * 5] : C;
+                    int cls = owner >= 0 ? gt_class(gtb + owner * 5, C) : C;
                     for (int c = 0; c < NC; ++c) gr[c] = (p[c] - (c == cls ? 1.f : 0.f)) * gs;
                     if (owner >= 0) {
                         float t[4]; encode_loc(gtb + owner * 5, anchors + a * 4, t);
@@ -541,7 +549,7 @@ __global__ void __launch_bounds__(RT) loss_rows_kernel(
             ws.own[(long long)b * A + a] = (signed char)owner;
             if (match_out) match_out[(long long)b * A + a] = owner;
             pos = owner >= 0;
-            const int cls = pos ? (int)gtb[owner * 5] : C;
+            const int cls = pos ? gt_class(gtb + owner * 5, C) : C;
             cev = lse - zr[cls];
             if (pos) {
                 float t[4]; encode_loc(gtb + owner * 5, anchors + a * 4, t);
@@ -701,7 +709,7 @@ __global__ void __launch_bounds__(RT) loss_grad_kernel(
             if (GT_MODE) {
                 const int owner = ws.own[(long long)b * A + a];
                 const double* gtb = gt + (long long)b * G * 5;
-                const int cls = owner >= 0 ? (int)gtb[owner * 5] : C;
+                const int cls = owner >= 0 ? gt_class(gtb + owner * 5, C) : C;
 #pragma unroll
                 for (int c = 0; c < VMAX; ++c) if (c < NC) gr[c] = (expf(z[c] - m) * inv - (c == cls ? 1.f : 0.f)) * gs;
                 if (owner >= 0) {
@@ -774,7 +782,8 @@ int loss_v2(const float* output, const float* labels, const double* gt, const in
         SSDB_LAUNCH_CHECK();
     }
     const size_t sh_rows = (size_t)RT * V * 4 * (GT_MODE ? 1 : 2), sh_sel = (size_t)A * 5 + 16, sh_grad = (size_t)RT * V * 4;
-    static size_t sel_max = 0;    // per template instantiation; 227 KB per CTA minus the select kernel's static shared memory
+    static PerDevice<size_t> sel_pd;    // per template instantiation; 227 KB per CTA minus the select kernel's static shared memory
+    size_t& sel_max = sel_pd.get();
     if (!sel_max) {
         int rc = opt_in_smem(loss_rows_kernel<GT_MODE, VT>, (size_t)RT * MAXV * 8); if (rc) return rc;
         cudaFuncAttributes fa;
@@ -787,7 +796,8 @@ int loss_v2(const float* output, const float* labels, const double* gt, const in
     loss_rows_kernel<GT_MODE, VT><<<dim3(S, B), RT, sh_rows, st>>>(output, labels, gt, gt_count, G, anchors, A, C, S, bulk_rows, ws,
                                                                    result_out, match_out);
     SSDB_LAUNCH_CHECK();
-    static long long* trace_dev = nullptr;
+    static PerDevice<long long*> trace_pd;
+    long long*& trace_dev = trace_pd.get();
     const bool tracing = getenv("SSDB_TRACE") != nullptr;
     if (tracing) {
         if (!trace_dev) SSDB_CUDA(cudaMalloc(&trace_dev, 16 * sizeof(long long)));
@@ -848,12 +858,14 @@ int multibox_loss_launch(const float* output, const float* labels, const double*
     LossWs w = carve_ws(ws, B, A);
     size_t sh = (size_t)A * 4 + (size_t)A * 2 + 16;
     if (labels) {
-        static bool attr0 = false;
+        static PerDevice<bool> attr0_pd;
+        bool& attr0 = attr0_pd.get();
         if (!attr0) { SSDB_CUDA(cudaFuncSetAttribute(multibox_loss_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr0 = true; }
         multibox_loss_kernel<false><<<B, LT, sh, st>>>(output, labels, nullptr, nullptr, 0, nullptr, B, A, C, grad_scale,
                                                         losses_out, grad_out, result_out, nullptr, w.per_image, w.counter);
     } else {
-        static bool attr1 = false;
+        static PerDevice<bool> attr1_pd;
+        bool& attr1 = attr1_pd.get();
         if (!attr1) { SSDB_CUDA(cudaFuncSetAttribute(multibox_loss_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr1 = true; }
         multibox_loss_kernel<true><<<B, LT, sh, st>>>(output, nullptr, gt, gt_count, G, anchors_prop, B, A, C, grad_scale,
                                                        losses_out, grad_out, result_out, match_out, w.per_image, w.counter);

@@ -1211,7 +1211,8 @@ int ssdb_nms_host(const int* boxes, const int* labelid, const float* conf, int n
 
 // grow-only workspace of the stateless loss entry points (one caller thread per process, like the reference)
 static int loss_ws(int B, int A, void** ws_out) {
-    static void* ws = nullptr; static size_t cap = 0;
+    static PerDevice<void*> ws_pd; static PerDevice<size_t> cap_pd;
+    void*& ws = ws_pd.get(); size_t& cap = cap_pd.get();
     const size_t need = multibox_loss_ws_bytes(B, A);
     if (need > cap) {
         if (ws) { SSDB_CUDA(cudaDeviceSynchronize()); cudaFree(ws); ws = nullptr; cap = 0; }
