@@ -242,6 +242,16 @@ int ssdb_train_step_host_gt(ssdb_net* net, const float* images_host, const doubl
                             int G, int B, float lr, float momentum, float weight_decay, int apply_update,
                             float* losses_out_host, float* result_host, int* match_out_host);
 
+/* The data-parallel host-fed step in two halves.  _begin enqueues upload, forward, loss, backward and the result download on
+ * the engine's streams and returns WITHOUT waiting (labels_host, or NULL with gt_host / gt_count_host / G); the caller
+ * overlaps the bucketed gradient all-reduce (ssdb_grad_buckets / ssdb_wait_grad_bucket) and ssdb_apply_update on its own
+ * stream with the rest of the backward, then calls _end, which waits for the engine's streams and returns net.losses.
+ * The host buffers must stay valid until _end returns. */
+int ssdb_train_step_host_begin(ssdb_net* net, const float* images_host, const float* labels_host, const double* gt_host,
+                               const int* gt_count_host, int G, int B, float weight_decay, float* result_host,
+                               int* match_out_host);
+int ssdb_train_step_host_end(ssdb_net* net, float* losses_out_host);
+
 /* infer.py:225-235 / detect.py:103-112 as ONE call: sess.run(net.result) followed per image by decode_boxes +
  * suppress_overlaps.  The result tensor stays in device memory, the fused decode + top-k + class-wise NMS kernels
  * (ssdb_decode_nms) read it there, and only the detections come back: [B, cap_eff, 8] int32 rows + [B, 2] counts in

@@ -991,10 +991,25 @@ static int train_step_host_impl(ssdb_net* n, const float* images_host, const flo
         if (match_out_host) SSDB_CUDA(cudaMemcpyAsync(match_out_host, n->match_stage, (size_t)B * n->A * sizeof(int), cudaMemcpyDeviceToHost, cs));
     }
     if (apply_update >= 0) { rc = run_backward(n, B, st); if (rc) return rc; }
-    if (apply_update > 0) { rc = ssdb_apply_update(n, lr, momentum, weight_decay, 1.0f, st); if (rc) return rc; }
+    if (apply_update == 1) { rc = ssdb_apply_update(n, lr, momentum, weight_decay, 1.0f, st); if (rc) return rc; }
     SSDB_CUDA(cudaMemcpyAsync(n->host_small, n->small_ws, 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (apply_update == 2) return SSDB_OK;         // ssdb_train_step_host_begin: the caller finishes with ssdb_train_step_host_end
     SSDB_CUDA(cudaStreamSynchronize(st));
     SSDB_CUDA(cudaStreamSynchronize(cs));
+    if (losses_out_host) memcpy(losses_out_host, n->host_small, 4 * sizeof(float));
+    return SSDB_OK;
+}
+
+int ssdb_train_step_host_begin(ssdb_net* n, const float* images_host, const float* labels_host, const double* gt_host, const int* gt_count_host,
+                               int G, int B, float weight_decay, float* result_host, int* match_out_host) {
+    return train_step_host_impl(n, images_host, labels_host, gt_host, gt_count_host, G, B, 0.f, 0.f, weight_decay, 2, nullptr, result_host,
+                                labels_host ? nullptr : match_out_host);
+}
+
+int ssdb_train_step_host_end(ssdb_net* n, float* losses_out_host) {
+    SSDB_REQUIRE(n, "bad arguments");
+    SSDB_CUDA(cudaStreamSynchronize(n->own_stream));
+    SSDB_CUDA(cudaStreamSynchronize(n->copy_stream));
     if (losses_out_host) memcpy(losses_out_host, n->host_small, 4 * sizeof(float));
     return SSDB_OK;
 }

@@ -68,26 +68,32 @@ class DataParallelTrainer:
         if self.world > 1:
             dist.broadcast(self.params, src=src, group=self.group)
 
+    def _step_host(self, lr, momentum, weight_decay, **feed):
+        import torch
+        if self.world == 1:
+            if 'labels' in feed:
+                return self.net.train_step_host(feed['images'], feed['labels'], lr, momentum, weight_decay)
+            res, losses, _ = self.net.train_step_host_gt(feed['images'], feed['gt'], feed['gt_count'], lr, momentum, weight_decay)
+            return res, losses
+        # everything of the local step is enqueued on the engine's streams without waiting; the all-reduce of each gradient
+        # bucket and then the fused update run on the side stream as the buckets complete, beside the remaining backward
+        res = self.net.train_step_host_begin(weight_decay=weight_decay, **feed)
+        with torch.cuda.stream(self.side):
+            scale = allreduce_buckets(self.grads, self.buckets, self.world, self.group,
+                                      before=lambda k: self.net.wait_grad_bucket(k, self.side.cuda_stream))
+            self.net.apply_update(lr, momentum, weight_decay, grad_post_scale=scale, stream=self.side.cuda_stream)
+        losses = self.net.train_step_host_end()
+        self.side.synchronize()
+        return res, losses
+
     def step_host(self, images, labels, lr, momentum, weight_decay):
         """The data-parallel equivalent of sess.run([net.result, net.losses, net.optimizer], feed_dict): host arrays in,
-        (result, losses) out; copies overlap the compute inside the library, then one all-reduce and the fused update."""
-        import torch
-        res, losses = self.net.train_step_host_noupdate(images, labels, weight_decay)
-        scale = average_gradients(self.grads, self.world, self.group)
-        st = torch.cuda.current_stream().cuda_stream
-        self.net.apply_update(lr, momentum, weight_decay, grad_post_scale=scale, stream=st)
-        torch.cuda.current_stream().synchronize()
-        return res, losses
+        (result, losses) out; copies overlap the compute inside the library, the all-reduce overlaps the backward."""
+        return self._step_host(lr, momentum, weight_decay, images=images, labels=labels)
 
     def step_host_gt(self, images, gt, gt_count, lr, momentum, weight_decay):
         """step_host with raw ground truth [B,G,5] + counts instead of dense labels (fused anchor matching)."""
-        import torch
-        res, losses, _ = self.net.train_step_host_gt(images, gt, gt_count, weight_decay=weight_decay, apply_update=0)
-        scale = average_gradients(self.grads, self.world, self.group)
-        st = torch.cuda.current_stream().cuda_stream
-        self.net.apply_update(lr, momentum, weight_decay, grad_post_scale=scale, stream=st)
-        torch.cuda.current_stream().synchronize()
-        return res, losses
+        return self._step_host(lr, momentum, weight_decay, images=images, gt=gt, gt_count=gt_count)
 
     def step(self, images_ptr, labels_ptr, local_batch, lr, momentum, weight_decay, losses_ptr=None, result_ptr=None,
              gt_ptr=None, gt_count_ptr=None, G=0):

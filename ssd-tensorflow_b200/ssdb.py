@@ -79,6 +79,8 @@ SIGNATURES = {
     'ssdb_train_step_host_noupdate': (_i, [_p, _p, _p, _i, _f, _p, _p]),
     'ssdb_train_step_host_gt': (_i, [_p, _p, _p, _p, _i, _i, _f, _f, _f, _i, _p, _p, _p]),
     'ssdb_forward_detect_host': (_i, [_p, _p, _i, _f, _i, _d, _p, _p, _p]),
+    'ssdb_train_step_host_begin': (_i, [_p, _p, _p, _p, _p, _i, _i, _f, _p, _p]),
+    'ssdb_train_step_host_end': (_i, [_p, _p]),
     'ssdb_eval_step': (_i, [_p, _p, _p, _i, _f, _p, _p, _p]),
     'ssdb_apply_update': (_i, [_p, _f, _f, _f, _f, _p]),
     'ssdb_pinned_alloc': (_i, [_ll, C.POINTER(_p)]),
@@ -360,6 +362,32 @@ class Net:
                                             losses.ctypes.data_as(_p), res.ctypes.data_as(_p) if res is not None else None,
                                             match.ctypes.data_as(_p) if want_match else None))
         return res, losses, match
+
+    def train_step_host_begin(self, images, labels=None, gt=None, gt_count=None, weight_decay=0.0005, want_result=True):
+        """Enqueue upload + forward + loss + backward from host buffers and return without waiting (data-parallel callers
+        overlap the gradient all-reduce); returns the result array that train_step_host_end() completes."""
+        x, px = _np(images, np.float32)
+        B = x.shape[0]
+        self._pending = [x]                       # the host buffers must outlive the asynchronous copies
+        if labels is not None:
+            y, py = _np(labels, np.float32)
+            pg = pc = None; G = 0
+            self._pending.append(y)
+        else:
+            g, pg = _np(gt, np.float64)
+            c, pc = _np(gt_count, np.int32)
+            py = None; G = g.shape[1]
+            self._pending += [g, c]
+        res = self.result_buffer(B) if want_result else None
+        check(lib().ssdb_train_step_host_begin(self._h, px, py, pg, pc, G, B, weight_decay,
+                                               res.ctypes.data_as(_p) if res is not None else None, None))
+        return res
+
+    def train_step_host_end(self):
+        losses = np.empty(4, np.float32)
+        check(lib().ssdb_train_step_host_end(self._h, losses.ctypes.data_as(_p)))
+        self._pending = None
+        return losses
 
     def forward_detect_host(self, images, conf_thr=0.01, cap=200, iou_thr=0.45, want_result=False):
         """forward + decode + class-wise NMS with the result tensor kept on the device:
