@@ -138,7 +138,7 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
 // 8-row groups 1024 B apart (SBO), rows 128 B apart, 16-byte units.
-// Measured on B200 (tools/kw3_probe.py): the 128-byte swizzle is applied to the ABSOLUTE shared-memory address, so a
+// Measured on B200 (round-1 probe, recorded in DESIGN.md): the 128-byte swizzle is applied to the ABSOLUTE shared-memory address, so a
 // descriptor may start at any 128-byte row of a TMA-written box and use any row-multiple SBO; the base-offset field must
 // stay 0 (setting it to the start's row phase gives garbage).
 __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t sbo_bytes = 1024, int use_base_offset = 0) {
