@@ -1582,7 +1582,9 @@ int launch_tc(const CUtensorMap& ms, const CUtensorMap& mw, const TcArgs& a_in, 
     if (dual_mode < 0) { const char* ov = getenv("SSDB_TC_DUAL"); dual_mode = ov ? (atoi(ov) ? 1 : 0) : 2; }
     int kblocks = 0;
     for (int g = 0; g < a.ngroups; ++g) kblocks += a.g_nt[g] * a.cblocks;
-    const bool dual_wanted = dual_mode == 1 || (dual_mode == 2 && (kblocks <= 2 || (a.mode == 1 && a.mask && kblocks <= 18)));
+    // (split mode, 8 epilogue warps: conv1_2 dgrad is faster with ONE CTA and two tiles per unit -- 1.37 -> 1.25 ms -- so only the
+    //  K <= 64 layer conv1_1 keeps two CTAs there: 0.406 -> 0.387 ms)
+    const bool dual_wanted = dual_mode == 1 || (dual_mode == 2 && (kblocks <= 2 || (!a.split && a.mode == 1 && a.mask && kblocks <= 18)));
     if (dual_wanted && a.block_n <= 64 && !a.scatter) {
         const int sb1 = (a.a_slot + a.b_tiles * a.block_n * 128 + 1023) / 1024 * 1024;     // stage with one M tile per unit
         if (2 * sb1 <= DUAL_RING_BYTES && m_tiles * a.n_tiles >= 4LL * num_sms()) {
