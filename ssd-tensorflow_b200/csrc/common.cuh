@@ -74,6 +74,10 @@ struct ConvEpilogue {
     int preprocess = 0;
     int swap_rb = 0;
     float mean[3] = {0, 0, 0};
+    // fused 2x2 / stride-2 max pool (tensor-core fprop in split mode only, see conv_tc_fprop_can_pool): the kernel writes the
+    // pooled activation [B, Ho/2, Wo/2, Cout] and the pool's code bytes INSTEAD of y
+    float* pool_dst = nullptr;
+    unsigned char* pool_code = nullptr;
     // round the stored activation to tf32 (round-to-nearest) so that the tensor-core kernels that
     // read it later see exactly representable operands (the MMA itself truncates)
     int round_tf32 = 0;
@@ -176,6 +180,7 @@ int bias_grad(const float* dz, int fmt, long long pixels, int Cout, float* db, f
 // fmt = ACT_F32: tf32 operands (activations stored tf32-rounded), ACT_S32: split bf16 operands (3 MMAs per product);
 // fp32 accumulation in tensor memory either way
 bool conv_tc_supported_fprop(const ConvGeom& g);
+bool conv_tc_fprop_can_pool(const ConvGeom& g, int fmt);
 bool conv_tc_supported_dgrad(const ConvGeom& g);
 bool conv_tc_supported_wgrad(const ConvGeom& g, int fmt);
 // w_t: per-tap transposed filter [k*k][CoutPad][Cin] (K-major B operand) in format fmt, see pack_filter_t

@@ -191,6 +191,9 @@ struct TcArgs {
     // 32-channel group; every 32-channel slab is contracted by six kind::f16 MMAs (hi*hi, lo*hi, hi*lo; K = 16 each)
     // instead of four kind::tf32 ones.  split_terms (bring-up): 1 = hi*hi only, 2 = + lo*hi, 3 = all.
     int split, split_terms;
+    // fused 2x2 / stride-2 max pool (fprop, split mode, row-window tiles with TH even): the epilogue writes the POOLED
+    // activation + the pool's code bytes instead of the full-resolution one (which nothing else reads)
+    int pool; float* pool_dst; unsigned char* pool_code; int Hp, Wp;
 };
 
 // epilogue of one 128-row tile: TMEM -> registers -> (per-warp shared-memory transpose) -> global.
@@ -239,6 +242,59 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& p, int mt, int nt, u
             stage[lane * 8 + (j4 ^ (lane & 7))] = make_float4(__uint_as_float(r[j4 * 4]), __uint_as_float(r[j4 * 4 + 1]),
                                                               __uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3]));
         __syncwarp();
+        if (FMT == ACT_S32 && p.pool) {
+            // Fused max pool.  TW = 8 and TH even: the warp's 32 rows are 4 line slots of 8 pixels, slots (0,1) and (2,3) are
+            // vertical neighbours of one image -> 2 x 4 complete 2x2 windows.  A lane owns one window and 8 channels: bias +
+            // ReLU, round each cell to the stored (hi + lo) value like the stand-alone pool sees it, first maximum in row-major
+            // order, code byte = winning cell | (winner > 0) << 2 (maxpool2x2_fwd_code_kernel's format).
+            const int q = lane & 3, wp = lane >> 2;                  // channel octet, window 0..7
+            const int r00 = (wp >> 2) * 16 + (wp & 3) * 2;            // staged row of the window's top-left pixel
+            const int chs = ch0 + q * 8;
+            float bv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bv[j] = 0.f;
+            if (p.bias && chs < p.cd_valid) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + chs)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + chs + 4));
+                bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+            }
+            float best[8]; int arg[8];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int rr = r00 + (t >> 1) * 8 + (t & 1);
+                const float4 v0 = stage[rr * 8 + ((2 * q) ^ (rr & 7))], v1 = stage[rr * 8 + ((2 * q + 1) ^ (rr & 7))];
+                float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    float a = v[j] + bv[j], b = v[j + 1] + bv[j + 1];
+                    if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                    uint32_t h, l;
+                    split2(a, b, h, l);
+                    v[j] = bf16_lo_f(h) + bf16_lo_f(l); v[j + 1] = bf16_hi_f(h) + bf16_hi_f(l);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (t == 0 || v[j] > best[j]) { best[j] = v[j]; arg[j] = t; }
+            }
+            // the window's coordinates: the same row -> pixel map as above, for the top-left staged row
+            const int R = (row & ~31) + r00;
+            const int wlx = R % p.TW, w2 = R / p.TW;
+            const int wxi = tx * p.TW + wlx, wyi = ty * p.TH + (w2 % p.TH), wn = tn * p.TN + w2 / p.TH;
+            if (R < rows_valid && wxi < p.Wd && wyi < p.Hd && wn < p.Bn && chs < p.cd_valid) {
+                const long long e = (((long long)wn * p.Hp + (wyi >> 1)) * p.Wp + (wxi >> 1)) * p.Cd + chs;
+                uint4 h, l;
+                split2(best[0], best[1], h.x, l.x); split2(best[2], best[3], h.y, l.y); split2(best[4], best[5], h.z, l.z); split2(best[6], best[7], h.w, l.w);
+                unsigned char* a = s32_addr(p.pool_dst, e);
+                *reinterpret_cast<uint4*>(a) = h;
+                *reinterpret_cast<uint4*>(a + 64) = l;
+                uint32_t c0w = 0, c1w = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    c0w |= (uint32_t)(arg[j] | (best[j] > 0.f ? 4 : 0)) << (8 * j);
+                    c1w |= (uint32_t)(arg[4 + j] | (best[4 + j] > 0.f ? 4 : 0)) << (8 * j);
+                }
+                *reinterpret_cast<uint2*>(p.pool_code + e) = make_uint2(c0w, c1w);
+            }
+            continue;
+        }
         if (FMT == ACT_S32) {
             // split storage: 4 lanes per pixel, 8 channels each = one 16-byte piece of the pixel's 64 high-part bytes and
             // one of its 64 low-part bytes; an instruction moves 8 rows x 64 contiguous bytes.  Every mask / old-value load
@@ -1739,8 +1795,19 @@ static int split_terms_env() {
     return (t < 1 || t > 3) ? 3 : t;
 }
 
+// can this fprop write the 2x2 / stride-2 max pool of its output instead of the output (see TcArgs::pool)?
+bool conv_tc_fprop_can_pool(const ConvGeom& g, int fmt) {
+    if (fmt != ACT_S32 || !conv_tc_supported_fprop(g) || (g.Ho & 1) || (g.Wo & 1) || g.Cout % 32 != 0) return false;
+    const int block_n = block_n_for(g.Cout);
+    TileGeom t = pick_tile(g.B, g.Ho, g.Wo);
+    int wth = 0, wtn = 0;
+    if (!want_row_window(g, block_n, g.B, g.Ho, g.Wo, t.eff, &wth, &wtn)) return false;
+    return wth >= 2 && (wth & 1) == 0;
+}
+
 int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_pad, int fmt, const ConvEpilogue& ep, float* y, cudaStream_t st) {
     SSDB_REQUIRE(conv_tc_supported_fprop(g), "shape not supported by the tcgen05 fprop kernel");
+    SSDB_REQUIRE(!ep.pool_dst || conv_tc_fprop_can_pool(g, fmt), "this layer cannot fuse its max pool");
     TileGeom t = pick_tile(g.B, g.Ho, g.Wo);
     TcArgs a{};
     a.TW = t.TW; a.TH = t.TH; a.TN = t.TN;
@@ -1765,6 +1832,7 @@ int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_
     SSDB_REQUIRE(g.pad_t == g.pad_l, "tcgen05 path assumes equal top/left padding");
     a.dst = y; a.bias = ep.bias; a.mask = nullptr; a.relu = ep.relu; a.beta = 0; a.round_out = ep.round_tf32;
     a.split = fmt == ACT_S32 ? 1 : 0; a.split_terms = split_terms_env();
+    a.pool = ep.pool_dst ? 1 : 0; a.pool_dst = ep.pool_dst; a.pool_code = ep.pool_code; a.Hp = g.Ho / 2; a.Wp = g.Wo / 2;
     a.scatter = ep.scatter; a.V = ep.V; a.n_valid = ep.n_valid; a.anchor_base = ep.anchor_base; a.A = ep.A;
     CUtensorMap ms, mw;
     int rc = encode_act_map(&ms, x, g.B, g.H, g.W, g.Cin, rw ? a.a_sbo / 128 : t.TW, t.TH, t.TN, CU_TENSOR_MAP_SWIZZLE_128B, g.stride); if (rc) return rc;

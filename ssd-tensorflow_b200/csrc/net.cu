@@ -65,6 +65,7 @@ struct Op {
     int anchor_base = 0, nbox = 0;
     int w = -1, b = -1;                // master indices
     size_t wt_off = 0; int cout_pad = 0; bool has_wt = false;
+    int pool_after = -1;               // conv: index of the 2x2/s2 pool that is the ONLY reader of its output (fusable), else -1
 };
 
 int same_pad_before(int n, int keff, int stride) {
@@ -116,6 +117,8 @@ struct ssdb_net {
     float* host_small = nullptr;       // pinned
     bool wt_dirty = true, have_forward = false;
     bool inference = false;            // SSDB_FLAG_INFERENCE: forward / detection only, no training state
+    bool fuse_pool = true;             // conv1_2 / conv2_2 write their max pool instead of their output (SSDB_FUSE_POOL=0: off)
+    std::vector<char> fused_now;       // per op: this forward pass fused it away (its activation was not materialised)
     // CUDA graphs of the frozen forward + detection (ssdb_forward_detect_host on an inference handle), one per
     // (batch, threshold, cap, IoU); dropped when a parameter changes
     struct DetGraph { int B; float thr; int cap; double iou; bool warmed; cudaGraphExec_t exec; };
@@ -285,6 +288,16 @@ void build_plan(ssdb_net* n) {
         base += nbox * fb.H * fb.W;
     }
     n->A = base;
+    // conv -> 2x2/s2 pool pairs where the pool is the only reader of the conv output (conv1_2, conv2_2, conv3_3; conv4_3 also
+    // feeds the L2 normalisation): candidates for the fused epilogue
+    for (size_t i = 0; i < n->ops.size(); ++i) {
+        Op& c = n->ops[i];
+        if (c.type != OP_CONV || c.head || c.out < 0) continue;
+        int readers = 0, pool = -1;
+        for (size_t j = 0; j < n->ops.size(); ++j)
+            if (n->ops[j].in == c.out) { ++readers; if (n->ops[j].type == OP_POOL && n->ops[j].k == 2 && n->ops[j].stride == 2 && n->ops[j].pad == 0) pool = (int)j; }
+        if (readers == 1 && pool == (int)i + 1) c.pool_after = pool;
+    }
     // transposed filter copies for the tcgen05 fprop kernel
     for (Op& op : n->ops) {
         if (op.type != OP_CONV || op.cin % 32 != 0) continue;
@@ -372,7 +385,7 @@ bool dual_stream(const ssdb_net* n) {
     return on && !n->prof && n->side_stream != nullptr;
 }
 
-int run_one_forward_op(ssdb_net* n, const Op& op, const float* images, int B, cudaStream_t st) {
+int run_one_forward_op(ssdb_net* n, const Op& op, const float* images, int B, cudaStream_t st, const Op* fused_pool = nullptr) {
     int rc = SSDB_OK;
     ProfScope ps(n, st, std::string("fwd:") + op.name, op.type == OP_CONV ? conv_flops(geom_of(n, op, B)) : 0.0);
     if (op.type == OP_CONV) {
@@ -389,9 +402,10 @@ int run_one_forward_op(ssdb_net* n, const Op& op, const float* images, int B, cu
             ConvGeom g1 = g; g1.Cin = 32; g1.k = 1; g1.pad_t = g1.pad_l = 0; g1.dil = 1;
             ConvEpilogue e1 = ep; e1.preprocess = 0;
             rc = conv_tc_fprop(g1, n->patches, n->c1_wt, op.cout, n->fmt, e1, y, st);
-        } else if (op.has_wt && use_tc(n, conv_tc_supported_fprop(g)))
+        } else if (op.has_wt && use_tc(n, conv_tc_supported_fprop(g))) {
+            if (fused_pool) { ep.pool_dst = n->act(fused_pool->out, B); ep.pool_code = n->pool_code[fused_pool - n->ops.data()]; }
             rc = conv_tc_fprop(g, x, n->wt + op.wt_off, op.cout_pad, n->fmt, ep, y, st);
-        else
+        } else
             rc = conv_simt_fprop(g, x, n->params + n->masters[op.w].off, n->fmt, ep, y, st);
     } else if (op.type == OP_POOL) {
         const Buf& bi = n->bufs[op.in]; const Buf& bo = n->bufs[op.out];
@@ -414,10 +428,20 @@ int run_forward(ssdb_net* n, const float* images, int B, cudaStream_t st, bool s
     const bool two = dual_stream(n);
     cudaStream_t s2 = n->side_stream;
     bool forked = false;
+    n->fused_now.assign(n->ops.size(), 0);
     for (const Op& op : n->ops) {
-        if (skip_first && &op == &n->ops[0]) continue;
+        const size_t oi = &op - n->ops.data();
+        if (skip_first && oi == 0) continue;
         if (op.head && two) continue;                      // launched right after the op that writes its feature map (below)
-        int rc = run_one_forward_op(n, op, images, B, st); if (rc) return rc;
+        if (n->fused_now[oi]) continue;                    // a pool that the previous conv already computed
+        // conv + the 2x2 pool that alone reads it: the conv's epilogue writes the pooled map and the pool's code bytes
+        const Op* fp = nullptr;
+        if (op.type == OP_CONV && op.pool_after >= 0 && n->fuse_pool && n->pool_code[op.pool_after] && op.has_wt && n->fmt == ACT_S32 &&
+            use_tc(n, true) && conv_tc_fprop_can_pool(geom_of(n, op, B), n->fmt)) {
+            fp = &n->ops[op.pool_after];
+            n->fused_now[op.pool_after] = 1; n->fused_now[oi] = 2;
+        }
+        int rc = run_one_forward_op(n, op, images, B, st, fp); if (rc) return rc;
         if (!two) continue;
         for (const Op& h : n->ops) {
             if (!h.head || h.in != op.out) continue;
@@ -586,6 +610,7 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
     ssdb_net* n = new ssdb_net();
     n->preset = P; n->C = num_classes; n->V = num_classes + 5; n->S = P->image; n->max_batch = max_batch;
     n->inference = (flags & SSDB_FLAG_INFERENCE) != 0;
+    { const char* ov = getenv("SSDB_FUSE_POOL"); if (ov && !atoi(ov)) n->fuse_pool = false; }
     const bool train = !n->inference;
     // SSDB_CONV: (unset) / "split" = tensor cores with split bf16 operands (fp32-grade products, the product mode);
     // "tf32" = tensor cores with tf32 operands (10-bit significands: outside the 1e-3 parity bar, kept for comparison);
@@ -873,6 +898,11 @@ int ssdb_debug_read(ssdb_net* n, const char* name, int B, float* host_out, long 
         const Buf& b = n->bufs[op.out];
         const long long want = (long long)B * b.H * b.W * b.C;
         SSDB_REQUIRE(count == want, "element count does not match the activation shape");
+        const size_t oi = &op - n->ops.data();
+        if (!grad && oi < n->fused_now.size() && n->fused_now[oi] == 2) {
+            set_error("the activation of %s was not materialised: its max pool is fused into the convolution (SSDB_FUSE_POOL=0 disables it)", name);
+            return SSDB_ESTATE;
+        }
         const float* src = grad ? n->gact(op.out, B) : n->act(op.out, B);
         if (n->fmt == ACT_S32) {
             float* tmp = nullptr;

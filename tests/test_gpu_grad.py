@@ -29,10 +29,12 @@ RELU_LAYERS = ['conv1_1', 'conv1_2', 'conv2_1', 'conv2_2', 'conv3_1', 'conv3_2',
 def test_gradients_with_the_engines_own_decisions(preset, B, mode):
     if mode != 'default':
         os.environ['SSDB_CONV'] = mode
+    os.environ['SSDB_FUSE_POOL'] = '0'        # this test reads the activations of conv1_2 / conv2_2, which the fused pool never writes
     try:
         net = ssdb.Net(preset, 20, max_batch=B)
     finally:
         os.environ.pop('SSDB_CONV', None)
+        os.environ.pop('SSDB_FUSE_POOL', None)
     side = bo.PRESETS[preset]['image']
     P = no.init_params(preset, dtype=torch.float64)
     for k, shape in net.tensors():
@@ -82,3 +84,37 @@ def test_gradients_with_the_engines_own_decisions(preset, B, mode):
     print('GRAD', json.dumps(report))
     assert not bad, bad[:10]
     net.close()
+
+
+@pytest.mark.parametrize('preset,B', [('vgg300', 2), ('vgg512', 1)])
+def test_fused_pool_epilogue_is_bit_identical(preset, B):
+    """conv1_2 / conv2_2 write their 2x2 max pool (and its code bytes) from the convolution epilogue instead of their own
+    output: pooled maps, result, losses and every gradient must equal the unfused path bit for bit."""
+    side = bo.PRESETS[preset]['image']
+    P = no.init_params(preset, dtype=torch.float32)
+    anc = bo.anchors(preset); aabs = bo.anchors_abs(anc)
+    x = synth.images(3, B, side)
+    labels = np.stack([bo.make_labels(synth.gt_boxes(3 + i), anc, aabs, 20)[0] for i in range(B)])
+    got = {}
+    for fuse in ('1', '0'):
+        os.environ['SSDB_FUSE_POOL'] = fuse
+        try:
+            net = ssdb.Net(preset, 20, max_batch=B)
+        finally:
+            os.environ.pop('SSDB_FUSE_POOL', None)
+        for k, shape in net.tensors():
+            net.set_tensor(k, P[k].numpy())
+        res, losses = net.train_step_host(x, labels, 0.0, 0.0, 0.0005)
+        got[fuse] = dict(res=np.array(res), losses=losses, pool1=net.debug_read('pool1', B), pool2=net.debug_read('pool2', B),
+                         grads={k: net.get_tensor(k, shape, ssdb.GRAD) for k, shape in net.tensors()})
+        if fuse == '1':
+            with pytest.raises(ssdb.SSDBError):
+                net.debug_read('conv1_2', B)                 # never materialised
+        else:
+            assert net.debug_read('conv1_2', B).shape == (B, side, side, 64)
+        net.close()
+    a, b = got['1'], got['0']
+    assert np.array_equal(a['pool1'], b['pool1']) and np.array_equal(a['pool2'], b['pool2'])
+    assert np.array_equal(a['res'], b['res']) and np.array_equal(a['losses'], b['losses'])
+    for k in a['grads']:
+        assert np.array_equal(a['grads'][k], b['grads'][k]), k
