@@ -126,7 +126,8 @@ struct ssdb_net {
     int conv_mode = SSDB_CONV_AUTO;
     int swap_rb = 1; float mean[3] = {103.939f, 116.779f, 123.68f};
     cudaStream_t own_stream = nullptr, copy_stream = nullptr, side_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_side = nullptr, ev_l2 = nullptr;
+    bool l2_pending = false;           // the L2 term of this step is being summed on the side stream (ev_l2)
     cudaEvent_t ev_labels = nullptr, ev_result = nullptr, ev_images = nullptr;
     cudaEvent_t ev_chunk[8] = {};      // image chunks of the host entry points
     // gradient buckets for an all-reduce that overlaps the rest of the backward (ssdb_grad_buckets): contiguous ranges of
@@ -385,7 +386,8 @@ bool dual_stream(const ssdb_net* n) {
     return on && !n->prof && n->side_stream != nullptr;
 }
 
-int run_one_forward_op(ssdb_net* n, const Op& op, const float* images, int B, cudaStream_t st, const Op* fused_pool = nullptr) {
+int run_one_forward_op(ssdb_net* n, const Op& op, const float* images, int B, cudaStream_t st, const Op* fused_pool = nullptr,
+                       cudaEvent_t filters_ready = nullptr) {
     int rc = SSDB_OK;
     ProfScope ps(n, st, std::string("fwd:") + op.name, op.type == OP_CONV ? conv_flops(geom_of(n, op, B)) : 0.0);
     if (op.type == OP_CONV) {
@@ -399,6 +401,7 @@ int run_one_forward_op(ssdb_net* n, const Op& op, const float* images, int B, cu
         if (op.in < 0) { ep.preprocess = 1; ep.swap_rb = n->swap_rb; ep.mean[0] = n->mean[0]; ep.mean[1] = n->mean[1]; ep.mean[2] = n->mean[2]; }
         if (op.in < 0 && n->patches) {
             rc = conv1_im2col(images, B, n->S, n->swap_rb, n->mean, n->fmt, n->patches, st); if (rc) return rc;
+            if (filters_ready) SSDB_CUDA(cudaStreamWaitEvent(st, filters_ready, 0));       // the patch matrix needs no filters: it ran beside their re-split
             ConvGeom g1 = g; g1.Cin = 32; g1.k = 1; g1.pad_t = g1.pad_l = 0; g1.dil = 1;
             ConvEpilogue e1 = ep; e1.preprocess = 0;
             rc = conv_tc_fprop(g1, n->patches, n->c1_wt, op.cout, n->fmt, e1, y, st);
@@ -422,11 +425,28 @@ int run_one_forward_op(ssdb_net* n, const Op& op, const float* images, int B, cu
     return rc;
 }
 
-int run_forward(ssdb_net* n, const float* images, int B, cudaStream_t st, bool skip_first = false) {
+// want_l2: also start the L2 term of the loss (sum of squares of 26 M parameters, 0.1 ms; it depends on nothing the step
+// computes) on the side stream; loss_and_finalize waits for it
+int run_forward(ssdb_net* n, const float* images, int B, cudaStream_t st, bool skip_first = false, bool want_l2 = false) {
     SSDB_REQUIRE(B >= 1 && B <= n->max_batch, "batch size out of range");
-    if (n->wt_dirty) { ProfScope ps(n, st, "repack"); int rc = repack_filters(n, st); if (rc) return rc; }
     const bool two = dual_stream(n);
     cudaStream_t s2 = n->side_stream;
+    cudaEvent_t filters_ready = nullptr;
+    if (n->wt_dirty) {
+        // the per-step re-split of the filters (58 small launches, 0.25 ms) runs on the side stream beside the patch matrix of
+        // conv1_1, which needs no filters
+        const bool beside = two && !skip_first && n->patches != nullptr;
+        if (beside) { SSDB_CUDA(cudaEventRecord(n->ev_fork, st)); SSDB_CUDA(cudaStreamWaitEvent(s2, n->ev_fork, 0)); }
+        { ProfScope ps(n, beside ? s2 : st, "repack"); int rc = repack_filters(n, beside ? s2 : st); if (rc) return rc; }
+        if (beside) { SSDB_CUDA(cudaEventRecord(n->ev_side, s2)); filters_ready = n->ev_side; }
+    }
+    if (want_l2 && two) {
+        SSDB_CUDA(cudaEventRecord(n->ev_fork, st));                  // the parameters are final in stream order here
+        SSDB_CUDA(cudaStreamWaitEvent(s2, n->ev_fork, 0));
+        int rc = l2_sum(n->params, (long long)n->n_flat, n->decay_mask, n->small_ws + 8, n->small_ws + 6, s2); if (rc) return rc;
+        SSDB_CUDA(cudaEventRecord(n->ev_l2, s2));
+        n->l2_pending = true;
+    }
     bool forked = false;
     n->fused_now.assign(n->ops.size(), 0);
     for (const Op& op : n->ops) {
@@ -441,7 +461,8 @@ int run_forward(ssdb_net* n, const float* images, int B, cudaStream_t st, bool s
             fp = &n->ops[op.pool_after];
             n->fused_now[op.pool_after] = 1; n->fused_now[oi] = 2;
         }
-        int rc = run_one_forward_op(n, op, images, B, st, fp); if (rc) return rc;
+        int rc = run_one_forward_op(n, op, images, B, st, fp, oi == 0 ? filters_ready : nullptr); if (rc) return rc;
+        if (oi == 0 && filters_ready && !(op.in < 0 && n->patches)) SSDB_CUDA(cudaStreamWaitEvent(st, filters_ready, 0));
         if (!two) continue;
         for (const Op& h : n->ops) {
             if (!h.head || h.in != op.out) continue;
@@ -703,6 +724,8 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
     SSDB_CUDA(cudaStreamCreateWithFlags(&n->side_stream, cudaStreamNonBlocking));
     SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming));
     SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming));
+    SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_side, cudaEventDisableTiming));
+    SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_l2, cudaEventDisableTiming));
     SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_labels, cudaEventDisableTiming));
     SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_result, cudaEventDisableTiming));
     SSDB_CUDA(cudaEventCreateWithFlags(&n->ev_images, cudaEventDisableTiming));
@@ -739,6 +762,8 @@ int ssdb_destroy(ssdb_net* n) {
     if (n->side_stream) cudaStreamDestroy(n->side_stream);
     if (n->ev_fork) cudaEventDestroy(n->ev_fork);
     if (n->ev_join) cudaEventDestroy(n->ev_join);
+    if (n->ev_side) cudaEventDestroy(n->ev_side);
+    if (n->ev_l2) cudaEventDestroy(n->ev_l2);
     if (n->ev_labels) cudaEventDestroy(n->ev_labels);
     if (n->ev_result) cudaEventDestroy(n->ev_result);
     if (n->ev_images) cudaEventDestroy(n->ev_images);
@@ -940,7 +965,8 @@ static int loss_and_finalize(ssdb_net* n, const float* labels_dev, const double*
     int rc = multibox_loss_launch(n->out, labels_dev, gt_dev, gt_count_dev, G, n->anchors, B, n->A, n->C, grad_scale, conf_loc,
                                   want_grad ? n->out_grad : nullptr, result_dev ? result_dev : n->result, match_out_dev, n->loss_ws, st);
     if (rc) return rc;
-    rc = l2_sum(n->params, (long long)n->n_flat, n->decay_mask, n->small_ws + 8, l2s, st); if (rc) return rc;
+    if (n->l2_pending) { SSDB_CUDA(cudaStreamWaitEvent(st, n->ev_l2, 0)); n->l2_pending = false; }     // summed beside the forward
+    else { rc = l2_sum(n->params, (long long)n->n_flat, n->decay_mask, n->small_ws + 8, l2s, st); if (rc) return rc; }
     finalize_losses_kernel<<<1, 32, 0, st>>>(conf_loc, l2s, weight_decay, losses_out_dev ? losses_out_dev : n->small_ws);
     SSDB_LAUNCH_CHECK();
     return SSDB_OK;
@@ -963,7 +989,7 @@ int ssdb_train_step(ssdb_net* n, const float* images_dev, const float* labels_de
     SSDB_REQUIRE(!n->inference, "training entry point called on an inference handle");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = remember_images(n, images_dev, B, st); if (rc) return rc;
-    rc = run_forward(n, images_dev, B, st); if (rc) return rc;
+    rc = run_forward(n, images_dev, B, st, false, true); if (rc) return rc;
     rc = loss_and_finalize(n, labels_dev, gt_dev, gt_count_dev, G, B, weight_decay, grad_scale, true, losses_out_dev, result_dev, st); if (rc) return rc;
     rc = run_backward(n, B, st); if (rc) return rc;
     if (apply_update) rc = ssdb_apply_update(n, lr, momentum, weight_decay, 1.0f, stream);
@@ -1007,7 +1033,7 @@ static int train_step_host_impl(ssdb_net* n, const float* images_host, const flo
         SSDB_CUDA(cudaMemcpyAsync(n->gt_count_stage, gt_count_host, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, cs));
     }
     SSDB_CUDA(cudaEventRecord(n->ev_labels, cs));
-    rc = run_forward(n, n->images_stage, B, st, first_done); if (rc) return rc;
+    rc = run_forward(n, n->images_stage, B, st, first_done, true); if (rc) return rc;
     SSDB_CUDA(cudaStreamWaitEvent(st, n->ev_labels, 0));
     const bool want_grad = apply_update >= 0;
     if (labels_host) rc = loss_and_finalize(n, n->labels_stage, nullptr, nullptr, 0, B, weight_decay, 1.0f, want_grad, n->small_ws, n->result, st);
