@@ -2052,6 +2052,37 @@ int encode_rw_map(CUtensorMap* m, const float* ptr, int B, int H, int W, int C, 
     return SSDB_OK;
 }
 
+// Split the pixel range of a weight gradient so that the units fill whole waves of the persistent grid: between 2 and 8 units
+// per SM, the count whose last wave is fullest (every split adds one partial filter to write and reduce, so fewer wins ties).
+// `ut` = units per split, `min_tiles` = fewest pixel tiles a unit should still own.
+// upper bound of what pick_splits can return for ANY batch size (the engine sizes its partial-sum workspace at max_batch, and a
+// smaller batch may well pick more splits)
+long long max_splits_bound(long long ut, int max_splits_cap) {
+    long long hi = (8LL * num_sms() + ut - 1) / ut;
+    if (hi > max_splits_cap) hi = max_splits_cap;
+    return hi < 1 ? 1 : hi;
+}
+
+void pick_splits(long long pix_tiles, long long ut, int min_tiles, int max_splits_cap, int* tiles_per_split, int* splits) {
+    const long long sms = num_sms();
+    long long max_splits = (pix_tiles + min_tiles - 1) / min_tiles;
+    if (max_splits > max_splits_cap) max_splits = max_splits_cap;
+    if (max_splits < 1) max_splits = 1;
+    long long lo = (2 * sms + ut - 1) / ut, hi = (8 * sms + ut - 1) / ut;
+    if (lo < 1) lo = 1;
+    if (hi > max_splits) hi = max_splits;
+    if (lo > hi) lo = hi;
+    long long pick = lo; double pick_eff = 0.0;
+    for (long long sp = lo; sp <= hi; ++sp) {
+        const long long tps = (pix_tiles + sp - 1) / sp, real = (pix_tiles + tps - 1) / tps;
+        const long long units = real * ut, waves = (units + sms - 1) / sms;
+        const double eff = (double)units / (double)(waves * sms);
+        if (eff > pick_eff + 0.02) { pick_eff = eff; pick = sp; }
+    }
+    *tiles_per_split = (int)((pix_tiles + pick - 1) / pick);
+    *splits = (int)((pix_tiles + *tiles_per_split - 1) / *tiles_per_split);
+}
+
 struct WgR2Plan { WgR2Args a; bool ok; };
 
 // rw2 plan: 3x3, stride 1, SAME (pad = dilation), split operands, Cout a multiple of 128, a pixel tiling that wastes little
@@ -2087,24 +2118,7 @@ WgR2Plan plan_wgrad_r2(const ConvGeom& g, int fmt) {
     a.want_bias = 1; a.terms = split_terms_env();
     const long long pix_tiles = (long long)a.ptx * a.pty * a.ptn;
     const long long ut = (long long)a.cblocks * a.mblocks;
-    // split the pixel range so that the units fill whole waves of the persistent grid: between 2 and 8 units per SM, the
-    // count whose last wave is fullest (every split adds one partial filter to write and reduce, so fewer wins ties)
-    const long long sms = num_sms();
-    const long long max_splits = (pix_tiles + 7) / 8;
-    long long lo = (2 * sms + ut - 1) / ut, hi = (8 * sms + ut - 1) / ut;
-    if (lo < 1) lo = 1;
-    if (hi > max_splits) hi = max_splits;
-    if (hi > 512) hi = 512;
-    if (lo > hi) lo = hi;
-    long long pick = lo; double pick_eff = 0.0;
-    for (long long sp = lo; sp <= hi; ++sp) {
-        const long long tps = (pix_tiles + sp - 1) / sp, real = (pix_tiles + tps - 1) / tps;
-        const long long units = real * ut, waves = (units + sms - 1) / sms;
-        const double eff = (double)units / (double)(waves * sms);
-        if (eff > pick_eff + 0.02) { pick_eff = eff; pick = sp; }
-    }
-    a.tiles_per_split = (int)((pix_tiles + pick - 1) / pick);
-    a.splits = (int)((pix_tiles + a.tiles_per_split - 1) / a.tiles_per_split);
+    pick_splits(pix_tiles, ut, 8, 512, &a.tiles_per_split, &a.splits);
     a.partial = nullptr;
     pl.ok = true;
     return pl;
@@ -2147,13 +2161,16 @@ WgPlan plan_wgrad(const ConvGeom& g, int fmt) {
     a.psize = (long long)a.taps * g.Cin * g.Cout + g.Cout;
     long long pix_tiles = (long long)a.ptx * a.pty * a.ptn;
     long long base_units = (long long)a.m_tiles * a.n_tiles;
-    long long want = (2LL * num_sms() + base_units - 1) / base_units;     // ~2 units per SM
-    long long max_splits = (pix_tiles + 7) / 8;                            // at least 8 stages per unit
-    if (want > max_splits) want = max_splits;
-    if (want < 1) want = 1;
-    if (want > 256) want = 256;
-    a.tiles_per_split = (int)((pix_tiles + want - 1) / want);
-    a.splits = (int)((pix_tiles + a.tiles_per_split - 1) / a.tiles_per_split);
+    if (fmt == ACT_S32) pick_splits(pix_tiles, base_units, 8, 256, &a.tiles_per_split, &a.splits);
+    else {
+        long long want = (2LL * num_sms() + base_units - 1) / base_units;     // ~2 units per SM
+        long long max_splits = (pix_tiles + 7) / 8;                            // at least 8 stages per unit
+        if (want > max_splits) want = max_splits;
+        if (want < 1) want = 1;
+        if (want > 256) want = 256;
+        a.tiles_per_split = (int)((pix_tiles + want - 1) / want);
+        a.splits = (int)((pix_tiles + a.tiles_per_split - 1) / a.tiles_per_split);
+    }
     a.partial = nullptr; a.ones = nullptr;
     pl.ok = true;
     return pl;
@@ -2165,12 +2182,22 @@ bool conv_tc_supported_wgrad(const ConvGeom& g, int fmt) { return plan_wgrad_r2(
 
 size_t conv_tc_wgrad_ws(const ConvGeom& g, int fmt) {
     size_t need = 0;
+    // the wave-fitted kernels (r2, split plain) are sized for the most splits any batch <= g.B can pick
     WgR2Plan r2 = plan_wgrad_r2(g, fmt);
-    if (r2.ok) need = (size_t)r2.a.splits * (size_t)r2.a.psize;
+    if (r2.ok) need = (size_t)max_splits_bound((long long)r2.a.cblocks * r2.a.mblocks, 512) * (size_t)r2.a.psize;
     WgRwPlan rw = plan_wgrad_rw(g, fmt);
     if (rw.ok) { size_t n1 = (size_t)rw.a.splits * (size_t)rw.a.psize; if (n1 > need) need = n1; }
     WgPlan pl = plan_wgrad(g, fmt);
-    if (pl.ok) { size_t n2 = (size_t)pl.a.splits * (size_t)pl.a.psize; if (n2 > need) need = n2; }
+    if (pl.ok) {
+        size_t n2 = (size_t)pl.a.splits * (size_t)pl.a.psize;
+        if (fmt == ACT_S32) {
+            // with and without the bias slot (m_tiles differs by at most one)
+            const long long ut = (long long)pl.a.m_tiles * pl.a.n_tiles, ut2 = (long long)(pl.a.m_tiles > 1 ? pl.a.m_tiles - 1 : 1) * pl.a.n_tiles;
+            const long long b = max_splits_bound(ut, 256), b2 = max_splits_bound(ut2, 256);
+            n2 = (size_t)(b > b2 ? b : b2) * (size_t)pl.a.psize;
+        }
+        if (n2 > need) need = n2;
+    }
     return need;
 }
 

@@ -685,8 +685,9 @@ int ssdb_create(const char* preset, int num_classes, int max_batch, unsigned fla
         for (const Op& op : n->ops)
             if (op.type == OP_POOL && op.stride == 1) { const Buf& bo = n->bufs[op.out]; ALLOC(n->pool5_arg, (size_t)max_batch * bo.H * bo.W * bo.C, unsigned char); }
     }
+    // (inference handles keep the code bytes too: they are what lets conv1_2 / conv2_2 write their pool from the epilogue)
     n->pool_code.assign(n->ops.size(), nullptr);
-    if (train && (!getenv("SSDB_POOL_CODE") || atoi(getenv("SSDB_POOL_CODE"))))
+    if (!getenv("SSDB_POOL_CODE") || atoi(getenv("SSDB_POOL_CODE")))
         for (size_t i = 0; i < n->ops.size(); ++i) {
             const Op& op = n->ops[i];
             if (op.type != OP_POOL || op.k != 2 || op.stride != 2 || op.pad != 0) continue;

@@ -118,3 +118,28 @@ def test_fused_pool_epilogue_is_bit_identical(preset, B):
     assert np.array_equal(a['res'], b['res']) and np.array_equal(a['losses'], b['losses'])
     for k in a['grads']:
         assert np.array_equal(a['grads'][k], b['grads'][k]), k
+
+
+def test_smaller_batch_than_max_batch_is_the_same_step():
+    """An engine created for max_batch images runs a smaller batch exactly like an engine created for that batch (tile plans,
+    split counts and workspaces depend on the batch that runs, and the workspace is sized for any batch up to max_batch)."""
+    preset = 'vgg300'
+    P = no.init_params(preset, dtype=torch.float32)
+    anc = bo.anchors(preset); aabs = bo.anchors_abs(anc)
+    x = synth.images(9, 3, 300)
+    labels = np.stack([bo.make_labels(synth.gt_boxes(9 + i), anc, aabs, 20)[0] for i in range(3)])
+    got = []
+    for max_batch in (3, 16):
+        net = ssdb.Net(preset, 20, max_batch=max_batch)
+        for k, shape in net.tensors():
+            net.set_tensor(k, P[k].numpy())
+        for B in (3, 1):                                  # a full-size step, then a smaller one on the same handle
+            res, losses = net.train_step_host(x[:B], labels[:B], 1e-4, 0.9, 0.0005)
+        got.append((np.array(res), losses, {k: net.get_tensor(k, shape, ssdb.GRAD) for k, shape in net.tensors()},
+                    {k: net.get_tensor(k, shape) for k, shape in net.tensors()}))
+        net.close()
+    a, b = got
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    for k in a[2]:
+        assert np.array_equal(a[2][k], b[2][k]), k
+        assert np.array_equal(a[3][k], b[3][k]), k
