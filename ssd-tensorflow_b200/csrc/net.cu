@@ -111,7 +111,7 @@ struct ssdb_net {
     float *small_ws = nullptr;         // [0..3] losses, [4..5] conf/loc, [6] l2 sum, then per-image + partials
     unsigned int* counter = nullptr;
     void* loss_ws = nullptr;           // workspace of the multibox loss kernels (multibox_loss_ws_bytes)
-    void* det_ws = nullptr;            // workspace of ssdb_decode_nms_net (decode_nms_scratch_bytes at max_batch)
+    void* det_ws = nullptr;            // workspace of the decode + NMS launched on n->result (ssdb_forward_detect_host; decode_nms_scratch_bytes at max_batch)
     unsigned char* decay_mask = nullptr;
     double* anchors = nullptr;
     float* host_small = nullptr;       // pinned

@@ -8,8 +8,6 @@ run tests/test_gpu_conv.py tests/test_gpu_net.py -m gpu
 grep -E "^===|^exit|passed|failed|^FAILED|^ERROR" $LOG | cut -c1-300 | head -20
 echo "=== layer bench, 8 epilogue warps"
 timeout 300 python tools/layer_bench.py vgg300 64 split > gpurun_out/layer_bench_$R.txt 2>&1; cut -c1-170 gpurun_out/layer_bench_$R.txt
-echo "=== 4 epilogue warps (A/B)"
-SSDB_TC_EPI8=0 timeout 300 python tools/layer_bench.py vgg300 64 split conv1_2 conv2_2 conv3_2 conv4_2 mod_conv6 2>&1 | cut -c1-170
 echo "=== bench"
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$R.json 2> gpurun_out/bench_$R.err; tail -3 gpurun_out/bench_$R.err
 python - <<PY
