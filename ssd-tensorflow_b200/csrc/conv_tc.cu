@@ -194,6 +194,12 @@ struct TcArgs {
     // fused 2x2 / stride-2 max pool (fprop, split mode, row-window tiles with TH even): the epilogue writes the POOLED
     // activation + the pool's code bytes instead of the full-resolution one (which nothing else reads)
     int pool; float* pool_dst; unsigned char* pool_code; int Hp, Wp;
+    // resident-filter window mode (3x3, stride 1, split operands, one N tile, whole filter <= 144 KB: conv1_2 both ways).
+    // The filter -- 9 taps x cblocks tiles of block_n x 128 B -- is loaded ONCE per persistent CTA and stays in shared memory;
+    // a stage holds only ONE source box of (TW+2) x (TH+2) pixels x 32 channels that serves all nine taps (tap t reads the rows
+    // starting r_win[t] pixels into it).  L2 -> SM bytes per 128 pixels: 2 x 23 KB instead of 6 x (16.6 + 24) KB.
+    int resb, res_bytes;
+    unsigned char r_win[9];
 };
 
 // epilogue of one 128-row tile: TMEM -> registers -> (per-warp shared-memory transpose) -> global.
@@ -420,6 +426,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
     // barrier layout: full[MAX_STAGES] empty[MAX_STAGES] tfull[2] tempty[2] then tmem pointer
     const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
     const uint32_t tmem_slot = tempty0 + 16;
+    const uint32_t bres0 = tmem_slot + 8;                          // resident-filter mode: "the filter has landed"
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
     const int STAGES = p.stages;
     const int STAGE_BYTES = p.stage_bytes;
@@ -431,6 +438,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
     if (threadIdx.x == 0) {
         for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, (uint32_t)nepi); }
+        mbar_init(bres0, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_src) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
@@ -455,7 +463,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (elect_one_sync()) {
+        if (p.resb) {
+            if (elect_one_sync()) {
+                const uint32_t ring = base + (uint32_t)p.res_bytes;
+                mbar_expect_tx(bres0, (uint32_t)p.res_bytes);
+                for (int t = 0; t < 9; ++t)
+                    for (int cb = 0; cb < p.cblocks; ++cb)
+                        tma_load_2d(base + (uint32_t)(t * p.cblocks + cb) * b_bytes, &map_w, bres0, cb * BLOCK_K, t * p.rows_per_tap);
+                int stage = 0; uint32_t phase = 0;
+                const int dy = p.g_dy[0], dx = p.g_dx[0];
+                for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+                    const int tx = u % p.tiles_x; const int r1 = u / p.tiles_x;
+                    const int x0 = tx * p.TW, y0 = (r1 % p.tiles_y) * p.TH, n0 = (r1 / p.tiles_y) * p.TN;
+                    for (int cb = 0; cb < p.cblocks; ++cb) {
+                        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                        const uint32_t fb = full0 + 8 * stage;
+                        mbar_expect_tx(fb, a_bytes);
+                        tma_load_4d(ring + stage * STAGE_BYTES, &map_src, fb, cb * BLOCK_K, x0 + dx, y0 + dy, n0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        } else if (elect_one_sync()) {
             int stage = 0; uint32_t phase = 0;
             for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
                 const int mp = u / p.n_tiles, nt = u - mp * p.n_tiles;
@@ -491,6 +520,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
+            if (FMT == ACT_S32 && p.resb) {
+                const uint32_t ring = base + (uint32_t)p.res_bytes;
+                mbar_wait(bres0, 0);                                    // the whole filter has landed
+                tc_fence_after();
+                for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+                    mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d0 = tmem_base + (uint32_t)(acc * p.acc_stride);
+                    uint32_t started = 0;
+                    for (int cb = 0; cb < p.cblocks; ++cb) {
+                        mbar_wait(full0 + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint32_t sa = ring + stage * STAGE_BYTES;
+                        for (int t = 0; t < 9; ++t) {
+                            const uint64_t a0 = make_kmajor_desc(sa + (uint32_t)p.r_win[t] * 128u, (uint32_t)p.a_sbo, p.use_bo);
+                            const uint64_t bd = make_kmajor_desc(base + (uint32_t)(t * p.cblocks + cb) * b_bytes);
+#pragma unroll
+                            for (int c = 0; c < 6; ++c) {
+                                if (c >= 2 * p.split_terms) break;
+                                const int ka = (c < 4) ? c : c - 4;                     // 0 1 | 2 3 | 0 1
+                                const int kb = (c < 2) ? c : c - 2;                     // 0 1 | 0 1 | 2 3
+                                tc_mma_bf16(d0, a0 + (uint64_t)(ka * 2), bd + (uint64_t)(kb * 2), idesc, started);
+                                started = 1;
+                            }
+                        }
+                        tc_commit(empty0 + 8 * stage);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    tc_commit(tfull0 + 8 * acc);
+                    if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
+                }
+            } else
             for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
                 const int mp = u / p.n_tiles;
                 const bool two = p.mtu == 2 && 2 * mp + 1 < m_tiles;
@@ -635,6 +696,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const uint32_t bars = base + RING_BYTES;
     const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
     const uint32_t tmem_slot = tempty0 + 16;
+    const uint32_t bres0 = tmem_slot + 8;                          // resident-filter mode: "the filter has landed"
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int STAGES = stages_for(p.mtu);
@@ -808,6 +870,7 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     const uint32_t bars = base + RING_BYTES;
     const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
     const uint32_t tmem_slot = tempty0 + 16;
+    const uint32_t bres0 = tmem_slot + 8;                          // resident-filter mode: "the filter has landed"
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
     const uint32_t ones_addr = bars + 1024u;                                  // 8 KB of 1.0f inside the epilogue staging area
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -982,6 +1045,7 @@ conv_tc_wgrad_s_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     const uint32_t bars = base + RING_BYTES;
     const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
     const uint32_t tmem_slot = tempty0 + 16;
+    const uint32_t bres0 = tmem_slot + 8;                          // resident-filter mode: "the filter has landed"
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int STAGES = stages_for(p.mtu);
@@ -1151,6 +1215,7 @@ conv_tc_wgrad_rw_s_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
     const uint32_t bars = base + RING_BYTES;
     const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
     const uint32_t tmem_slot = tempty0 + 16;
+    const uint32_t bres0 = tmem_slot + 8;                          // resident-filter mode: "the filter has landed"
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
     const uint32_t ones_addr = bars + 1024u;                                  // 2 KB of bf16 1.0 inside the epilogue staging area
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1337,6 +1402,7 @@ conv_tc_wgrad_r2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     const uint32_t bars = base + RING_BYTES;
     const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
     const uint32_t tmem_slot = tempty0 + 16;
+    const uint32_t bres0 = tmem_slot + 8;                          // resident-filter mode: "the filter has landed"
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
     const uint32_t ones_addr = bars + 1024u;                                  // 2 KB of bf16 1.0 inside the epilogue staging area
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1641,7 +1707,7 @@ int launch_tc(const CUtensorMap& ms, const CUtensorMap& mw, const TcArgs& a_in, 
     // (split mode, 8 epilogue warps: conv1_2 dgrad is faster with ONE CTA and two tiles per unit -- 1.37 -> 1.25 ms -- so only the
     //  K <= 64 layer conv1_1 keeps two CTAs there: 0.406 -> 0.387 ms)
     const bool dual_wanted = dual_mode == 1 || (dual_mode == 2 && (kblocks <= 2 || (!a.split && a.mode == 1 && a.mask && kblocks <= 18)));
-    if (dual_wanted && a.block_n <= 64 && !a.scatter) {
+    if (dual_wanted && a.block_n <= 64 && !a.scatter && !a.resb) {
         const int sb1 = (a.a_slot + a.b_tiles * a.block_n * 128 + 1023) / 1024 * 1024;     // stage with one M tile per unit
         if (2 * sb1 <= DUAL_RING_BYTES && m_tiles * a.n_tiles >= 4LL * num_sms()) {
             a.mtu = 1; a.stage_bytes = sb1;
@@ -1712,6 +1778,36 @@ void fill_groups(TcArgs& a, int k, const int* dy, const int* dx, bool row_window
     a.stage_bytes = a.mtu * a.a_slot + a.b_tiles * a.block_n * 128;
     a.stage_bytes = (a.stage_bytes + 1023) / 1024 * 1024;
     a.stages = RING_BYTES / a.stage_bytes; if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
+}
+
+// Resident-filter window mode (TcArgs::resb): a 3x3 / stride-1 / dilation-1 layer in split mode whose WHOLE filter (one N tile)
+// fits in shared memory beside at least two full-window source boxes -- conv1_2, fprop and dgrad (144 KB of filter + 2 x 23 KB).
+// Measured before (ncu, conv1_2 fprop, batch 64): 9 GB of L2 -> SM traffic per launch for a 1.5 GB input, 37 % of it the
+// filter re-loaded for every unit, the rest the input read once per filter row; the N = 64 MMAs already use 96 of the 128 B/cycle
+// of the shared-memory port for their operand reads, and the TMA fills competed for the rest.  Tiles are 8 x 16 pixels of ONE
+// image (the box carries a halo line above and below, so boxes of two images cannot be stacked with a constant row pitch).
+bool try_resident_filter(TcArgs& a, int k, const int* dy, const int* dx, int B, int Hd, int Wd, bool split, double cur_eff) {
+    static int on = -1;
+    if (on < 0) { const char* ov = getenv("SSDB_RESIDENT_FILTER"); on = ov ? (atoi(ov) ? 1 : 0) : 1; }
+    if (!on || !split || k != 3 || a.n_tiles != 1 || Hd < 16) return false;
+    const int boxw = 8 + 2, boxh = 16 + 2;
+    const int slot = (boxw * boxh * 128 + 1023) / 1024 * 1024;
+    const int res = 9 * a.cblocks * a.block_n * 128;
+    if (res % 1024 != 0 || res + 2 * slot > RING_BYTES) return false;
+    const long long tiles = (long long)((Wd + 7) / 8) * ((Hd + 15) / 16) * B;
+    const double eff = (double)B * Hd * Wd / (tiles * 128.0);
+    if (eff < 0.9 || eff < 0.95 * cur_eff) return false;
+    int dymin = dy[0], dxmin = dx[0];
+    for (int t = 1; t < 9; ++t) { if (dy[t] < dymin) dymin = dy[t]; if (dx[t] < dxmin) dxmin = dx[t]; }
+    a.TW = 8; a.TH = 16; a.TN = 1;
+    a.tiles_x = (Wd + 7) / 8; a.tiles_y = (Hd + 15) / 16; a.tiles_n = B;
+    a.mtu = 1; a.resb = 1; a.res_bytes = res;
+    a.ngroups = 1; a.g_dy[0] = (signed char)dymin; a.g_dx[0] = (signed char)dxmin; a.g_nt[0] = 9;
+    for (int t = 0; t < 9; ++t) a.r_win[t] = (unsigned char)((dy[t] - dymin) * boxw + (dx[t] - dxmin));
+    a.a_rows = boxw * boxh; a.a_slot = slot; a.a_sbo = boxw * 128; a.b_tiles = 0;
+    a.stage_bytes = slot;
+    a.stages = (RING_BYTES - res) / slot; if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
+    return true;
 }
 
 // row-window geometry: TW = 8 and TH*TN = 16 (128 rows); returns efficiency, 0 if impossible
@@ -1829,13 +1925,16 @@ int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_
         if (a.block_n > 64) a.mtu = rw_wide_mtu(a.mtu);        // 2 x 20 KB + 3 x 16 KB would leave only two stages
     }
     fill_groups(a, g.k, tdy, tdx, rw);
+    const bool resb = rw && !ep.scatter && try_resident_filter(a, g.k, tdy, tdx, g.B, g.Ho, g.Wo, fmt == ACT_S32,
+                                                               (double)g.B * g.Ho * g.Wo / ((double)a.tiles_x * a.tiles_y * a.tiles_n * 128.0));
+    if (resb) { t.TW = 8; t.TH = 16; t.TN = 1; }
     SSDB_REQUIRE(g.pad_t == g.pad_l, "tcgen05 path assumes equal top/left padding");
     a.dst = y; a.bias = ep.bias; a.mask = nullptr; a.relu = ep.relu; a.beta = 0; a.round_out = ep.round_tf32;
     a.split = fmt == ACT_S32 ? 1 : 0; a.split_terms = split_terms_env();
     a.pool = ep.pool_dst ? 1 : 0; a.pool_dst = ep.pool_dst; a.pool_code = ep.pool_code; a.Hp = g.Ho / 2; a.Wp = g.Wo / 2;
     a.scatter = ep.scatter; a.V = ep.V; a.n_valid = ep.n_valid; a.anchor_base = ep.anchor_base; a.A = ep.A;
     CUtensorMap ms, mw;
-    int rc = encode_act_map(&ms, x, g.B, g.H, g.W, g.Cin, rw ? a.a_sbo / 128 : t.TW, t.TH, t.TN, CU_TENSOR_MAP_SWIZZLE_128B, g.stride); if (rc) return rc;
+    int rc = encode_act_map(&ms, x, g.B, g.H, g.W, g.Cin, rw ? a.a_sbo / 128 : t.TW, resb ? t.TH + 2 : t.TH, t.TN, CU_TENSOR_MAP_SWIZZLE_128B, g.stride); if (rc) return rc;
     rc = encode_w_map(&mw, w_t, (long long)g.k * g.k * cout_pad, g.Cin, a.block_n); if (rc) return rc;
     return launch_tc(ms, mw, a, st);
 }
@@ -1860,6 +1959,7 @@ int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, int f
             a.mtu = tc_mtu(a.block_n, (long long)a.tiles_x * a.tiles_y * a.tiles_n, a.n_tiles, g.k * g.k * a.cblocks / (s * s), true, fmt == ACT_S32);
             SSDB_REQUIRE(g.k <= 3, "tcgen05 path supports 1x1 and 3x3 filters");
             int wth = 0, wtn = 0;
+            bool resb = false;
             const bool rw = s == 1 && want_row_window(g, a.block_n, g.B, Hc, Wc, t.eff, &wth, &wtn);
             if (rw) {
                 t.TW = 8; t.TH = wth; t.TN = wtn; a.TW = 8; a.TH = wth; a.TN = wtn;
@@ -1868,6 +1968,9 @@ int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, int f
                 int tdy[9], tdx[9];
                 for (int tt = 0; tt < g.k * g.k; ++tt) { tdy[tt] = g.pad_t - (tt / g.k) * g.dil; tdx[tt] = g.pad_l - (tt % g.k) * g.dil; }
                 fill_groups(a, g.k, tdy, tdx, true);
+                resb = try_resident_filter(a, g.k, tdy, tdx, g.B, Hc, Wc, fmt == ACT_S32,
+                                           (double)g.B * Hc * Wc / ((double)a.tiles_x * a.tiles_y * a.tiles_n * 128.0));
+                if (resb) { t.TW = 8; t.TH = 16; t.TN = 1; }
             } else {
                 int ntap = 0;
                 a.ngroups = 0;
@@ -1891,7 +1994,7 @@ int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, int f
             a.dst = dx; a.bias = nullptr; a.mask = mask_x; a.relu = 0; a.beta = beta; a.round_out = round_out;
             a.split = fmt == ACT_S32 ? 1 : 0; a.split_terms = split_terms_env();
             CUtensorMap ms, mw;
-            int rc = encode_act_map(&ms, dz, g.B, g.Ho, g.Wo, g.Cout, rw ? a.a_sbo / 128 : t.TW, t.TH, t.TN); if (rc) return rc;
+            int rc = encode_act_map(&ms, dz, g.B, g.Ho, g.Wo, g.Cout, rw ? a.a_sbo / 128 : t.TW, resb ? t.TH + 2 : t.TH, t.TN); if (rc) return rc;
             rc = encode_w_map(&mw, w_hwio, (long long)g.k * g.k * g.Cin, g.Cout, a.block_n); if (rc) return rc;
             rc = launch_tc(ms, mw, a, st); if (rc) return rc;
         }

@@ -143,3 +143,49 @@ def test_smaller_batch_than_max_batch_is_the_same_step():
     for k in a[2]:
         assert np.array_equal(a[2][k], b[2][k]), k
         assert np.array_equal(a[3][k], b[3][k]), k
+
+
+@pytest.mark.parametrize('preset,B,chunk', [('vgg300', 64, 16), ('vgg512', 32, 8)])
+def test_full_size_batch_is_the_mean_of_its_chunks(preset, B, chunk):
+    """BASELINE.json's full sizes (configs[1] / configs[3]) through a size-independent property: the multibox loss is a batch
+    mean of per-image terms (ssdvgg.py:513-521,552-560), so one step on B images must give, per image, the result of running the
+    images in chunks on a smaller engine (other tile plans, unit sizes, split counts), and its losses / gradients must be the
+    mean of the chunks' losses / gradients.  Raw ground truth feed = the fused match + loss path."""
+    side = bo.PRESETS[preset]['image']
+    P = no.init_params(preset, dtype=torch.float32)
+    x = synth.images(100, B, side)
+    gt, cnt = synth.pack_gt([synth.gt_boxes(100 + i) for i in range(B)], 8)
+
+    def run(max_batch, lo, hi):
+        res, losses, _ = net.train_step_host_gt(x[lo:hi], gt[lo:hi], cnt[lo:hi], 0.0, 0.0, 0.0005, apply_update=False)
+        return np.array(res), np.array(losses, dtype=np.float64), {k: net.get_tensor(k, shape, ssdb.GRAD).astype(np.float64) for k, shape in net.tensors()}
+
+    net = ssdb.Net(preset, 20, max_batch=B)
+    for k, shape in net.tensors():
+        net.set_tensor(k, P[k].numpy())
+    res, losses, grads = run(B, 0, B)
+    net.close()
+    net = ssdb.Net(preset, 20, max_batch=chunk)
+    for k, shape in net.tensors():
+        net.set_tensor(k, P[k].numpy())
+    parts = [run(chunk, lo, lo + chunk) for lo in range(0, B, chunk)]
+    net.close()
+    res_c = np.concatenate([p[0] for p in parts])
+    scale = np.abs(res_c[..., :21]).max()
+    assert np.abs(res - res_c)[..., :21].max() <= 2e-5 * max(scale, 1.0)            # softmax rows
+    assert np.abs(res - res_c)[..., 21:].max() <= 2e-5 * np.abs(res_c[..., 21:]).max()
+    losses_c = np.mean([p[1] for p in parts], axis=0)
+    # total / localization / confidence are batch means; the l2 term is batch independent
+    assert np.allclose(losses, losses_c, rtol=2e-5), (losses, losses_c)
+    worst = ('', 0.0)
+    for k in grads:
+        gc = np.mean([p[2][k] for p in parts], axis=0)
+        err = np.abs(grads[k] - gc).max() / max(np.abs(gc).max(), 1e-30)
+        if err > worst[1]:
+            worst = (k, float(err))
+    rec = dict(preset=preset, B=B, chunk=chunk, worst_grad_vs_chunk_mean=worst, losses=losses.tolist())
+    print('FULLSIZE', json.dumps(rec))
+    out = os.path.join(os.path.dirname(__file__), '..', 'gpurun_out')
+    os.makedirs(out, exist_ok=True)
+    json.dump(rec, open(os.path.join(out, 'fullsize_chunks_%s.json' % preset), 'w'), indent=1)
+    assert worst[1] <= 2e-3, worst
