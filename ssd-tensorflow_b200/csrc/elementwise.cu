@@ -377,42 +377,60 @@ __global__ void unsplit_copy_kernel(const float* __restrict__ src, float* __rest
     if (i < n4) reinterpret_cast<float4*>(dst)[i] = act_ld4<ACT_S32>(src, i * 4);
 }
 
-// one thread per pixel: 27 taps (kh, kw, c) + 5 zeros = one 128-byte row
+// one thread per pixel builds the 27 taps (kh, kw, c) + 5 zeros = one 128-byte row; the warp then transposes its 32 rows
+// through 4 KB of shared memory (16-byte pieces XOR-swizzled by row) so that every store instruction writes four complete
+// rows -- one thread writing its own row put 16 bytes into each of 32 rows per instruction (1.9 TB/s); eight threads per
+// pixel, each computing one piece, was slower still (index arithmetic: 1.1 ms).
 template <int FMT>
-__global__ void conv1_im2col_kernel(const float* __restrict__ img, int B, int S, int swap_rb, float m0, float m1, float m2,
-                                    float* __restrict__ patches) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)B * S * S;
-    if (i >= total) return;
-    int x = (int)(i % S); long long r = i / S;
-    int y = (int)(r % S); int b = (int)(r / S);
-    float v[32];
+__global__ void __launch_bounds__(128)
+conv1_im2col_kernel(const float* __restrict__ img, int B, int S, int swap_rb, float m0, float m1, float m2, float* __restrict__ patches) {
+    __shared__ uint4 stage[4][32 * 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long total = (long long)B * S * S;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane;     // first pixel of this warp
+    const long long i = warp0 + lane;
+    uint4 piece[8];
+    if (i < total) {
+        int x = (int)(i % S); long long r = i / S;
+        int y = (int)(r % S); int b = (int)(r / S);
+        float v[32];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-        int iy = y + t / 3 - 1, ix = x + t % 3 - 1;
-        bool ok = iy >= 0 && iy < S && ix >= 0 && ix < S;
-        const float* px = img + (((long long)b * S + (ok ? iy : 0)) * S + (ok ? ix : 0)) * 3;
-        float p0 = px[0], p1 = px[1], p2 = px[2];
-        float c0 = (swap_rb ? p2 : p0) - m0, c1 = p1 - m1, c2 = (swap_rb ? p0 : p2) - m2;
-        if (FMT == ACT_F32) { c0 = tf32_rn(c0); c1 = tf32_rn(c1); c2 = tf32_rn(c2); }
-        v[t * 3 + 0] = ok ? c0 : 0.f; v[t * 3 + 1] = ok ? c1 : 0.f; v[t * 3 + 2] = ok ? c2 : 0.f;
+        for (int t = 0; t < 9; ++t) {
+            int iy = y + t / 3 - 1, ix = x + t % 3 - 1;
+            bool ok = iy >= 0 && iy < S && ix >= 0 && ix < S;
+            const float* px = img + (((long long)b * S + (ok ? iy : 0)) * S + (ok ? ix : 0)) * 3;
+            float p0 = __ldg(px), p1 = __ldg(px + 1), p2 = __ldg(px + 2);
+            float c0 = (swap_rb ? p2 : p0) - m0, c1 = p1 - m1, c2 = (swap_rb ? p0 : p2) - m2;
+            if (FMT == ACT_F32) { c0 = tf32_rn(c0); c1 = tf32_rn(c1); c2 = tf32_rn(c2); }
+            v[t * 3 + 0] = ok ? c0 : 0.f; v[t * 3 + 1] = ok ? c1 : 0.f; v[t * 3 + 2] = ok ? c2 : 0.f;
+        }
+#pragma unroll
+        for (int t = 27; t < 32; ++t) v[t] = 0.f;
+        if (FMT == ACT_F32) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                piece[q] = make_uint4(__float_as_uint(v[q * 4]), __float_as_uint(v[q * 4 + 1]), __float_as_uint(v[q * 4 + 2]), __float_as_uint(v[q * 4 + 3]));
+        } else {
+            // the pixel's 128-byte row: 32 bf16 high parts, then 32 bf16 low parts
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) split2(v[2 * q], v[2 * q + 1], hi[q], lo[q]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                piece[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+                piece[4 + q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) stage[warp][lane * 8 + (q ^ (lane & 7))] = piece[q];
     }
+    __syncwarp();
+    const int q = lane & 7;
+    uint4* out = reinterpret_cast<uint4*>(patches);
 #pragma unroll
-    for (int t = 27; t < 32; ++t) v[t] = 0.f;
-    if (FMT == ACT_F32) {
-        float4* o = reinterpret_cast<float4*>(patches + i * 32);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) o[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-    } else {
-        // the pixel's 128-byte row: 32 bf16 high parts, then 32 bf16 low parts
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) split2(v[2 * q], v[2 * q + 1], hi[q], lo[q]);
-        uint4* o = reinterpret_cast<uint4*>(patches + i * 32);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) o[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) o[4 + q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+    for (int k = 0; k < 8; ++k) {
+        const int row = k * 4 + (lane >> 3);
+        if (warp0 + row < total) out[(warp0 + row) * 8 + q] = stage[warp][row * 8 + (q ^ (row & 7))];
     }
 }
 
