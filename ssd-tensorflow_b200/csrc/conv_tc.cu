@@ -696,7 +696,6 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const uint32_t bars = base + RING_BYTES;
     const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
     const uint32_t tmem_slot = tempty0 + 16;
-    const uint32_t bres0 = tmem_slot + 8;                          // resident-filter mode: "the filter has landed"
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int STAGES = stages_for(p.mtu);
@@ -870,7 +869,6 @@ conv_tc_wgrad_rw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     const uint32_t bars = base + RING_BYTES;
     const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
     const uint32_t tmem_slot = tempty0 + 16;
-    const uint32_t bres0 = tmem_slot + 8;                          // resident-filter mode: "the filter has landed"
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
     const uint32_t ones_addr = bars + 1024u;                                  // 8 KB of 1.0f inside the epilogue staging area
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1045,7 +1043,6 @@ conv_tc_wgrad_s_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     const uint32_t bars = base + RING_BYTES;
     const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
     const uint32_t tmem_slot = tempty0 + 16;
-    const uint32_t bres0 = tmem_slot + 8;                          // resident-filter mode: "the filter has landed"
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int STAGES = stages_for(p.mtu);
@@ -1215,7 +1212,6 @@ conv_tc_wgrad_rw_s_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
     const uint32_t bars = base + RING_BYTES;
     const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
     const uint32_t tmem_slot = tempty0 + 16;
-    const uint32_t bres0 = tmem_slot + 8;                          // resident-filter mode: "the filter has landed"
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
     const uint32_t ones_addr = bars + 1024u;                                  // 2 KB of bf16 1.0 inside the epilogue staging area
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1390,6 +1386,7 @@ struct WgR2Args {
     int splits, tiles_per_split;
     int want_bias, terms;
     int stage_bytes, stages;
+    int c2;                         // run on SM pairs (conv_tc_wgrad_r2c2_kernel): Cout % 256 == 0
     long long psize;
     float* partial;
 };
@@ -1402,7 +1399,6 @@ conv_tc_wgrad_r2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     const uint32_t bars = base + RING_BYTES;
     const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
     const uint32_t tmem_slot = tempty0 + 16;
-    const uint32_t bres0 = tmem_slot + 8;                          // resident-filter mode: "the filter has landed"
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
     const uint32_t ones_addr = bars + 1024u;                                  // 2 KB of bf16 1.0 inside the epilogue staging area
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1555,6 +1551,229 @@ conv_tc_wgrad_r2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ rw2 wgrad on an SM PAIR (cta_group::2): Cout % 256 == 0
+// The kernel above is bound by the shared-memory port: an M128 x N96 x K16 MMA reads 4 KB of dz and 3 KB of x windows per 48 tensor
+// cycles and the TMA fills (45 KB per 36 MMAs) use the same 128 B/cycle (model: 1728 / 2320 cycles = 74 %, measured 66-71 %).
+// Here a cluster of two CTAs on the two SMs of a TPC issues ONE M256 x N96 x K16 MMA per step: each SM supplies its own 128
+// output channels of dz (the A operand, same shared-memory offsets in both CTAs) and HALF of the N operand -- channels 16*rank ..
+// 16*rank+15 of the x block for all three kw windows (SWIZZLE_32B boxes, MN-major blocks of 16 channels one pixel = 32 B apart) --
+// so per SM and MMA 4 + 1.5 KB are read and 38 KB filled per stage: 1846 cycles of port time for 1728 of tensor time.
+// Protocol (the CUTLASS 2-SM scheme): both producers aim their TMA loads at the LEADER's full barrier (cp.async.bulk.tensor
+// .cta_group::2, expect_tx for both halves by the leader), the leader's MMA warp issues tcgen05.mma.cta_group::2 and releases the
+// stage / publishes the accumulators with tcgen05.commit .multicast::cluster to BOTH CTAs, every epilogue warp of both CTAs reads
+// its own TMEM and arrives on the leader's accumulator-free barrier.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_c2(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tc_commit_c2(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_c2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+// MN-major, SWIZZLE_32B: 16-element (32-byte) rows, blocks of 16 elements LBO apart, 8-row groups SBO apart
+__device__ __forceinline__ uint64_t make_mn32_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;                      // SWIZZLE_32B
+    return d;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+conv_tc_wgrad_r2c2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz, const WgR2Args p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t bars = base + RING_BYTES;
+    const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
+    const uint32_t tmem_slot = tempty0 + 16;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+    const uint32_t ones_addr = bars + 1024u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull0, 1); mbar_init(tempty0, 8);                 // 4 epilogue warps of each CTA
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dz) : "memory");
+    }
+    {
+        uint32_t* ones = reinterpret_cast<uint32_t*>(smem_raw + (ones_addr - raw));
+        for (int i = threadIdx.x; i < 512; i += NUM_THREADS) ones[i] = 0x3f803f80u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                              // the peer's barriers exist before anything arrives on them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int mpairs = p.mblocks / 2;
+    const int utypes = p.cblocks * mpairs;                         // (channel block of x, 256 output channels)
+    const int units = utypes * p.splits;
+    const int npairs = (int)(gridDim.x >> 1), pair = (int)(blockIdx.x >> 1);
+    const int pix_tiles = p.ptx * p.pty * p.ptn;
+    const int bw = 8 + 2 * p.dil, bh = p.PH + 2 * p.dil;
+    const uint32_t xsub = (uint32_t)(bw * bh) * 32u;              // one part (hi or lo) of this CTA's 16 channels of the x box
+    const uint32_t zsub = (uint32_t)(8 * p.PH) * 64u;
+    const uint32_t z_off = (2u * xsub + 1023u) & ~1023u;
+    const int STAGES = p.stages;
+    constexpr uint32_t ACC_N = 96;
+
+    if (warp == 0) {
+        if (elect_one_sync()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int u = pair; u < units; u += npairs) {
+                const int ut = u % utypes, sp = u / utypes;
+                const int cb = ut % p.cblocks, mt = 2 * (ut / p.cblocks) + (int)rank;
+                const int q0 = sp * p.tiles_per_split;
+                const int q1 = min(pix_tiles, q0 + p.tiles_per_split);
+                for (int q = q0; q < q1; ++q) {
+                    const int qx = q % p.ptx; const int r2 = q / p.ptx;
+                    const int qy = r2 % p.pty; const int n0 = r2 / p.pty;
+                    const int x0 = qx * 8, y0 = qy * p.PH;
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t fb = mapa_u32(full0 + 8 * stage, 0);          // the leader's barrier collects both halves
+                    if (leader) mbar_expect_tx(full0 + 8 * stage, 2u * (2u * xsub + 8u * zsub));
+                    const uint32_t sa = base + stage * p.stage_bytes;
+                    tma_load_5d_c2(sa, &map_x, fb, 16 * (int)rank, x0 - p.dil, y0 - p.dil, n0, 2 * cb);
+                    tma_load_5d_c2(sa + z_off, &map_dz, fb, 0, x0, y0, n0, 8 * mt);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && elect_one_sync()) {
+            const uint32_t idesc_common = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(256 >> 4) << 24);
+            const uint32_t idesc = idesc_common | ((ACC_N >> 3) << 17);
+            const uint32_t idesc_bias = idesc_common | ((32u >> 3) << 17);
+            int stage = 0; uint32_t phase = 0; uint32_t acc_phase = 0;
+            const uint64_t ones_desc = make_mn64_desc(ones_addr, 0u, 512u);
+            const int terms = p.terms;
+            for (int u = pair; u < units; u += npairs) {
+                const int ut = u % utypes, sp = u / utypes;
+                const int cb = ut % p.cblocks;
+                const bool do_bias = p.want_bias && cb == 0;
+                const int q0 = sp * p.tiles_per_split;
+                const int q1 = min(pix_tiles, q0 + p.tiles_per_split);
+                mbar_wait(tempty0, acc_phase ^ 1);
+                tc_fence_after();
+                for (int q = q0; q < q1; ++q) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * p.stage_bytes;
+                    const uint64_t az[2] = {make_mn64_desc(sa + z_off, 2u * zsub, 512u), make_mn64_desc(sa + z_off + zsub, 2u * zsub, 512u)};
+                    for (int jp = 0; jp < p.PH / 2; ++jp) {
+                        const uint32_t first = (q > q0 || jp > 0) ? 1u : 0u;
+                        const uint64_t zo = (uint64_t)(jp * 64);
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh) {
+                            const uint32_t xa = sa + (uint32_t)((2 * jp + kh * p.dil) * bw) * 32u;
+                            const uint64_t bx[2] = {make_mn32_desc(xa, (uint32_t)p.dil * 32u, (uint32_t)bw * 32u),
+                                                    make_mn32_desc(xa + xsub, (uint32_t)p.dil * 32u, (uint32_t)bw * 32u)};
+                            const uint32_t d = tmem_base + (uint32_t)kh * ACC_N;
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                if (c >= terms) break;
+                                const int ha = c == 1 ? 1 : 0, hb = c == 2 ? 1 : 0;
+                                tc_mma_bf16_c2(d, az[ha] + zo, bx[hb], idesc, (first || c > 0) ? 1u : 0u);
+                            }
+                        }
+                        if (do_bias) {
+                            const uint32_t d = tmem_base + 3u * ACC_N;
+                            tc_mma_bf16_c2(d, az[0] + zo, ones_desc, idesc_bias, first);
+                            tc_mma_bf16_c2(d, az[1] + zo, ones_desc, idesc_bias, 1u);
+                        }
+                    }
+                    tc_commit_c2(empty0 + 8 * stage, 3);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit_c2(tfull0, 3);
+                acc_phase ^= 1;
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        uint32_t acc_phase = 0;
+        const long long wsize = 9LL * p.Cin * p.Cout;
+        const uint32_t tempty_leader = mapa_u32(tempty0, 0);
+        for (int u = pair; u < units; u += npairs) {
+            const int ut = u % utypes, sp = u / utypes;
+            const int cb = ut % p.cblocks, mt = 2 * (ut / p.cblocks) + (int)rank;
+            const bool do_bias = p.want_bias && cb == 0;
+            mbar_wait(tfull0, acc_phase);
+            tc_fence_after();
+            const int m = mt * 128 + quarter * 32 + lane;                   // this thread's output channel
+            float* pbase = p.partial + (long long)sp * p.psize;
+            const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+            for (int kh = 0; kh < 3; ++kh)
+                for (int h = 0; h < 2; ++h)                                 // accumulator columns: [half of the pair][window][16 channels]
+                    for (int w = 0; w < 3; ++w) {
+                        uint32_t r[16];
+                        __syncwarp();
+                        tc_ld16(t_lane + (uint32_t)(kh * ACC_N + h * 48 + w * 16), r);
+                        tc_wait_ld();
+                        float* dst = pbase + ((long long)(kh * 3 + w) * p.Cin + cb * 32 + h * 16) * p.Cout + m;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) dst[(long long)j * p.Cout] = __uint_as_float(r[j]);
+                    }
+            if (do_bias) {
+                uint32_t r[16];
+                __syncwarp();
+                tc_ld16(t_lane + 3u * ACC_N, r);
+                tc_wait_ld();
+                pbase[wsize + m] = __uint_as_float(r[0]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_leader);
+            acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                              // no commit / remote arrive is still on its way to a CTA that exits
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -2048,15 +2267,15 @@ int encode_act_map5(CUtensorMap* m, const float* ptr, int B, int H, int W, int C
 }
 
 // 5-D view of an ACT_S32 tensor for the MN-major (wgrad) operands: (32 bf16 of one part, x, y, image, q = 2 * channel block + part)
-int encode_act_map5s(CUtensorMap* m, const float* ptr, int B, int H, int W, int C, int bw, int bh, int bn, int nq, int estride) {
+int encode_act_map5s(CUtensorMap* m, const float* ptr, int B, int H, int W, int C, int bw, int bh, int bn, int nq, int estride, int inner = 32) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return SSDB_ECUDA; }
     cuuint64_t dims[5] = {32, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)(C / 32 * 2)};
     cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4, 64};
-    cuuint32_t box[5] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn, (cuuint32_t)nq};
+    cuuint32_t box[5] = {(cuuint32_t)inner, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn, (cuuint32_t)nq};     // inner = 16: half a block, SWIZZLE_32B
     cuuint32_t es[5] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<float*>(ptr), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, inner == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(split 5-D activation %dx%dx%dx%d box %d,%d,%d,%d) failed: %d", B, H, W, C, bw, bh, bn, nq, (int)r); return SSDB_ECUDA; }
     return SSDB_OK;
@@ -2166,8 +2385,8 @@ long long max_splits_bound(long long ut, int max_splits_cap) {
     return hi < 1 ? 1 : hi;
 }
 
-void pick_splits(long long pix_tiles, long long ut, int min_tiles, int max_splits_cap, int* tiles_per_split, int* splits) {
-    const long long sms = num_sms();
+void pick_splits(long long pix_tiles, long long ut, int min_tiles, int max_splits_cap, int* tiles_per_split, int* splits, long long slots = 0) {
+    const long long sms = slots > 0 ? slots : num_sms();     // CTAs (or CTA pairs) of the persistent grid
     long long max_splits = (pix_tiles + min_tiles - 1) / min_tiles;
     if (max_splits > max_splits_cap) max_splits = max_splits_cap;
     if (max_splits < 1) max_splits = 1;
@@ -2222,6 +2441,16 @@ WgR2Plan plan_wgrad_r2(const ConvGeom& g, int fmt) {
     const long long pix_tiles = (long long)a.ptx * a.pty * a.ptn;
     const long long ut = (long long)a.cblocks * a.mblocks;
     pick_splits(pix_tiles, ut, 8, 512, &a.tiles_per_split, &a.splits);
+    // SM-pair variant (cta_group::2): 256 output channels per unit, each CTA loads 16 of the 32 x channels
+    int c2 = 1;
+    if (const char* ov = getenv("SSDB_WG_C2")) c2 = atoi(ov) ? 1 : 0;
+    if (c2 && g.Cout % 256 == 0 && num_sms() % 2 == 0) {
+        int sb2 = (2 * bw * bh * 32 + 1023) / 1024 * 1024 + 8 * 8 * PH * 64;
+        sb2 = (sb2 + 1023) / 1024 * 1024;
+        a.c2 = 1; a.stage_bytes = sb2;
+        a.stages = RING_BYTES / sb2; if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
+        pick_splits(pix_tiles, ut / 2, 8, 512, &a.tiles_per_split, &a.splits, num_sms() / 2);
+    }
     a.partial = nullptr;
     pl.ok = true;
     return pl;
@@ -2312,14 +2541,25 @@ int conv_tc_wgrad(const ConvGeom& g, const float* x, const float* dz, int fmt, f
         a.partial = partial;
         a.want_bias = db ? 1 : 0;
         CUtensorMap mx, mz;
-        int rc = encode_act_map5s(&mx, x, g.B, g.H, g.W, g.Cin, 8 + 2 * a.dil, a.PH + 2 * a.dil, 1, 2, 1); if (rc) return rc;
+        int rc = encode_act_map5s(&mx, x, g.B, g.H, g.W, g.Cin, 8 + 2 * a.dil, a.PH + 2 * a.dil, 1, 2, 1, a.c2 ? 16 : 32); if (rc) return rc;
         rc = encode_act_map5s(&mz, dz, g.B, g.Ho, g.Wo, g.Cout, 8, a.PH, 1, 8, 1); if (rc) return rc;
         static PerDevice<bool> attr_r2_pd;
         bool& attr_r2 = attr_r2_pd.get();
-        if (!attr_r2) { SSDB_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_r2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_r2 = true; }
-        long long units = (long long)a.cblocks * a.mblocks * a.splits;
-        int grid = (int)(units < num_sms() ? units : num_sms());
-        conv_tc_wgrad_r2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mx, mz, a);
+        if (!attr_r2) {
+            SSDB_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_r2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            SSDB_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_r2c2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            attr_r2 = true;
+        }
+        if (a.c2) {
+            long long units = (long long)a.cblocks * (a.mblocks / 2) * a.splits;
+            const long long pairs = num_sms() / 2;
+            int grid = 2 * (int)(units < pairs ? units : pairs);
+            conv_tc_wgrad_r2c2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mx, mz, a);
+        } else {
+            long long units = (long long)a.cblocks * a.mblocks * a.splits;
+            int grid = (int)(units < num_sms() ? units : num_sms());
+            conv_tc_wgrad_r2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mx, mz, a);
+        }
         SSDB_LAUNCH_CHECK();
         long long nw = 9LL * g.Cin * g.Cout;
         reduce_partials_kernel<<<(unsigned)((a.psize / 4 + 255) / 256), 256, 0, st>>>(partial, a.psize, nw, a.splits, dw, db);
