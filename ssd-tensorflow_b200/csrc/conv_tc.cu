@@ -136,6 +136,43 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- 2-CTA clusters (cta_group::2): helpers shared by the pair kernels
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_c2(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tc_commit_c2(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_c2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_c2(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_c2(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
 // 8-row groups 1024 B apart (SBO), rows 128 B apart, 16-byte units.
 // Measured on B200 (round-1 probe, recorded in DESIGN.md): the 128-byte swizzle is applied to the ABSOLUTE shared-memory address, so a
@@ -200,6 +237,10 @@ struct TcArgs {
     // starting r_win[t] pixels into it).  L2 -> SM bytes per 128 pixels: 2 x 23 KB instead of 6 x (16.6 + 24) KB.
     int resb, res_bytes;
     unsigned char r_win[9];
+    // pair mode (conv_tc_kernel<.., PAIR = true>, clusters of two CTAs): ONE tcgen05.mma.cta_group::2 M256 x N per step -- each CTA
+    // supplies its own M tiles (A) and HALF of the filter rows of the N tile (B), so a CTA fills mtu * 16 + N / 2 * 128 B per
+    // 32-channel slab instead of mtu * 16 KB + N * 128 B and reads half of the B bytes per MMA
+    int c2;
 };
 
 // epilogue of one 128-row tile: TMEM -> registers -> (per-warp shared-memory transpose) -> global.
@@ -416,7 +457,9 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& p, int mt, int nt, u
 }
 
 // FMT: operand / storage format (ACT_F32 = tf32 MMAs, ACT_S32 = split bf16 MMAs); SCATTER: the head epilogue (fprop only)
-template <int FMT, bool SCATTER>
+// PAIR: the cta_group::2 variant (TcArgs::c2; must be launched as clusters of two CTAs -- a kernel that contains cta_group::2
+// instructions cannot be launched without a cluster, so it is its own instantiation)
+template <int FMT, bool SCATTER, bool PAIR = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w, const TcArgs p) {
     extern __shared__ unsigned char smem_raw[];
@@ -434,21 +477,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nepi = (int)(blockDim.x >> 5) - 2;                  // epilogue warps: 4 (two CTAs per SM) or 8
+    constexpr bool c2 = PAIR;
+    const uint32_t rank = c2 ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, (uint32_t)nepi); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, (uint32_t)(c2 ? 2 * nepi : nepi)); }
         mbar_init(bres0, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_src) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (c2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (c2) cluster_sync_all();                                   // the peer's barriers exist before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -456,6 +508,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
     const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
     const int m_pairs = (m_tiles + p.mtu - 1) / p.mtu;
     const int total_units = m_pairs * p.n_tiles;
+    // pair mode: a pair unit = two consecutive units of the SAME N tile, one per CTA (an odd count: the peer recomputes the last one)
+    const int pair_units = ((m_pairs + 1) >> 1) * p.n_tiles;
+    const int u_first = c2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int u_step = c2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int u_end = c2 ? pair_units : total_units;
+    const uint32_t hb_bytes = c2 ? ((uint32_t)p.block_n * 64u) : ((uint32_t)p.block_n * 128u);     // bytes of this CTA's part of a B tile
     const uint32_t a_bytes = (uint32_t)p.a_rows * 128u;
     const uint32_t b_bytes = (uint32_t)p.block_n * 128u;
     const int noff = (p.block_n + 31) & ~31;                       // TMEM column offset of the second tile's accumulator
@@ -486,13 +544,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
             }
         } else if (elect_one_sync()) {
             int stage = 0; uint32_t phase = 0;
-            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-                const int mp = u / p.n_tiles, nt = u - mp * p.n_tiles;
+            for (int u = u_first; u < u_end; u += u_step) {
+                int mp, nt;
+                if (c2) { nt = u % p.n_tiles; mp = 2 * (u / p.n_tiles) + (int)rank; if (mp >= m_pairs) mp = m_pairs - 1; }
+                else { mp = u / p.n_tiles; nt = u - mp * p.n_tiles; }
                 int x0[2], y0[2], n0[2];
-                const bool two = p.mtu == 2 && 2 * mp + 1 < m_tiles;
+                // pair mode always moves mtu tiles (a missing second tile re-reads the last one; its rows are never stored)
+                const bool two = p.mtu == 2 && (c2 || 2 * mp + 1 < m_tiles);
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const int mt = p.mtu * mp + j;
+                    int mt = p.mtu * mp + j; if (c2 && mt >= m_tiles) mt = m_tiles - 1;
                     const int tx = mt % p.tiles_x; const int r1 = mt / p.tiles_x;
                     x0[j] = tx * p.TW; y0[j] = (r1 % p.tiles_y) * p.TH; n0[j] = (r1 / p.tiles_y) * p.TN;
                 }
@@ -500,13 +561,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
                     const int dy = p.g_dy[gi], dx = p.g_dx[gi], ntap = p.g_nt[gi];
                     for (int cb = 0; cb < p.cblocks; ++cb) {
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                        const uint32_t fb = full0 + 8 * stage;
-                        mbar_expect_tx(fb, (two ? 2u : 1u) * a_bytes + (uint32_t)ntap * b_bytes);
                         const uint32_t sa = base + stage * STAGE_BYTES;
-                        tma_load_4d(sa, &map_src, fb, cb * BLOCK_K, x0[0] * p.sstride + dx, y0[0] * p.sstride + dy, n0[0]);
-                        if (two) tma_load_4d(sa + p.a_slot, &map_src, fb, cb * BLOCK_K, x0[1] * p.sstride + dx, y0[1] * p.sstride + dy, n0[1]);
-                        for (int t = 0; t < ntap; ++t)
-                            tma_load_2d(sa + b_off + (uint32_t)t * b_bytes, &map_w, fb, cb * BLOCK_K, (int)p.g_w[gi][t] * p.rows_per_tap + nt * p.block_n);
+                        const uint32_t bytes = (two ? 2u : 1u) * a_bytes + (uint32_t)ntap * hb_bytes;
+                        if (!c2) {
+                            const uint32_t fb = full0 + 8 * stage;
+                            mbar_expect_tx(fb, bytes);
+                            tma_load_4d(sa, &map_src, fb, cb * BLOCK_K, x0[0] * p.sstride + dx, y0[0] * p.sstride + dy, n0[0]);
+                            if (two) tma_load_4d(sa + p.a_slot, &map_src, fb, cb * BLOCK_K, x0[1] * p.sstride + dx, y0[1] * p.sstride + dy, n0[1]);
+                            for (int t = 0; t < ntap; ++t)
+                                tma_load_2d(sa + b_off + (uint32_t)t * b_bytes, &map_w, fb, cb * BLOCK_K, (int)p.g_w[gi][t] * p.rows_per_tap + nt * p.block_n);
+                        } else {
+                            // every load of the pair signals the LEADER's barrier, which expects the bytes of both CTAs
+                            const uint32_t fb = mapa_u32(full0 + 8 * stage, 0);
+                            if (leader) mbar_expect_tx(full0 + 8 * stage, 2u * bytes);
+                            tma_load_4d_c2(sa, &map_src, fb, cb * BLOCK_K, x0[0] * p.sstride + dx, y0[0] * p.sstride + dy, n0[0]);
+                            if (two) tma_load_4d_c2(sa + p.a_slot, &map_src, fb, cb * BLOCK_K, x0[1] * p.sstride + dx, y0[1] * p.sstride + dy, n0[1]);
+                            for (int t = 0; t < ntap; ++t)        // this CTA's half of the filter rows of the N tile
+                                tma_load_2d_c2(sa + b_off + (uint32_t)t * hb_bytes, &map_w, fb, cb * BLOCK_K,
+                                               (int)p.g_w[gi][t] * p.rows_per_tap + nt * p.block_n + (int)rank * (p.block_n >> 1));
+                        }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -518,6 +591,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
             // instruction descriptor: fp32 accumulate, A / B format tf32 (2) or bf16 (1), both K-major, N, M
             const uint32_t fmt = FMT == ACT_S32 ? 1u : 2u;
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+            const uint32_t idesc2 = (idesc & ~(0x1fu << 24)) | ((uint32_t)(256 >> 4) << 24);      // the pair's M = 256
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             if (FMT == ACT_S32 && p.resb) {
@@ -551,10 +625,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
                     tc_commit(tfull0 + 8 * acc);
                     if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
                 }
-            } else
-            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+            } else if (!c2 || leader)
+            for (int u = u_first; u < u_end; u += u_step) {
                 const int mp = u / p.n_tiles;
-                const bool two = p.mtu == 2 && 2 * mp + 1 < m_tiles;
+                const bool two = p.mtu == 2 && (c2 || 2 * mp + 1 < m_tiles);
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(acc * p.acc_stride);
@@ -570,7 +644,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
                             const uint32_t woff = (uint32_t)p.g_win[gi][t] * 128u;
                             const uint64_t a0 = make_kmajor_desc(sa + woff, (uint32_t)p.a_sbo, p.use_bo);
                             const uint64_t a1 = make_kmajor_desc(sa + (uint32_t)p.a_slot + woff, (uint32_t)p.a_sbo, p.use_bo);
-                            const uint64_t bd = make_kmajor_desc(sa + b_off + (uint32_t)t * b_bytes);
+                            const uint64_t bd = make_kmajor_desc(sa + b_off + (uint32_t)t * hb_bytes);
                             if (FMT == ACT_S32) {
                                 // a 128-byte row = 16 hi | 16 hi | 16 lo | 16 lo (bf16) of 32 channels: K offsets 0, 1 = high parts,
                                 // 2, 3 = low parts (32 bytes = +2 in 16-byte units each).  x*w ~ xh*wh + xl*wh + xh*wl.
@@ -579,8 +653,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
                                     if (c >= 2 * p.split_terms) break;
                                     const int ka = (c < 2) ? c : (c < 4 ? c : c - 4);       // 0 1 | 2 3 | 0 1
                                     const int kb = (c < 2) ? c : (c < 4 ? c - 2 : c - 2);   // 0 1 | 0 1 | 2 3
-                                    tc_mma_bf16(d0, a0 + (uint64_t)(ka * 2), bd + (uint64_t)(kb * 2), idesc, started);
-                                    if (two) tc_mma_bf16(d1, a1 + (uint64_t)(ka * 2), bd + (uint64_t)(kb * 2), idesc, started);
+                                    if (c2) {
+                                        tc_mma_bf16_c2(d0, a0 + (uint64_t)(ka * 2), bd + (uint64_t)(kb * 2), idesc2, started);
+                                        if (two) tc_mma_bf16_c2(d1, a1 + (uint64_t)(ka * 2), bd + (uint64_t)(kb * 2), idesc2, started);
+                                    } else {
+                                        tc_mma_bf16(d0, a0 + (uint64_t)(ka * 2), bd + (uint64_t)(kb * 2), idesc, started);
+                                        if (two) tc_mma_bf16(d1, a1 + (uint64_t)(ka * 2), bd + (uint64_t)(kb * 2), idesc, started);
+                                    }
                                     started = 1;
                                 }
                             } else {
@@ -593,11 +672,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
                                 }
                             }
                         }
-                        tc_commit(empty0 + 8 * stage);              // frees the smem slot when these MMAs retire
+                        if (c2) tc_commit_c2(empty0 + 8 * stage, 3);  // ... in both CTAs
+                        else tc_commit(empty0 + 8 * stage);         // frees the smem slot when these MMAs retire
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
-                tc_commit(tfull0 + 8 * acc);                    // accumulators complete -> epilogue
+                if (c2) tc_commit_c2(tfull0 + 8 * acc, 3);
+                else tc_commit(tfull0 + 8 * acc);               // accumulators complete -> epilogue
                 if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -609,26 +690,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constan
         const int chunk0 = ew >> 2, chunk_step = nepi >> 2;           // with 8 warps the two warps of a quarter alternate chunks
         float4* stage = reinterpret_cast<float4*>(smem_raw + (bars + 256 - raw)) + ew * 256;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-            const int mp = u / p.n_tiles, nt = u - mp * p.n_tiles;
-            const bool two = p.mtu == 2 && 2 * mp + 1 < m_tiles;
+        const uint32_t tempty_l = c2 ? mapa_u32(tempty0, 0) : tempty0;       // pair mode: the leader's MMA warp waits for both CTAs
+        for (int u = u_first; u < u_end; u += u_step) {
+            int mp, nt;
+            if (c2) { nt = u % p.n_tiles; mp = 2 * (u / p.n_tiles) + (int)rank; }
+            else { mp = u / p.n_tiles; nt = u - mp * p.n_tiles; }
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
-            for (int j = 0; j < (two ? 2 : 1); ++j)      // one copy of the epilogue code for both tiles of a unit
-                epilogue_tile<FMT, SCATTER>(p, p.mtu * mp + j, nt, t_row + (uint32_t)(j * noff), row, lane, stage, chunk0, chunk_step);
+            for (int j = 0; j < p.mtu; ++j)              // one copy of the epilogue code for both tiles of a unit
+                if (mp < m_pairs && p.mtu * mp + j < m_tiles)
+                    epilogue_tile<FMT, SCATTER>(p, p.mtu * mp + j, nt, t_row + (uint32_t)(j * noff), row, lane, stage, chunk0, chunk_step);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            if (lane == 0) { if (c2) mbar_arrive_cluster(tempty_l + 8 * acc); else mbar_arrive(tempty0 + 8 * acc); }
             if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (c2) cluster_sync_all();                                   // no commit / remote arrive is still on its way to a CTA that exits
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+        if (c2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
     }
 }
 
@@ -1565,31 +1651,6 @@ conv_tc_wgrad_r2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
 // .cta_group::2, expect_tx for both halves by the leader), the leader's MMA warp issues tcgen05.mma.cta_group::2 and releases the
 // stage / publishes the accumulators with tcgen05.commit .multicast::cluster to BOTH CTAs, every epilogue warp of both CTAs reads
 // its own TMEM and arrives on the leader's accumulator-free barrier.
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
-    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void tma_load_5d_c2(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2, int c3, int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
-}
-__device__ __forceinline__ void tc_commit_c2(uint32_t bar, uint16_t cta_mask) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16_c2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -1909,6 +1970,7 @@ int launch_tc(const CUtensorMap& ms, const CUtensorMap& mw, const TcArgs& a_in, 
         SSDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<ACT_F32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         SSDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<ACT_S32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         SSDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<ACT_S32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        SSDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<ACT_S32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr = true;
     }
     TcArgs a = a_in;
@@ -1942,6 +2004,20 @@ int launch_tc(const CUtensorMap& ms, const CUtensorMap& mw, const TcArgs& a_in, 
     static int wide = -1;
     if (wide < 0) { const char* ov = getenv("SSDB_TC_EPI8"); wide = ov ? (atoi(ov) ? 1 : 0) : 1; }
     const int threads = (ctas_per_sm == 2 || !wide) ? NUM_THREADS : TC_THREADS;
+    if (a.c2 && ctas_per_sm == 1) {
+        // clusters of two CTAs (the two SMs of a TPC); a pair owns two consecutive units of one N tile
+        const long long m_pairs = (m_tiles + a.mtu - 1) / a.mtu;
+        const long long pairs = ((m_pairs + 1) / 2) * a.n_tiles, pslots = num_sms() / 2;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(2 * (pairs < pslots ? pairs : pslots))); cfg.blockDim = dim3((unsigned)threads);
+        cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        ++::ssdb::g_launches;
+        SSDB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<ACT_S32, false, true>, ms, mw, a));
+        return SSDB_OK;
+    }
     if (a.split) {
         if (scatter) conv_tc_kernel<ACT_S32, true><<<grid, threads, smem, st>>>(ms, mw, a);
         else conv_tc_kernel<ACT_S32, false><<<grid, threads, smem, st>>>(ms, mw, a);
@@ -2110,6 +2186,20 @@ static int split_terms_env() {
     return (t < 1 || t > 3) ? 3 : t;
 }
 
+// Pair mode of the fprop / dgrad kernel (TcArgs::c2): split operands, N tile >= 128, enough units for two waves of the 74 SM pairs.
+// Measured on B200 (vgg300, batch 64, same box, SSDB_TC_PAIR=0 / 1): see DESIGN.md section 4.
+static void maybe_pair(TcArgs& a, bool split, bool scatter) {
+    static int on = -1;
+    if (on < 0) { const char* ov = getenv("SSDB_TC_PAIR"); on = ov ? atoi(ov) : 1; }       // 0 off, 1 fprop + dgrad, 2 fprop only
+    if (!on || (on == 2 && a.mode != 0) || !split || scatter || a.resb || a.block_n < 128 || a.block_n % 16 != 0 || num_sms() % 2 != 0) return;
+    const long long m_tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_n;
+    const long long units = ((m_tiles + a.mtu - 1) / a.mtu) * a.n_tiles;
+    if (units < 2LL * num_sms()) return;
+    a.c2 = 1;
+    a.stage_bytes = (a.mtu * a.a_slot + a.b_tiles * a.block_n * 64 + 1023) / 1024 * 1024;
+    a.stages = RING_BYTES / a.stage_bytes; if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
+}
+
 // can this fprop write the 2x2 / stride-2 max pool of its output instead of the output (see TcArgs::pool)?
 bool conv_tc_fprop_can_pool(const ConvGeom& g, int fmt) {
     if (fmt != ACT_S32 || !conv_tc_supported_fprop(g) || (g.Ho & 1) || (g.Wo & 1) || g.Cout % 32 != 0) return false;
@@ -2147,6 +2237,7 @@ int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_
     const bool resb = rw && !ep.scatter && try_resident_filter(a, g.k, tdy, tdx, g.B, g.Ho, g.Wo, fmt == ACT_S32,
                                                                (double)g.B * g.Ho * g.Wo / ((double)a.tiles_x * a.tiles_y * a.tiles_n * 128.0));
     if (resb) { t.TW = 8; t.TH = 16; t.TN = 1; }
+    maybe_pair(a, fmt == ACT_S32, ep.scatter != 0);
     SSDB_REQUIRE(g.pad_t == g.pad_l, "tcgen05 path assumes equal top/left padding");
     a.dst = y; a.bias = ep.bias; a.mask = nullptr; a.relu = ep.relu; a.beta = 0; a.round_out = ep.round_tf32;
     a.split = fmt == ACT_S32 ? 1 : 0; a.split_terms = split_terms_env();
@@ -2154,7 +2245,7 @@ int conv_tc_fprop(const ConvGeom& g, const float* x, const float* w_t, int cout_
     a.scatter = ep.scatter; a.V = ep.V; a.n_valid = ep.n_valid; a.anchor_base = ep.anchor_base; a.A = ep.A;
     CUtensorMap ms, mw;
     int rc = encode_act_map(&ms, x, g.B, g.H, g.W, g.Cin, rw ? a.a_sbo / 128 : t.TW, resb ? t.TH + 2 : t.TH, t.TN, CU_TENSOR_MAP_SWIZZLE_128B, g.stride); if (rc) return rc;
-    rc = encode_w_map(&mw, w_t, (long long)g.k * g.k * cout_pad, g.Cin, a.block_n); if (rc) return rc;
+    rc = encode_w_map(&mw, w_t, (long long)g.k * g.k * cout_pad, g.Cin, a.c2 ? a.block_n / 2 : a.block_n); if (rc) return rc;
     return launch_tc(ms, mw, a, st);
 }
 
@@ -2212,9 +2303,10 @@ int conv_tc_dgrad(const ConvGeom& g, const float* dz, const float* w_hwio, int f
             }
             a.dst = dx; a.bias = nullptr; a.mask = mask_x; a.relu = 0; a.beta = beta; a.round_out = round_out;
             a.split = fmt == ACT_S32 ? 1 : 0; a.split_terms = split_terms_env();
+            maybe_pair(a, fmt == ACT_S32, false);
             CUtensorMap ms, mw;
             int rc = encode_act_map(&ms, dz, g.B, g.Ho, g.Wo, g.Cout, rw ? a.a_sbo / 128 : t.TW, resb ? t.TH + 2 : t.TH, t.TN); if (rc) return rc;
-            rc = encode_w_map(&mw, w_hwio, (long long)g.k * g.k * g.Cin, g.Cout, a.block_n); if (rc) return rc;
+            rc = encode_w_map(&mw, w_hwio, (long long)g.k * g.k * g.Cin, g.Cout, a.c2 ? a.block_n / 2 : a.block_n); if (rc) return rc;
             rc = launch_tc(ms, mw, a, st); if (rc) return rc;
         }
     }
