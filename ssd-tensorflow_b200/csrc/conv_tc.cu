@@ -2189,8 +2189,8 @@ static int split_terms_env() {
 // Pair mode of the fprop / dgrad kernel (TcArgs::c2): split operands, N tile >= 128, enough units for two waves of the 74 SM pairs.
 // Measured on B200 (vgg300, batch 64, same box, SSDB_TC_PAIR=0 / 1): see DESIGN.md section 4.
 static void maybe_pair(TcArgs& a, bool split, bool scatter) {
-    static int on = -1;
-    if (on < 0) { const char* ov = getenv("SSDB_TC_PAIR"); on = ov ? atoi(ov) : 1; }       // 0 off, 1 fprop + dgrad, 2 fprop only
+    const char* ov = getenv("SSDB_TC_PAIR");                    // read per call (tests compare both paths): 0 off, 1 fprop + dgrad, 2 fprop only
+    const int on = ov ? atoi(ov) : 1;
     if (!on || (on == 2 && a.mode != 0) || !split || scatter || a.resb || a.block_n < 128 || a.block_n % 16 != 0 || num_sms() % 2 != 0) return;
     const long long m_tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_n;
     const long long units = ((m_tiles + a.mtu - 1) / a.mtu) * a.n_tiles;

@@ -159,3 +159,43 @@ def test_tcgen05_row_window_wgrad_matches_simt(case, impl, tol):
         os.environ.pop('SSDB_WG_RW_MAXN', None)
     assert rel_err(w_t, w_s) < tol, ('wgrad rw', case, rel_err(w_t, w_s))
     assert rel_err(b_t, b_s) < tol, ('bias rw', case, rel_err(b_t, b_s))
+
+
+def _with_env(name, value, fn):
+    old = os.environ.get(name)
+    os.environ[name] = value
+    try:
+        return fn()
+    finally:
+        if old is None:
+            os.environ.pop(name, None)
+        else:
+            os.environ[name] = old
+
+
+@pytest.mark.parametrize('case', [(64, 38, 256, 512), (16, 75, 128, 256), (8, 150, 128, 128), (64, 38, 512, 128)])
+def test_sm_pair_kernels_equal_single_cta_kernels(case):
+    """The cta_group::2 variants (clusters of two CTAs: conv_tc_kernel<.., PAIR> for fprop / dgrad, conv_tc_wgrad_r2c2_kernel for
+    the 3x3 weight gradients with Cout % 256 == 0) contract the same products in the same order as the single-CTA kernels:
+    every output must be bit-identical.  Shapes with at least two waves of units, so that the pair paths are the ones taken."""
+    B, H, Cin, Cout = case
+    x, w, b, pad, Ho = conv_case(B, H, Cin, Cout, 3, 1, 1, 'SAME', seed=H + Cout)
+    rng = np.random.default_rng(21)
+    dz = rng.standard_normal((B, Ho, Ho, Cout), dtype=np.float32)
+    impl = ssdb.CONV_TC_SPLIT
+    got = {}
+    for pair in ('1', '0'):
+        got[pair] = _with_env('SSDB_TC_PAIR', pair, lambda: _with_env('SSDB_WG_C2', pair, lambda: (
+            run_fprop(impl, x, w, b, 3, 1, 1, pad, Ho),
+            run_dgrad(impl, dz, w, x, x.shape, 3, 1, 1, pad),
+            run_wgrad(impl, x, dz, 3, 1, 1, pad))))
+    y1, d1, (w1, b1) = got['1']
+    y0, d0, (w0, b0) = got['0']
+    assert np.array_equal(y1, y0), ('fprop', rel_err(y1, y0))
+    assert np.array_equal(d1, d0), ('dgrad', rel_err(d1, d0))
+    assert np.array_equal(w1, w0) and np.array_equal(b1, b0), ('wgrad', rel_err(w1, w0))
+    # and they are right: against the CUDA-core kernels on the same data
+    y_s = run_fprop(ssdb.CONV_SIMT, x, w, b, 3, 1, 1, pad, Ho)
+    assert rel_err(y1, y_s) < SPLIT_TOL
+    w_s, _ = run_wgrad(ssdb.CONV_SIMT, x, dz, 3, 1, 1, pad)
+    assert rel_err(w1, w_s) < SPLIT_TOL
