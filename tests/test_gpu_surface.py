@@ -314,3 +314,29 @@ def test_frozen_model_export_detect_and_cuda_graph(tmp_path):
         assert os.path.exists(os.path.join(out, base))
         lines = open(os.path.join(out, base + '.txt')).read().splitlines()
         assert 0 < len(lines) <= 200 and all(len(l.split()) == 6 for l in lines)
+
+
+def test_cuda_graph_forward_with_cluster_launches_at_batch_32():
+    """At batch 32 the N >= 128 layers of the forward run as clusters of two CTAs (cta_group::2 pair kernels, cudaLaunchKernelEx with
+    a cluster dimension): the CUDA graph of an inference handle must capture and replay them, with the detections of the eager
+    training engine."""
+    import ssdb
+    preset = 'vgg300'
+    x = synth.images(40, 32, 300)
+    nets = [ssdb.Net(preset, 20, max_batch=32), ssdb.Net(preset, 20, max_batch=32, inference=True)]
+    P = SSDVGG(Session(), ssdutils.get_preset_by_name(preset))._initial_params(20, seed=3)
+    for net in nets:
+        for k, shape in net.tensors():
+            net.set_tensor(k, P[k])
+    want = nets[0].forward_detect_host(x, 0.01, 200, 0.45)
+    launches = []
+    for it in range(3):                               # eager, capture + launch, replay
+        l0 = ssdb.launch_count()
+        got = nets[1].forward_detect_host(x, 0.01, 200, 0.45)
+        launches.append(ssdb.launch_count() - l0)
+        assert np.array_equal(got[1], want[1]), it
+        for i in range(32):
+            assert np.array_equal(got[0][i, :got[1][i, 0]], want[0][i, :want[1][i, 0]]), (it, i)
+    assert launches[0] > 50 and launches[2] == 1, launches
+    for net in nets:
+        net.close()
