@@ -2049,10 +2049,11 @@ int tc_mtu(int block_n, long long m_tiles, int n_tiles, int kblocks, bool dgrad,
 
 // fill the tap-group table: plain (one tap per group) or row-window (3 taps of a filter row per group, TW must be 8)
 void fill_groups(TcArgs& a, int k, const int* dy, const int* dx, bool row_window) {
+    if (k > 3) k = 3;                                            // callers require k <= 3 (the tables hold 9 taps)
     const int taps = k * k;
     if (!row_window) {
         a.ngroups = taps;
-        for (int t = 0; t < taps; ++t) {
+        for (int t = 0; t < taps && t < 9; ++t) {
             a.g_dy[t] = (signed char)dy[t]; a.g_dx[t] = (signed char)dx[t]; a.g_nt[t] = 1; a.g_win[t][0] = 0; a.g_w[t][0] = (unsigned char)t;
         }
         a.a_rows = a.TW * a.TH * a.TN; a.a_slot = A_BYTES; a.a_sbo = 1024; a.b_tiles = 1;
