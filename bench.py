@@ -343,7 +343,7 @@ class TrainBench:
                 'traffic': traffic,
                 'traffic_note': ('mean dram__bytes_read+write per launch over the %s conv launches captured in profiles/r2_ncu_conv_split_b64.txt '
                                  '(ncu --set full of conv1_2 / conv2_2 / conv4_2 fprop, dgrad, wgrad at this batch; committed, not re-measured by this run)' % ncap) if traffic else None,
-                'kernel': 'conv_tc_kernel + conv_tc_wgrad_r2_kernel + conv_tc_wgrad_s_kernel + conv_tc_wgrad_rw_s_kernel (tcgen05 kind::%s implicit GEMM), all conv launches of one step'
+                'kernel': 'conv_tc_kernel (single CTAs and SM pairs) + conv_tc_wgrad_r2c2_kernel (SM pairs) + conv_tc_wgrad_r2 / _s / _rw_s kernels (tcgen05 kind::%s implicit GEMM, cta_group::1 and ::2), all conv launches of one step'
                           % ('f16, split bf16 operands' if self.mode == 'split' else 'tf32'),
                 'launches': conv_launch, 'ms_per_step_in_kernel': conv_ms,
                 'timing_note': 'per-op CUDA events with the two streams serialised (ssdb_profile_step); the timed step overlaps them, so the sum can exceed ms_per_step',
